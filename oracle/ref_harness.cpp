@@ -1,0 +1,430 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Thin C-ABI shim around the UNMODIFIED reference (UFOMap, headers included from
+// /root/reference at compile time; nothing is copied into this repo).  It is
+// built into oracle/_ref/libufo_ref.so by oracle/Makefile and is used
+//   * by tests/ to pin the CPU restatement (oracle/ufo_oracle.c) and the CUDA
+//     path against the real reference implementation, and to generate the
+//     committed fixtures in tests/golden/ (tests/golden/make_golden.py);
+//   * by bench.py's cpu_baseline / --impl reference leg (kind = "reference").
+// Nothing in the product path (ufomap_b200/) may link or load this file.
+//
+// State is read through a subclass that walks the pointer octree directly
+// (root -> children), NOT through getOccupancy(code): Octree::getNode has an
+// off-by-one (octree.h:974-985) and returns the depth-1 parent.
+
+#include <ufo/map/occupancy_map.h>
+#include <ufo/map/occupancy_map_color.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+// ---- LZ4 stubs (compressed file I/O is never used by the oracle) -------------
+extern "C" {
+int LZ4_compressBound(int) { return 0; }
+int LZ4_compress_fast(const char*, char*, int, int, int) { return -1; }
+int LZ4_decompress_safe(const char*, char*, int, int) { return -1; }
+int LZ4_compress_HC(const char*, char*, int, int, int) { return -1; }
+}
+
+namespace
+{
+using ufo::map::Code;
+using ufo::map::CodeMap;
+using ufo::map::Color;
+using ufo::map::DepthType;
+using ufo::map::Key;
+using ufo::map::Point3;
+using ufo::map::Point3Color;
+using ufo::map::PointCloud;
+using ufo::map::PointCloudColor;
+
+struct NodeRec {
+	uint64_t code;
+	uint32_t depth;
+	float occ;
+	uint8_t rgb[3];
+	uint8_t flags;  // bit0 contains_free, bit1 contains_unknown, bit2 is_leaf
+};
+
+inline void colorOf(ufo::map::OccupancyNode<float> const&, uint8_t* rgb)
+{
+	rgb[0] = rgb[1] = rgb[2] = 0;
+}
+inline void colorOf(ufo::map::ColorOccupancyNode<float> const& v, uint8_t* rgb)
+{
+	rgb[0] = v.color.r;
+	rgb[1] = v.color.g;
+	rgb[2] = v.color.b;
+}
+
+template <class MAP>
+class Probe : public MAP
+{
+ public:
+	using MAP::MAP;
+
+	// Pre-order walk of the real pointer tree.  leaves=true: emit nodes without
+	// children (depth-0 voxels and collapsed / never-split inner nodes);
+	// leaves=false: emit nodes that have children.
+	void walk(std::vector<NodeRec>& out, bool leaves) const
+	{
+		walkRec(this->getRoot(), this->getTreeDepthLevels(), 0, out, leaves);
+	}
+
+	// getNodePath semantics (octree.h:957-972): deepest existing node on the
+	// path to `code`.
+	bool nodeAt(uint64_t code, unsigned depth, NodeRec& rec)
+	{
+		auto [path, d] = this->getNodePath(Code(code, depth));
+		rec.code = code;
+		rec.depth = d;
+		rec.occ = path[d]->value.occupancy;
+		colorOf(path[d]->value, rec.rgb);
+		rec.flags = 0;
+		if (d > 0) {
+			auto const& in = static_cast<typename MAP::INNER_NODE const&>(*path[d]);
+			rec.flags = (in.contains_free ? 1 : 0) | (in.contains_unknown ? 2 : 0) |
+			            (in.is_leaf ? 4 : 0);
+		} else {
+			rec.flags = (this->isFree(*path[0]) ? 1 : 0) | (this->isUnknown(*path[0]) ? 2 : 0) | 4;
+		}
+		return d == depth;
+	}
+
+	// Protected freeSpace (occupancy_map_base.h:1229-1259) exposed: returns the
+	// per-scan free set exactly as the integrator builds it.
+	void freeSet(Point3 const& origin, PointCloud const& ends, unsigned depth, bool simple,
+	             unsigned early_stopping, std::vector<uint64_t>& codes) const
+	{
+		CodeMap<float> free_hits;
+		this->freeSpace(origin, ends, free_hits, -1.0f, depth, simple, early_stopping);
+		codes.clear();
+		codes.reserve(free_hits.size());
+		for (auto const& [code, value] : free_hits) {
+			codes.push_back(code.getCode());
+		}
+	}
+
+	bool moveLine(Point3& a, Point3& b) const { return this->moveLineInside(a, b); }
+
+	// The stored (double) log-odds parameters (occupancy_map_base.h:1537-1542).
+	void sensorModel(double* out6) const
+	{
+		out6[0] = this->occupied_thres_log_;
+		out6[1] = this->free_thres_log_;
+		out6[2] = this->prob_hit_log_;
+		out6[3] = this->prob_miss_log_;
+		out6[4] = this->clamping_thres_min_log_;
+		out6[5] = this->clamping_thres_max_log_;
+	}
+
+ private:
+	template <class NODE>
+	void walkRec(NODE const& node, unsigned depth, uint64_t code, std::vector<NodeRec>& out,
+	             bool leaves) const
+	{
+		bool is_leaf = node.is_leaf;
+		if (is_leaf == leaves) {
+			NodeRec r;
+			r.code = code;
+			r.depth = depth;
+			r.occ = node.value.occupancy;
+			colorOf(node.value, r.rgb);
+			r.flags = (node.contains_free ? 1 : 0) | (node.contains_unknown ? 2 : 0) |
+			          (is_leaf ? 4 : 0);
+			out.push_back(r);
+		}
+		if (is_leaf) {
+			return;
+		}
+		unsigned cd = depth - 1;
+		for (unsigned i = 0; i < 8; ++i) {
+			uint64_t ccode = code + (uint64_t(i) << (3 * cd));
+			if (0 == cd) {
+				if (leaves) {
+					auto const& leaf = MAP::getLeafChild(node, i);
+					NodeRec r;
+					r.code = ccode;
+					r.depth = 0;
+					r.occ = leaf.value.occupancy;
+					colorOf(leaf.value, r.rgb);
+					r.flags = (this->isFree(leaf) ? 1 : 0) | (this->isUnknown(leaf) ? 2 : 0) | 4;
+					out.push_back(r);
+				}
+			} else {
+				walkRec(MAP::getInnerChild(node, i), cd, ccode, out, leaves);
+			}
+		}
+	}
+};
+
+struct RefMap {
+	bool color;
+	Probe<ufo::map::OccupancyMap>* mono = nullptr;
+	Probe<ufo::map::OccupancyMapColor>* col = nullptr;
+	std::vector<NodeRec> scratch;
+	~RefMap()
+	{
+		delete mono;
+		delete col;
+	}
+};
+
+template <class F>
+auto withMap(RefMap* m, F&& f)
+{
+	if (m->color) {
+		return f(*m->col);
+	}
+	return f(*m->mono);
+}
+}  // namespace
+
+extern "C" {
+
+void* ufo_ref_create(double resolution, unsigned depth_levels, int automatic_pruning,
+                     double occupied_thres, double free_thres, double prob_hit,
+                     double prob_miss, double clamp_min, double clamp_max, int color)
+{
+	try {
+		RefMap* m = new RefMap;
+		m->color = color != 0;
+		if (m->color) {
+			m->col = new Probe<ufo::map::OccupancyMapColor>(
+			    resolution, depth_levels, automatic_pruning != 0, occupied_thres, free_thres,
+			    prob_hit, prob_miss, clamp_min, clamp_max);
+			m->col->enableMinMaxChangeDetection(true);
+		} else {
+			m->mono = new Probe<ufo::map::OccupancyMap>(
+			    resolution, depth_levels, automatic_pruning != 0, occupied_thres, free_thres,
+			    prob_hit, prob_miss, clamp_min, clamp_max);
+			m->mono->enableMinMaxChangeDetection(true);
+		}
+		return m;
+	} catch (std::exception const&) {
+		return nullptr;
+	}
+}
+
+void ufo_ref_destroy(void* h) { delete static_cast<RefMap*>(h); }
+
+// xyz: n*3 doubles; rgb: n*3 bytes or NULL.  discrete!=0 selects
+// insertPointCloudDiscrete.  Returns wall seconds spent inside the reference call
+// (steady_clock, as ufomap_mapping/src/server.cpp:111-125 times it).
+double ufo_ref_insert(void* h, const double* origin, const double* xyz, const uint8_t* rgb,
+                      size_t n, double max_range, unsigned depth, int simple,
+                      unsigned early_stopping, int discrete, int async)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	Point3 o(origin[0], origin[1], origin[2]);
+	double secs = 0;
+	if (rgb) {
+		PointCloudColor cloud;
+		cloud.reserve(n);
+		for (size_t i = 0; i < n; ++i) {
+			cloud.push_back(Point3Color(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], rgb[3 * i],
+			                            rgb[3 * i + 1], rgb[3 * i + 2]));
+		}
+		auto t0 = std::chrono::steady_clock::now();
+		if (m->color) {
+			// OccupancyMapColor::insertPointCloud(PointCloudColor) does not compile in
+			// the reference (occupancy_map_color.h:113); only the discrete variant exists.
+			if (!discrete) {
+				return -1.0;
+			}
+			m->col->insertPointCloudDiscrete(o, cloud, max_range, depth, simple != 0,
+			                                 early_stopping, async != 0);
+			m->col->insertPointCloudWait();
+		} else {
+			if (!discrete) {
+				return -1.0;
+			}
+			m->mono->insertPointCloudDiscrete(o, cloud, max_range, depth, simple != 0,
+			                                  early_stopping, async != 0);
+			m->mono->insertPointCloudWait();
+		}
+		secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	} else {
+		PointCloud cloud;
+		cloud.reserve(n);
+		for (size_t i = 0; i < n; ++i) {
+			cloud.push_back(Point3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+		}
+		auto t0 = std::chrono::steady_clock::now();
+		withMap(m, [&](auto& map) {
+			if (discrete) {
+				map.insertPointCloudDiscrete(o, cloud, max_range, depth, simple != 0,
+				                             early_stopping, async != 0);
+			} else {
+				map.insertPointCloud(o, cloud, max_range, depth, simple != 0, early_stopping,
+				                     async != 0);
+			}
+			map.insertPointCloudWait();
+		});
+		secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	}
+	return secs;
+}
+
+// Two-phase dump: ufo_ref_walk() fills an internal buffer and returns the count;
+// ufo_ref_walk_fetch() copies it out as SoA.
+size_t ufo_ref_walk(void* h, int leaves)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	m->scratch.clear();
+	withMap(m, [&](auto& map) { map.walk(m->scratch, leaves != 0); });
+	return m->scratch.size();
+}
+
+void ufo_ref_walk_fetch(void* h, uint64_t* codes, uint32_t* depths, float* occ, uint8_t* rgb,
+                        uint8_t* flags)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	for (size_t i = 0; i < m->scratch.size(); ++i) {
+		NodeRec const& r = m->scratch[i];
+		if (codes) codes[i] = r.code;
+		if (depths) depths[i] = r.depth;
+		if (occ) occ[i] = r.occ;
+		if (rgb) std::memcpy(rgb + 3 * i, r.rgb, 3);
+		if (flags) flags[i] = r.flags;
+	}
+	m->scratch.clear();
+	m->scratch.shrink_to_fit();
+}
+
+// Returns 1 if a node exists at exactly (code, depth); out describes the deepest
+// existing node on the path either way.
+int ufo_ref_node(void* h, uint64_t code, unsigned depth, float* occ, uint8_t* rgb,
+                 uint8_t* flags, unsigned* found_depth)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	NodeRec r;
+	bool exact = withMap(m, [&](auto& map) { return map.nodeAt(code, depth, r); });
+	*occ = r.occ;
+	std::memcpy(rgb, r.rgb, 3);
+	*flags = r.flags;
+	*found_depth = r.depth;
+	return exact ? 1 : 0;
+}
+
+size_t ufo_ref_compute_ray(void* h, const double* origin, const double* end, double max_range,
+                           unsigned depth, uint64_t* codes, size_t cap)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	auto ray = withMap(m, [&](auto& map) {
+		return map.computeRay(Point3(origin[0], origin[1], origin[2]),
+		                      Point3(end[0], end[1], end[2]), max_range, depth);
+	});
+	for (size_t i = 0; i < ray.size() && i < cap; ++i) {
+		codes[i] = ray[i].getCode();
+	}
+	return ray.size();
+}
+
+// The integrator's free set (protected freeSpace) for rays origin -> ends[i].
+size_t ufo_ref_free_set(void* h, const double* origin, const double* ends, size_t n,
+                        unsigned depth, int simple, unsigned early_stopping, uint64_t* codes,
+                        size_t cap)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	PointCloud cloud;
+	cloud.reserve(n);
+	for (size_t i = 0; i < n; ++i) {
+		cloud.push_back(Point3(ends[3 * i], ends[3 * i + 1], ends[3 * i + 2]));
+	}
+	std::vector<uint64_t> out;
+	withMap(m, [&](auto& map) {
+		map.freeSet(Point3(origin[0], origin[1], origin[2]), cloud, depth, simple != 0,
+		            early_stopping, out);
+	});
+	for (size_t i = 0; i < out.size() && i < cap; ++i) {
+		codes[i] = out[i];
+	}
+	return out.size();
+}
+
+void ufo_ref_to_key(void* h, const double* xyz, unsigned depth, uint32_t* key)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	Key k = withMap(m, [&](auto& map) { return map.toKey(Point3(xyz[0], xyz[1], xyz[2]), depth); });
+	key[0] = k[0];
+	key[1] = k[1];
+	key[2] = k[2];
+}
+
+uint64_t ufo_ref_to_code(void* h, const double* xyz, unsigned depth)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	return withMap(m, [&](auto& map) {
+		return map.toCode(Point3(xyz[0], xyz[1], xyz[2]), depth).getCode();
+	});
+}
+
+uint64_t ufo_ref_key_to_code(const uint32_t* key, unsigned depth)
+{
+	return Code(Key(key[0], key[1], key[2], depth)).getCode();
+}
+
+void ufo_ref_code_to_key(uint64_t code, unsigned depth, uint32_t* key)
+{
+	Key k = Code(code, depth).toKey();
+	key[0] = k[0];
+	key[1] = k[1];
+	key[2] = k[2];
+}
+
+void ufo_ref_key_to_coord(void* h, const uint32_t* key, unsigned depth, double* xyz)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	Point3 p = withMap(m, [&](auto& map) { return map.toCoord(Key(key[0], key[1], key[2], depth)); });
+	xyz[0] = p[0];
+	xyz[1] = p[1];
+	xyz[2] = p[2];
+}
+
+int ufo_ref_move_line_inside(void* h, double* a, double* b)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	Point3 pa(a[0], a[1], a[2]), pb(b[0], b[1], b[2]);
+	bool ok = withMap(m, [&](auto& map) { return map.moveLine(pa, pb); });
+	for (int i = 0; i < 3; ++i) {
+		a[i] = pa[i];
+		b[i] = pb[i];
+	}
+	return ok ? 1 : 0;
+}
+
+void ufo_ref_change_bbox(void* h, double* mn, double* mx)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	withMap(m, [&](auto& map) {
+		for (int i = 0; i < 3; ++i) {
+			mn[i] = map.minChange()[i];
+			mx[i] = map.maxChange()[i];
+		}
+	});
+}
+
+void ufo_ref_reset_change_bbox(void* h)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	withMap(m, [&](auto& map) { map.resetMinMaxChangeDetection(); });
+}
+
+// Sensor model constants as the reference stores them (double log-odds).
+void ufo_ref_sensor_model(void* h, double* out6)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	withMap(m, [&](auto& map) { map.sensorModel(out6); });
+}
+
+size_t ufo_ref_memory_usage(void* h)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	return withMap(m, [&](auto& map) { return size_t(map.memoryUsage()); });
+}
+
+}  // extern "C"
