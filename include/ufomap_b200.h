@@ -1,0 +1,173 @@
+/* ufomap_b200.h -- C ABI of the B200-native UFOMap point-cloud integration path.
+ *
+ * The reference (UFOMap) has no FFI or plugin layer: its boundary for this path
+ * is the C++ class API of libMap (ufo::map::OccupancyMap / OccupancyMapColor,
+ * mostly header templates).  Each entry point below names the reference member
+ * it stands in for (paths relative to /root/reference/ufomap/include/ufo/map/).
+ * The source-compatible C++ facade in include/ufomap_b200/ufomap.hpp forwards to
+ * these functions; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns a
+ * ufo_b200_status (0 = OK) unless stated otherwise; a map is bound to one CUDA
+ * device and one CUDA stream and is not thread-safe (same as the reference).
+ * The library never falls back to a CPU implementation: without a usable
+ * device ufo_b200_create fails with UFO_B200_E_CUDA.
+ */
+#ifndef UFOMAP_B200_H
+#define UFOMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ufo_b200_map ufo_b200_map;
+
+typedef enum {
+	UFO_B200_OK = 0,
+	UFO_B200_E_INVALID = 1,     /* bad argument (e.g. depth_levels outside [2,21], octree.h:931-935) */
+	UFO_B200_E_CUDA = 2,        /* CUDA runtime error; see ufo_b200_last_error() */
+	UFO_B200_E_NOMEM = 3,       /* device pool could not grow */
+	UFO_B200_E_UNSUPPORTED = 4  /* documented out-of-scope option */
+} ufo_b200_status;
+
+/* Point buffer layouts accepted by ufo_b200_insert_*: tightly packed AoS. */
+typedef enum {
+	UFO_B200_XYZ_F64 = 0,     /* double x,y,z             (PointCloud,      point_cloud.h:277) */
+	UFO_B200_XYZ_F32 = 1,     /* float  x,y,z             (ROS PointCloud2 payload)            */
+	UFO_B200_XYZRGB_F64 = 2,  /* double x,y,z + u8 r,g,b + 5 pad = 32 B (Point3Color, types.h:60-102) */
+	UFO_B200_XYZRGB_F32 = 3   /* float  x,y,z + u8 r,g,b + 1 pad = 16 B                        */
+} ufo_b200_layout;
+
+/* Constructor arguments of OccupancyMap / OccupancyMapColor (occupancy_map.h:60-63,
+ * occupancy_map_base.h:859-876) plus device-side sizing hints. */
+typedef struct {
+	double resolution;
+	uint32_t depth_levels;       /* 2..21, default 16 */
+	int32_t automatic_pruning;   /* accepted for API parity; pruning is representational only */
+	double occupied_thres;       /* 0.5 */
+	double free_thres;           /* 0.5 */
+	double prob_hit;             /* 0.7 */
+	double prob_miss;            /* 0.4 */
+	double clamping_thres_min;   /* 0.1192 */
+	double clamping_thres_max;   /* 0.971 */
+	int32_t color;               /* 0: OccupancyMap, 1: OccupancyMapColor */
+	int32_t device;              /* CUDA device ordinal, -1 = current, -2 = geometry-only handle
+	                              * (host indexing / computeRay helpers only, no device state) */
+	uint64_t initial_blocks;     /* capacity hint: 4^3-voxel blocks (0 = default) */
+	uint64_t initial_bricks;     /* capacity hint: 16^3-voxel bricks (0 = default) */
+} ufo_b200_params;
+
+/* Fills *p with the reference's default constructor arguments. */
+void ufo_b200_default_params(ufo_b200_params* p);
+
+/* OccupancyMap::OccupancyMap(...)  occupancy_map.h:60-63 */
+int ufo_b200_create(const ufo_b200_params* p, ufo_b200_map** out);
+void ufo_b200_destroy(ufo_b200_map* m);
+const char* ufo_b200_last_error(const ufo_b200_map* m);
+
+/* Run all work of this map on an externally owned CUDA stream (cudaStream_t as
+ * void*).  NULL restores the map's own stream. */
+int ufo_b200_set_stream(ufo_b200_map* m, void* cuda_stream);
+
+/* insertPointCloud          occupancy_map_base.h:270-327, occupancy_map_color.h:87-160
+ * insertPointCloudDiscrete  occupancy_map_base.h:340-417, occupancy_map_color.h:177-267
+ *
+ * `points` is HOST memory holding n points in `layout`; it is copied before the
+ * call returns (the reference takes the cloud by value).  max_range < 0 means
+ * unlimited.  depth = insert depth of the free-space rays.  async != 0 returns
+ * after the work is enqueued; ufo_b200_wait / ufo_b200_done mirror
+ * insertPointCloudWait / insertPointCloudDone (occupancy_map_base.h:430-443).
+ * early_stopping != 0 is order-dependent in the reference and is rejected with
+ * UFO_B200_E_UNSUPPORTED. */
+int ufo_b200_insert_pointcloud(ufo_b200_map* m, const double origin[3], const void* points,
+                               size_t n, int layout, double max_range, uint32_t depth,
+                               int simple_ray_casting, uint32_t early_stopping, int discrete,
+                               int async);
+
+/* Same, but `points` is DEVICE memory on the map's device (no copy is made; the
+ * buffer must stay valid until the call's work has finished). */
+int ufo_b200_insert_device(ufo_b200_map* m, const double origin[3], const void* d_points,
+                           size_t n, int layout, double max_range, uint32_t depth,
+                           int simple_ray_casting, uint32_t early_stopping, int discrete,
+                           int async);
+
+int ufo_b200_wait(ufo_b200_map* m);           /* insertPointCloudWait */
+int ufo_b200_done(ufo_b200_map* m, int* done); /* insertPointCloudDone */
+
+/* Octree::computeRay  octree.h:449-496 -- forward walk, origin voxel included,
+ * end voxel excluded.  Writes up to cap codes, *n receives the full count. */
+int ufo_b200_compute_ray(const ufo_b200_map* m, const double origin[3], const double end[3],
+                         double max_range, uint32_t depth, uint64_t* codes, size_t cap, size_t* n);
+
+/* Octree::toKey / toCode / toCoord  octree.h:299-394, Code <-> Key code.h:183-230 */
+int ufo_b200_to_key(const ufo_b200_map* m, const double xyz[3], uint32_t depth, uint32_t key[3]);
+int ufo_b200_to_code(const ufo_b200_map* m, const double xyz[3], uint32_t depth, uint64_t* code);
+int ufo_b200_key_to_coord(const ufo_b200_map* m, const uint32_t key[3], uint32_t depth,
+                          double xyz[3]);
+uint64_t ufo_b200_key_to_code(const uint32_t key[3]);
+void ufo_b200_code_to_key(uint64_t code, uint32_t key[3]);
+
+/* Node state at (code, depth) with the INTENDED semantics of getOccupancy /
+ * getColor / containsFree / containsUnknown (occupancy_map_base.h:599-728; the
+ * reference's own Code-based getters read the depth-1 parent, octree.h:974-985).
+ * logodds[i]: float log-odds (max over the subtree for depth > 0);
+ * flags[i]: bit0 contains_free, bit1 contains_unknown; rgb: 3 bytes per query or NULL.
+ * Host pointers. */
+int ufo_b200_query(ufo_b200_map* m, const uint64_t* codes, const uint32_t* depths, size_t n,
+                   float* logodds, uint8_t* flags, uint8_t* rgb);
+
+/* Dump of the value field: every depth-0 voxel whose payload differs from the
+ * default (log-odds 0, colour unset).  Call with codes == NULL to get the count
+ * in *n; then with buffers of that capacity (host pointers; rgb may be NULL). */
+int ufo_b200_export_leaves(ufo_b200_map* m, uint64_t* codes, float* logodds, uint8_t* rgb,
+                           size_t cap, size_t* n);
+
+/* Sensor model  occupancy_map_base.h:734-773.  out6/in: occupied_thres,
+ * free_thres, prob_hit, prob_miss, clamping_thres_min, clamping_thres_max as
+ * probabilities (setters) or as stored double log-odds (ufo_b200_sensor_model_logit). */
+int ufo_b200_set_sensor_model(ufo_b200_map* m, const double prob6[6]);
+int ufo_b200_sensor_model_logit(const ufo_b200_map* m, double logit6[6]);
+
+/* min/max change detection  occupancy_map_base.h:792-822 (always enabled). */
+int ufo_b200_change_bbox(ufo_b200_map* m, double min_change[3], double max_change[3]);
+int ufo_b200_reset_change_bbox(ufo_b200_map* m);
+
+/* Counters and timings of the most recent insert (waits for it to finish). */
+typedef struct {
+	uint64_t points;          /* N                                         */
+	uint64_t rays;            /* rays cast                                 */
+	uint64_t visits;          /* V: voxel visits of the ray walk (only when profiling) */
+	uint64_t touched_voxels;  /* U: unique voxels that received an update  */
+	uint64_t hit_voxels;      /* U_h                                       */
+	uint64_t touched_octets;  /* D_1                                       */
+	uint64_t touched_blocks;  /* D_2 (4^3 blocks)                          */
+	uint64_t touched_bricks;  /* D_4 (16^3 bricks)                         */
+	uint64_t upper_nodes;     /* sum of D_l, l >= 5                        */
+	uint64_t blocks_in_map;   /* pool occupancy                            */
+	uint64_t bricks_in_map;
+	uint64_t device_bytes;    /* device memory held by the map             */
+	uint64_t regrows;         /* pool growth events during this insert     */
+	float ms_total;           /* CUDA-event time of the whole insert (device work) */
+	float ms_h2d;
+	float ms_points;          /* K1: discretise + hit marking              */
+	float ms_rays;            /* K2: ray walk / free-set marking           */
+	float ms_update;          /* K3: leaf log-odds update + in-block aggregates */
+	float ms_propagate;       /* K4: brick + upper-level aggregates        */
+} ufo_b200_scan_stats;
+
+int ufo_b200_last_scan_stats(ufo_b200_map* m, ufo_b200_scan_stats* out);
+/* Enable per-kernel CUDA-event timing and the visit counter (adds event records). */
+int ufo_b200_set_profiling(ufo_b200_map* m, int enable);
+
+/* Forget everything (Octree::clear, octree.h:541-560): keeps device pools. */
+int ufo_b200_clear(ufo_b200_map* m);
+
+const char* ufo_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UFOMAP_B200_H */

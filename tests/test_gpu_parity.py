@@ -1,0 +1,190 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Log-odds are compared bit-for-bit, codes/keys exactly, colours +-1.
+
+The oracle is oracle/libufo_oracle.so (plain-C restatement, pinned to the real
+reference by tests/test_oracle_vs_reference.py and tests/golden/); when the
+prebuilt reference harness travelled (oracle/_ref/libufo_ref.so) the same cases
+are also checked directly against it.
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_value_fields_equal, check_inner_against_field
+from oracle_lib import OracleMap, RefMap, have_ref
+from ufomap_b200 import scans
+from ufomap_b200.capi import Map, UfoError, E_UNSUPPORTED
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_case(map_kw, inserts, color=False, color_tol=1, with_ref=True, levels=(1, 2, 3, 4, 5, 6, 9, 16)):
+    gpu = Map(color=color, initial_blocks=1 << 14, **map_kw)
+    cpus = [OracleMap(color=color, **map_kw)]
+    if with_ref and have_ref():
+        cpus.append(RefMap(color=color, **map_kw))
+    for ins in inserts:
+        gpu.insert(**ins)
+        for c in cpus:
+            c.insert(**ins)
+    field = gpu.value_field()
+    for c in cpus:
+        assert_value_fields_equal(field, c.value_field(), color_tol=color_tol if color else 0,
+                                  what=type(c).__name__)
+    check_inner_against_field(gpu, cpus[0].value_field(), cpus[0].sensor_model(), levels=levels)
+    mn, mx = gpu.change_bbox()
+    rmn, rmx = cpus[0].change_bbox()
+    assert np.array_equal(mn, rmn) and np.array_equal(mx, rmx), (mn, rmn, mx, rmx)
+    st = gpu.stats()
+    gpu.close()
+    return st
+
+
+def test_single_ray_known_answer():
+    """SURVEY.md 8(c) KAT: ray (0,0,0)->(1,0,0) @ 2 cm: end voxel hit+miss, 49 free, origin untouched."""
+    gpu = Map(0.02)
+    gpu.insert([0, 0, 0], [[1.0, 0, 0]], max_range=5.0)
+    codes, occ, _ = gpu.value_field()
+    bits = occ.view(np.uint32)
+    assert len(codes) == 50
+    assert (bits == 0xBECF991F).sum() == 49
+    assert (bits == 0x3EE237E7).sum() == 1
+    gpu.close()
+
+
+def test_config1_plumbing():
+    """BASELINE config #1: 16 cm, 10 k random-shell points, max_range 5 m."""
+    o, p = scans.random_shell()
+    st = _run_case(dict(resolution=0.16), [dict(origin=o, xyz=p, max_range=5.0)])
+    assert st["rays"] == 10000 and st["points"] == 10000
+
+
+def test_config1_discrete_float32_input():
+    o, p = scans.random_shell()
+    _run_case(dict(resolution=0.16, automatic_pruning=False),
+              [dict(origin=o, xyz=p, max_range=5.0, discrete=True)])
+    # float32 payload (ROS PointCloud2) gives the same map as its widened copy
+    a = Map(0.16)
+    b = Map(0.16)
+    a.insert(o, p, max_range=5.0, dtype=np.float32)
+    b.insert(o, p, max_range=5.0, dtype=np.float64)
+    assert_value_fields_equal(a.value_field(), b.value_field())
+
+
+def test_velodyne_stream_with_clamping():
+    """A stream of scans from a moving sensor: exercises hit-then-miss order, clamping
+    and pool growth (initial pool is far too small)."""
+    ins = []
+    for k in range(5):
+        o, p = scans.velodyne64(k=k, rings=32, azimuths=512)
+        ins.append(dict(origin=o, xyz=p, max_range=30.0))
+    st = _run_case(dict(resolution=0.1), ins)
+    assert st["blocks_in_map"] > (1 << 14)
+
+
+def test_velodyne_fine_resolution_full_ring_subset():
+    """2 cm / 30 m (config #2 geometry) on a 16x1024 subset the oracle finishes in seconds."""
+    o, p = scans.velodyne64(rings=16, azimuths=1024)
+    _run_case(dict(resolution=0.02), [dict(origin=o, xyz=p, max_range=30.0)], with_ref=False)
+
+
+def test_long_range_truncation():
+    """5 cm / 100 m (config #4 geometry): rays beyond max_range are truncated, no hit."""
+    o, p = scans.velodyne64(rings=8, azimuths=512)
+    _run_case(dict(resolution=0.05), [dict(origin=o, xyz=p, max_range=20.0)])
+
+
+def test_color_rgbd_discrete():
+    """Config #3-reduced shape: OccupancyMapColor, RGB-D, insertPointCloudDiscrete."""
+    ins = []
+    for k in range(3):
+        o, p, c = scans.rgbd(k=k, width=160, height=120)
+        ins.append(dict(origin=o, xyz=p, rgb=c, max_range=5.0, discrete=True))
+    _run_case(dict(resolution=0.01), ins, color=True)
+
+
+def test_color_map_plain_cloud_and_mono_map_color_cloud():
+    o, p, c = scans.rgbd(width=80, height=60)
+    _run_case(dict(resolution=0.02), [dict(origin=o, xyz=p, max_range=4.0)], color=True)
+    _run_case(dict(resolution=0.02), [dict(origin=o, xyz=p, rgb=c, max_range=4.0, discrete=True)],
+              color=False)
+
+
+def test_insert_depth_1_and_2():
+    o, p, c = scans.rgbd(width=80, height=60)
+    o2, p2, c2 = scans.rgbd(k=1, width=80, height=60)
+    _run_case(dict(resolution=0.02),
+              [dict(origin=o, xyz=p, rgb=c, max_range=3.0, discrete=True, depth=2),
+               dict(origin=o2, xyz=p2, rgb=c2, max_range=3.0, discrete=True, depth=1)], color=True)
+    _run_case(dict(resolution=0.05),
+              [dict(origin=o, xyz=p, max_range=3.0, depth=1), dict(origin=o2, xyz=p2, max_range=4.0, depth=2)])
+
+
+def test_simple_ray_casting():
+    o, p, _ = scans.rgbd(width=80, height=60)
+    _run_case(dict(resolution=0.05), [dict(origin=o, xyz=p, max_range=4.0, simple=True)])
+
+
+def test_rays_leaving_the_map_and_degenerate_points():
+    """Tiny map (depth_levels 6 @ 0.5 m = +-16 m): points outside are clipped or skipped;
+    includes zero-length rays, axis-aligned rays and points on voxel borders."""
+    o = np.array([0.3, -0.2, 0.1])
+    rng = np.random.default_rng(7)
+    p = rng.uniform(-40, 40, size=(4000, 3))
+    special = np.array([o, o + [0.5, 0, 0], o + [0, 0, 3.0], [1.0, 1.0, 1.0], [0.5, 0.5, 0.5],
+                        [16.0, 0, 0], [-16.0, -16.0, -16.0], [15.99, 15.99, 15.99], [100, 0.1, 0.1]])
+    p = np.concatenate([special, p]).astype(np.float32).astype(np.float64)
+    for disc in (False, True):
+        _run_case(dict(resolution=0.5, depth_levels=6), [dict(origin=o, xyz=p, max_range=-1.0, discrete=disc)],
+                  levels=(1, 2, 3, 4, 5, 6))
+        _run_case(dict(resolution=0.5, depth_levels=6), [dict(origin=o, xyz=p, max_range=25.0, discrete=disc)],
+                  levels=(1, 2, 3, 4, 5, 6))
+    # sensor outside the map looking in
+    _run_case(dict(resolution=0.5, depth_levels=6),
+              [dict(origin=[30.0, 2.0, 1.0], xyz=p[:500], max_range=-1.0)], levels=(1, 2, 3, 4, 5, 6))
+
+
+def test_small_trees_and_nondefault_sensor_model():
+    o, p = scans.random_shell(n=2000, rmin=0.5, rmax=3.0)
+    for levels in (2, 3, 4, 5):
+        _run_case(dict(resolution=0.25, depth_levels=levels), [dict(origin=o, xyz=p, max_range=2.0)],
+                  levels=tuple(range(1, levels + 1)))
+    _run_case(dict(resolution=0.1, occupied_thres=0.6, free_thres=0.3, prob_hit=0.8, prob_miss=0.45,
+                   clamping_thres_min=0.2, clamping_thres_max=0.9),
+              [dict(origin=o, xyz=p, max_range=2.0)] * 6)
+
+
+def test_empty_and_unsupported():
+    gpu = Map(0.1)
+    gpu.insert([0, 0, 0], np.zeros((0, 3)))
+    assert len(gpu.value_field()[0]) == 0
+    with pytest.raises(UfoError) as e:
+        gpu.insert([0, 0, 0], [[1.0, 0, 0]], early_stopping=3)
+    assert e.value.status == E_UNSUPPORTED
+    gpu.close()
+
+
+def test_async_matches_sync_and_determinism():
+    o, p = scans.velodyne64(rings=16, azimuths=512)
+    a = Map(0.1)
+    b = Map(0.1)
+    for k in range(3):
+        a.insert(o + [0.1 * k, 0, 0], p, max_range=30.0, async_=True)
+        b.insert(o + [0.1 * k, 0, 0], p, max_range=30.0)
+    a.wait()
+    assert a.done()
+    assert_value_fields_equal(a.value_field(), b.value_field())
+
+
+def test_query_leaf_and_missing_nodes():
+    gpu = Map(0.02)
+    gpu.insert([0, 0, 0], [[1.0, 0, 0]], max_range=5.0)
+    end = gpu.to_code([1.0, 0, 0])
+    mid = gpu.to_code([0.5, 0, 0])
+    org = gpu.to_code([0.0, 0, 0])
+    far = gpu.to_code([-3.0, 2.0, 1.0])
+    occ, flags, _ = gpu.query([end, mid, org, far], 0)
+    assert occ.view(np.uint32).tolist() == [0x3EE237E7, 0xBECF991F, 0, 0]
+    assert flags.tolist() == [0, 1, 2, 2]  # occupied / free / unknown / unknown
+    occ, flags, _ = gpu.query([0], 16)
+    assert occ.view(np.uint32)[0] == 0x3EE237E7 and flags[0] == 3
+    gpu.close()

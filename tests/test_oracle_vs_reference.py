@@ -1,0 +1,99 @@
+"""Pins the plain-C restatement (oracle/ufo_oracle.c) to the UNMODIFIED reference
+compiled from /root/reference (oracle/_ref/libufo_ref.so): every node of the two
+trees must agree -- value field, inner aggregates, flags, colours, change bbox.
+Skipped only when neither the reference tree nor a prebuilt harness is present
+(then tests/test_golden.py still pins the oracle to reference-generated fixtures)."""
+import numpy as np
+import pytest
+
+from oracle_lib import OracleMap, RefMap, have_ref
+from ufomap_b200 import scans
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="reference harness not built")
+
+
+def _same_trees(map_kw, inserts, color=False):
+    r = RefMap(color=color, **map_kw)
+    o = OracleMap(color=color, **map_kw)
+    for ins in inserts:
+        r.insert(**ins)
+        o.insert(**ins)
+    for leaves in (True, False):
+        a, b = r.walk(leaves), o.walk(leaves)
+        ka = np.lexsort((a[0], a[1]))
+        kb = np.lexsort((b[0], b[1]))
+        assert len(a[0]) == len(b[0])
+        for x, y in zip(a, b):
+            x, y = x[ka], y[kb]
+            if x.dtype == np.float32:
+                x, y = x.view(np.uint32), y.view(np.uint32)
+            assert np.array_equal(x, y)
+    assert all(np.array_equal(x, y) for x, y in zip(r.change_bbox(), o.change_bbox()))
+    assert np.array_equal(r.sensor_model(), o.sensor_model())
+
+
+def test_plain_and_discrete_shell():
+    o, p = scans.random_shell()
+    _same_trees(dict(resolution=0.16), [dict(origin=o, xyz=p, max_range=5.0)])
+    _same_trees(dict(resolution=0.16, automatic_pruning=False),
+                [dict(origin=o, xyz=p, max_range=5.0, discrete=True)])
+
+
+def test_velodyne_stream():
+    ins = []
+    for k in range(3):
+        o, p = scans.velodyne64(k=k, rings=16, azimuths=256)
+        ins.append(dict(origin=o, xyz=p, max_range=30.0))
+    _same_trees(dict(resolution=0.1), ins)
+
+
+def test_color_discrete_and_depths():
+    o, p, c = scans.rgbd(width=80, height=60)
+    o2, p2, c2 = scans.rgbd(k=1, width=80, height=60)
+    _same_trees(dict(resolution=0.02),
+                [dict(origin=o, xyz=p, rgb=c, max_range=5.0, discrete=True),
+                 dict(origin=o2, xyz=p2, rgb=c2, max_range=5.0, discrete=True)], color=True)
+    _same_trees(dict(resolution=0.02),
+                [dict(origin=o, xyz=p, rgb=c, max_range=3.0, discrete=True, depth=2),
+                 dict(origin=o2, xyz=p2, rgb=c2, max_range=3.0, discrete=True, depth=1)], color=True)
+    _same_trees(dict(resolution=0.05),
+                [dict(origin=o, xyz=p, max_range=3.0, depth=3),
+                 dict(origin=o2, xyz=p2, max_range=4.0, simple=True)])
+
+
+def test_early_stopping_and_sensor_model():
+    o, p = scans.velodyne64(rings=8, azimuths=256)
+    _same_trees(dict(resolution=0.2, occupied_thres=0.6, free_thres=0.3, prob_hit=0.8, prob_miss=0.45,
+                     clamping_thres_min=0.2, clamping_thres_max=0.9),
+                [dict(origin=o, xyz=p, max_range=25.0, early_stopping=2)] * 4)
+
+
+def test_out_of_map_rays():
+    o = np.array([0.3, -0.2, 0.1])
+    rng = np.random.default_rng(7)
+    p = rng.uniform(-40, 40, size=(3000, 3))
+    for disc in (False, True):
+        _same_trees(dict(resolution=0.5, depth_levels=6), [dict(origin=o, xyz=p, discrete=disc)])
+        _same_trees(dict(resolution=0.5, depth_levels=6), [dict(origin=o, xyz=p, max_range=25.0, discrete=disc)])
+    _same_trees(dict(resolution=0.5, depth_levels=6), [dict(origin=[30.0, 2.0, 1.0], xyz=p[:500])])
+
+
+def test_indexing_and_rays():
+    r, o = RefMap(0.05), OracleMap(0.05)
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([rng.uniform(-100, 100, (300, 3)), [[0, 0, 0], [0.05, 0.05, 0.05], [-0.05, 0, 0.025]]])
+    for p in pts:
+        for d in (0, 1, 3, 7):
+            k = r.to_key(p, d)
+            assert np.array_equal(k, o.to_key(p, d))
+            assert r.to_code(p, d) == o.to_code(p, d)
+            assert np.array_equal(r.key_to_coord(k, d), o.key_to_coord(k, d))
+            assert r.key_to_code(k, d) == o.key_to_code(k, d)
+            assert np.array_equal(r.code_to_key(r.key_to_code(k, d), d), o.code_to_key(o.key_to_code(k, d), d))
+    for a, b in zip(pts[:60], pts[60:120]):
+        for d, mr in ((0, -1.0), (0, 20.0), (2, -1.0)):
+            assert np.array_equal(r.compute_ray(a / 10, b / 10, mr, d), o.compute_ray(a / 10, b / 10, mr, d))
+    ends = pts[:200] / 5
+    for d, simple in ((0, False), (1, False), (0, True)):
+        assert np.array_equal(np.sort(r.free_set([0.01, 0.02, 0.03], ends, d, simple)),
+                              np.sort(o.free_set([0.01, 0.02, 0.03], ends, d, simple)))

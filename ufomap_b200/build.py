@@ -1,0 +1,46 @@
+"""Builds ufomap_b200/libufomap_b200.so (hand-written CUDA for sm_100a) in-tree.
+
+    python -m ufomap_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU
+box with the gpurun snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libufomap_b200.so")
+SOURCES = [os.path.join(CSRC, "ufo_map.cu")]
+HEADERS = [os.path.join(CSRC, f) for f in ("ufo_index.cuh", "ufo_device.cuh", "ufo_kernels.cuh")] + [
+    os.path.join(os.path.dirname(HERE), "include", "ufomap_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    # the DDA must not be FMA-contracted (bit-exact parity with the reference)
+    "-fmad=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall",
+    "-shared", "-cudart", "static",
+]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS + [__file__])
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

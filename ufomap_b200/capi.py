@@ -1,0 +1,303 @@
+"""ctypes binding of libufomap_b200.so (include/ufomap_b200.h).
+
+This is plumbing for tests/, bench.py and __graft_entry__: the product is the
+shared library and its C ABI; the reference-facing host API is the C++ facade in
+include/ufomap_b200/ufomap.hpp.  Loading fails loudly when the library has not
+been built -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libufomap_b200.so")
+
+OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, 1, 2, 3, 4
+XYZ_F64, XYZ_F32, XYZRGB_F64, XYZRGB_F32 = 0, 1, 2, 3
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("resolution", C.c_double),
+        ("depth_levels", C.c_uint32),
+        ("automatic_pruning", C.c_int32),
+        ("occupied_thres", C.c_double),
+        ("free_thres", C.c_double),
+        ("prob_hit", C.c_double),
+        ("prob_miss", C.c_double),
+        ("clamping_thres_min", C.c_double),
+        ("clamping_thres_max", C.c_double),
+        ("color", C.c_int32),
+        ("device", C.c_int32),
+        ("initial_blocks", C.c_uint64),
+        ("initial_bricks", C.c_uint64),
+    ]
+
+
+class ScanStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "points", "rays", "visits", "touched_voxels", "hit_voxels", "touched_octets",
+        "touched_blocks", "touched_bricks", "upper_nodes", "blocks_in_map", "bricks_in_map",
+        "device_bytes", "regrows")] + [(n, C.c_float) for n in (
+            "ms_total", "ms_h2d", "ms_points", "ms_rays", "ms_update", "ms_propagate")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/ufomap_b200.h declares
+SYMBOLS = [
+    "ufo_b200_default_params", "ufo_b200_create", "ufo_b200_destroy", "ufo_b200_last_error",
+    "ufo_b200_set_stream", "ufo_b200_insert_pointcloud", "ufo_b200_insert_device", "ufo_b200_wait",
+    "ufo_b200_done", "ufo_b200_compute_ray", "ufo_b200_to_key", "ufo_b200_to_code",
+    "ufo_b200_key_to_coord", "ufo_b200_key_to_code", "ufo_b200_code_to_key", "ufo_b200_query",
+    "ufo_b200_export_leaves", "ufo_b200_set_sensor_model", "ufo_b200_sensor_model_logit",
+    "ufo_b200_change_bbox", "ufo_b200_reset_change_bbox", "ufo_b200_last_scan_stats",
+    "ufo_b200_set_profiling", "ufo_b200_clear", "ufo_b200_version",
+]
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "ufomap_b200: %s is missing -- build it with `python -m ufomap_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, dbl, u32, i32, u64p = C.c_void_p, C.c_size_t, C.c_double, C.c_uint32, C.c_int, C.c_void_p
+    lib.ufo_b200_default_params.argtypes = [C.POINTER(Params)]
+    lib.ufo_b200_default_params.restype = None
+    lib.ufo_b200_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    lib.ufo_b200_destroy.argtypes = [vp]
+    lib.ufo_b200_destroy.restype = None
+    lib.ufo_b200_last_error.argtypes = [vp]
+    lib.ufo_b200_last_error.restype = C.c_char_p
+    lib.ufo_b200_set_stream.argtypes = [vp, vp]
+    for f in (lib.ufo_b200_insert_pointcloud, lib.ufo_b200_insert_device):
+        f.argtypes = [vp, vp, vp, sz, i32, dbl, u32, i32, u32, i32, i32]
+    lib.ufo_b200_wait.argtypes = [vp]
+    lib.ufo_b200_done.argtypes = [vp, C.POINTER(C.c_int)]
+    lib.ufo_b200_compute_ray.argtypes = [vp, vp, vp, dbl, u32, u64p, sz, C.POINTER(sz)]
+    lib.ufo_b200_to_key.argtypes = [vp, vp, u32, vp]
+    lib.ufo_b200_to_code.argtypes = [vp, vp, u32, C.POINTER(C.c_uint64)]
+    lib.ufo_b200_key_to_coord.argtypes = [vp, vp, u32, vp]
+    lib.ufo_b200_key_to_code.argtypes = [vp]
+    lib.ufo_b200_key_to_code.restype = C.c_uint64
+    lib.ufo_b200_code_to_key.argtypes = [C.c_uint64, vp]
+    lib.ufo_b200_code_to_key.restype = None
+    lib.ufo_b200_query.argtypes = [vp, vp, vp, sz, vp, vp, vp]
+    lib.ufo_b200_export_leaves.argtypes = [vp, vp, vp, vp, sz, C.POINTER(sz)]
+    lib.ufo_b200_set_sensor_model.argtypes = [vp, vp]
+    lib.ufo_b200_sensor_model_logit.argtypes = [vp, vp]
+    lib.ufo_b200_change_bbox.argtypes = [vp, vp, vp]
+    lib.ufo_b200_reset_change_bbox.argtypes = [vp]
+    lib.ufo_b200_last_scan_stats.argtypes = [vp, C.POINTER(ScanStats)]
+    lib.ufo_b200_set_profiling.argtypes = [vp, i32]
+    lib.ufo_b200_clear.argtypes = [vp]
+    lib.ufo_b200_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+class UfoError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("ufomap_b200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+def pack_points(xyz, rgb=None, dtype=np.float64):
+    """Pack points into one of the C-ABI layouts; returns (buffer, layout)."""
+    xyz = np.asarray(xyz)
+    n = len(xyz)
+    if rgb is None:
+        buf = np.ascontiguousarray(xyz, dtype=dtype).reshape(n, 3)
+        return buf, (XYZ_F64 if dtype == np.float64 else XYZ_F32)
+    rgb = np.asarray(rgb, dtype=np.uint8).reshape(n, 3)
+    if dtype == np.float64:
+        buf = np.zeros((n, 32), np.uint8)
+        buf[:, :24] = np.ascontiguousarray(xyz, dtype=np.float64).reshape(n, 3).view(np.uint8).reshape(n, 24)
+        buf[:, 24:27] = rgb
+        return buf, XYZRGB_F64
+    buf = np.zeros((n, 16), np.uint8)
+    buf[:, :12] = np.ascontiguousarray(xyz, dtype=np.float32).reshape(n, 3).view(np.uint8).reshape(n, 12)
+    buf[:, 12:15] = rgb
+    return buf, XYZRGB_F32
+
+
+class Map:
+    """Thin object wrapper over the C ABI (one map = one device + one stream)."""
+
+    def __init__(self, resolution, depth_levels=16, automatic_pruning=True, color=False,
+                 device=-1, initial_blocks=0, initial_bricks=0, **model):
+        self.lib = load()
+        p = Params()
+        self.lib.ufo_b200_default_params(C.byref(p))
+        p.resolution = resolution
+        p.depth_levels = depth_levels
+        p.automatic_pruning = int(automatic_pruning)
+        p.color = int(color)
+        p.device = device
+        p.initial_blocks = int(initial_blocks)
+        p.initial_bricks = int(initial_bricks)
+        for k, v in model.items():
+            setattr(p, k, v)
+        self.color = bool(color)
+        self.resolution = resolution
+        self.depth_levels = depth_levels
+        self.h = C.c_void_p()
+        rc = self.lib.ufo_b200_create(C.byref(p), C.byref(self.h))
+        if rc == E_INVALID:
+            raise ValueError("invalid map parameters (depth_levels has to be [2, 21])")
+        if rc != OK:
+            raise UfoError(rc, "ufo_b200_create failed (no usable CUDA device?)")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ufo_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise UfoError(rc, (self.lib.ufo_b200_last_error(self.h) or b"").decode())
+
+    # -- integration --------------------------------------------------------
+    def insert(self, origin, xyz, rgb=None, max_range=-1.0, depth=0, simple=False,
+               early_stopping=0, discrete=False, async_=False, dtype=np.float64):
+        buf, layout = pack_points(xyz, rgb, dtype)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        self._keep = (buf, o)
+        self._check(self.lib.ufo_b200_insert_pointcloud(
+            self.h, o.ctypes.data, buf.ctypes.data, len(buf), layout, float(max_range), int(depth),
+            int(simple), int(early_stopping), int(discrete), int(async_)))
+
+    def insert_packed(self, origin, buf_ptr, n, layout, max_range=-1.0, depth=0, simple=False,
+                      discrete=False, async_=False, on_device=False):
+        """Insert from an already packed buffer (host pointer, or device pointer when
+        on_device=True)."""
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        f = self.lib.ufo_b200_insert_device if on_device else self.lib.ufo_b200_insert_pointcloud
+        self._check(f(self.h, o.ctypes.data, buf_ptr, int(n), int(layout), float(max_range),
+                      int(depth), int(simple), 0, int(discrete), int(async_)))
+
+    def wait(self):
+        self._check(self.lib.ufo_b200_wait(self.h))
+
+    def done(self):
+        d = C.c_int()
+        self._check(self.lib.ufo_b200_done(self.h, C.byref(d)))
+        return bool(d.value)
+
+    def set_stream(self, stream_ptr):
+        self._check(self.lib.ufo_b200_set_stream(self.h, stream_ptr))
+
+    def set_profiling(self, enable=True):
+        self._check(self.lib.ufo_b200_set_profiling(self.h, int(enable)))
+
+    def stats(self):
+        st = ScanStats()
+        self._check(self.lib.ufo_b200_last_scan_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def clear(self):
+        self._check(self.lib.ufo_b200_clear(self.h))
+
+    # -- state ----------------------------------------------------------------
+    def value_field(self):
+        """(codes sorted, occ f32, rgb u8[n,3]): every voxel with a non-default payload."""
+        n = C.c_size_t()
+        self._check(self.lib.ufo_b200_export_leaves(self.h, None, None, None, 0, C.byref(n)))
+        cnt = n.value
+        codes = np.empty(cnt, np.uint64)
+        occ = np.empty(cnt, np.float32)
+        rgb = np.zeros((cnt, 3), np.uint8)
+        if cnt:
+            self._check(self.lib.ufo_b200_export_leaves(
+                self.h, codes.ctypes.data, occ.ctypes.data, rgb.ctypes.data if self.color else None,
+                cnt, C.byref(n)))
+            assert n.value == cnt
+        order = np.argsort(codes, kind="stable")
+        return codes[order], occ[order], rgb[order]
+
+    def query(self, codes, depths):
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        depths = np.ascontiguousarray(np.broadcast_to(depths, codes.shape), dtype=np.uint32)
+        n = len(codes)
+        occ = np.empty(n, np.float32)
+        flags = np.empty(n, np.uint8)
+        rgb = np.zeros((n, 3), np.uint8)
+        self._check(self.lib.ufo_b200_query(self.h, codes.ctypes.data, depths.ctypes.data, n,
+                                            occ.ctypes.data, flags.ctypes.data,
+                                            rgb.ctypes.data if self.color else None))
+        return occ, flags, rgb
+
+    # -- geometry -----------------------------------------------------------
+    def compute_ray(self, origin, end, max_range=-1.0, depth=0):
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        e = np.ascontiguousarray(end, dtype=np.float64)
+        n = C.c_size_t()
+        self._check(self.lib.ufo_b200_compute_ray(self.h, o.ctypes.data, e.ctypes.data,
+                                                  float(max_range), int(depth), None, 0, C.byref(n)))
+        out = np.empty(n.value, np.uint64)
+        if n.value:
+            self._check(self.lib.ufo_b200_compute_ray(self.h, o.ctypes.data, e.ctypes.data,
+                                                      float(max_range), int(depth), out.ctypes.data,
+                                                      n.value, C.byref(n)))
+        return out
+
+    def to_key(self, xyz, depth=0):
+        p = np.ascontiguousarray(xyz, dtype=np.float64)
+        k = np.empty(3, np.uint32)
+        self._check(self.lib.ufo_b200_to_key(self.h, p.ctypes.data, int(depth), k.ctypes.data))
+        return k
+
+    def to_code(self, xyz, depth=0):
+        p = np.ascontiguousarray(xyz, dtype=np.float64)
+        c = C.c_uint64()
+        self._check(self.lib.ufo_b200_to_code(self.h, p.ctypes.data, int(depth), C.byref(c)))
+        return int(c.value)
+
+    def key_to_code(self, key, depth=0):
+        k = np.ascontiguousarray(key, dtype=np.uint32)
+        return int(self.lib.ufo_b200_key_to_code(k.ctypes.data))
+
+    def code_to_key(self, code, depth=0):
+        k = np.empty(3, np.uint32)
+        self.lib.ufo_b200_code_to_key(int(code), k.ctypes.data)
+        return k
+
+    def key_to_coord(self, key, depth=0):
+        k = np.ascontiguousarray(key, dtype=np.uint32)
+        p = np.empty(3, np.float64)
+        self._check(self.lib.ufo_b200_key_to_coord(self.h, k.ctypes.data, int(depth), p.ctypes.data))
+        return p
+
+    def change_bbox(self):
+        mn, mx = np.empty(3), np.empty(3)
+        self._check(self.lib.ufo_b200_change_bbox(self.h, mn.ctypes.data, mx.ctypes.data))
+        return mn, mx
+
+    def reset_change_bbox(self):
+        self._check(self.lib.ufo_b200_reset_change_bbox(self.h))
+
+    def sensor_model(self):
+        out = np.empty(6)
+        self._check(self.lib.ufo_b200_sensor_model_logit(self.h, out.ctypes.data))
+        return out
+
+    def set_sensor_model(self, occupied_thres=0.5, free_thres=0.5, prob_hit=0.7, prob_miss=0.4,
+                         clamping_thres_min=0.1192, clamping_thres_max=0.971):
+        p = np.array([occupied_thres, free_thres, prob_hit, prob_miss, clamping_thres_min,
+                      clamping_thres_max], dtype=np.float64)
+        self._check(self.lib.ufo_b200_set_sensor_model(self.h, p.ctypes.data))

@@ -1,0 +1,325 @@
+// ufo_device.cuh -- device-side data layout of one map and the lock-free
+// find-or-create primitives the integration kernels share.
+//
+// Layout (DESIGN.md "Data layout in HBM"):
+//   voxel  = depth-0 leaf            float log-odds (+ packed rgb for colour maps)
+//   block  = 4^3 voxels  (depth 2)   64 floats = 256 B, Morton order inside the block, so
+//                                    one 2^3 octet (depth-1 node) = 8 consecutive floats = one
+//                                    32 B sector; per-scan miss/hit bit masks are one u64 each
+//   brick  = 4^3 blocks  (depth 4)   hashed by packed (kx>>4, ky>>4, kz>>4); holds the 64
+//                                    block slots and the depth-3/4 aggregates
+//   upper  = depth >= 5 nodes        hashed by (depth, key>>depth); aggregates only
+// This replaces the reference's pointer octree (octree_node.h:52-111,
+// occupancy_map_node.h:55-185) with flat SoA pools addressed by slot index.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+
+#include "ufo_index.cuh"
+
+namespace ufo_b200
+{
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr uint32_t kPending = 0xffffffffu;  // hash value not published yet
+constexpr uint32_t kFailed = 0xfffffffeu;   // allocation behind this key overflowed
+constexpr uint32_t kNone = 0xffffffffu;     // "no such brick / node"
+constexpr uint32_t kLock = 0xffffffffu;     // child pointer being allocated
+
+// aggregate of an inner node: max log-odds of the subtree + contains_* flags
+// (occupancy_map_base.h:1179-1224).  flags: bit0 contains_free, bit1 contains_unknown.
+struct Agg {
+	float occ;
+	uint32_t flags;
+};
+
+struct Counters {
+	uint32_t n_blocks;   // next free block slot (slot 0 is the null block)
+	uint32_t n_bricks;   // next free brick slot
+	uint32_t n_upper;    // next free upper-node slot
+	uint32_t overflow;   // bit0 blocks, bit1 bricks/brick hash, bit2 upper nodes
+	uint32_t list_count[2];  // ping-pong dirty lists of the upper-level pass
+	uint32_t n_rays;
+	uint32_t pad0;
+	unsigned long long visits;
+	unsigned long long touched_voxels;
+	unsigned long long hit_voxels;
+	unsigned long long touched_octets;
+	unsigned long long touched_blocks;
+	unsigned long long touched_bricks;
+	unsigned long long upper_nodes;
+	unsigned long long bbox[6];  // order-preserving encoding of min xyz / max xyz of this scan
+};
+
+struct DeviceMap {
+	Geometry g;
+	// sensor model (occupancy_map_base.h:1537-1542): thresholds compared in double,
+	// updates applied in float
+	double occ_thr, free_thr;
+	float hit, clamp_min, clamp_max;
+	double prob_hit;         // toProb(float(hit)) used by the colour blend
+	uint32_t default_flags;  // flags of a never-touched voxel / subtree (value 0.0)
+	uint32_t color;
+	uint32_t scan_id;
+
+	// brick hash (open addressing, linear probing)
+	unsigned long long* bh_keys;
+	uint32_t* bh_vals;
+	uint32_t bh_mask;
+	// brick pool
+	unsigned long long* brick_key;
+	uint32_t* brick_child;  // [brick][64] block slots, 0 = none
+	uint32_t* brick_stamp;  // scan id of the last scan that touched the brick
+	Agg* brick_sum3;        // [brick][8]
+	Agg* brick_sum4;        // [brick]
+	uint32_t* brick_rgb3;   // colour maps: [brick][8] packed rgb of depth-3 nodes
+	uint32_t* brick_rgb4;
+	uint32_t brick_cap;
+	// block pool
+	float* leaf;                    // [block][64]
+	uint32_t* leaf_rgb;             // colour maps: [block][64] packed r | g<<8 | b<<16
+	unsigned long long* miss_mask;  // [block]
+	unsigned long long* hit_mask;   // [block]
+	unsigned long long* block_key;  // packed (kx>>2, ky>>2, kz>>2)
+	float* sum1_occ;                // [block][8]
+	uint32_t* sum1_meta;            // [block] bits 0..15: flags of the 8 octets, bits 16..23: octet initialised
+	Agg* sum2;                      // [block]
+	uint32_t* sum1_rgb;             // colour maps: [block][8]
+	uint32_t* sum2_rgb;             // colour maps: [block]
+	uint32_t block_cap;
+	// upper nodes
+	unsigned long long* uh_keys;
+	uint32_t* uh_vals;
+	uint32_t uh_mask;
+	unsigned long long* up_key;
+	Agg* up_agg;
+	uint32_t* up_rgb;
+	uint32_t* up_stamp;
+	uint32_t up_cap;
+
+	Counters* ctr;
+};
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
+{
+	return *reinterpret_cast<const volatile uint32_t*>(p);
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p)
+{
+	return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v)
+{
+	*reinterpret_cast<volatile uint32_t*>(p) = v;
+}
+
+UFO_HD uint32_t hash_u64(uint64_t k)
+{
+	k ^= k >> 33;
+	k *= 0xff51afd7ed558ccdull;
+	k ^= k >> 33;
+	k *= 0xc4ceb9fe1a85ec53ull;
+	k ^= k >> 33;
+	return (uint32_t)k;
+}
+
+// 21 bits per axis
+UFO_HD uint64_t pack_key(uint32_t x, uint32_t y, uint32_t z)
+{
+	return (uint64_t)x | ((uint64_t)y << 21) | ((uint64_t)z << 42);
+}
+UFO_HD void unpack_key(uint64_t k, uint32_t& x, uint32_t& y, uint32_t& z)
+{
+	x = (uint32_t)(k & 0x1fffffu);
+	y = (uint32_t)((k >> 21) & 0x1fffffu);
+	z = (uint32_t)((k >> 42) & 0x1fffffu);
+}
+// key of an upper node: depth tag in bits 63.. is not available (3*21 = 63 bits
+// used), but an upper node at depth d >= 5 only uses 16 bits per axis, so the tag
+// sits in the unused high bits of the x field.
+UFO_HD uint64_t upper_key(uint32_t depth, uint32_t x, uint32_t y, uint32_t z)
+{
+	return pack_key(x, y, z) | ((uint64_t)depth << 16);
+}
+
+// ---------------------------------------------------------------------------
+// brick hash
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t brick_find(const DeviceMap& M, uint64_t key)
+{
+	uint32_t i = hash_u64(key) & M.bh_mask;
+	for (uint32_t probes = 0; probes <= M.bh_mask; ++probes) {
+		unsigned long long k = ld_volatile_u64(&M.bh_keys[i]);
+		if (k == key) {
+			uint32_t v = ld_volatile_u32(&M.bh_vals[i]);
+			return (v == kPending || v == kFailed) ? kNone : v;
+		}
+		if (k == kEmptyKey) return kNone;
+		i = (i + 1) & M.bh_mask;
+	}
+	return kNone;
+}
+
+__device__ __forceinline__ uint32_t brick_find_or_create(const DeviceMap& M, uint64_t key)
+{
+	uint32_t i = hash_u64(key) & M.bh_mask;
+	for (uint32_t probes = 0; probes <= M.bh_mask; ++probes) {
+		unsigned long long k = ld_volatile_u64(&M.bh_keys[i]);
+		if (k == kEmptyKey) {
+			if (ld_volatile_u32(&M.ctr->overflow) & 2u) return kNone;
+			k = atomicCAS(&M.bh_keys[i], kEmptyKey, (unsigned long long)key);
+			if (k == kEmptyKey) {
+				uint32_t s = atomicAdd(&M.ctr->n_bricks, 1u);
+				if (s >= M.brick_cap) {
+					atomicOr(&M.ctr->overflow, 2u);
+					st_volatile_u32(&M.bh_vals[i], kFailed);
+					return kNone;
+				}
+				M.brick_key[s] = key;
+				__threadfence();
+				st_volatile_u32(&M.bh_vals[i], s);
+				return s;
+			}
+		}
+		if (k == key) {
+			uint32_t v;
+			while ((v = ld_volatile_u32(&M.bh_vals[i])) == kPending) {
+			}
+			return v == kFailed ? kNone : v;
+		}
+		i = (i + 1) & M.bh_mask;
+	}
+	atomicOr(&M.ctr->overflow, 2u);
+	return kNone;
+}
+
+// block slot of child b (0..63) of a brick; 0 when the pool overflowed
+__device__ __forceinline__ uint32_t block_find_or_create(const DeviceMap& M, uint32_t brick,
+                                                         uint32_t b, uint64_t block_key)
+{
+	uint32_t* p = &M.brick_child[(size_t)brick * 64 + b];
+	uint32_t s = ld_volatile_u32(p);
+	if (s == 0) {
+		uint32_t prev = atomicCAS(p, 0u, kLock);
+		if (prev == 0) {
+			s = atomicAdd(&M.ctr->n_blocks, 1u);
+			if (s >= M.block_cap) {
+				atomicOr(&M.ctr->overflow, 1u);
+				atomicExch(p, 0u);
+				return 0;
+			}
+			M.block_key[s] = block_key;
+			__threadfence();
+			atomicExch(p, s);
+			return s;
+		}
+		s = prev;
+	}
+	while (s == kLock) s = ld_volatile_u32(p);
+	return s;
+}
+
+__device__ __forceinline__ uint32_t upper_find(const DeviceMap& M, uint64_t key)
+{
+	uint32_t i = hash_u64(key) & M.uh_mask;
+	for (uint32_t probes = 0; probes <= M.uh_mask; ++probes) {
+		unsigned long long k = ld_volatile_u64(&M.uh_keys[i]);
+		if (k == key) {
+			uint32_t v = ld_volatile_u32(&M.uh_vals[i]);
+			return (v == kPending || v == kFailed) ? kNone : v;
+		}
+		if (k == kEmptyKey) return kNone;
+		i = (i + 1) & M.uh_mask;
+	}
+	return kNone;
+}
+
+__device__ __forceinline__ uint32_t upper_find_or_create(const DeviceMap& M, uint64_t key)
+{
+	uint32_t i = hash_u64(key) & M.uh_mask;
+	for (uint32_t probes = 0; probes <= M.uh_mask; ++probes) {
+		unsigned long long k = ld_volatile_u64(&M.uh_keys[i]);
+		if (k == kEmptyKey) {
+			if (ld_volatile_u32(&M.ctr->overflow) & 4u) return kNone;
+			k = atomicCAS(&M.uh_keys[i], kEmptyKey, (unsigned long long)key);
+			if (k == kEmptyKey) {
+				uint32_t s = atomicAdd(&M.ctr->n_upper, 1u);
+				if (s >= M.up_cap) {
+					atomicOr(&M.ctr->overflow, 4u);
+					st_volatile_u32(&M.uh_vals[i], kFailed);
+					return kNone;
+				}
+				M.up_key[s] = key;
+				__threadfence();
+				st_volatile_u32(&M.uh_vals[i], s);
+				return s;
+			}
+		}
+		if (k == key) {
+			uint32_t v;
+			while ((v = ld_volatile_u32(&M.uh_vals[i])) == kPending) {
+			}
+			return v == kFailed ? kNone : v;
+		}
+		i = (i + 1) & M.uh_mask;
+	}
+	atomicOr(&M.ctr->overflow, 4u);
+	return kNone;
+}
+
+// ---------------------------------------------------------------------------
+// order-preserving double <-> u64 for atomicMin/atomicMax on the change bbox
+// ---------------------------------------------------------------------------
+UFO_HD unsigned long long encode_ordered(double d)
+{
+	unsigned long long u;
+#if defined(__CUDA_ARCH__)
+	u = (unsigned long long)__double_as_longlong(d);
+#else
+	memcpy(&u, &d, sizeof(u));
+#endif
+	return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+
+UFO_HD double decode_ordered(unsigned long long u)
+{
+	u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+#if defined(__CUDA_ARCH__)
+	return __longlong_as_double((long long)u);
+#else
+	double d;
+	memcpy(&d, &u, sizeof(d));
+	return d;
+#endif
+}
+
+// sensor-model predicates (occupancy_map_base.h:926-940): double thresholds vs float value
+__device__ __forceinline__ uint32_t leaf_flags(const DeviceMap& M, float v)
+{
+	double d = (double)v;
+	uint32_t f = (M.free_thr > d) ? 1u : 0u;
+	if (M.free_thr <= d && M.occ_thr >= d) f |= 2u;
+	return f;
+}
+
+// float add + float clamp (occupancy_map_base.h:1139-1145)
+__device__ __forceinline__ float apply_update(const DeviceMap& M, float v, float u)
+{
+	float r = __fadd_rn(v, u);
+	if (r < M.clamp_min) r = M.clamp_min;
+	else if (M.clamp_max < r) r = M.clamp_max;
+	return r;
+}
+
+// toProb(float) (occupancy_map_base.h:911): 1/(1+expf(-x)); expf evaluated via the
+// double exp and rounded to float, which matches a correctly rounded expf.
+__device__ __forceinline__ double to_prob(float logit)
+{
+	float e = (float)exp((double)(-logit));
+	return 1.0 / (1.0 + (double)e);
+}
+
+}  // namespace ufo_b200

@@ -1,0 +1,835 @@
+// ufo_kernels.cuh -- the integration kernels (sm_100a).
+//
+//   k_points   K1  per point: range test, BBX clip, hit voxel, ray end, change bbox
+//                  (insertPointCloud front end, occupancy_map_base.h:281-309; discrete
+//                  front end :354-399 / occupancy_map_color.h:195-246)
+//   k_hits     K1b colour maps: first point per voxel blends its colour into the leaf
+//                  (updateNodeColor, occupancy_map_color.cpp:142-171) and marks the hit
+//   k_rays     K2  one thread per ray: exact FP64 backward voxel walk
+//                  (freeSpaceNormal, occupancy_map_base.h:1261-1301); visited voxels are
+//                  OR-accumulated per 4^3 block in a register and flushed with one atomicOr
+//                  when the ray leaves the block (set semantics of CodeMap::try_emplace)
+//   k_rays_simple  fixed-step variant (freeSpaceSimple, occupancy_map_base.h:1303-1339)
+//   k_update   K3  one warp per touched brick: hit-then-miss float log-odds update of the
+//                  marked voxels (updateOccupancy :1139-1145), depth-1/2 aggregates per block,
+//                  depth-3/4 aggregates per brick (updateNode :1179-1224)
+//   k_upper_*  K4  aggregates of the dirty nodes of depth >= 5, one launch per level
+#pragma once
+
+#include "ufo_device.cuh"
+
+namespace ufo_b200
+{
+struct ScanArgs {
+	Vec3 origin;       // sensor origin
+	double max_range;  // < 0: unlimited
+	uint32_t n;        // points
+	uint32_t depth;    // insert depth of the free-space rays
+	int layout;        // ufo_b200_layout
+	int discrete;
+	int use_color;     // colour map AND the cloud carries colour
+	float miss;        // float(prob_miss_log / (2*depth+1)), occupancy_map_base.h:311
+	const void* points;
+	double* ray_end;   // [n][3], x = NaN when the point casts no ray
+	// scan-local dedup table (discrete mode / colour hits)
+	unsigned long long* tab_keys;
+	uint32_t* tab_min;
+	uint32_t tab_mask;
+	uint32_t* hit_tab;  // [n] table position of the point's hit voxel or kNone
+	int count_visits;
+};
+
+__device__ __forceinline__ void load_point(const ScanArgs& a, uint32_t i, Vec3& p, uint32_t& rgb)
+{
+	rgb = 0;
+	switch (a.layout) {
+		case 0: {
+			const double* q = reinterpret_cast<const double*>(a.points) + 3 * (size_t)i;
+			p = {q[0], q[1], q[2]};
+		} break;
+		case 1: {
+			const float* q = reinterpret_cast<const float*>(a.points) + 3 * (size_t)i;
+			p = {(double)q[0], (double)q[1], (double)q[2]};
+		} break;
+		case 2: {
+			const double* q = reinterpret_cast<const double*>(a.points) + 4 * (size_t)i;
+			p = {q[0], q[1], q[2]};
+			rgb = reinterpret_cast<const uint32_t*>(q + 3)[0] & 0xffffffu;
+		} break;
+		default: {
+			const float4 q = reinterpret_cast<const float4*>(a.points)[i];
+			p = {(double)q.x, (double)q.y, (double)q.z};
+			rgb = __float_as_uint(q.w) & 0xffffffu;
+		} break;
+	}
+}
+
+__device__ __forceinline__ void bbox_accumulate(const DeviceMap& M, double lo[3], double hi[3],
+                                                bool any, bool cast)
+{
+	uint32_t rays = __ballot_sync(0xffffffffu, cast);
+	if ((threadIdx.x & 31) == 0 && rays) atomicAdd(&M.ctr->n_rays, (uint32_t)__popc(rays));
+	// warp-reduce, then one atomic per warp and component
+	for (int c = 0; c < 3; ++c) {
+		unsigned long long l = any ? encode_ordered(lo[c]) : ~0ull;
+		unsigned long long h = any ? encode_ordered(hi[c]) : 0ull;
+		for (int o = 16; o > 0; o >>= 1) {
+			unsigned long long l2 = __shfl_xor_sync(0xffffffffu, l, o);
+			unsigned long long h2 = __shfl_xor_sync(0xffffffffu, h, o);
+			l = l2 < l ? l2 : l;
+			h = h2 > h ? h2 : h;
+		}
+		if ((threadIdx.x & 31) == 0) {
+			if (l != ~0ull) atomicMin(&M.ctr->bbox[c], l);
+			if (h != 0ull) atomicMax(&M.ctr->bbox[3 + c], h);
+		}
+	}
+}
+
+// scan-local table: returns the slot of `key`; *first is true for the thread that
+// inserted it.
+__device__ __forceinline__ uint32_t table_insert(const ScanArgs& a, uint64_t key, bool* first)
+{
+	uint32_t i = hash_u64(key) & a.tab_mask;
+	while (true) {
+		unsigned long long k = ld_volatile_u64(&a.tab_keys[i]);
+		if (k == kEmptyKey) {
+			k = atomicCAS(&a.tab_keys[i], kEmptyKey, (unsigned long long)key);
+			if (k == kEmptyKey) {
+				*first = true;
+				return i;
+			}
+		}
+		if (k == key) {
+			*first = false;
+			return i;
+		}
+		i = (i + 1) & a.tab_mask;
+	}
+}
+
+// mark a depth-0 hit voxel directly (mono maps)
+__device__ __forceinline__ void mark_hit(const DeviceMap& M, Key3 k)
+{
+	k.x &= M.g.key_mask;
+	k.y &= M.g.key_mask;
+	k.z &= M.g.key_mask;
+	uint32_t brick = brick_find_or_create(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
+	if (brick == kNone) return;
+	M.brick_stamp[brick] = M.scan_id;
+	uint32_t slot = block_find_or_create(M, brick, morton2(k.x >> 2, k.y >> 2, k.z >> 2),
+	                                     pack_key(k.x >> 2, k.y >> 2, k.z >> 2));
+	if (!slot) return;
+	atomicOr(&M.hit_mask[slot], 1ull << morton2(k.x, k.y, k.z));
+}
+
+// ---------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_points(DeviceMap M, ScanArgs a)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	double lo[3], hi[3];
+	bool contributes = false, cast = false;
+	if (i < a.n) {
+		Vec3 end;
+		uint32_t rgb;
+		load_point(a, i, end, rgb);
+		const Geometry& g = M.g;
+		const double bhi = node_half(g, g.depth_levels), blo = -bhi;
+		uint32_t hit_slot = kNone;
+		if (!a.discrete) {
+			// occupancy_map_base.h:281-309
+			Vec3 origin = a.origin;
+			Vec3 dir = vsub(end, origin);
+			double dist = vnorm(dir);
+			if (move_line_inside(g, origin, end)) {
+				if (0 > a.max_range || dist <= a.max_range) {
+					Key3 k = point_to_key(g, end, 0);
+					if (a.use_color) {
+						bool first;
+						hit_slot = table_insert(a, key_to_code(k), &first);
+						atomicMin(&a.tab_min[hit_slot], i);
+					} else {
+						mark_hit(M, k);
+					}
+				} else {
+					dir = vdiv(dir, dist);
+					end = vadd(origin, vscale(dir, a.max_range));
+				}
+				cast = true;
+				for (int c = 0; c < 3; ++c) {
+					lo[c] = end[c] < origin[c] ? end[c] : origin[c];
+					hi[c] = end[c] < origin[c] ? origin[c] : end[c];
+				}
+				contributes = true;
+			}
+		} else {
+			// occupancy_map_base.h:354-399 / occupancy_map_color.h:195-246
+			bool skip = false;
+			double sq_max = dop::mul(a.max_range, a.max_range);
+			if (0 > a.max_range || vsqnorm(vsub(end, a.origin)) < sq_max) {
+				if (in_bbx(end, blo, bhi)) {
+					Key3 k = point_to_key(g, end, 0);
+					bool first;
+					uint32_t slot = table_insert(a, key_to_code(k), &first);
+					if (a.use_color) {
+						hit_slot = slot;
+						atomicMin(&a.tab_min[slot], i);
+					} else if (first) {
+						mark_hit(M, k);
+					}
+					// a later point in an already seen end voxel is dropped together with
+					// its ray; the ray it would cast is identical to the first one's
+					skip = !first;
+				}
+			} else {
+				Vec3 dir = vsub(key_to_coord(g, point_to_key(g, end, a.depth), a.depth), a.origin);
+				if (a.use_color) {
+					double sq = vsqnorm(dir);
+					if (0 <= a.max_range && sq > sq_max) {
+						dir = vdiv(dir, dop::sqrt(sq));
+						end = vadd(a.origin, vscale(dir, a.max_range));
+					}
+				} else {
+					double nrm = vnorm(dir);
+					dir = vdiv(dir, nrm);
+					if (0 <= a.max_range && nrm > a.max_range) {
+						end = vadd(a.origin, vscale(dir, a.max_range));
+					}
+				}
+			}
+			Vec3 cur = a.origin;
+			if (!skip && move_line_inside(g, cur, end)) {
+				Key3 ek = point_to_key(g, end, a.depth);
+				// rays are deduplicated per end node (explicitly at depth > 0 in the
+				// reference, implicitly by the set semantics at depth 0)
+				bool first;
+				table_insert(a, key_to_code(ek) | (1ull << 63), &first);
+				Vec3 ec = key_to_coord(g, ek, a.depth);
+				if (first) {
+					end = ec;
+					cast = true;
+				}
+				Vec3 cc = key_to_coord(g, point_to_key(g, cur, a.depth), a.depth);
+				double t = node_half(g, a.depth);
+				for (int c = 0; c < 3; ++c) {
+					double e0 = dop::sub(ec[c], t), c0 = dop::sub(cc[c], t);
+					double e1 = dop::add(ec[c], t), c1 = dop::add(cc[c], t);
+					lo[c] = c0 < e0 ? c0 : e0;
+					hi[c] = e1 < c1 ? c1 : e1;
+				}
+				contributes = true;
+			}
+		}
+		double* r = a.ray_end + 3 * (size_t)i;
+		if (cast) {
+			r[0] = end.x;
+			r[1] = end.y;
+			r[2] = end.z;
+		} else {
+			r[0] = __longlong_as_double(0x7ff8000000000000ll);
+		}
+		if (a.hit_tab) a.hit_tab[i] = hit_slot;
+	}
+	bbox_accumulate(M, lo, hi, contributes, cast);
+}
+
+// K1b: colour maps.  The first point (lowest cloud index) of every hit voxel blends
+// its colour into the leaf BEFORE the occupancy update of this scan
+// (occupancy_map_color.h:269-287) and marks the hit bit.
+__global__ void __launch_bounds__(256) k_hits(DeviceMap M, ScanArgs a)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.n) return;
+	uint32_t t = a.hit_tab[i];
+	if (t == kNone || a.tab_min[t] != i) return;
+	Key3 k = code_to_key(a.tab_keys[t]);
+	k.x &= M.g.key_mask;
+	k.y &= M.g.key_mask;
+	k.z &= M.g.key_mask;
+	uint32_t brick = brick_find_or_create(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
+	if (brick == kNone) return;
+	M.brick_stamp[brick] = M.scan_id;
+	uint32_t slot = block_find_or_create(M, brick, morton2(k.x >> 2, k.y >> 2, k.z >> 2),
+	                                     pack_key(k.x >> 2, k.y >> 2, k.z >> 2));
+	if (!slot) return;
+	uint32_t v = morton2(k.x, k.y, k.z);
+	unsigned long long old = atomicOr(&M.hit_mask[slot], 1ull << v);
+	if (old & (1ull << v)) return;  // re-run after a pool regrow: colour already blended
+	Vec3 p;
+	uint32_t upd;
+	load_point(a, i, p, upd);
+	size_t li = (size_t)slot * 64 + v;
+	uint32_t cur = M.leaf_rgb[li];
+	if (cur == upd) return;
+	if (cur == 0) {
+		M.leaf_rgb[li] = upd;
+		return;
+	}
+	double prob = M.prob_hit;
+	double total = prob + to_prob(M.leaf[li]);
+	prob = prob / total;
+	double inv = 1.0 - prob;
+	uint32_t out = 0;
+	for (int c = 0; c < 3; ++c) {
+		double cc = (double)((cur >> (8 * c)) & 0xffu), uu = (double)((upd >> (8 * c)) & 0xffu);
+		double r = dop::sqrt(dop::add(dop::mul(dop::mul(cc, cc), inv), dop::mul(dop::mul(uu, uu), prob)));
+		out |= ((uint32_t)(int)r & 0xffu) << (8 * c);
+	}
+	M.leaf_rgb[li] = out;
+}
+
+// ---------------------------------------------------------------------------
+// K2
+// ---------------------------------------------------------------------------
+template <int DEPTH>
+__device__ __forceinline__ unsigned long long voxel_bits(Key3 k)
+{
+	if (DEPTH == 0) return 1ull << morton2(k.x, k.y, k.z);
+	if (DEPTH == 1) return 0xffull << (8 * (((k.x >> 1) & 1u) | (((k.y >> 1) & 1u) << 1) | (((k.z >> 1) & 1u) << 2)));
+	return ~0ull;
+}
+
+struct BrickCache {
+	uint32_t bx, by, bz, slot;
+};
+
+// OR `bits` into the miss mask of the block that contains unmasked key k
+__device__ __forceinline__ void flush_block(const DeviceMap& M, BrickCache& bc, uint32_t kx,
+                                            uint32_t ky, uint32_t kz, unsigned long long bits)
+{
+	kx &= M.g.key_mask;
+	ky &= M.g.key_mask;
+	kz &= M.g.key_mask;
+	uint32_t bx = kx >> 4, by = ky >> 4, bz = kz >> 4;
+	if (bc.slot == kNone || bx != bc.bx || by != bc.by || bz != bc.bz) {
+		bc.bx = bx;
+		bc.by = by;
+		bc.bz = bz;
+		bc.slot = brick_find_or_create(M, pack_key(bx, by, bz));
+		if (bc.slot != kNone) M.brick_stamp[bc.slot] = M.scan_id;
+	}
+	if (bc.slot == kNone) return;
+	uint32_t slot = block_find_or_create(M, bc.slot, morton2(kx >> 2, ky >> 2, kz >> 2),
+	                                     pack_key(kx >> 2, ky >> 2, kz >> 2));
+	if (slot) atomicOr(&M.miss_mask[slot], bits);
+}
+
+template <int DEPTH>
+__global__ void __launch_bounds__(128) k_rays(DeviceMap M, ScanArgs a)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.n) return;
+	const double* r = a.ray_end + 3 * (size_t)i;
+	Vec3 to = {r[0], r[1], r[2]};
+	if (to.x != to.x) return;
+	Vec3 from = a.origin;
+	if (!move_line_inside(M.g, from, to)) return;  // occupancy_map_base.h:1248-1251
+
+	// walked backwards: end point -> sensor (occupancy_map_base.h:1266-1279)
+	Vec3 dir = vsub(from, to);
+	double dist = vnorm(dir);
+	dir = vdiv(dir, dist);
+	Walk w;
+	walk_init(M.g, to, from, dir, DEPTH, w);
+
+	BrickCache bc = {0, 0, 0, kNone};
+	unsigned int visits = 0;
+	if (w.same) {
+		flush_block(M, bc, w.cur.x, w.cur.y, w.cur.z, voxel_bits<DEPTH>(w.cur));
+		visits = 1;
+	} else {
+		bool finished = false;
+		while (!finished) {
+			const uint32_t ox = w.cur.x, oy = w.cur.y, oz = w.cur.z;
+			unsigned long long acc = 0;
+#pragma unroll 1
+			while (true) {
+				acc |= voxel_bits<DEPTH>(w.cur);
+				++visits;
+				walk_step(w);
+				if (!(w.cur != w.end && walk_tmin(w) <= dist)) {
+					finished = true;
+					break;
+				}
+				if ((((w.cur.x ^ ox) | (w.cur.y ^ oy) | (w.cur.z ^ oz)) >> 2) != 0) break;
+			}
+			flush_block(M, bc, ox, oy, oz, acc);
+		}
+	}
+	if (a.count_visits) atomicAdd(&M.ctr->visits, (unsigned long long)visits);
+}
+
+// freeSpaceSimple (occupancy_map_base.h:1303-1339): samples at fixed spacing
+__global__ void __launch_bounds__(128) k_rays_simple(DeviceMap M, ScanArgs a)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.n) return;
+	const double* r = a.ray_end + 3 * (size_t)i;
+	Vec3 to = {r[0], r[1], r[2]};
+	if (to.x != to.x) return;
+	Vec3 from = a.origin;
+	if (!move_line_inside(M.g, from, to)) return;
+	Vec3 cur = to;
+	Vec3 dir = vsub(from, to);
+	double dist = vnorm(dir);
+	dir = vdiv(dir, dist);
+	const double size = node_size(M.g, a.depth);
+	int num_steps = (int)dop::div(dist, size);
+	Vec3 step = vscale(dir, size);
+	BrickCache bc = {0, 0, 0, kNone};
+	unsigned long long acc = 0;
+	uint32_t ox = 0, oy = 0, oz = 0;
+	bool have = false;
+	unsigned int visits = 0;
+	for (int s = 0; s <= num_steps; ++s) {
+		Key3 k = point_to_key(M.g, cur, a.depth);
+		if (have && ((((k.x ^ ox) | (k.y ^ oy) | (k.z ^ oz)) >> 2) != 0)) {
+			flush_block(M, bc, ox, oy, oz, acc);
+			acc = 0;
+			have = false;
+		}
+		if (!have) {
+			ox = k.x;
+			oy = k.y;
+			oz = k.z;
+			have = true;
+		}
+		acc |= a.depth == 0 ? voxel_bits<0>(k) : (a.depth == 1 ? voxel_bits<1>(k) : voxel_bits<2>(k));
+		++visits;
+		cur = vadd(cur, step);
+	}
+	if (have) flush_block(M, bc, ox, oy, oz, acc);
+	if (a.count_visits) atomicAdd(&M.ctr->visits, (unsigned long long)visits);
+}
+
+// ---------------------------------------------------------------------------
+// K3
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rms_rgb(const uint32_t* c, int n)
+{
+	// getAverageColor (occupancy_map_color.cpp:200-222) over the set colours
+	double s[3] = {0, 0, 0};
+	int cnt = 0;
+	for (int i = 0; i < n; ++i) {
+		if (!c[i]) continue;
+		for (int k = 0; k < 3; ++k) {
+			double v = (double)((c[i] >> (8 * k)) & 0xffu);
+			s[k] = dop::add(s[k], dop::mul(v, v));
+		}
+		++cnt;
+	}
+	if (!cnt) return 0;
+	uint32_t out = 0;
+	for (int k = 0; k < 3; ++k)
+		out |= ((uint32_t)(int)dop::sqrt(dop::div(s[k], (double)cnt)) & 0xffu) << (8 * k);
+	return out;
+}
+
+// One warp per brick.  Touched blocks of the brick are processed four at a time:
+// lane group g = lane/8 owns one block, lane%8 owns one octet (8 voxels = one 32 B
+// sector) of it.
+__global__ void __launch_bounds__(256) k_update(DeviceMap M, float miss, uint32_t n_bricks)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+	const uint32_t grp = lane >> 3, oct = lane & 7;
+	unsigned int st_vox = 0, st_hit = 0, st_oct = 0, st_blk = 0, st_brk = 0;
+
+	for (uint32_t brick = warp; brick < n_bricks; brick += n_warps) {
+		if (M.brick_stamp[brick] != M.scan_id) continue;
+		if (lane == 0) ++st_brk;
+		for (int round = 0; round < 2; ++round) {
+			uint32_t c = round * 32 + lane;
+			uint32_t slot = M.brick_child[(size_t)brick * 64 + c];
+			unsigned long long mm = 0, hm = 0;
+			if (slot) {
+				mm = M.miss_mask[slot];
+				hm = M.hit_mask[slot];
+			}
+			uint32_t ballot = __ballot_sync(0xffffffffu, (mm | hm) != 0ull);
+			while (ballot) {
+				int n = __popc(ballot);
+				bool active = (int)grp < n;
+				int src = active ? (int)__fns(ballot, 0, grp + 1) : 0;
+				uint32_t bslot = __shfl_sync(0xffffffffu, slot, src);
+				unsigned long long bmm = __shfl_sync(0xffffffffu, mm, src);
+				unsigned long long bhm = __shfl_sync(0xffffffffu, hm, src);
+				// drop the (up to) four blocks taken this iteration
+				for (int k = 0; k < 4 && ballot; ++k) ballot &= ballot - 1;
+
+				float omax = 0.0f;
+				uint32_t oflags = 0;  // bit0 free, bit1 unknown, bit8 touched
+				uint32_t orgb = 0;
+				uint32_t meta = 0;
+				if (active) {
+					uint32_t m8 = (uint32_t)(bmm >> (8 * oct)) & 0xffu;
+					uint32_t h8 = (uint32_t)(bhm >> (8 * oct)) & 0xffu;
+					meta = M.sum1_meta[bslot];
+					if (m8 | h8) {
+						float4* lp = reinterpret_cast<float4*>(M.leaf + (size_t)bslot * 64 + 8 * oct);
+						float4 a0 = lp[0], a1 = lp[1];
+						float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+						omax = -3.402823466e+38f;
+#pragma unroll
+						for (int j = 0; j < 8; ++j) {
+							// all hits of a scan are applied before its misses
+							// (occupancy_map_base.h:1351-1365)
+							if ((h8 >> j) & 1u) v[j] = apply_update(M, v[j], M.hit);
+							if ((m8 >> j) & 1u) v[j] = apply_update(M, v[j], miss);
+							omax = fmaxf(omax, v[j]);
+							oflags |= leaf_flags(M, v[j]);
+						}
+						lp[0] = make_float4(v[0], v[1], v[2], v[3]);
+						lp[1] = make_float4(v[4], v[5], v[6], v[7]);
+						oflags |= 0x100u;
+						st_vox += __popc(m8 | h8);
+						st_hit += __popc(h8);
+						++st_oct;
+						M.sum1_occ[(size_t)bslot * 8 + oct] = omax;
+						if (M.color) {
+							uint4* cp = reinterpret_cast<uint4*>(M.leaf_rgb + (size_t)bslot * 64 + 8 * oct);
+							uint4 c0 = cp[0], c1 = cp[1];
+							uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+							orgb = rms_rgb(cc, 8);
+							M.sum1_rgb[(size_t)bslot * 8 + oct] = orgb;
+						}
+					} else if ((meta >> (16 + oct)) & 1u) {
+						omax = M.sum1_occ[(size_t)bslot * 8 + oct];
+						oflags = (meta >> (2 * oct)) & 3u;
+						if (M.color) orgb = M.sum1_rgb[(size_t)bslot * 8 + oct];
+					} else {
+						omax = 0.0f;
+						oflags = M.default_flags;
+					}
+				}
+				// depth-2 aggregate over the 8 octets of the block (8-lane groups)
+				float bmax = omax;
+				uint32_t bfl = oflags & 3u;
+				uint32_t newmeta = ((oflags & 3u) << (2 * oct)) | (((oflags >> 8) & 1u) << (16 + oct));
+#pragma unroll
+				for (int o = 1; o < 8; o <<= 1) {
+					bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+					bfl |= __shfl_xor_sync(0xffffffffu, bfl, o);
+					newmeta |= __shfl_xor_sync(0xffffffffu, newmeta, o);
+				}
+				uint32_t brgb = 0;
+				if (M.color) {
+					uint32_t oc[8];
+#pragma unroll
+					for (int j = 0; j < 8; ++j) oc[j] = __shfl_sync(0xffffffffu, orgb, (lane & 24) + j);
+					brgb = rms_rgb(oc, 8);
+				}
+				if (active && oct == 0) {
+					// newmeta carries the flags of all 8 octets (fresh, kept or default)
+					// plus the octets initialised by this scan
+					M.sum1_meta[bslot] = (newmeta & 0xffffffu) | (meta & 0xff0000u);
+					M.sum2[bslot] = {bmax, bfl};
+					if (M.color) M.sum2_rgb[bslot] = brgb;
+					M.miss_mask[bslot] = 0ull;
+					M.hit_mask[bslot] = 0ull;
+					++st_blk;
+				}
+			}
+		}
+		__syncwarp();
+		// depth-3 / depth-4 aggregates of the brick from its 64 blocks: lane owns
+		// children 2*lane, 2*lane+1 (both under depth-3 node lane/4)
+		float cmax[2];
+		uint32_t cfl[2], crgb[2];
+#pragma unroll
+		for (int j = 0; j < 2; ++j) {
+			uint32_t slot = ld_volatile_u32(&M.brick_child[(size_t)brick * 64 + 2 * lane + j]);
+			if (slot) {
+				unsigned long long raw = ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&M.sum2[slot]));
+				cmax[j] = __uint_as_float((uint32_t)raw);
+				cfl[j] = (uint32_t)(raw >> 32);
+				crgb[j] = M.color ? ld_volatile_u32(&M.sum2_rgb[slot]) : 0u;
+			} else {
+				cmax[j] = 0.0f;
+				cfl[j] = M.default_flags;
+				crgb[j] = 0;
+			}
+		}
+		float m3 = fmaxf(cmax[0], cmax[1]);
+		uint32_t f3 = cfl[0] | cfl[1];
+#pragma unroll
+		for (int o = 1; o < 4; o <<= 1) {
+			m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, o));
+			f3 |= __shfl_xor_sync(0xffffffffu, f3, o);
+		}
+		uint32_t rgb3 = 0;
+		if (M.color) {
+			uint32_t cc[8];
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				cc[2 * j] = __shfl_sync(0xffffffffu, crgb[0], (lane & 28) + j);
+				cc[2 * j + 1] = __shfl_sync(0xffffffffu, crgb[1], (lane & 28) + j);
+			}
+			rgb3 = rms_rgb(cc, 8);
+		}
+		float m4 = m3;
+		uint32_t f4 = f3;
+#pragma unroll
+		for (int o = 4; o < 32; o <<= 1) {
+			m4 = fmaxf(m4, __shfl_xor_sync(0xffffffffu, m4, o));
+			f4 |= __shfl_xor_sync(0xffffffffu, f4, o);
+		}
+		uint32_t rgb4 = 0;
+		if (M.color) {
+			uint32_t cc[8];
+#pragma unroll
+			for (int j = 0; j < 8; ++j) cc[j] = __shfl_sync(0xffffffffu, rgb3, 4 * j);
+			rgb4 = rms_rgb(cc, 8);
+		}
+		if ((lane & 3) == 0) {
+			M.brick_sum3[(size_t)brick * 8 + (lane >> 2)] = {m3, f3};
+			if (M.color) M.brick_rgb3[(size_t)brick * 8 + (lane >> 2)] = rgb3;
+		}
+		if (lane == 0) {
+			M.brick_sum4[brick] = {m4, f4};
+			if (M.color) M.brick_rgb4[brick] = rgb4;
+		}
+	}
+	// statistics: one atomic per warp and counter
+	for (int o = 16; o > 0; o >>= 1) {
+		st_vox += __shfl_xor_sync(0xffffffffu, st_vox, o);
+		st_hit += __shfl_xor_sync(0xffffffffu, st_hit, o);
+		st_oct += __shfl_xor_sync(0xffffffffu, st_oct, o);
+		st_blk += __shfl_xor_sync(0xffffffffu, st_blk, o);
+		st_brk += __shfl_xor_sync(0xffffffffu, st_brk, o);
+	}
+	if (lane == 0 && st_brk) {
+		atomicAdd(&M.ctr->touched_voxels, (unsigned long long)st_vox);
+		atomicAdd(&M.ctr->hit_voxels, (unsigned long long)st_hit);
+		atomicAdd(&M.ctr->touched_octets, (unsigned long long)st_oct);
+		atomicAdd(&M.ctr->touched_blocks, (unsigned long long)st_blk);
+		atomicAdd(&M.ctr->touched_bricks, (unsigned long long)st_brk);
+	}
+}
+
+// ---------------------------------------------------------------------------
+// K4: upper levels (depth >= 5)
+// ---------------------------------------------------------------------------
+// Seeds the depth-5 dirty list with the parents of the bricks touched this scan.
+__global__ void __launch_bounds__(256) k_upper_seed(DeviceMap M, uint32_t n_bricks, uint32_t* list,
+                                                    uint32_t list_cap)
+{
+	uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_bricks || M.brick_stamp[b] != M.scan_id) return;
+	uint32_t x, y, z;
+	unpack_key(M.brick_key[b], x, y, z);
+	uint32_t s = upper_find_or_create(M, upper_key(5, x >> 1, y >> 1, z >> 1));
+	if (s == kNone) return;
+	if (atomicExch(&M.up_stamp[s], M.scan_id) != M.scan_id) {
+		uint32_t idx = atomicAdd(&M.ctr->list_count[0], 1u);
+		if (idx < list_cap) list[idx] = s;
+	}
+}
+
+// Recomputes the nodes of `in` (all at depth d) from their 8 children and pushes
+// their parents to `out`.  which = index of the input counter (0/1).
+__global__ void __launch_bounds__(256) k_upper_level(DeviceMap M, uint32_t depth, const uint32_t* in,
+                                                     uint32_t* out, uint32_t list_cap, int which)
+{
+	uint32_t n = M.ctr->list_count[which];
+	if (n > list_cap) n = list_cap;
+	const uint32_t lane8 = threadIdx.x & 7;
+	uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+	uint32_t stride = (gridDim.x * blockDim.x) >> 3;
+	const uint32_t gmask = 0xffu << (threadIdx.x & 24);
+	// n is uniform, groups of 8 lanes stay together
+	for (uint32_t i = gid; i < ((n + 3) & ~3u); i += stride) {
+		bool valid = i < n;
+		uint32_t s = valid ? in[i] : 0;
+		float occ = 0.0f;
+		uint32_t fl = M.default_flags, rgb = 0;
+		uint32_t x = 0, y = 0, z = 0;
+		if (valid) {
+			uint64_t key = M.up_key[s];
+			unpack_key(key, x, y, z);
+			x &= 0xffffu;  // strip the depth tag
+			uint32_t cx = 2 * x + (lane8 & 1), cy = 2 * y + ((lane8 >> 1) & 1), cz = 2 * z + (lane8 >> 2);
+			if (depth == 5) {
+				uint32_t c = brick_find(M, pack_key(cx, cy, cz));
+				if (c != kNone) {
+					Agg a = M.brick_sum4[c];
+					occ = a.occ;
+					fl = a.flags;
+					if (M.color) rgb = M.brick_rgb4[c];
+				}
+			} else {
+				uint32_t c = upper_find(M, upper_key(depth - 1, cx, cy, cz));
+				if (c != kNone) {
+					Agg a = M.up_agg[c];
+					occ = a.occ;
+					fl = a.flags;
+					if (M.color) rgb = M.up_rgb[c];
+				}
+			}
+		}
+		uint32_t crgb[8];
+		if (M.color) {
+#pragma unroll
+			for (int j = 0; j < 8; ++j) crgb[j] = __shfl_sync(0xffffffffu, rgb, (threadIdx.x & 24) + j);
+		}
+#pragma unroll
+		for (int o = 1; o < 8; o <<= 1) {
+			occ = fmaxf(occ, __shfl_xor_sync(0xffffffffu, occ, o));
+			fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+		}
+		(void)gmask;
+		if (valid && lane8 == 0) {
+			M.up_agg[s] = {occ, fl};
+			if (M.color) M.up_rgb[s] = rms_rgb(crgb, 8);
+			atomicAdd(&M.ctr->upper_nodes, 1ull);
+			if (depth < M.g.depth_levels) {
+				uint32_t p = upper_find_or_create(M, upper_key(depth + 1, x >> 1, y >> 1, z >> 1));
+				if (p != kNone && atomicExch(&M.up_stamp[p], M.scan_id) != M.scan_id) {
+					uint32_t idx = atomicAdd(&M.ctr->list_count[which ^ 1], 1u);
+					if (idx < list_cap) out[idx] = p;
+				}
+			}
+		}
+	}
+}
+
+__global__ void k_reset_list(DeviceMap M, int which) { M.ctr->list_count[which] = 0; }
+
+// ---------------------------------------------------------------------------
+// utility kernels
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rebuild_brick_hash(DeviceMap M, uint32_t n_bricks)
+{
+	uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_bricks) return;
+	unsigned long long key = M.brick_key[b];
+	uint32_t i = hash_u64(key) & M.bh_mask;
+	while (true) {
+		unsigned long long k = atomicCAS(&M.bh_keys[i], kEmptyKey, key);
+		if (k == kEmptyKey) {
+			M.bh_vals[i] = b;
+			return;
+		}
+		i = (i + 1) & M.bh_mask;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_rebuild_upper_hash(DeviceMap M, uint32_t n_upper)
+{
+	uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_upper) return;
+	unsigned long long key = M.up_key[b];
+	uint32_t i = hash_u64(key) & M.uh_mask;
+	while (true) {
+		unsigned long long k = atomicCAS(&M.uh_keys[i], kEmptyKey, key);
+		if (k == kEmptyKey) {
+			M.uh_vals[i] = b;
+			return;
+		}
+		i = (i + 1) & M.uh_mask;
+	}
+}
+
+// value-field export: one thread per voxel of every block
+__global__ void __launch_bounds__(256) k_export(DeviceMap M, uint32_t n_blocks, unsigned long long* codes,
+                                                float* occ, uint32_t* rgb, unsigned long long cap,
+                                                unsigned long long* count)
+{
+	size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t slot = (uint32_t)(t >> 6) + 1, v = (uint32_t)(t & 63);
+	bool emit = false;
+	float o = 0.0f;
+	uint32_t c = 0;
+	if (slot < n_blocks) {
+		o = M.leaf[(size_t)slot * 64 + v];
+		c = M.color ? M.leaf_rgb[(size_t)slot * 64 + v] : 0u;
+		emit = (o != 0.0f) || (c != 0u);
+	}
+	uint32_t ballot = __ballot_sync(0xffffffffu, emit);
+	if (!ballot) return;
+	unsigned long long base = 0;
+	uint32_t lane = threadIdx.x & 31;
+	if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(ballot));
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (!emit || !codes) return;
+	unsigned long long idx = base + __popc(ballot & ((1u << lane) - 1u));
+	if (idx >= cap) return;
+	uint32_t bx, by, bz;
+	unpack_key(M.block_key[slot], bx, by, bz);
+	// v is the Morton index inside the block: de-interleave 2 bits per axis
+	uint32_t vx = (v & 1u) | ((v >> 2) & 2u), vy = ((v >> 1) & 1u) | ((v >> 3) & 2u),
+	         vz = ((v >> 2) & 1u) | ((v >> 4) & 2u);
+	codes[idx] = key_to_code({(bx << 2) | vx, (by << 2) | vy, (bz << 2) | vz});
+	occ[idx] = o;
+	if (rgb) rgb[idx] = c;
+}
+
+// node queries with the intended getNode semantics
+__global__ void __launch_bounds__(256) k_query(DeviceMap M, const unsigned long long* codes,
+                                               const uint32_t* depths, uint32_t n, float* occ,
+                                               uint8_t* flags, uint32_t* rgb)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	Key3 k = code_to_key(codes[i]);
+	k.x &= M.g.key_mask;
+	k.y &= M.g.key_mask;
+	k.z &= M.g.key_mask;
+	uint32_t d = depths[i];
+	float o = 0.0f;
+	uint32_t f = M.default_flags, c = 0;
+	if (d >= 5) {
+		if (d <= M.g.depth_levels) {
+			uint32_t s = upper_find(M, upper_key(d, k.x >> d, k.y >> d, k.z >> d));
+			if (s != kNone) {
+				o = M.up_agg[s].occ;
+				f = M.up_agg[s].flags;
+				if (M.color) c = M.up_rgb[s];
+			}
+		}
+	} else {
+		uint32_t brick = brick_find(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
+		if (brick != kNone) {
+			if (d == 4) {
+				o = M.brick_sum4[brick].occ;
+				f = M.brick_sum4[brick].flags;
+				if (M.color) c = M.brick_rgb4[brick];
+			} else if (d == 3) {
+				uint32_t j = ((k.x >> 3) & 1u) | (((k.y >> 3) & 1u) << 1) | (((k.z >> 3) & 1u) << 2);
+				o = M.brick_sum3[(size_t)brick * 8 + j].occ;
+				f = M.brick_sum3[(size_t)brick * 8 + j].flags;
+				if (M.color) c = M.brick_rgb3[(size_t)brick * 8 + j];
+			} else {
+				uint32_t slot = M.brick_child[(size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2)];
+				if (slot && slot != kLock) {
+					if (d == 2) {
+						o = M.sum2[slot].occ;
+						f = M.sum2[slot].flags;
+						if (M.color) c = M.sum2_rgb[slot];
+					} else if (d == 1) {
+						uint32_t j = ((k.x >> 1) & 1u) | (((k.y >> 1) & 1u) << 1) | (((k.z >> 1) & 1u) << 2);
+						uint32_t meta = M.sum1_meta[slot];
+						if ((meta >> (16 + j)) & 1u) {
+							o = M.sum1_occ[(size_t)slot * 8 + j];
+							f = (meta >> (2 * j)) & 3u;
+							if (M.color) c = M.sum1_rgb[(size_t)slot * 8 + j];
+						}
+					} else {
+						uint32_t v = morton2(k.x, k.y, k.z);
+						o = M.leaf[(size_t)slot * 64 + v];
+						f = leaf_flags(M, o);
+						if (M.color) c = M.leaf_rgb[(size_t)slot * 64 + v];
+					}
+				}
+			}
+		}
+	}
+	occ[i] = o;
+	flags[i] = (uint8_t)f;
+	if (rgb) rgb[i] = c;
+}
+
+}  // namespace ufo_b200

@@ -1,0 +1,997 @@
+// ufo_map.cu -- host side of libufomap_b200.so: device pools, scan orchestration
+// and the C ABI declared in include/ufomap_b200.h.
+//
+// One map = one CUDA device + one stream.  An insert enqueues
+//   H2D(points) -> K1 k_points [-> K1b k_hits] -> K2 k_rays -> (counter read-back,
+//   grow pools and re-run K1/K2 if an allocation overflowed) -> K3 k_update -> K4 k_upper_*
+// which mirrors insertPointCloud + insertPointCloudHelper
+// (/root/reference/ufomap/include/ufo/map/occupancy_map_base.h:270-327, :1345-1373).
+// There is no CPU fallback anywhere in this file.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ufomap_b200.h"
+#include "ufo_kernels.cuh"
+
+using namespace ufo_b200;
+
+namespace
+{
+constexpr uint32_t kMinHash = 1u << 16;
+
+uint32_t next_pow2(uint64_t v)
+{
+	uint64_t p = 1;
+	while (p < v) p <<= 1;
+	return (uint32_t)std::min<uint64_t>(p, 1ull << 31);
+}
+
+struct CudaError {
+	cudaError_t e;
+	const char* what;
+	int line;
+};
+
+#define CK(call)                                         \
+	do {                                                   \
+		cudaError_t e__ = (call);                            \
+		if (e__ != cudaSuccess) throw CudaError{e__, #call, __LINE__}; \
+	} while (0)
+
+template <class T>
+void dev_alloc(T*& p, size_t n, int fill_byte, cudaStream_t s, size_t& total)
+{
+	p = nullptr;
+	if (n == 0) n = 1;
+	CK(cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T)));
+	CK(cudaMemsetAsync(p, fill_byte, n * sizeof(T), s));
+	total += n * sizeof(T);
+}
+
+// grow p from old_n to new_n elements (new part filled with fill_byte)
+template <class T>
+void dev_grow(T*& p, size_t old_n, size_t new_n, int fill_byte, cudaStream_t s, size_t& total)
+{
+	if (!p) return;
+	T* q = nullptr;
+	CK(cudaMalloc(reinterpret_cast<void**>(&q), new_n * sizeof(T)));
+	CK(cudaMemcpyAsync(q, p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+	CK(cudaMemsetAsync(q + old_n, fill_byte, (new_n - old_n) * sizeof(T), s));
+	CK(cudaStreamSynchronize(s));
+	CK(cudaFree(p));
+	p = q;
+	total += (new_n - old_n) * sizeof(T);
+}
+
+double to_logit(double p) { return std::log(p / (1.0 - p)); }
+}  // namespace
+
+struct ufo_b200_map {
+	ufo_b200_params params{};
+	DeviceMap M{};
+	int device = 0;
+	cudaStream_t own_stream = nullptr, stream = nullptr;
+	// sensor model as the reference stores it (double log-odds)
+	double occ_thr_log = 0, free_thr_log = 0, hit_log = 0, miss_log = 0, cmin_log = 0, cmax_log = 0;
+	// host mirror of the counters (pinned)
+	Counters* h_ctr = nullptr;
+	// scan staging
+	void* d_points = nullptr;
+	size_t d_points_cap = 0;
+	double* d_ray_end = nullptr;
+	uint32_t* d_hit_tab = nullptr;
+	size_t ray_cap = 0;
+	unsigned long long* d_tab_keys = nullptr;
+	uint32_t* d_tab_min = nullptr;
+	uint32_t tab_size = 0;
+	uint32_t* d_list[2] = {nullptr, nullptr};
+	// bookkeeping
+	uint32_t n_blocks = 1, n_bricks = 0, n_upper = 0;  // host view after the last sync
+	size_t device_bytes = 0;
+	bool profiling = false;
+	cudaEvent_t ev[8]{};
+	bool ev_valid = false;
+	cudaEvent_t ev_done = nullptr;
+	ufo_b200_scan_stats stats{};
+	bool stats_pending = false;
+	double min_change[3], max_change[3];
+	std::string err;
+	int sm_count = 148;
+
+	void set_error(const char* fmt, ...)
+	{
+		char buf[512];
+		va_list ap;
+		va_start(ap, fmt);
+		vsnprintf(buf, sizeof(buf), fmt, ap);
+		va_end(ap);
+		err = buf;
+	}
+};
+
+namespace
+{
+using Map = ufo_b200_map;
+
+void refresh_model(Map* m)
+{
+	DeviceMap& M = m->M;
+	M.occ_thr = m->occ_thr_log;
+	M.free_thr = m->free_thr_log;
+	M.hit = (float)m->hit_log;
+	M.clamp_min = (float)m->cmin_log;
+	M.clamp_max = (float)m->cmax_log;
+	// toProb(float) with expf, as the reference evaluates it on the host
+	M.prob_hit = 1.0 / (1.0 + (double)expf(-M.hit));
+	uint32_t f = (m->free_thr_log > 0.0) ? 1u : 0u;
+	if (m->free_thr_log <= 0.0 && m->occ_thr_log >= 0.0) f |= 2u;
+	M.default_flags = f;
+}
+
+void reset_bbox(Map* m)
+{
+	double h = node_half(m->M.g, m->M.g.depth_levels);
+	for (int i = 0; i < 3; ++i) {
+		m->min_change[i] = h;
+		m->max_change[i] = -h;
+	}
+}
+
+void alloc_pools(Map* m, uint32_t block_cap, uint32_t brick_cap, uint32_t up_cap)
+{
+	DeviceMap& M = m->M;
+	cudaStream_t s = m->stream;
+	size_t& tot = m->device_bytes;
+	M.block_cap = block_cap;
+	M.brick_cap = brick_cap;
+	M.up_cap = up_cap;
+	M.bh_mask = std::max(kMinHash, next_pow2(2ull * brick_cap)) - 1;
+	M.uh_mask = std::max(kMinHash, next_pow2(2ull * up_cap)) - 1;
+	dev_alloc(M.bh_keys, (size_t)M.bh_mask + 1, 0xff, s, tot);
+	dev_alloc(M.bh_vals, (size_t)M.bh_mask + 1, 0xff, s, tot);
+	dev_alloc(M.brick_key, brick_cap, 0, s, tot);
+	dev_alloc(M.brick_child, (size_t)brick_cap * 64, 0, s, tot);
+	dev_alloc(M.brick_stamp, brick_cap, 0, s, tot);
+	dev_alloc(M.brick_sum3, (size_t)brick_cap * 8, 0, s, tot);
+	dev_alloc(M.brick_sum4, brick_cap, 0, s, tot);
+	dev_alloc(M.leaf, (size_t)block_cap * 64, 0, s, tot);
+	dev_alloc(M.miss_mask, block_cap, 0, s, tot);
+	dev_alloc(M.hit_mask, block_cap, 0, s, tot);
+	dev_alloc(M.block_key, block_cap, 0, s, tot);
+	dev_alloc(M.sum1_occ, (size_t)block_cap * 8, 0, s, tot);
+	dev_alloc(M.sum1_meta, block_cap, 0, s, tot);
+	dev_alloc(M.sum2, block_cap, 0, s, tot);
+	dev_alloc(M.uh_keys, (size_t)M.uh_mask + 1, 0xff, s, tot);
+	dev_alloc(M.uh_vals, (size_t)M.uh_mask + 1, 0xff, s, tot);
+	dev_alloc(M.up_key, up_cap, 0, s, tot);
+	dev_alloc(M.up_agg, up_cap, 0, s, tot);
+	dev_alloc(M.up_stamp, up_cap, 0, s, tot);
+	dev_alloc(m->d_list[0], up_cap, 0, s, tot);
+	dev_alloc(m->d_list[1], up_cap, 0, s, tot);
+	if (M.color) {
+		dev_alloc(M.brick_rgb3, (size_t)brick_cap * 8, 0, s, tot);
+		dev_alloc(M.brick_rgb4, brick_cap, 0, s, tot);
+		dev_alloc(M.leaf_rgb, (size_t)block_cap * 64, 0, s, tot);
+		dev_alloc(M.sum1_rgb, (size_t)block_cap * 8, 0, s, tot);
+		dev_alloc(M.sum2_rgb, block_cap, 0, s, tot);
+		dev_alloc(M.up_rgb, up_cap, 0, s, tot);
+	}
+	dev_alloc(M.ctr, 1, 0, s, tot);
+}
+
+void free_pools(Map* m)
+{
+	DeviceMap& M = m->M;
+	void* ptrs[] = {M.bh_keys,   M.bh_vals,   M.brick_key, M.brick_child, M.brick_stamp, M.brick_sum3,
+	                M.brick_sum4, M.brick_rgb3, M.brick_rgb4, M.leaf,       M.leaf_rgb,    M.miss_mask,
+	                M.hit_mask,  M.block_key, M.sum1_occ,  M.sum1_meta,   M.sum2,        M.sum1_rgb,
+	                M.sum2_rgb,  M.uh_keys,   M.uh_vals,   M.up_key,      M.up_agg,      M.up_rgb,
+	                M.up_stamp,  M.ctr,       m->d_list[0], m->d_list[1], m->d_points,   m->d_ray_end,
+	                m->d_hit_tab, m->d_tab_keys, m->d_tab_min};
+	for (void* p : ptrs)
+		if (p) cudaFree(p);
+}
+
+void push_counters(Map* m)
+{
+	// host view -> device allocation counters, clears the per-scan part
+	Counters c{};
+	c.n_blocks = m->n_blocks;
+	c.n_bricks = m->n_bricks;
+	c.n_upper = m->n_upper;
+	for (int i = 0; i < 3; ++i) {
+		c.bbox[i] = ~0ull;
+		c.bbox[3 + i] = 0ull;
+	}
+	*m->h_ctr = c;
+	CK(cudaMemcpyAsync(m->M.ctr, m->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice, m->stream));
+}
+
+void pull_counters(Map* m)
+{
+	CK(cudaMemcpyAsync(m->h_ctr, m->M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+	CK(cudaStreamSynchronize(m->stream));
+}
+
+// grow whichever pool overflowed; `want_*` are the allocation counters the failed
+// run reached (an over-estimate of the need)
+void grow_pools(Map* m, uint32_t overflow, uint32_t want_blocks, uint32_t want_bricks,
+                uint32_t want_upper)
+{
+	DeviceMap& M = m->M;
+	cudaStream_t s = m->stream;
+	size_t& tot = m->device_bytes;
+	CK(cudaStreamSynchronize(s));
+	if (overflow & 1u) {
+		uint32_t oc = M.block_cap;
+		uint64_t nc64 = std::max<uint64_t>(2ull * oc, (uint64_t)want_blocks + want_blocks / 4);
+		if (nc64 > 0xfffffff0ull) throw std::bad_alloc();
+		uint32_t nc = (uint32_t)nc64;
+		dev_grow(M.leaf, (size_t)oc * 64, (size_t)nc * 64, 0, s, tot);
+		dev_grow(M.miss_mask, oc, nc, 0, s, tot);
+		dev_grow(M.hit_mask, oc, nc, 0, s, tot);
+		dev_grow(M.block_key, oc, nc, 0, s, tot);
+		dev_grow(M.sum1_occ, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
+		dev_grow(M.sum1_meta, oc, nc, 0, s, tot);
+		dev_grow(M.sum2, oc, nc, 0, s, tot);
+		dev_grow(M.leaf_rgb, (size_t)oc * 64, (size_t)nc * 64, 0, s, tot);
+		dev_grow(M.sum1_rgb, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
+		dev_grow(M.sum2_rgb, oc, nc, 0, s, tot);
+		M.block_cap = nc;
+	}
+	if (overflow & 2u) {
+		uint32_t oc = M.brick_cap;
+		uint32_t nc = (uint32_t)std::max<uint64_t>(2ull * oc, (uint64_t)want_bricks + want_bricks / 4);
+		dev_grow(M.brick_key, oc, nc, 0, s, tot);
+		dev_grow(M.brick_child, (size_t)oc * 64, (size_t)nc * 64, 0, s, tot);
+		dev_grow(M.brick_stamp, oc, nc, 0, s, tot);
+		dev_grow(M.brick_sum3, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
+		dev_grow(M.brick_sum4, oc, nc, 0, s, tot);
+		dev_grow(M.brick_rgb3, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
+		dev_grow(M.brick_rgb4, oc, nc, 0, s, tot);
+		M.brick_cap = nc;
+		// rebuild the hash from the surviving bricks (drops kFailed entries)
+		size_t old_tab = (size_t)M.bh_mask + 1;
+		uint32_t new_tab = std::max(kMinHash, next_pow2(2ull * nc));
+		CK(cudaFree(M.bh_keys));
+		CK(cudaFree(M.bh_vals));
+		tot -= old_tab * (sizeof(unsigned long long) + sizeof(uint32_t));
+		M.bh_mask = new_tab - 1;
+		dev_alloc(M.bh_keys, new_tab, 0xff, s, tot);
+		dev_alloc(M.bh_vals, new_tab, 0xff, s, tot);
+		uint32_t nb = std::min(m->h_ctr->n_bricks, oc);
+		if (nb) k_rebuild_brick_hash<<<(nb + 255) / 256, 256, 0, s>>>(M, nb);
+	}
+	if (overflow & 4u) {
+		uint32_t oc = M.up_cap;
+		uint32_t nc = (uint32_t)std::max<uint64_t>(2ull * oc, (uint64_t)want_upper + want_upper / 4);
+		dev_grow(M.up_key, oc, nc, 0, s, tot);
+		dev_grow(M.up_agg, oc, nc, 0, s, tot);
+		dev_grow(M.up_stamp, oc, nc, 0, s, tot);
+		dev_grow(M.up_rgb, oc, nc, 0, s, tot);
+		dev_grow(m->d_list[0], oc, nc, 0, s, tot);
+		dev_grow(m->d_list[1], oc, nc, 0, s, tot);
+		M.up_cap = nc;
+		size_t old_tab = (size_t)M.uh_mask + 1;
+		uint32_t new_tab = std::max(kMinHash, next_pow2(2ull * nc));
+		CK(cudaFree(M.uh_keys));
+		CK(cudaFree(M.uh_vals));
+		tot -= old_tab * (sizeof(unsigned long long) + sizeof(uint32_t));
+		M.uh_mask = new_tab - 1;
+		dev_alloc(M.uh_keys, new_tab, 0xff, s, tot);
+		dev_alloc(M.uh_vals, new_tab, 0xff, s, tot);
+		uint32_t nu = std::min(m->h_ctr->n_upper, oc);
+		if (nu) k_rebuild_upper_hash<<<(nu + 255) / 256, 256, 0, s>>>(M, nu);
+	}
+	CK(cudaGetLastError());
+}
+
+size_t layout_stride(int layout)
+{
+	switch (layout) {
+		case UFO_B200_XYZ_F64: return 24;
+		case UFO_B200_XYZ_F32: return 12;
+		case UFO_B200_XYZRGB_F64: return 32;
+		case UFO_B200_XYZRGB_F32: return 16;
+		default: return 0;
+	}
+}
+
+void ensure_scan_buffers(Map* m, size_t n, bool need_table)
+{
+	size_t& tot = m->device_bytes;
+	if (n > m->ray_cap) {
+		CK(cudaStreamSynchronize(m->stream));
+		if (m->d_ray_end) {
+			cudaFree(m->d_ray_end);
+			cudaFree(m->d_hit_tab);
+			tot -= m->ray_cap * (3 * sizeof(double) + sizeof(uint32_t));
+		}
+		size_t cap = std::max<size_t>(n, 1024);
+		dev_alloc(m->d_ray_end, cap * 3, 0, m->stream, tot);
+		dev_alloc(m->d_hit_tab, cap, 0xff, m->stream, tot);
+		m->ray_cap = cap;
+	}
+	if (need_table) {
+		uint32_t want = std::max(1u << 12, next_pow2(4ull * n));
+		if (want > m->tab_size) {
+			CK(cudaStreamSynchronize(m->stream));
+			if (m->d_tab_keys) {
+				cudaFree(m->d_tab_keys);
+				cudaFree(m->d_tab_min);
+				tot -= (size_t)m->tab_size * 12;
+			}
+			dev_alloc(m->d_tab_keys, want, 0xff, m->stream, tot);
+			dev_alloc(m->d_tab_min, want, 0xff, m->stream, tot);
+			m->tab_size = want;
+		}
+	}
+}
+
+void finish_stats(Map* m)
+{
+	// called after the stream is idle and h_ctr holds the end-of-scan counters
+	if (!m->stats_pending) return;
+	const Counters& c = *m->h_ctr;
+	ufo_b200_scan_stats& st = m->stats;
+	st.rays = c.n_rays;
+	st.visits = c.visits;
+	st.touched_voxels = c.touched_voxels;
+	st.hit_voxels = c.hit_voxels;
+	st.touched_octets = c.touched_octets;
+	st.touched_blocks = c.touched_blocks;
+	st.touched_bricks = c.touched_bricks;
+	st.upper_nodes = c.upper_nodes;
+	m->n_blocks = std::min(c.n_blocks, m->M.block_cap);
+	m->n_bricks = std::min(c.n_bricks, m->M.brick_cap);
+	m->n_upper = std::min(c.n_upper, m->M.up_cap);
+	st.blocks_in_map = m->n_blocks - 1;
+	st.bricks_in_map = m->n_bricks;
+	st.device_bytes = m->device_bytes;
+	if (c.n_rays || c.touched_voxels) {
+		for (int i = 0; i < 3; ++i) {
+			if (c.bbox[i] != ~0ull) m->min_change[i] = std::min(m->min_change[i], decode_ordered(c.bbox[i]));
+			if (c.bbox[3 + i] != 0ull)
+				m->max_change[i] = std::max(m->max_change[i], decode_ordered(c.bbox[3 + i]));
+		}
+	}
+	if (m->ev_valid) {
+		cudaEventElapsedTime(&st.ms_total, m->ev[0], m->ev[6]);
+		if (m->profiling) {
+			cudaEventElapsedTime(&st.ms_h2d, m->ev[0], m->ev[1]);
+			cudaEventElapsedTime(&st.ms_points, m->ev[1], m->ev[2]);
+			cudaEventElapsedTime(&st.ms_rays, m->ev[2], m->ev[3]);
+			cudaEventElapsedTime(&st.ms_update, m->ev[4], m->ev[5]);
+			cudaEventElapsedTime(&st.ms_propagate, m->ev[5], m->ev[6]);
+		}
+	}
+	m->stats_pending = false;
+}
+
+int sync_map(Map* m)
+{
+	CK(cudaStreamSynchronize(m->stream));
+	if (m->stats_pending) {
+		// end-of-scan counters were copied to h_ctr by the scan itself
+		finish_stats(m);
+	}
+	return UFO_B200_OK;
+}
+
+void launch_rays(Map* m, const ScanArgs& a, int simple)
+{
+	uint32_t grid = (a.n + 127) / 128;
+	if (simple) {
+		k_rays_simple<<<grid, 128, 0, m->stream>>>(m->M, a);
+	} else if (a.depth == 0) {
+		k_rays<0><<<grid, 128, 0, m->stream>>>(m->M, a);
+	} else if (a.depth == 1) {
+		k_rays<1><<<grid, 128, 0, m->stream>>>(m->M, a);
+	} else {
+		k_rays<2><<<grid, 128, 0, m->stream>>>(m->M, a);
+	}
+}
+
+int do_insert(Map* m, const double origin[3], const void* points, bool on_device, size_t n,
+              int layout, double max_range, uint32_t depth, int simple, uint32_t early_stopping,
+              int discrete, int async)
+{
+	if (!m || !origin || (!points && n)) return UFO_B200_E_INVALID;
+	size_t stride = layout_stride(layout);
+	if (!stride || n > 0x7fffffffull) {
+		m->set_error("invalid layout %d or point count %zu", layout, n);
+		return UFO_B200_E_INVALID;
+	}
+	if (early_stopping != 0) {
+		m->set_error("early_stopping is order-dependent in the reference (occupancy_map_base.h:1289-1298) and is not supported");
+		return UFO_B200_E_UNSUPPORTED;
+	}
+	if (depth > 2) {
+		m->set_error("insert depth %u > 2 is not supported yet", depth);
+		return UFO_B200_E_UNSUPPORTED;
+	}
+	CK(cudaSetDevice(m->device));
+	// one integration in flight at most (insertPointCloudWait, occupancy_map_base.h:315)
+	sync_map(m);
+
+	DeviceMap& M = m->M;
+	cudaStream_t s = m->stream;
+	const bool has_rgb = layout == UFO_B200_XYZRGB_F64 || layout == UFO_B200_XYZRGB_F32;
+	const bool use_color = M.color && has_rgb;
+	const bool need_table = discrete || use_color;
+	ensure_scan_buffers(m, n, need_table);
+
+	ScanArgs a{};
+	a.origin = {origin[0], origin[1], origin[2]};
+	a.max_range = max_range;
+	a.n = (uint32_t)n;
+	a.depth = depth;
+	a.layout = layout;
+	a.discrete = discrete;
+	a.use_color = use_color;
+	a.miss = (float)(m->miss_log / (double)((2.0 * depth) + 1));
+	a.ray_end = m->d_ray_end;
+	a.tab_keys = m->d_tab_keys;
+	a.tab_min = m->d_tab_min;
+	a.tab_mask = m->tab_size ? m->tab_size - 1 : 0;
+	a.hit_tab = use_color ? m->d_hit_tab : nullptr;
+	a.count_visits = m->profiling;
+
+	m->stats = ufo_b200_scan_stats{};
+	m->stats.points = n;
+	M.scan_id++;
+	if (M.scan_id == 0) M.scan_id = 1;
+
+	CK(cudaEventRecord(m->ev[0], s));
+	if (on_device) {
+		a.points = points;
+	} else {
+		size_t bytes = n * stride;
+		if (bytes > m->d_points_cap) {
+			if (m->d_points) {
+				cudaFree(m->d_points);
+				m->device_bytes -= m->d_points_cap;
+			}
+			m->d_points_cap = std::max<size_t>(bytes, 1 << 16);
+			CK(cudaMalloc(&m->d_points, m->d_points_cap));
+			m->device_bytes += m->d_points_cap;
+		}
+		if (bytes) CK(cudaMemcpyAsync(m->d_points, points, bytes, cudaMemcpyHostToDevice, s));
+		a.points = m->d_points;
+	}
+	if (m->profiling) CK(cudaEventRecord(m->ev[1], s));
+
+	push_counters(m);
+	const uint32_t bricks_before = m->n_bricks;
+	uint32_t regrows = 0;
+	while (true) {
+		if (need_table) {
+			CK(cudaMemsetAsync(m->d_tab_keys, 0xff, (size_t)m->tab_size * sizeof(unsigned long long), s));
+			CK(cudaMemsetAsync(m->d_tab_min, 0xff, (size_t)m->tab_size * sizeof(uint32_t), s));
+		}
+		if (n) {
+			uint32_t grid = (uint32_t)((n + 255) / 256);
+			k_points<<<grid, 256, 0, s>>>(M, a);
+			if (use_color) k_hits<<<grid, 256, 0, s>>>(M, a);
+			if (m->profiling && regrows == 0) CK(cudaEventRecord(m->ev[2], s));
+			launch_rays(m, a, simple);
+		} else if (m->profiling) {
+			CK(cudaEventRecord(m->ev[2], s));
+		}
+		if (m->profiling) CK(cudaEventRecord(m->ev[3], s));
+		CK(cudaGetLastError());
+		pull_counters(m);
+		uint32_t ov = m->h_ctr->overflow;
+		if (!ov) break;
+		// an allocation failed: grow, restore consistent counters, run K1/K2 again
+		// (marking is idempotent: OR into masks, find-or-create of blocks)
+		++regrows;
+		if (regrows > 8) {
+			m->set_error("device pools keep overflowing");
+			return UFO_B200_E_NOMEM;
+		}
+		uint32_t wb = m->h_ctr->n_blocks, wk = m->h_ctr->n_bricks, wu = m->h_ctr->n_upper;
+		m->n_blocks = std::min(wb, M.block_cap);
+		m->n_bricks = std::min(wk, M.brick_cap);
+		try {
+			grow_pools(m, ov, wb, wk, wu);
+		} catch (std::bad_alloc&) {
+			m->set_error("block pool cannot grow beyond 2^32 slots");
+			return UFO_B200_E_NOMEM;
+		}
+		push_counters(m);  // resets the per-scan counters; n_rays/bbox are recomputed by the re-run
+	}
+	m->n_blocks = m->h_ctr->n_blocks;
+	m->n_bricks = m->h_ctr->n_bricks;
+	m->stats.regrows = regrows;
+
+	if (m->profiling) CK(cudaEventRecord(m->ev[4], s));
+	// K3
+	if (m->n_bricks) {
+		uint32_t warps_needed = m->n_bricks;
+		uint32_t grid = std::min<uint32_t>((warps_needed + 7) / 8, (uint32_t)m->sm_count * 32);
+		k_update<<<grid, 256, 0, s>>>(M, a.miss, m->n_bricks);
+	}
+	if (m->profiling) CK(cudaEventRecord(m->ev[5], s));
+	// K4: upper levels, depth 5 .. L.  Only bricks created by this scan can create upper
+	// nodes (at most one per level each), so the pool is grown up front to the exact
+	// worst case and the kernels never overflow.
+	if (M.g.depth_levels >= 5 && m->n_bricks) {
+		uint64_t new_bricks = m->n_bricks - bricks_before;
+		uint64_t need = (uint64_t)m->n_upper + new_bricks * (M.g.depth_levels - 4) + 1;
+		if (need > M.up_cap) {
+			m->h_ctr->n_upper = m->n_upper;
+			grow_pools(m, 4u, 0, 0, (uint32_t)std::min<uint64_t>(need, 0x7fffffffull));
+		}
+		k_reset_list<<<1, 1, 0, s>>>(M, 0);
+		k_reset_list<<<1, 1, 0, s>>>(M, 1);
+		k_upper_seed<<<(m->n_bricks + 255) / 256, 256, 0, s>>>(M, m->n_bricks, m->d_list[0], M.up_cap);
+		int which = 0;
+		for (uint32_t d = 5; d <= M.g.depth_levels; ++d) {
+			k_upper_level<<<std::max(1, m->sm_count / (d > 7 ? 16 : 1)), 256, 0, s>>>(
+			    M, d, m->d_list[which], m->d_list[which ^ 1], M.up_cap, which);
+			k_reset_list<<<1, 1, 0, s>>>(M, which);
+			which ^= 1;
+		}
+		CK(cudaGetLastError());
+	}
+	CK(cudaEventRecord(m->ev[6], s));
+	m->ev_valid = true;
+	CK(cudaMemcpyAsync(m->h_ctr, M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+	m->stats_pending = true;
+	if (!async) return sync_map(m);
+	return UFO_B200_OK;
+}
+
+template <class F>
+int guarded(Map* m, F&& f)
+{
+	if (m && m->device == -2) {
+		m->set_error("geometry-only handle: no CUDA device bound");
+		return UFO_B200_E_CUDA;
+	}
+	try {
+		return f();
+	} catch (CudaError& e) {
+		if (m) m->set_error("CUDA error %s (%d) at ufo_map.cu:%d: %s", cudaGetErrorName(e.e), (int)e.e, e.line, e.what);
+		return UFO_B200_E_CUDA;
+	} catch (std::bad_alloc&) {
+		if (m) m->set_error("out of memory");
+		return UFO_B200_E_NOMEM;
+	}
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* ufo_b200_version(void) { return "ufomap_b200 0.1 (sm_100a)"; }
+
+void ufo_b200_default_params(ufo_b200_params* p)
+{
+	if (!p) return;
+	memset(p, 0, sizeof(*p));
+	p->resolution = 0.1;
+	p->depth_levels = 16;
+	p->automatic_pruning = 1;
+	p->occupied_thres = 0.5;
+	p->free_thres = 0.5;
+	p->prob_hit = 0.7;
+	p->prob_miss = 0.4;
+	p->clamping_thres_min = 0.1192;
+	p->clamping_thres_max = 0.971;
+	p->color = 0;
+	p->device = -1;
+}
+
+int ufo_b200_create(const ufo_b200_params* p, ufo_b200_map** out)
+{
+	if (!p || !out) return UFO_B200_E_INVALID;
+	*out = nullptr;
+	if (p->depth_levels < 2 || p->depth_levels > 21 || !(p->resolution > 0)) return UFO_B200_E_INVALID;
+	Map* m = new (std::nothrow) Map;
+	if (!m) return UFO_B200_E_NOMEM;
+	if (p->device == -2) {
+		// geometry-only handle: indexing / computeRay helpers run on the host and need no
+		// device; every call that touches map state fails with UFO_B200_E_CUDA
+		m->device = -2;
+		m->params = *p;
+		m->M.g = make_geometry(p->resolution, p->depth_levels);
+		m->occ_thr_log = to_logit(p->occupied_thres);
+		m->free_thr_log = to_logit(p->free_thres);
+		m->hit_log = to_logit(p->prob_hit);
+		m->miss_log = to_logit(p->prob_miss);
+		m->cmin_log = to_logit(p->clamping_thres_min);
+		m->cmax_log = to_logit(p->clamping_thres_max);
+		*out = m;
+		return UFO_B200_OK;
+	}
+	int rc = guarded(m, [&]() {
+		int dev = p->device;
+		if (dev < 0) CK(cudaGetDevice(&dev));
+		CK(cudaSetDevice(dev));
+		m->device = dev;
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, dev));
+		m->sm_count = prop.multiProcessorCount;
+		m->params = *p;
+		CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+		m->stream = m->own_stream;
+		for (auto& e : m->ev) CK(cudaEventCreate(&e));
+		CK(cudaHostAlloc(reinterpret_cast<void**>(&m->h_ctr), sizeof(Counters), cudaHostAllocDefault));
+		m->M.g = make_geometry(p->resolution, p->depth_levels);
+		m->M.color = p->color ? 1u : 0u;
+		m->occ_thr_log = to_logit(p->occupied_thres);
+		m->free_thr_log = to_logit(p->free_thres);
+		m->hit_log = to_logit(p->prob_hit);
+		m->miss_log = to_logit(p->prob_miss);
+		m->cmin_log = to_logit(p->clamping_thres_min);
+		m->cmax_log = to_logit(p->clamping_thres_max);
+		refresh_model(m);
+		uint32_t blocks = (uint32_t)std::min<uint64_t>(p->initial_blocks ? p->initial_blocks : (1ull << 20), 0xfffffff0ull);
+		uint32_t bricks = (uint32_t)std::min<uint64_t>(p->initial_bricks ? p->initial_bricks : std::max<uint64_t>(blocks / 16, 4096), 0x7ffffff0ull);
+		blocks = std::max(blocks, 64u);
+		bricks = std::max(bricks, 16u);
+		uint32_t upper = std::max(bricks / 2, 4096u);
+		alloc_pools(m, blocks, bricks, upper);
+		m->n_blocks = 1;
+		m->n_bricks = 0;
+		m->n_upper = 0;
+		reset_bbox(m);
+		CK(cudaStreamSynchronize(m->stream));
+		return (int)UFO_B200_OK;
+	});
+	if (rc != UFO_B200_OK) {
+		fprintf(stderr, "ufo_b200_create failed: %s\n", m->err.c_str());
+		free_pools(m);
+		delete m;
+		return rc;
+	}
+	*out = m;
+	return UFO_B200_OK;
+}
+
+void ufo_b200_destroy(ufo_b200_map* m)
+{
+	if (!m) return;
+	if (m->device == -2) {
+		delete m;
+		return;
+	}
+	cudaSetDevice(m->device);
+	cudaStreamSynchronize(m->stream);
+	free_pools(m);
+	for (auto& e : m->ev)
+		if (e) cudaEventDestroy(e);
+	if (m->h_ctr) cudaFreeHost(m->h_ctr);
+	if (m->own_stream) cudaStreamDestroy(m->own_stream);
+	delete m;
+}
+
+const char* ufo_b200_last_error(const ufo_b200_map* m) { return m ? m->err.c_str() : "null map"; }
+
+int ufo_b200_set_stream(ufo_b200_map* m, void* cuda_stream)
+{
+	if (!m) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		sync_map(m);
+		m->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : m->own_stream;
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_insert_pointcloud(ufo_b200_map* m, const double origin[3], const void* points,
+                               size_t n, int layout, double max_range, uint32_t depth,
+                               int simple_ray_casting, uint32_t early_stopping, int discrete,
+                               int async)
+{
+	return guarded(m, [&]() {
+		return do_insert(m, origin, points, false, n, layout, max_range, depth, simple_ray_casting,
+		                 early_stopping, discrete, async);
+	});
+}
+
+int ufo_b200_insert_device(ufo_b200_map* m, const double origin[3], const void* d_points,
+                           size_t n, int layout, double max_range, uint32_t depth,
+                           int simple_ray_casting, uint32_t early_stopping, int discrete,
+                           int async)
+{
+	return guarded(m, [&]() {
+		return do_insert(m, origin, d_points, true, n, layout, max_range, depth, simple_ray_casting,
+		                 early_stopping, discrete, async);
+	});
+}
+
+int ufo_b200_wait(ufo_b200_map* m)
+{
+	if (!m) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		CK(cudaSetDevice(m->device));
+		return sync_map(m);
+	});
+}
+
+int ufo_b200_done(ufo_b200_map* m, int* done)
+{
+	if (!m || !done) return UFO_B200_E_INVALID;
+	if (m->device == -2) return UFO_B200_E_CUDA;
+	cudaError_t e = cudaStreamQuery(m->stream);
+	if (e == cudaSuccess) {
+		*done = 1;
+		return UFO_B200_OK;
+	}
+	if (e == cudaErrorNotReady) {
+		*done = 0;
+		return UFO_B200_OK;
+	}
+	m->set_error("cudaStreamQuery: %s", cudaGetErrorString(e));
+	return UFO_B200_E_CUDA;
+}
+
+int ufo_b200_compute_ray(const ufo_b200_map* m, const double origin[3], const double end_in[3],
+                         double max_range, uint32_t depth, uint64_t* codes, size_t cap, size_t* n)
+{
+	if (!m || !origin || !end_in || !n) return UFO_B200_E_INVALID;
+	const Geometry& g = m->M.g;
+	Vec3 o = {origin[0], origin[1], origin[2]}, e = {end_in[0], end_in[1], end_in[2]};
+	Vec3 dir = vsub(e, o);
+	double dist = vnorm(dir);
+	dir = vdiv(dir, dist);
+	if (0 <= max_range && dist > max_range) {
+		e = vadd(o, vscale(dir, max_range));
+		dist = max_range;
+	}
+	Walk w;
+	walk_init(g, o, e, dir, depth, w);
+	size_t cnt = 0;
+	if (!w.same) {
+		while (w.cur != w.end && walk_tmin(w) <= dist) {
+			if (codes && cnt < cap) codes[cnt] = key_to_code(w.cur);
+			++cnt;
+			walk_step(w);
+		}
+	}
+	*n = cnt;
+	return UFO_B200_OK;
+}
+
+int ufo_b200_to_key(const ufo_b200_map* m, const double xyz[3], uint32_t depth, uint32_t key[3])
+{
+	if (!m || !xyz || !key) return UFO_B200_E_INVALID;
+	Key3 k = point_to_key(m->M.g, {xyz[0], xyz[1], xyz[2]}, depth);
+	key[0] = k.x;
+	key[1] = k.y;
+	key[2] = k.z;
+	return UFO_B200_OK;
+}
+
+int ufo_b200_to_code(const ufo_b200_map* m, const double xyz[3], uint32_t depth, uint64_t* code)
+{
+	if (!m || !xyz || !code) return UFO_B200_E_INVALID;
+	*code = key_to_code(point_to_key(m->M.g, {xyz[0], xyz[1], xyz[2]}, depth));
+	return UFO_B200_OK;
+}
+
+int ufo_b200_key_to_coord(const ufo_b200_map* m, const uint32_t key[3], uint32_t depth, double xyz[3])
+{
+	if (!m || !key || !xyz) return UFO_B200_E_INVALID;
+	Vec3 p = key_to_coord(m->M.g, {key[0], key[1], key[2]}, depth);
+	xyz[0] = p.x;
+	xyz[1] = p.y;
+	xyz[2] = p.z;
+	return UFO_B200_OK;
+}
+
+uint64_t ufo_b200_key_to_code(const uint32_t key[3]) { return key_to_code({key[0], key[1], key[2]}); }
+
+void ufo_b200_code_to_key(uint64_t code, uint32_t key[3])
+{
+	Key3 k = code_to_key(code);
+	key[0] = k.x;
+	key[1] = k.y;
+	key[2] = k.z;
+}
+
+int ufo_b200_query(ufo_b200_map* m, const uint64_t* codes, const uint32_t* depths, size_t n,
+                   float* logodds, uint8_t* flags, uint8_t* rgb)
+{
+	if (!m || (n && (!codes || !depths || !logodds || !flags))) return UFO_B200_E_INVALID;
+	if (!n) return UFO_B200_OK;
+	return guarded(m, [&]() {
+		CK(cudaSetDevice(m->device));
+		sync_map(m);
+		cudaStream_t s = m->stream;
+		unsigned long long* d_codes = nullptr;
+		uint32_t *d_depths = nullptr, *d_rgb = nullptr;
+		float* d_occ = nullptr;
+		uint8_t* d_flags = nullptr;
+		CK(cudaMalloc(&d_codes, n * 8));
+		CK(cudaMalloc(&d_depths, n * 4));
+		CK(cudaMalloc(&d_occ, n * 4));
+		CK(cudaMalloc(&d_flags, n));
+		if (rgb) CK(cudaMalloc(&d_rgb, n * 4));
+		CK(cudaMemcpyAsync(d_codes, codes, n * 8, cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(d_depths, depths, n * 4, cudaMemcpyHostToDevice, s));
+		k_query<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(m->M, d_codes, d_depths, (uint32_t)n, d_occ, d_flags, d_rgb);
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(logodds, d_occ, n * 4, cudaMemcpyDeviceToHost, s));
+		CK(cudaMemcpyAsync(flags, d_flags, n, cudaMemcpyDeviceToHost, s));
+		std::vector<uint32_t> h_rgb;
+		if (rgb) {
+			h_rgb.resize(n);
+			CK(cudaMemcpyAsync(h_rgb.data(), d_rgb, n * 4, cudaMemcpyDeviceToHost, s));
+		}
+		CK(cudaStreamSynchronize(s));
+		if (rgb)
+			for (size_t i = 0; i < n; ++i) {
+				rgb[3 * i] = h_rgb[i] & 0xff;
+				rgb[3 * i + 1] = (h_rgb[i] >> 8) & 0xff;
+				rgb[3 * i + 2] = (h_rgb[i] >> 16) & 0xff;
+			}
+		cudaFree(d_codes);
+		cudaFree(d_depths);
+		cudaFree(d_occ);
+		cudaFree(d_flags);
+		if (d_rgb) cudaFree(d_rgb);
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_export_leaves(ufo_b200_map* m, uint64_t* codes, float* logodds, uint8_t* rgb,
+                           size_t cap, size_t* n)
+{
+	if (!m || !n) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		CK(cudaSetDevice(m->device));
+		sync_map(m);
+		cudaStream_t s = m->stream;
+		unsigned long long* d_count = nullptr;
+		CK(cudaMalloc(&d_count, 8));
+		CK(cudaMemsetAsync(d_count, 0, 8, s));
+		unsigned long long* d_codes = nullptr;
+		float* d_occ = nullptr;
+		uint32_t* d_rgb = nullptr;
+		bool fill = codes != nullptr && cap > 0;
+		if (fill) {
+			CK(cudaMalloc(&d_codes, cap * 8));
+			CK(cudaMalloc(&d_occ, cap * 4));
+			if (rgb) CK(cudaMalloc(&d_rgb, cap * 4));
+		}
+		size_t threads = (size_t)(m->n_blocks > 1 ? m->n_blocks - 1 : 0) * 64;
+		if (threads)
+			k_export<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>(m->M, m->n_blocks, d_codes, d_occ, d_rgb, fill ? cap : 0, d_count);
+		CK(cudaGetLastError());
+		unsigned long long cnt = 0;
+		CK(cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		*n = (size_t)cnt;
+		if (fill) {
+			size_t k = std::min<size_t>(cnt, cap);
+			CK(cudaMemcpy(codes, d_codes, k * 8, cudaMemcpyDeviceToHost));
+			if (logodds) CK(cudaMemcpy(logodds, d_occ, k * 4, cudaMemcpyDeviceToHost));
+			if (rgb) {
+				std::vector<uint32_t> h(k);
+				CK(cudaMemcpy(h.data(), d_rgb, k * 4, cudaMemcpyDeviceToHost));
+				for (size_t i = 0; i < k; ++i) {
+					rgb[3 * i] = h[i] & 0xff;
+					rgb[3 * i + 1] = (h[i] >> 8) & 0xff;
+					rgb[3 * i + 2] = (h[i] >> 16) & 0xff;
+				}
+			}
+			cudaFree(d_codes);
+			cudaFree(d_occ);
+			if (d_rgb) cudaFree(d_rgb);
+		}
+		cudaFree(d_count);
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_set_sensor_model(ufo_b200_map* m, const double p[6])
+{
+	if (!m || !p) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		sync_map(m);
+		m->occ_thr_log = to_logit(p[0]);
+		m->free_thr_log = to_logit(p[1]);
+		m->hit_log = to_logit(p[2]);
+		m->miss_log = to_logit(p[3]);
+		m->cmin_log = to_logit(p[4]);
+		m->cmax_log = to_logit(p[5]);
+		refresh_model(m);
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_sensor_model_logit(const ufo_b200_map* m, double o[6])
+{
+	if (!m || !o) return UFO_B200_E_INVALID;
+	o[0] = m->occ_thr_log;
+	o[1] = m->free_thr_log;
+	o[2] = m->hit_log;
+	o[3] = m->miss_log;
+	o[4] = m->cmin_log;
+	o[5] = m->cmax_log;
+	return UFO_B200_OK;
+}
+
+int ufo_b200_change_bbox(ufo_b200_map* m, double mn[3], double mx[3])
+{
+	if (!m || !mn || !mx) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		sync_map(m);
+		memcpy(mn, m->min_change, sizeof(m->min_change));
+		memcpy(mx, m->max_change, sizeof(m->max_change));
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_reset_change_bbox(ufo_b200_map* m)
+{
+	if (!m) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		sync_map(m);
+		reset_bbox(m);
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_last_scan_stats(ufo_b200_map* m, ufo_b200_scan_stats* out)
+{
+	if (!m || !out) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		sync_map(m);
+		*out = m->stats;
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_set_profiling(ufo_b200_map* m, int enable)
+{
+	if (!m) return UFO_B200_E_INVALID;
+	m->profiling = enable != 0;
+	return UFO_B200_OK;
+}
+
+int ufo_b200_clear(ufo_b200_map* m)
+{
+	if (!m) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		CK(cudaSetDevice(m->device));
+		sync_map(m);
+		DeviceMap& M = m->M;
+		cudaStream_t s = m->stream;
+		CK(cudaMemsetAsync(M.bh_keys, 0xff, ((size_t)M.bh_mask + 1) * 8, s));
+		CK(cudaMemsetAsync(M.bh_vals, 0xff, ((size_t)M.bh_mask + 1) * 4, s));
+		CK(cudaMemsetAsync(M.uh_keys, 0xff, ((size_t)M.uh_mask + 1) * 8, s));
+		CK(cudaMemsetAsync(M.uh_vals, 0xff, ((size_t)M.uh_mask + 1) * 4, s));
+		CK(cudaMemsetAsync(M.brick_child, 0, (size_t)m->n_bricks * 64 * 4, s));
+		CK(cudaMemsetAsync(M.brick_stamp, 0, (size_t)m->n_bricks * 4, s));
+		CK(cudaMemsetAsync(M.up_stamp, 0, (size_t)m->n_upper * 4, s));
+		CK(cudaMemsetAsync(M.leaf, 0, (size_t)m->n_blocks * 64 * 4, s));
+		CK(cudaMemsetAsync(M.sum1_meta, 0, (size_t)m->n_blocks * 4, s));
+		CK(cudaMemsetAsync(M.miss_mask, 0, (size_t)m->n_blocks * 8, s));
+		CK(cudaMemsetAsync(M.hit_mask, 0, (size_t)m->n_blocks * 8, s));
+		if (M.color) CK(cudaMemsetAsync(M.leaf_rgb, 0, (size_t)m->n_blocks * 64 * 4, s));
+		m->n_blocks = 1;
+		m->n_bricks = 0;
+		m->n_upper = 0;
+		M.scan_id = 0;
+		reset_bbox(m);
+		CK(cudaStreamSynchronize(s));
+		return (int)UFO_B200_OK;
+	});
+}
+
+}  // extern "C"
