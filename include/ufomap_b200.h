@@ -144,12 +144,14 @@ typedef struct {
 	uint64_t hit_voxels;      /* U_h                                       */
 	uint64_t touched_octets;  /* D_1                                       */
 	uint64_t touched_blocks;  /* D_2 (4^3 blocks)                          */
+	uint64_t touched_d3;      /* D_3 (8^3 nodes)                           */
 	uint64_t touched_bricks;  /* D_4 (16^3 bricks)                         */
 	uint64_t upper_nodes;     /* sum of D_l, l >= 5                        */
 	uint64_t blocks_in_map;   /* pool occupancy                            */
 	uint64_t bricks_in_map;
 	uint64_t device_bytes;    /* device memory held by the map             */
 	uint64_t regrows;         /* pool growth events during this insert     */
+	uint64_t launches;        /* kernels launched by this insert           */
 	float ms_total;           /* CUDA-event time of the whole insert (device work) */
 	float ms_h2d;
 	float ms_points;          /* K1: discretise + hit marking              */
@@ -159,7 +161,8 @@ typedef struct {
 } ufo_b200_scan_stats;
 
 int ufo_b200_last_scan_stats(ufo_b200_map* m, ufo_b200_scan_stats* out);
-/* Enable per-kernel CUDA-event timing and the visit counter (adds event records). */
+/* 0: off; 1: per-kernel CUDA-event timing; 2: additionally count ray-walk visits
+ * (one extra atomic per ray). */
 int ufo_b200_set_profiling(ufo_b200_map* m, int enable);
 
 /* Forget everything (Octree::clear, octree.h:541-560): keeps device pools. */

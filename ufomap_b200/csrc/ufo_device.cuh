@@ -48,6 +48,7 @@ struct Counters {
 	unsigned long long hit_voxels;
 	unsigned long long touched_octets;
 	unsigned long long touched_blocks;
+	unsigned long long touched_d3;
 	unsigned long long touched_bricks;
 	unsigned long long upper_nodes;
 	unsigned long long bbox[6];  // order-preserving encoding of min xyz / max xyz of this scan

@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(256) k_update(DeviceMap M, float miss, uint32_
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
 	const uint32_t grp = lane >> 3, oct = lane & 7;
-	unsigned int st_vox = 0, st_hit = 0, st_oct = 0, st_blk = 0, st_brk = 0;
+	unsigned int st_vox = 0, st_hit = 0, st_oct = 0, st_blk = 0, st_brk = 0, st_d3 = 0;
 
 	for (uint32_t brick = warp; brick < n_bricks; brick += n_warps) {
 		if (M.brick_stamp[brick] != M.scan_id) continue;
@@ -450,6 +450,8 @@ __global__ void __launch_bounds__(256) k_update(DeviceMap M, float miss, uint32_
 				hm = M.hit_mask[slot];
 			}
 			uint32_t ballot = __ballot_sync(0xffffffffu, (mm | hm) != 0ull);
+			// touched depth-3 nodes: groups of 8 consecutive children
+			if (lane < 4) st_d3 += ((ballot >> (8 * lane)) & 0xffu) ? 1u : 0u;
 			while (ballot) {
 				int n = __popc(ballot);
 				bool active = (int)grp < n;
@@ -600,6 +602,7 @@ __global__ void __launch_bounds__(256) k_update(DeviceMap M, float miss, uint32_
 		st_oct += __shfl_xor_sync(0xffffffffu, st_oct, o);
 		st_blk += __shfl_xor_sync(0xffffffffu, st_blk, o);
 		st_brk += __shfl_xor_sync(0xffffffffu, st_brk, o);
+		st_d3 += __shfl_xor_sync(0xffffffffu, st_d3, o);
 	}
 	if (lane == 0 && st_brk) {
 		atomicAdd(&M.ctr->touched_voxels, (unsigned long long)st_vox);
@@ -607,6 +610,7 @@ __global__ void __launch_bounds__(256) k_update(DeviceMap M, float miss, uint32_
 		atomicAdd(&M.ctr->touched_octets, (unsigned long long)st_oct);
 		atomicAdd(&M.ctr->touched_blocks, (unsigned long long)st_blk);
 		atomicAdd(&M.ctr->touched_bricks, (unsigned long long)st_brk);
+		atomicAdd(&M.ctr->touched_d3, (unsigned long long)st_d3);
 	}
 }
 

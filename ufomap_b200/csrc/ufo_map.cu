@@ -97,7 +97,8 @@ struct ufo_b200_map {
 	// bookkeeping
 	uint32_t n_blocks = 1, n_bricks = 0, n_upper = 0;  // host view after the last sync
 	size_t device_bytes = 0;
-	bool profiling = false;
+	int profiling = 0;
+	uint64_t launches = 0;
 	cudaEvent_t ev[8]{};
 	bool ev_valid = false;
 	cudaEvent_t ev_done = nullptr;
@@ -349,6 +350,7 @@ void finish_stats(Map* m)
 	st.hit_voxels = c.hit_voxels;
 	st.touched_octets = c.touched_octets;
 	st.touched_blocks = c.touched_blocks;
+	st.touched_d3 = c.touched_d3;
 	st.touched_bricks = c.touched_bricks;
 	st.upper_nodes = c.upper_nodes;
 	m->n_blocks = std::min(c.n_blocks, m->M.block_cap);
@@ -444,10 +446,11 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	a.tab_min = m->d_tab_min;
 	a.tab_mask = m->tab_size ? m->tab_size - 1 : 0;
 	a.hit_tab = use_color ? m->d_hit_tab : nullptr;
-	a.count_visits = m->profiling;
+	a.count_visits = m->profiling >= 2;
 
 	m->stats = ufo_b200_scan_stats{};
 	m->stats.points = n;
+	m->launches = 0;
 	M.scan_id++;
 	if (M.scan_id == 0) M.scan_id = 1;
 
@@ -481,9 +484,14 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		if (n) {
 			uint32_t grid = (uint32_t)((n + 255) / 256);
 			k_points<<<grid, 256, 0, s>>>(M, a);
-			if (use_color) k_hits<<<grid, 256, 0, s>>>(M, a);
+			++m->launches;
+			if (use_color) {
+				k_hits<<<grid, 256, 0, s>>>(M, a);
+				++m->launches;
+			}
 			if (m->profiling && regrows == 0) CK(cudaEventRecord(m->ev[2], s));
 			launch_rays(m, a, simple);
+			++m->launches;
 		} else if (m->profiling) {
 			CK(cudaEventRecord(m->ev[2], s));
 		}
@@ -520,6 +528,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		uint32_t warps_needed = m->n_bricks;
 		uint32_t grid = std::min<uint32_t>((warps_needed + 7) / 8, (uint32_t)m->sm_count * 32);
 		k_update<<<grid, 256, 0, s>>>(M, a.miss, m->n_bricks);
+		++m->launches;
 	}
 	if (m->profiling) CK(cudaEventRecord(m->ev[5], s));
 	// K4: upper levels, depth 5 .. L.  Only bricks created by this scan can create upper
@@ -541,11 +550,14 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 			    M, d, m->d_list[which], m->d_list[which ^ 1], M.up_cap, which);
 			k_reset_list<<<1, 1, 0, s>>>(M, which);
 			which ^= 1;
+			m->launches += 2;
 		}
+		m->launches += 3;
 		CK(cudaGetLastError());
 	}
 	CK(cudaEventRecord(m->ev[6], s));
 	m->ev_valid = true;
+	m->stats.launches = m->launches;
 	CK(cudaMemcpyAsync(m->h_ctr, M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
 	m->stats_pending = true;
 	if (!async) return sync_map(m);
@@ -960,7 +972,7 @@ int ufo_b200_last_scan_stats(ufo_b200_map* m, ufo_b200_scan_stats* out)
 int ufo_b200_set_profiling(ufo_b200_map* m, int enable)
 {
 	if (!m) return UFO_B200_E_INVALID;
-	m->profiling = enable != 0;
+	m->profiling = enable < 0 ? 0 : enable;
 	return UFO_B200_OK;
 }
 
