@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libufomap_b200.so")
+# UFOMAP_B200_LIB selects an experimental build of the same library (kernel variants)
+LIB_PATH = os.environ.get("UFOMAP_B200_LIB") or os.path.join(HERE, "libufomap_b200.so")
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, 1, 2, 3, 4
 XYZ_F64, XYZ_F32, XYZRGB_F64, XYZRGB_F32 = 0, 1, 2, 3

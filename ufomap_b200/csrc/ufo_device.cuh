@@ -35,6 +35,18 @@ struct Agg {
 	uint32_t flags;
 };
 
+// Per-block record, one 64-byte line: the first sector is everything the ray walk and
+// the brick scan need (per-scan masks + depth-2 aggregate), the second the depth-1 maxima.
+struct __align__(64) BlockRec {
+	unsigned long long miss;  // per-scan free-set bits, linear order x + 4y + 16z
+	unsigned long long hit;   // per-scan hit bits
+	float occ2;               // depth-2 aggregate: max log-odds of the 64 voxels
+	uint32_t flags2;          // bit0 contains_free, bit1 contains_unknown
+	uint32_t meta;            // bits 0..15: flags of the 8 octets, bits 16..23: octet initialised
+	uint32_t rgb2;            // colour maps: depth-2 colour
+	float sum1[8];            // depth-1 aggregates: max log-odds per octet
+};
+
 struct Counters {
 	uint32_t n_blocks;   // next free block slot (slot 0 is the null block)
 	uint32_t n_bricks;   // next free brick slot
@@ -42,7 +54,7 @@ struct Counters {
 	uint32_t overflow;   // bit0 blocks, bit1 bricks/brick hash, bit2 upper nodes
 	uint32_t list_count[2];  // ping-pong dirty lists of the upper-level pass
 	uint32_t n_rays;
-	uint32_t pad0;
+	uint32_t ray_batch;  // next batch of 32 rays for the persistent ray-walk warps
 	unsigned long long visits;
 	unsigned long long touched_voxels;
 	unsigned long long hit_voxels;
@@ -60,14 +72,15 @@ struct DeviceMap {
 	// updates applied in float
 	double occ_thr, free_thr;
 	float hit, clamp_min, clamp_max;
+	float free_ceil, occ_floor;  // float thresholds equivalent to the double compares (see leaf_flags)
 	double prob_hit;         // toProb(float(hit)) used by the colour blend
 	uint32_t default_flags;  // flags of a never-touched voxel / subtree (value 0.0)
 	uint32_t color;
 	uint32_t scan_id;
 
-	// brick hash (open addressing, linear probing)
-	unsigned long long* bh_keys;
-	uint32_t* bh_vals;
+	// brick hash (open addressing, linear probing): 16-byte entries {key, slot} so one
+	// 128-bit load resolves a probe
+	ulonglong2* bh_tab;
 	uint32_t bh_mask;
 	// brick pool
 	unsigned long long* brick_key;
@@ -81,14 +94,9 @@ struct DeviceMap {
 	// block pool
 	float* leaf;                    // [block][64]
 	uint32_t* leaf_rgb;             // colour maps: [block][64] packed r | g<<8 | b<<16
-	unsigned long long* miss_mask;  // [block]
-	unsigned long long* hit_mask;   // [block]
+	BlockRec* rec;                  // [block] masks + depth-1/2 aggregates
 	unsigned long long* block_key;  // packed (kx>>2, ky>>2, kz>>2)
-	float* sum1_occ;                // [block][8]
-	uint32_t* sum1_meta;            // [block] bits 0..15: flags of the 8 octets, bits 16..23: octet initialised
-	Agg* sum2;                      // [block]
 	uint32_t* sum1_rgb;             // colour maps: [block][8]
-	uint32_t* sum2_rgb;             // colour maps: [block]
 	uint32_t block_cap;
 	// upper nodes
 	unsigned long long* uh_keys;
@@ -149,45 +157,55 @@ UFO_HD uint64_t upper_key(uint32_t depth, uint32_t x, uint32_t y, uint32_t z)
 // ---------------------------------------------------------------------------
 // brick hash
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ ulonglong2 ld_volatile_entry(const ulonglong2* p)
+{
+	ulonglong2 v;
+	asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+	return v;
+}
+
+// value field of an entry: low 32 bits = brick slot / kPending / kFailed
 __device__ __forceinline__ uint32_t brick_find(const DeviceMap& M, uint64_t key)
 {
 	uint32_t i = hash_u64(key) & M.bh_mask;
 	for (uint32_t probes = 0; probes <= M.bh_mask; ++probes) {
-		unsigned long long k = ld_volatile_u64(&M.bh_keys[i]);
-		if (k == key) {
-			uint32_t v = ld_volatile_u32(&M.bh_vals[i]);
+		ulonglong2 e = ld_volatile_entry(&M.bh_tab[i]);
+		if (e.x == key) {
+			uint32_t v = (uint32_t)e.y;
 			return (v == kPending || v == kFailed) ? kNone : v;
 		}
-		if (k == kEmptyKey) return kNone;
+		if (e.x == kEmptyKey) return kNone;
 		i = (i + 1) & M.bh_mask;
 	}
 	return kNone;
 }
 
-__device__ __forceinline__ uint32_t brick_find_or_create(const DeviceMap& M, uint64_t key)
+// continues a probe sequence at table index i (entry e already loaded or not)
+__device__ __forceinline__ uint32_t brick_find_or_create_from(const DeviceMap& M, uint64_t key, uint32_t i)
 {
-	uint32_t i = hash_u64(key) & M.bh_mask;
 	for (uint32_t probes = 0; probes <= M.bh_mask; ++probes) {
-		unsigned long long k = ld_volatile_u64(&M.bh_keys[i]);
+		unsigned long long* kp = &M.bh_tab[i].x;
+		uint32_t* vp = reinterpret_cast<uint32_t*>(&M.bh_tab[i].y);
+		unsigned long long k = ld_volatile_u64(kp);
 		if (k == kEmptyKey) {
 			if (ld_volatile_u32(&M.ctr->overflow) & 2u) return kNone;
-			k = atomicCAS(&M.bh_keys[i], kEmptyKey, (unsigned long long)key);
+			k = atomicCAS(kp, kEmptyKey, (unsigned long long)key);
 			if (k == kEmptyKey) {
 				uint32_t s = atomicAdd(&M.ctr->n_bricks, 1u);
 				if (s >= M.brick_cap) {
 					atomicOr(&M.ctr->overflow, 2u);
-					st_volatile_u32(&M.bh_vals[i], kFailed);
+					st_volatile_u32(vp, kFailed);
 					return kNone;
 				}
 				M.brick_key[s] = key;
 				__threadfence();
-				st_volatile_u32(&M.bh_vals[i], s);
+				st_volatile_u32(vp, s);
 				return s;
 			}
 		}
 		if (k == key) {
 			uint32_t v;
-			while ((v = ld_volatile_u32(&M.bh_vals[i])) == kPending) {
+			while ((v = ld_volatile_u32(vp)) == kPending) {
 			}
 			return v == kFailed ? kNone : v;
 		}
@@ -195,6 +213,11 @@ __device__ __forceinline__ uint32_t brick_find_or_create(const DeviceMap& M, uin
 	}
 	atomicOr(&M.ctr->overflow, 2u);
 	return kNone;
+}
+
+__device__ __forceinline__ uint32_t brick_find_or_create(const DeviceMap& M, uint64_t key)
+{
+	return brick_find_or_create_from(M, key, hash_u64(key) & M.bh_mask);
 }
 
 // block slot of child b (0..63) of a brick; 0 when the pool overflowed
@@ -297,22 +320,22 @@ UFO_HD double decode_ordered(unsigned long long u)
 #endif
 }
 
-// sensor-model predicates (occupancy_map_base.h:926-940): double thresholds vs float value
+// sensor-model predicates (occupancy_map_base.h:926-940).  The reference compares the
+// float value against DOUBLE thresholds; for a float v and a double T,
+//   T > v  <=>  v < ceil_f32(T)      T <= v  <=>  v >= ceil_f32(T)      T >= v  <=>  v <= floor_f32(T)
+// (no float lies strictly between floor_f32(T) and ceil_f32(T)), so two float compares
+// against host-computed free_ceil / occ_floor are exactly equivalent.
 __device__ __forceinline__ uint32_t leaf_flags(const DeviceMap& M, float v)
 {
-	double d = (double)v;
-	uint32_t f = (M.free_thr > d) ? 1u : 0u;
-	if (M.free_thr <= d && M.occ_thr >= d) f |= 2u;
+	uint32_t f = (v < M.free_ceil) ? 1u : 0u;
+	if (v >= M.free_ceil && v <= M.occ_floor) f |= 2u;
 	return f;
 }
 
 // float add + float clamp (occupancy_map_base.h:1139-1145)
 __device__ __forceinline__ float apply_update(const DeviceMap& M, float v, float u)
 {
-	float r = __fadd_rn(v, u);
-	if (r < M.clamp_min) r = M.clamp_min;
-	else if (M.clamp_max < r) r = M.clamp_max;
-	return r;
+	return fminf(fmaxf(__fadd_rn(v, u), M.clamp_min), M.clamp_max);
 }
 
 // toProb(float) (occupancy_map_base.h:911): 1/(1+expf(-x)); expf evaluated via the

@@ -162,6 +162,29 @@ UFO_HD uint32_t morton2(uint32_t x, uint32_t y, uint32_t z)
 	return a | (b << 1) | (c << 2);
 }
 
+// Per-scan hit/miss masks of a 4^3 block use the cheap linear bit order
+// x + 4y + 16z (three ops in the ray walk); the leaf array itself is in Morton order.
+UFO_HD uint32_t linear2(uint32_t x, uint32_t y, uint32_t z)
+{
+	return (x & 3u) | ((y & 3u) << 2) | ((z & 3u) << 4);
+}
+
+// the 8 mask bits of octet o (Morton child index of the depth-1 node inside the
+// block), returned in Morton order of the voxels inside the octet
+UFO_HD uint32_t octet_bits8(unsigned long long mask, uint32_t o)
+{
+	uint32_t base = ((o & 1u) << 1) | ((o & 2u) << 2) | ((o & 4u) << 3);
+	uint32_t s = (uint32_t)(mask >> base);
+	return (s & 3u) | ((s >> 2) & 0xcu) | ((s >> 12) & 0x30u) | ((s >> 14) & 0xc0u);
+}
+
+// all 8 voxels of the octet that contains key (x, y, z), in mask bit order
+UFO_HD unsigned long long octet_mask_of(uint32_t x, uint32_t y, uint32_t z)
+{
+	uint32_t base = (x & 2u) | ((y & 2u) << 2) | ((z & 2u) << 4);
+	return 0x330033ull << base;
+}
+
 // ---------------------------------------------------------------------------
 // coordinate <-> key
 // ---------------------------------------------------------------------------

@@ -120,7 +120,7 @@ __device__ __forceinline__ void mark_hit(const DeviceMap& M, Key3 k)
 	uint32_t slot = block_find_or_create(M, brick, morton2(k.x >> 2, k.y >> 2, k.z >> 2),
 	                                     pack_key(k.x >> 2, k.y >> 2, k.z >> 2));
 	if (!slot) return;
-	atomicOr(&M.hit_mask[slot], 1ull << morton2(k.x, k.y, k.z));
+	atomicOr(&M.rec[slot].hit, 1ull << linear2(k.x, k.y, k.z));
 }
 
 // ---------------------------------------------------------------------------
@@ -255,8 +255,9 @@ __global__ void __launch_bounds__(256) k_hits(DeviceMap M, ScanArgs a)
 	                                     pack_key(k.x >> 2, k.y >> 2, k.z >> 2));
 	if (!slot) return;
 	uint32_t v = morton2(k.x, k.y, k.z);
-	unsigned long long old = atomicOr(&M.hit_mask[slot], 1ull << v);
-	if (old & (1ull << v)) return;  // re-run after a pool regrow: colour already blended
+	const unsigned long long hbit = 1ull << linear2(k.x, k.y, k.z);
+	unsigned long long old = atomicOr(&M.rec[slot].hit, hbit);
+	if (old & hbit) return;  // re-run after a pool regrow: colour already blended
 	Vec3 p;
 	uint32_t upd;
 	load_point(a, i, p, upd);
@@ -286,8 +287,8 @@ __global__ void __launch_bounds__(256) k_hits(DeviceMap M, ScanArgs a)
 template <int DEPTH>
 __device__ __forceinline__ unsigned long long voxel_bits(Key3 k)
 {
-	if (DEPTH == 0) return 1ull << morton2(k.x, k.y, k.z);
-	if (DEPTH == 1) return 0xffull << (8 * (((k.x >> 1) & 1u) | (((k.y >> 1) & 1u) << 1) | (((k.z >> 1) & 1u) << 2)));
+	if (DEPTH == 0) return 1ull << linear2(k.x, k.y, k.z);
+	if (DEPTH == 1) return octet_mask_of(k.x, k.y, k.z);
 	return ~0ull;
 }
 
@@ -313,52 +314,238 @@ __device__ __forceinline__ void flush_block(const DeviceMap& M, BrickCache& bc, 
 	if (bc.slot == kNone) return;
 	uint32_t slot = block_find_or_create(M, bc.slot, morton2(kx >> 2, ky >> 2, kz >> 2),
 	                                     pack_key(kx >> 2, ky >> 2, kz >> 2));
-	if (slot) atomicOr(&M.miss_mask[slot], bits);
+	if (slot) atomicOr(&M.rec[slot].miss, bits);
 }
 
-template <int DEPTH>
-__global__ void __launch_bounds__(128) k_rays(DeviceMap M, ScanArgs a)
+// ---------------------------------------------------------------------------
+// K2: ray walk
+// ---------------------------------------------------------------------------
+// One thread per ray, whole warp in lock-step.  A lane ORs the voxels it visits into the
+// 64-bit mask of the 4^3 block it is in; when it leaves the block the (mask, block key)
+// pair goes into a small per-lane queue in shared memory.  When any lane's queue is full
+// the whole warp drains all queues: the lookups of a lane's kQueue entries (brick hash
+// probe -> block slot -> atomicOr) are issued stage by stage so that their L2 round
+// trips overlap, instead of paying a dependent chain per block and per lane.
+#ifndef UFO_QUEUE
+#define UFO_QUEUE 4
+#endif
+#ifndef UFO_RAY_MINBLOCKS
+#define UFO_RAY_MINBLOCKS 7
+#endif
+constexpr int kQueue = UFO_QUEUE;
+constexpr int kRayThreads = 128;
+
+struct QEntry {
+	unsigned long long acc;  // visited-voxel bits of the block
+	unsigned long long key;  // packed masked block coordinates (key >> 2)
+};
+
+__device__ __forceinline__ void drain_queue(const DeviceMap& M, BrickCache& bc, const QEntry* q,
+                                            int cnt)
 {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= a.n) return;
-	const double* r = a.ray_end + 3 * (size_t)i;
-	Vec3 to = {r[0], r[1], r[2]};
-	if (to.x != to.x) return;
-	Vec3 from = a.origin;
-	if (!move_line_inside(M.g, from, to)) return;  // occupancy_map_base.h:1248-1251
-
-	// walked backwards: end point -> sensor (occupancy_map_base.h:1266-1279)
-	Vec3 dir = vsub(from, to);
-	double dist = vnorm(dir);
-	dir = vdiv(dir, dist);
-	Walk w;
-	walk_init(M.g, to, from, dir, DEPTH, w);
-
-	BrickCache bc = {0, 0, 0, kNone};
-	unsigned int visits = 0;
-	if (w.same) {
-		flush_block(M, bc, w.cur.x, w.cur.y, w.cur.z, voxel_bits<DEPTH>(w.cur));
-		visits = 1;
-	} else {
-		bool finished = false;
-		while (!finished) {
-			const uint32_t ox = w.cur.x, oy = w.cur.y, oz = w.cur.z;
-			unsigned long long acc = 0;
-#pragma unroll 1
-			while (true) {
-				acc |= voxel_bits<DEPTH>(w.cur);
-				++visits;
-				walk_step(w);
-				if (!(w.cur != w.end && walk_tmin(w) <= dist)) {
-					finished = true;
-					break;
-				}
-				if ((((w.cur.x ^ ox) | (w.cur.y ^ oy) | (w.cur.z ^ oz)) >> 2) != 0) break;
-			}
-			flush_block(M, bc, ox, oy, oz, acc);
+	unsigned long long acc[kQueue], bkey[kQueue];
+	uint32_t cidx[kQueue], hidx[kQueue], bslot[kQueue], child[kQueue];
+	bool need[kQueue];
+	ulonglong2 ent[kQueue];
+	const unsigned long long cached = bc.slot == kNone ? kEmptyKey : pack_key(bc.bx, bc.by, bc.bz);
+	// stage 1: decode, find the entries whose brick is neither cached nor the previous entry's
+#pragma unroll
+	for (int e = 0; e < kQueue; ++e) {
+		acc[e] = 0;
+		bkey[e] = kEmptyKey;
+		cidx[e] = 0;
+		need[e] = false;
+		hidx[e] = 0;
+		if (e < cnt) {
+			QEntry v = q[e * 32];
+			acc[e] = v.acc;
+			uint32_t x, y, z;
+			unpack_key(v.key, x, y, z);
+			bkey[e] = pack_key(x >> 2, y >> 2, z >> 2);
+			cidx[e] = morton2(x, y, z);
+			need[e] = bkey[e] != cached && (e == 0 || bkey[e] != bkey[e - 1]);
+			hidx[e] = hash_u64(bkey[e]) & M.bh_mask;
 		}
 	}
-	if (a.count_visits) atomicAdd(&M.ctr->visits, (unsigned long long)visits);
+#pragma unroll
+	for (int e = 0; e < kQueue; ++e) {
+		ent[e].x = kEmptyKey;
+		ent[e].y = 0;
+		if (need[e]) ent[e] = ld_volatile_entry(&M.bh_tab[hidx[e]]);
+	}
+	// stage 2: brick slots
+#pragma unroll
+	for (int e = 0; e < kQueue; ++e) {
+		bslot[e] = kNone;
+		if (e < cnt) {
+			if (need[e]) {
+				uint32_t v = (uint32_t)ent[e].y;
+				if (ent[e].x == bkey[e] && v != kPending && v != kFailed) bslot[e] = v;
+				else bslot[e] = brick_find_or_create_from(M, bkey[e], hidx[e]);
+				if (bslot[e] != kNone) M.brick_stamp[bslot[e]] = M.scan_id;
+			} else {
+				bslot[e] = (bkey[e] == cached) ? bc.slot : (e > 0 ? bslot[e - 1] : kNone);
+			}
+		}
+	}
+	// stage 3: block slots
+#pragma unroll
+	for (int e = 0; e < kQueue; ++e) {
+		child[e] = 0;
+		if (bslot[e] != kNone) child[e] = ld_volatile_u32(&M.brick_child[(size_t)bslot[e] * 64 + cidx[e]]);
+	}
+	// stage 4: OR the masks
+#pragma unroll
+	for (int e = 0; e < kQueue; ++e) {
+		if (bslot[e] != kNone) {
+			uint32_t slot = child[e];
+			if (slot == 0 || slot == kLock) {
+				uint32_t x, y, z;
+				unpack_key(q[e * 32].key, x, y, z);
+				slot = block_find_or_create(M, bslot[e], cidx[e], pack_key(x, y, z));
+			}
+			if (slot) atomicOr(&M.rec[slot].miss, acc[e]);
+		}
+	}
+	// remember the brick of the newest entry
+#pragma unroll
+	for (int e = 0; e < kQueue; ++e) {
+		if (e == cnt - 1 && bslot[e] != kNone) {
+			uint32_t x, y, z;
+			unpack_key(bkey[e], x, y, z);
+			bc.bx = x;
+			bc.by = y;
+			bc.bz = z;
+			bc.slot = bslot[e];
+		}
+	}
+}
+
+// One voxel step of all three axes, branch-free: computeRayTakeStep (octree.h:1227-1233,
+// argmin with <= and x,y,z priority, vector3.h:244-251) followed by the loop condition
+// of freeSpaceNormal (occupancy_map_base.h:1300).  Written in PTX so the per-axis updates
+// stay predicated instead of becoming a three-way divergent branch.  Returns
+// bit0 = "walk continues", bit1 = "the 4^3 block changed".
+__device__ __forceinline__ uint32_t walk_step_pred(Walk& w, double dist)
+{
+	uint32_t flags;
+	asm volatile(
+	    "{\n\t"
+	    ".reg .pred px, py, pz, pt, pm, pn;\n\t"
+	    ".reg .u32 ox, oy, oz, m, l;\n\t"
+	    "setp.le.f64 px, %1, %2;\n\t"
+	    "setp.le.and.f64 px, %1, %3, px;\n\t"
+	    "setp.gt.f64 py, %1, %2;\n\t"
+	    "setp.le.and.f64 py, %2, %3, py;\n\t"
+	    "or.pred pt, px, py;\n\t"
+	    "not.pred pz, pt;\n\t"
+	    "mov.u32 ox, %4;\n\t"
+	    "mov.u32 oy, %5;\n\t"
+	    "mov.u32 oz, %6;\n\t"
+	    "@px add.rn.f64 %1, %1, %7;\n\t"
+	    "@py add.rn.f64 %2, %2, %8;\n\t"
+	    "@pz add.rn.f64 %3, %3, %9;\n\t"
+	    "@px add.u32 %4, %4, %10;\n\t"
+	    "@py add.u32 %5, %5, %11;\n\t"
+	    "@pz add.u32 %6, %6, %12;\n\t"
+	    // more = (cur != end) && (tx <= dist || ty <= dist || tz <= dist)
+	    "setp.le.f64 pm, %1, %16;\n\t"
+	    "setp.le.or.f64 pm, %2, %16, pm;\n\t"
+	    "setp.le.or.f64 pm, %3, %16, pm;\n\t"
+	    "setp.ne.u32 pn, %4, %13;\n\t"
+	    "setp.ne.or.u32 pn, %5, %14, pn;\n\t"
+	    "setp.ne.or.u32 pn, %6, %15, pn;\n\t"
+	    "and.pred pm, pm, pn;\n\t"
+	    "selp.u32 m, 1, 0, pm;\n\t"
+	    // left = ((cur ^ old) >> 2) != 0 on any axis
+	    "xor.b32 ox, ox, %4;\n\t"
+	    "xor.b32 oy, oy, %5;\n\t"
+	    "xor.b32 oz, oz, %6;\n\t"
+	    "or.b32 ox, ox, oy;\n\t"
+	    "or.b32 ox, ox, oz;\n\t"
+	    "setp.gt.u32 pt, ox, 3;\n\t"
+	    "selp.u32 l, 2, 0, pt;\n\t"
+	    "or.b32 %0, m, l;\n\t"
+	    "}"
+	    : "=r"(flags), "+d"(w.tx), "+d"(w.ty), "+d"(w.tz), "+r"(w.cur.x), "+r"(w.cur.y), "+r"(w.cur.z)
+	    : "d"(w.dx), "d"(w.dy), "d"(w.dz), "r"(w.sx), "r"(w.sy), "r"(w.sz), "r"(w.end.x), "r"(w.end.y),
+	      "r"(w.end.z), "d"(dist));
+	return flags;
+}
+
+// Persistent warps: each warp fetches batches of 32 consecutive rays until the scan is
+// exhausted, so short rays do not leave SMs idle behind long ones.
+template <int DEPTH>
+__global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceMap M, ScanArgs a, uint32_t* batch_counter)
+{
+	__shared__ QEntry queue[kRayThreads / 32][kQueue][32];
+	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	constexpr uint32_t FULL = 0xffffffffu;
+	QEntry* myq = &queue[wid][0][lane];
+	const uint32_t kmask = M.g.key_mask;
+	const uint32_t n_batches = (a.n + 31) / 32;
+	unsigned int visits = 0;
+	BrickCache bc = {0, 0, 0, kNone};
+	while (true) {
+		uint32_t batch = 0;
+		if (lane == 0) batch = atomicAdd(batch_counter, 1u);
+		batch = __shfl_sync(FULL, batch, 0);
+		if (batch >= n_batches) break;
+		const uint32_t i = batch * 32 + lane;
+		Walk w;
+		w.tx = w.ty = w.tz = 0.0;
+		w.dx = w.dy = w.dz = 0.0;
+		w.sx = w.sy = w.sz = 0;
+		w.cur = {0, 0, 0};
+		w.end = {0, 0, 0};
+		double dist = 0.0;
+		bool done = true;
+		unsigned long long acc = 0;
+		int qn = 0;
+		if (i < a.n) {
+			const double* r = a.ray_end + 3 * (size_t)i;
+			Vec3 to = {r[0], r[1], r[2]};
+			Vec3 from = a.origin;
+			// occupancy_map_base.h:1248-1251
+			if (to.x == to.x && move_line_inside(M.g, from, to)) {
+				// walked backwards: end point -> sensor (occupancy_map_base.h:1266-1279)
+				Vec3 dir = vsub(from, to);
+				dist = vnorm(dir);
+				dir = vdiv(dir, dist);
+				walk_init(M.g, to, from, dir, DEPTH, w);
+				if (w.same) {
+					myq[0].acc = voxel_bits<DEPTH>(w.cur);
+					myq[0].key = pack_key((w.cur.x & kmask) >> 2, (w.cur.y & kmask) >> 2, (w.cur.z & kmask) >> 2);
+					qn = 1;
+					++visits;
+				} else {
+					done = false;
+				}
+			}
+		}
+		while (true) {
+			if (!done) {
+				acc |= voxel_bits<DEPTH>(w.cur);
+				++visits;
+				const uint32_t ox = w.cur.x, oy = w.cur.y, oz = w.cur.z;
+				const uint32_t f = walk_step_pred(w, dist);
+				done = !(f & 1u);
+				if (f != 1u) {  // block left or walk finished: queue the block
+					myq[qn * 32].acc = acc;
+					myq[qn * 32].key = pack_key((ox & kmask) >> 2, (oy & kmask) >> 2, (oz & kmask) >> 2);
+					++qn;
+					acc = 0;
+				}
+			}
+			const bool all_done = __all_sync(FULL, done);
+			if (all_done || __any_sync(FULL, qn == kQueue)) {
+				drain_queue(M, bc, myq, qn);
+				qn = 0;
+			}
+			if (all_done) break;
+		}
+	}
+	if (a.count_visits && visits) atomicAdd(&M.ctr->visits, (unsigned long long)visits);
 }
 
 // freeSpaceSimple (occupancy_map_base.h:1303-1339): samples at fixed spacing
@@ -427,84 +614,147 @@ __device__ __forceinline__ uint32_t rms_rgb(const uint32_t* c, int n)
 	return out;
 }
 
-// One warp per brick.  Touched blocks of the brick are processed four at a time:
-// lane group g = lane/8 owns one block, lane%8 owns one octet (8 voxels = one 32 B
-// sector) of it.
-__global__ void __launch_bounds__(256) k_update(DeviceMap M, float miss, uint32_t n_bricks)
+// One warp per touched brick.
+//  phase A  lane l reads the block slots of children l and l+32 and the first sector of
+//           their records (masks + depth-2 aggregate); touched children are compacted
+//           into a shared-memory work list with a ballot.
+//  phase B  eight-lane groups: lane%8 owns one octet (8 voxels = one 32 B sector) of a
+//           block; each group works on two blocks per iteration so that four 16-byte leaf
+//           loads per lane are in flight.  Only touched octets are read and written.
+//  phase C  depth-3 / depth-4 aggregates of the brick from the 64 depth-2 aggregates
+//           (fresh ones from phase B, the rest already loaded in phase A).
+constexpr int kUpdWarps = 8;
+
+struct WorkItem {
+	unsigned long long miss, hit;
+	uint32_t slot, meta, child, pad;
+};
+
+__device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, uint32_t slot,
+                                             uint32_t oct, uint32_t m8, uint32_t h8, float4 a0,
+                                             float4 a1, float& omax, uint32_t& oflags)
 {
-	const uint32_t lane = threadIdx.x & 31;
+	float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+	omax = -3.402823466e+38f;
+	oflags = 0x100u;
+#pragma unroll
+	for (int j = 0; j < 8; ++j) {
+		// all hits of a scan are applied before its misses (occupancy_map_base.h:1351-1365)
+		float hv = apply_update(M, v[j], M.hit);
+		v[j] = ((h8 >> j) & 1u) ? hv : v[j];
+		float mv = apply_update(M, v[j], miss);
+		v[j] = ((m8 >> j) & 1u) ? mv : v[j];
+		omax = fmaxf(omax, v[j]);
+		oflags |= leaf_flags(M, v[j]);
+	}
+	float4* lp = reinterpret_cast<float4*>(M.leaf + (size_t)slot * 64 + 8 * oct);
+	lp[0] = make_float4(v[0], v[1], v[2], v[3]);
+	lp[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+__global__ void __launch_bounds__(kUpdWarps * 32) k_update(DeviceMap M, float miss, uint32_t n_bricks)
+{
+	__shared__ WorkItem work[kUpdWarps][64];
+	__shared__ Agg agg[kUpdWarps][64];
+	__shared__ uint32_t aggrgb[kUpdWarps][64];
+	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
 	const uint32_t grp = lane >> 3, oct = lane & 7;
+	constexpr uint32_t FULL = 0xffffffffu;
 	unsigned int st_vox = 0, st_hit = 0, st_oct = 0, st_blk = 0, st_brk = 0, st_d3 = 0;
+	WorkItem* wl = work[wid];
 
 	for (uint32_t brick = warp; brick < n_bricks; brick += n_warps) {
 		if (M.brick_stamp[brick] != M.scan_id) continue;
 		if (lane == 0) ++st_brk;
-		for (int round = 0; round < 2; ++round) {
-			uint32_t c = round * 32 + lane;
-			uint32_t slot = M.brick_child[(size_t)brick * 64 + c];
-			unsigned long long mm = 0, hm = 0;
-			if (slot) {
-				mm = M.miss_mask[slot];
-				hm = M.hit_mask[slot];
-			}
-			uint32_t ballot = __ballot_sync(0xffffffffu, (mm | hm) != 0ull);
-			// touched depth-3 nodes: groups of 8 consecutive children
-			if (lane < 4) st_d3 += ((ballot >> (8 * lane)) & 0xffu) ? 1u : 0u;
-			while (ballot) {
-				int n = __popc(ballot);
-				bool active = (int)grp < n;
-				int src = active ? (int)__fns(ballot, 0, grp + 1) : 0;
-				uint32_t bslot = __shfl_sync(0xffffffffu, slot, src);
-				unsigned long long bmm = __shfl_sync(0xffffffffu, mm, src);
-				unsigned long long bhm = __shfl_sync(0xffffffffu, hm, src);
-				// drop the (up to) four blocks taken this iteration
-				for (int k = 0; k < 4 && ballot; ++k) ballot &= ballot - 1;
-
-				float omax = 0.0f;
-				uint32_t oflags = 0;  // bit0 free, bit1 unknown, bit8 touched
-				uint32_t orgb = 0;
-				uint32_t meta = 0;
-				if (active) {
-					uint32_t m8 = (uint32_t)(bmm >> (8 * oct)) & 0xffu;
-					uint32_t h8 = (uint32_t)(bhm >> (8 * oct)) & 0xffu;
-					meta = M.sum1_meta[bslot];
-					if (m8 | h8) {
-						float4* lp = reinterpret_cast<float4*>(M.leaf + (size_t)bslot * 64 + 8 * oct);
-						float4 a0 = lp[0], a1 = lp[1];
-						float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-						omax = -3.402823466e+38f;
+		// ---- phase A
+		uint32_t slot[2];
+		slot[0] = M.brick_child[(size_t)brick * 64 + lane];
+		slot[1] = M.brick_child[(size_t)brick * 64 + 32 + lane];
+		ulonglong2 m01[2];
+		uint4 hd[2];
 #pragma unroll
-						for (int j = 0; j < 8; ++j) {
-							// all hits of a scan are applied before its misses
-							// (occupancy_map_base.h:1351-1365)
-							if ((h8 >> j) & 1u) v[j] = apply_update(M, v[j], M.hit);
-							if ((m8 >> j) & 1u) v[j] = apply_update(M, v[j], miss);
-							omax = fmaxf(omax, v[j]);
-							oflags |= leaf_flags(M, v[j]);
-						}
-						lp[0] = make_float4(v[0], v[1], v[2], v[3]);
-						lp[1] = make_float4(v[4], v[5], v[6], v[7]);
-						oflags |= 0x100u;
-						st_vox += __popc(m8 | h8);
-						st_hit += __popc(h8);
+		for (int r = 0; r < 2; ++r) {
+			m01[r] = make_ulonglong2(0ull, 0ull);
+			hd[r] = make_uint4(0u, M.default_flags, 0u, 0u);
+			if (slot[r]) {
+				const BlockRec* rp = &M.rec[slot[r]];
+				m01[r] = *reinterpret_cast<const ulonglong2*>(rp);
+				hd[r] = *reinterpret_cast<const uint4*>(&rp->occ2);
+			}
+		}
+		int n_work = 0;
+#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			const bool touched = (m01[r].x | m01[r].y) != 0ull;
+			const uint32_t ballot = __ballot_sync(FULL, touched);
+			if (lane < 4) st_d3 += ((ballot >> (8 * lane)) & 0xffu) ? 1u : 0u;
+			if (touched) {
+				WorkItem w;
+				w.miss = m01[r].x;
+				w.hit = m01[r].y;
+				w.slot = slot[r];
+				w.meta = hd[r].z;
+				w.child = r * 32 + lane;
+				w.pad = 0;
+				wl[n_work + __popc(ballot & ((1u << lane) - 1u))] = w;
+			}
+			n_work += __popc(ballot);
+			agg[wid][r * 32 + lane] = {__uint_as_float(hd[r].x), hd[r].y};
+			if (M.color) aggrgb[wid][r * 32 + lane] = hd[r].w;
+		}
+		__syncwarp();
+		// ---- phase B: 8 blocks per iteration (group g: items it*8+g and it*8+4+g)
+		for (int it = 0; it * 8 < n_work; ++it) {
+			WorkItem wi[2];
+			bool act[2];
+			uint32_t m8[2], h8[2];
+			float4 a0[2], a1[2];
+			float s1[2];
+#pragma unroll
+			for (int u = 0; u < 2; ++u) {
+				const int e = it * 8 + u * 4 + (int)grp;
+				act[u] = e < n_work;
+				m8[u] = h8[u] = 0;
+				s1[u] = 0.0f;
+				a0[u] = a1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (act[u]) {
+					wi[u] = wl[e];
+					m8[u] = octet_bits8(wi[u].miss, oct);
+					h8[u] = octet_bits8(wi[u].hit, oct);
+					if (m8[u] | h8[u]) {
+						const float4* lp = reinterpret_cast<const float4*>(M.leaf + (size_t)wi[u].slot * 64 + 8 * oct);
+						a0[u] = lp[0];
+						a1[u] = lp[1];
+					} else if ((wi[u].meta >> (16 + oct)) & 1u) {
+						s1[u] = M.rec[wi[u].slot].sum1[oct];
+					}
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < 2; ++u) {
+				float omax = 0.0f;
+				uint32_t oflags = M.default_flags;  // bit8: touched by this scan
+				uint32_t orgb = 0;
+				if (act[u]) {
+					if (m8[u] | h8[u]) {
+						update_octet(M, miss, wi[u].slot, oct, m8[u], h8[u], a0[u], a1[u], omax, oflags);
+						st_vox += __popc(m8[u] | h8[u]);
+						st_hit += __popc(h8[u]);
 						++st_oct;
-						M.sum1_occ[(size_t)bslot * 8 + oct] = omax;
+						M.rec[wi[u].slot].sum1[oct] = omax;
 						if (M.color) {
-							uint4* cp = reinterpret_cast<uint4*>(M.leaf_rgb + (size_t)bslot * 64 + 8 * oct);
+							const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + (size_t)wi[u].slot * 64 + 8 * oct);
 							uint4 c0 = cp[0], c1 = cp[1];
 							uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 							orgb = rms_rgb(cc, 8);
-							M.sum1_rgb[(size_t)bslot * 8 + oct] = orgb;
+							M.sum1_rgb[(size_t)wi[u].slot * 8 + oct] = orgb;
 						}
-					} else if ((meta >> (16 + oct)) & 1u) {
-						omax = M.sum1_occ[(size_t)bslot * 8 + oct];
-						oflags = (meta >> (2 * oct)) & 3u;
-						if (M.color) orgb = M.sum1_rgb[(size_t)bslot * 8 + oct];
-					} else {
-						omax = 0.0f;
-						oflags = M.default_flags;
+					} else if ((wi[u].meta >> (16 + oct)) & 1u) {
+						omax = s1[u];
+						oflags = (wi[u].meta >> (2 * oct)) & 3u;
+						if (M.color) orgb = M.sum1_rgb[(size_t)wi[u].slot * 8 + oct];
 					}
 				}
 				// depth-2 aggregate over the 8 octets of the block (8-lane groups)
@@ -513,77 +763,58 @@ __global__ void __launch_bounds__(256) k_update(DeviceMap M, float miss, uint32_
 				uint32_t newmeta = ((oflags & 3u) << (2 * oct)) | (((oflags >> 8) & 1u) << (16 + oct));
 #pragma unroll
 				for (int o = 1; o < 8; o <<= 1) {
-					bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-					bfl |= __shfl_xor_sync(0xffffffffu, bfl, o);
-					newmeta |= __shfl_xor_sync(0xffffffffu, newmeta, o);
+					bmax = fmaxf(bmax, __shfl_xor_sync(FULL, bmax, o));
+					bfl |= __shfl_xor_sync(FULL, bfl, o);
+					newmeta |= __shfl_xor_sync(FULL, newmeta, o);
 				}
 				uint32_t brgb = 0;
 				if (M.color) {
 					uint32_t oc[8];
 #pragma unroll
-					for (int j = 0; j < 8; ++j) oc[j] = __shfl_sync(0xffffffffu, orgb, (lane & 24) + j);
+					for (int j = 0; j < 8; ++j) oc[j] = __shfl_sync(FULL, orgb, (lane & 24) + j);
 					brgb = rms_rgb(oc, 8);
 				}
-				if (active && oct == 0) {
-					// newmeta carries the flags of all 8 octets (fresh, kept or default)
-					// plus the octets initialised by this scan
-					M.sum1_meta[bslot] = (newmeta & 0xffffffu) | (meta & 0xff0000u);
-					M.sum2[bslot] = {bmax, bfl};
-					if (M.color) M.sum2_rgb[bslot] = brgb;
-					M.miss_mask[bslot] = 0ull;
-					M.hit_mask[bslot] = 0ull;
+				if (act[u] && oct == 0) {
+					// new first sector of the record: masks cleared for the next scan
+					BlockRec* rp = &M.rec[wi[u].slot];
+					const uint32_t meta = (newmeta & 0xffffffu) | (wi[u].meta & 0xff0000u);
+					*reinterpret_cast<ulonglong2*>(rp) = make_ulonglong2(0ull, 0ull);
+					*reinterpret_cast<uint4*>(&rp->occ2) = make_uint4(__float_as_uint(bmax), bfl, meta, brgb);
+					agg[wid][wi[u].child] = {bmax, bfl};
+					if (M.color) aggrgb[wid][wi[u].child] = brgb;
 					++st_blk;
 				}
 			}
 		}
 		__syncwarp();
-		// depth-3 / depth-4 aggregates of the brick from its 64 blocks: lane owns
-		// children 2*lane, 2*lane+1 (both under depth-3 node lane/4)
-		float cmax[2];
-		uint32_t cfl[2], crgb[2];
-#pragma unroll
-		for (int j = 0; j < 2; ++j) {
-			uint32_t slot = ld_volatile_u32(&M.brick_child[(size_t)brick * 64 + 2 * lane + j]);
-			if (slot) {
-				unsigned long long raw = ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&M.sum2[slot]));
-				cmax[j] = __uint_as_float((uint32_t)raw);
-				cfl[j] = (uint32_t)(raw >> 32);
-				crgb[j] = M.color ? ld_volatile_u32(&M.sum2_rgb[slot]) : 0u;
-			} else {
-				cmax[j] = 0.0f;
-				cfl[j] = M.default_flags;
-				crgb[j] = 0;
-			}
-		}
-		float m3 = fmaxf(cmax[0], cmax[1]);
-		uint32_t f3 = cfl[0] | cfl[1];
+		// ---- phase C: lane owns children 2*lane, 2*lane+1 (both under depth-3 node lane/4)
+		const Agg c0 = agg[wid][2 * lane], c1 = agg[wid][2 * lane + 1];
+		float m3 = fmaxf(c0.occ, c1.occ);
+		uint32_t f3 = c0.flags | c1.flags;
 #pragma unroll
 		for (int o = 1; o < 4; o <<= 1) {
-			m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, o));
-			f3 |= __shfl_xor_sync(0xffffffffu, f3, o);
+			m3 = fmaxf(m3, __shfl_xor_sync(FULL, m3, o));
+			f3 |= __shfl_xor_sync(FULL, f3, o);
 		}
 		uint32_t rgb3 = 0;
 		if (M.color) {
 			uint32_t cc[8];
 #pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				cc[2 * j] = __shfl_sync(0xffffffffu, crgb[0], (lane & 28) + j);
-				cc[2 * j + 1] = __shfl_sync(0xffffffffu, crgb[1], (lane & 28) + j);
-			}
+			for (int j = 0; j < 8; ++j) cc[j] = aggrgb[wid][8 * (lane >> 2) + j];
 			rgb3 = rms_rgb(cc, 8);
 		}
 		float m4 = m3;
 		uint32_t f4 = f3;
 #pragma unroll
 		for (int o = 4; o < 32; o <<= 1) {
-			m4 = fmaxf(m4, __shfl_xor_sync(0xffffffffu, m4, o));
-			f4 |= __shfl_xor_sync(0xffffffffu, f4, o);
+			m4 = fmaxf(m4, __shfl_xor_sync(FULL, m4, o));
+			f4 |= __shfl_xor_sync(FULL, f4, o);
 		}
 		uint32_t rgb4 = 0;
 		if (M.color) {
 			uint32_t cc[8];
 #pragma unroll
-			for (int j = 0; j < 8; ++j) cc[j] = __shfl_sync(0xffffffffu, rgb3, 4 * j);
+			for (int j = 0; j < 8; ++j) cc[j] = __shfl_sync(FULL, rgb3, 4 * j);
 			rgb4 = rms_rgb(cc, 8);
 		}
 		if ((lane & 3) == 0) {
@@ -594,15 +825,16 @@ __global__ void __launch_bounds__(256) k_update(DeviceMap M, float miss, uint32_
 			M.brick_sum4[brick] = {m4, f4};
 			if (M.color) M.brick_rgb4[brick] = rgb4;
 		}
+		__syncwarp();
 	}
 	// statistics: one atomic per warp and counter
 	for (int o = 16; o > 0; o >>= 1) {
-		st_vox += __shfl_xor_sync(0xffffffffu, st_vox, o);
-		st_hit += __shfl_xor_sync(0xffffffffu, st_hit, o);
-		st_oct += __shfl_xor_sync(0xffffffffu, st_oct, o);
-		st_blk += __shfl_xor_sync(0xffffffffu, st_blk, o);
-		st_brk += __shfl_xor_sync(0xffffffffu, st_brk, o);
-		st_d3 += __shfl_xor_sync(0xffffffffu, st_d3, o);
+		st_vox += __shfl_xor_sync(FULL, st_vox, o);
+		st_hit += __shfl_xor_sync(FULL, st_hit, o);
+		st_oct += __shfl_xor_sync(FULL, st_oct, o);
+		st_blk += __shfl_xor_sync(FULL, st_blk, o);
+		st_brk += __shfl_xor_sync(FULL, st_brk, o);
+		st_d3 += __shfl_xor_sync(FULL, st_d3, o);
 	}
 	if (lane == 0 && st_brk) {
 		atomicAdd(&M.ctr->touched_voxels, (unsigned long long)st_vox);
@@ -712,9 +944,9 @@ __global__ void __launch_bounds__(256) k_rebuild_brick_hash(DeviceMap M, uint32_
 	unsigned long long key = M.brick_key[b];
 	uint32_t i = hash_u64(key) & M.bh_mask;
 	while (true) {
-		unsigned long long k = atomicCAS(&M.bh_keys[i], kEmptyKey, key);
+		unsigned long long k = atomicCAS(&M.bh_tab[i].x, kEmptyKey, key);
 		if (k == kEmptyKey) {
-			M.bh_vals[i] = b;
+			M.bh_tab[i].y = b;
 			return;
 		}
 		i = (i + 1) & M.bh_mask;
@@ -810,14 +1042,14 @@ __global__ void __launch_bounds__(256) k_query(DeviceMap M, const unsigned long 
 				uint32_t slot = M.brick_child[(size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2)];
 				if (slot && slot != kLock) {
 					if (d == 2) {
-						o = M.sum2[slot].occ;
-						f = M.sum2[slot].flags;
-						if (M.color) c = M.sum2_rgb[slot];
+						o = M.rec[slot].occ2;
+						f = M.rec[slot].flags2;
+						if (M.color) c = M.rec[slot].rgb2;
 					} else if (d == 1) {
 						uint32_t j = ((k.x >> 1) & 1u) | (((k.y >> 1) & 1u) << 1) | (((k.z >> 1) & 1u) << 2);
-						uint32_t meta = M.sum1_meta[slot];
+						uint32_t meta = M.rec[slot].meta;
 						if ((meta >> (16 + j)) & 1u) {
-							o = M.sum1_occ[(size_t)slot * 8 + j];
+							o = M.rec[slot].sum1[j];
 							f = (meta >> (2 * j)) & 3u;
 							if (M.color) c = M.sum1_rgb[(size_t)slot * 8 + j];
 						}

@@ -107,6 +107,7 @@ struct ufo_b200_map {
 	double min_change[3], max_change[3];
 	std::string err;
 	int sm_count = 148;
+	int ray_blocks_per_sm = 4;
 
 	void set_error(const char* fmt, ...)
 	{
@@ -133,6 +134,15 @@ void refresh_model(Map* m)
 	M.clamp_max = (float)m->cmax_log;
 	// toProb(float) with expf, as the reference evaluates it on the host
 	M.prob_hit = 1.0 / (1.0 + (double)expf(-M.hit));
+	// float thresholds exactly equivalent to the reference's double-vs-float compares
+	{
+		float fc = (float)m->free_thr_log;
+		if ((double)fc < m->free_thr_log) fc = nextafterf(fc, INFINITY);
+		float of = (float)m->occ_thr_log;
+		if ((double)of > m->occ_thr_log) of = nextafterf(of, -INFINITY);
+		M.free_ceil = fc;
+		M.occ_floor = of;
+	}
 	uint32_t f = (m->free_thr_log > 0.0) ? 1u : 0u;
 	if (m->free_thr_log <= 0.0 && m->occ_thr_log >= 0.0) f |= 2u;
 	M.default_flags = f;
@@ -157,20 +167,15 @@ void alloc_pools(Map* m, uint32_t block_cap, uint32_t brick_cap, uint32_t up_cap
 	M.up_cap = up_cap;
 	M.bh_mask = std::max(kMinHash, next_pow2(2ull * brick_cap)) - 1;
 	M.uh_mask = std::max(kMinHash, next_pow2(2ull * up_cap)) - 1;
-	dev_alloc(M.bh_keys, (size_t)M.bh_mask + 1, 0xff, s, tot);
-	dev_alloc(M.bh_vals, (size_t)M.bh_mask + 1, 0xff, s, tot);
+	dev_alloc(M.bh_tab, (size_t)M.bh_mask + 1, 0xff, s, tot);
 	dev_alloc(M.brick_key, brick_cap, 0, s, tot);
 	dev_alloc(M.brick_child, (size_t)brick_cap * 64, 0, s, tot);
 	dev_alloc(M.brick_stamp, brick_cap, 0, s, tot);
 	dev_alloc(M.brick_sum3, (size_t)brick_cap * 8, 0, s, tot);
 	dev_alloc(M.brick_sum4, brick_cap, 0, s, tot);
 	dev_alloc(M.leaf, (size_t)block_cap * 64, 0, s, tot);
-	dev_alloc(M.miss_mask, block_cap, 0, s, tot);
-	dev_alloc(M.hit_mask, block_cap, 0, s, tot);
+	dev_alloc(M.rec, block_cap, 0, s, tot);
 	dev_alloc(M.block_key, block_cap, 0, s, tot);
-	dev_alloc(M.sum1_occ, (size_t)block_cap * 8, 0, s, tot);
-	dev_alloc(M.sum1_meta, block_cap, 0, s, tot);
-	dev_alloc(M.sum2, block_cap, 0, s, tot);
 	dev_alloc(M.uh_keys, (size_t)M.uh_mask + 1, 0xff, s, tot);
 	dev_alloc(M.uh_vals, (size_t)M.uh_mask + 1, 0xff, s, tot);
 	dev_alloc(M.up_key, up_cap, 0, s, tot);
@@ -183,7 +188,6 @@ void alloc_pools(Map* m, uint32_t block_cap, uint32_t brick_cap, uint32_t up_cap
 		dev_alloc(M.brick_rgb4, brick_cap, 0, s, tot);
 		dev_alloc(M.leaf_rgb, (size_t)block_cap * 64, 0, s, tot);
 		dev_alloc(M.sum1_rgb, (size_t)block_cap * 8, 0, s, tot);
-		dev_alloc(M.sum2_rgb, block_cap, 0, s, tot);
 		dev_alloc(M.up_rgb, up_cap, 0, s, tot);
 	}
 	dev_alloc(M.ctr, 1, 0, s, tot);
@@ -192,10 +196,10 @@ void alloc_pools(Map* m, uint32_t block_cap, uint32_t brick_cap, uint32_t up_cap
 void free_pools(Map* m)
 {
 	DeviceMap& M = m->M;
-	void* ptrs[] = {M.bh_keys,   M.bh_vals,   M.brick_key, M.brick_child, M.brick_stamp, M.brick_sum3,
-	                M.brick_sum4, M.brick_rgb3, M.brick_rgb4, M.leaf,       M.leaf_rgb,    M.miss_mask,
-	                M.hit_mask,  M.block_key, M.sum1_occ,  M.sum1_meta,   M.sum2,        M.sum1_rgb,
-	                M.sum2_rgb,  M.uh_keys,   M.uh_vals,   M.up_key,      M.up_agg,      M.up_rgb,
+	void* ptrs[] = {M.bh_tab,   M.brick_key, M.brick_child, M.brick_stamp, M.brick_sum3,
+	                M.brick_sum4, M.brick_rgb3, M.brick_rgb4, M.leaf,       M.leaf_rgb,    M.rec,
+	                M.block_key, M.sum1_rgb,
+	                M.uh_keys,   M.uh_vals,   M.up_key,      M.up_agg,      M.up_rgb,
 	                M.up_stamp,  M.ctr,       m->d_list[0], m->d_list[1], m->d_points,   m->d_ray_end,
 	                m->d_hit_tab, m->d_tab_keys, m->d_tab_min};
 	for (void* p : ptrs)
@@ -238,15 +242,10 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_blocks, uint32_t want_b
 		if (nc64 > 0xfffffff0ull) throw std::bad_alloc();
 		uint32_t nc = (uint32_t)nc64;
 		dev_grow(M.leaf, (size_t)oc * 64, (size_t)nc * 64, 0, s, tot);
-		dev_grow(M.miss_mask, oc, nc, 0, s, tot);
-		dev_grow(M.hit_mask, oc, nc, 0, s, tot);
+		dev_grow(M.rec, oc, nc, 0, s, tot);
 		dev_grow(M.block_key, oc, nc, 0, s, tot);
-		dev_grow(M.sum1_occ, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
-		dev_grow(M.sum1_meta, oc, nc, 0, s, tot);
-		dev_grow(M.sum2, oc, nc, 0, s, tot);
 		dev_grow(M.leaf_rgb, (size_t)oc * 64, (size_t)nc * 64, 0, s, tot);
 		dev_grow(M.sum1_rgb, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
-		dev_grow(M.sum2_rgb, oc, nc, 0, s, tot);
 		M.block_cap = nc;
 	}
 	if (overflow & 2u) {
@@ -263,12 +262,10 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_blocks, uint32_t want_b
 		// rebuild the hash from the surviving bricks (drops kFailed entries)
 		size_t old_tab = (size_t)M.bh_mask + 1;
 		uint32_t new_tab = std::max(kMinHash, next_pow2(2ull * nc));
-		CK(cudaFree(M.bh_keys));
-		CK(cudaFree(M.bh_vals));
-		tot -= old_tab * (sizeof(unsigned long long) + sizeof(uint32_t));
+		CK(cudaFree(M.bh_tab));
+		tot -= old_tab * sizeof(ulonglong2);
 		M.bh_mask = new_tab - 1;
-		dev_alloc(M.bh_keys, new_tab, 0xff, s, tot);
-		dev_alloc(M.bh_vals, new_tab, 0xff, s, tot);
+		dev_alloc(M.bh_tab, new_tab, 0xff, s, tot);
 		uint32_t nb = std::min(m->h_ctr->n_bricks, oc);
 		if (nb) k_rebuild_brick_hash<<<(nb + 255) / 256, 256, 0, s>>>(M, nb);
 	}
@@ -391,15 +388,21 @@ int sync_map(Map* m)
 
 void launch_rays(Map* m, const ScanArgs& a, int simple)
 {
-	uint32_t grid = (a.n + 127) / 128;
 	if (simple) {
-		k_rays_simple<<<grid, 128, 0, m->stream>>>(m->M, a);
-	} else if (a.depth == 0) {
-		k_rays<0><<<grid, 128, 0, m->stream>>>(m->M, a);
+		k_rays_simple<<<(a.n + 127) / 128, 128, 0, m->stream>>>(m->M, a);
+		return;
+	}
+	// persistent warps: one resident wave, batches of 32 rays fetched dynamically
+	uint32_t* counter = &m->M.ctr->ray_batch;
+	CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), m->stream));
+	uint32_t need = (a.n + kRayThreads - 1) / kRayThreads;
+	uint32_t grid = std::min<uint32_t>(need, (uint32_t)m->sm_count * m->ray_blocks_per_sm);
+	if (a.depth == 0) {
+		k_rays<0><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
 	} else if (a.depth == 1) {
-		k_rays<1><<<grid, 128, 0, m->stream>>>(m->M, a);
+		k_rays<1><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
 	} else {
-		k_rays<2><<<grid, 128, 0, m->stream>>>(m->M, a);
+		k_rays<2><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
 	}
 }
 
@@ -525,9 +528,8 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	if (m->profiling) CK(cudaEventRecord(m->ev[4], s));
 	// K3
 	if (m->n_bricks) {
-		uint32_t warps_needed = m->n_bricks;
-		uint32_t grid = std::min<uint32_t>((warps_needed + 7) / 8, (uint32_t)m->sm_count * 32);
-		k_update<<<grid, 256, 0, s>>>(M, a.miss, m->n_bricks);
+		uint32_t grid = std::min<uint32_t>((m->n_bricks + kUpdWarps - 1) / kUpdWarps, (uint32_t)m->sm_count * 16);
+		k_update<<<grid, kUpdWarps * 32, 0, s>>>(M, a.miss, m->n_bricks);
 		++m->launches;
 	}
 	if (m->profiling) CK(cudaEventRecord(m->ev[5], s));
@@ -637,6 +639,8 @@ int ufo_b200_create(const ufo_b200_params* p, ufo_b200_map** out)
 		cudaDeviceProp prop;
 		CK(cudaGetDeviceProperties(&prop, dev));
 		m->sm_count = prop.multiProcessorCount;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->ray_blocks_per_sm, k_rays<0>, kRayThreads, 0));
+		if (m->ray_blocks_per_sm < 1) m->ray_blocks_per_sm = 1;
 		m->params = *p;
 		CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
 		m->stream = m->own_stream;
@@ -984,17 +988,14 @@ int ufo_b200_clear(ufo_b200_map* m)
 		sync_map(m);
 		DeviceMap& M = m->M;
 		cudaStream_t s = m->stream;
-		CK(cudaMemsetAsync(M.bh_keys, 0xff, ((size_t)M.bh_mask + 1) * 8, s));
-		CK(cudaMemsetAsync(M.bh_vals, 0xff, ((size_t)M.bh_mask + 1) * 4, s));
+		CK(cudaMemsetAsync(M.bh_tab, 0xff, ((size_t)M.bh_mask + 1) * sizeof(ulonglong2), s));
 		CK(cudaMemsetAsync(M.uh_keys, 0xff, ((size_t)M.uh_mask + 1) * 8, s));
 		CK(cudaMemsetAsync(M.uh_vals, 0xff, ((size_t)M.uh_mask + 1) * 4, s));
 		CK(cudaMemsetAsync(M.brick_child, 0, (size_t)m->n_bricks * 64 * 4, s));
 		CK(cudaMemsetAsync(M.brick_stamp, 0, (size_t)m->n_bricks * 4, s));
 		CK(cudaMemsetAsync(M.up_stamp, 0, (size_t)m->n_upper * 4, s));
 		CK(cudaMemsetAsync(M.leaf, 0, (size_t)m->n_blocks * 64 * 4, s));
-		CK(cudaMemsetAsync(M.sum1_meta, 0, (size_t)m->n_blocks * 4, s));
-		CK(cudaMemsetAsync(M.miss_mask, 0, (size_t)m->n_blocks * 8, s));
-		CK(cudaMemsetAsync(M.hit_mask, 0, (size_t)m->n_blocks * 8, s));
+		CK(cudaMemsetAsync(M.rec, 0, (size_t)m->n_blocks * sizeof(BlockRec), s));
 		if (M.color) CK(cudaMemsetAsync(M.leaf_rgb, 0, (size_t)m->n_blocks * 64 * 4, s));
 		m->n_blocks = 1;
 		m->n_bricks = 0;
