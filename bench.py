@@ -293,7 +293,7 @@ def main():
     alg = float(np.mean([algorithmic_bytes(s) for s in per_scan]))
     t_scan_ms = float(np.mean([s["ms_total"] for s in per_scan]))
     kern = {k: float(np.mean([s[k] for s in per_scan])) for k in
-            ("ms_h2d", "ms_points", "ms_rays", "ms_update", "ms_propagate")}
+            ("ms_h2d", "ms_points", "ms_rays", "ms_scatter", "ms_update", "ms_propagate")}
     achieved = alg / (t_scan_ms * 1e-3) / 1e9
     last = per_scan[-1]
 

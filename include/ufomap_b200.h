@@ -155,7 +155,8 @@ typedef struct {
 	float ms_total;           /* CUDA-event time of the whole insert (device work) */
 	float ms_h2d;
 	float ms_points;          /* K1: discretise + hit marking              */
-	float ms_rays;            /* K2: ray walk / free-set marking           */
+	float ms_rays;            /* K2: ray walk (k_rays)                     */
+	float ms_scatter;         /* K2b: record lookup + mask marking (k_scatter) */
 	float ms_update;          /* K3: leaf log-odds update + in-block aggregates */
 	float ms_propagate;       /* K4: brick + upper-level aggregates        */
 } ufo_b200_scan_stats;

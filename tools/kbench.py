@@ -33,7 +33,7 @@ for k in range(args.scans):
         m.insert(o, p, rgb=c, max_range=args.range, dtype=np.float32, discrete=True)
     st = m.stats()
     rows.append(st)
-keys = ("ms_total", "ms_points", "ms_rays", "ms_update", "ms_propagate")
+keys = ("ms_total", "ms_points", "ms_rays", "ms_scatter", "ms_update", "ms_propagate")
 tail = rows[2:] if len(rows) > 3 else rows
 print(os.environ.get("UFOMAP_B200_LIB", "default"), " ".join("%s=%.3f" % (k[3:], np.mean([r[k] for r in tail])) for k in keys),
       "first_scan_total=%.3f" % rows[0]["ms_total"], "U=%d blocks=%d regrows=%d" % (rows[-1]["touched_voxels"], rows[-1]["blocks_in_map"], sum(r["regrows"] for r in rows)))

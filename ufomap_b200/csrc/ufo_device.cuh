@@ -51,10 +51,13 @@ struct Counters {
 	uint32_t n_blocks;   // next free block slot (slot 0 is the null block)
 	uint32_t n_bricks;   // next free brick slot
 	uint32_t n_upper;    // next free upper-node slot
-	uint32_t overflow;   // bit0 blocks, bit1 bricks/brick hash, bit2 upper nodes
+	uint32_t overflow;   // bit0 blocks, bit1 bricks/brick hash, bit2 upper nodes, bit3 ray-record buffer, bit4 ray bound violated (bug)
 	uint32_t list_count[2];  // ping-pong dirty lists of the upper-level pass
 	uint32_t n_rays;
 	uint32_t ray_batch;  // next batch of 32 rays for the persistent ray-walk warps
+	uint32_t n_chunks;   // k_scatter work items published by k_rays
+	uint32_t pad1;
+	unsigned long long seg_total;  // ray-walk records reserved by K1
 	unsigned long long visits;
 	unsigned long long touched_voxels;
 	unsigned long long hit_voxels;
@@ -198,6 +201,7 @@ __device__ __forceinline__ uint32_t brick_find_or_create_from(const DeviceMap& M
 					return kNone;
 				}
 				M.brick_key[s] = key;
+				vp[1] = 0;  // cached scan stamp (see k_scatter)
 				__threadfence();
 				st_volatile_u32(vp, s);
 				return s;

@@ -20,6 +20,13 @@
 
 namespace ufo_b200
 {
+constexpr uint32_t kChunk = 256;  // records per k_scatter work item
+
+struct QEntry {
+	unsigned long long acc;  // visited-voxel bits of one 4^3 block (linear order)
+	unsigned long long key;  // packed masked block coordinates (key >> 2)
+};
+
 struct ScanArgs {
 	Vec3 origin;       // sensor origin
 	double max_range;  // < 0: unlimited
@@ -37,6 +44,12 @@ struct ScanArgs {
 	uint32_t tab_mask;
 	uint32_t* hit_tab;  // [n] table position of the point's hit voxel or kNone
 	int count_visits;
+	// ray-walk output: (block key, visited-voxel mask) records, one region per warp of 32 rays
+	struct QEntry* seg;
+	unsigned long long seg_cap;  // records
+	uint32_t* seg_base;          // [ceil(n/32)] first record of the warp's region
+	uint32_t* seg_count;         // [ceil(n/32)] K1: capacity of the region, K2: records written
+	uint2* chunks;               // work list for k_scatter: (first record, count <= kChunk)
 };
 
 __device__ __forceinline__ void load_point(const ScanArgs& a, uint32_t i, Vec3& p, uint32_t& rgb)
@@ -131,6 +144,7 @@ __global__ void __launch_bounds__(256) k_points(DeviceMap M, ScanArgs a)
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	double lo[3], hi[3];
 	bool contributes = false, cast = false;
+	uint32_t bound = 0;
 	if (i < a.n) {
 		Vec3 end;
 		uint32_t rgb;
@@ -231,8 +245,33 @@ __global__ void __launch_bounds__(256) k_points(DeviceMap M, ScanArgs a)
 			r[0] = __longlong_as_double(0x7ff8000000000000ll);
 		}
 		if (a.hit_tab) a.hit_tab[i] = hit_slot;
+		if (cast) {
+			// upper bound of the 4^3 blocks this ray's walk can leave: one per block
+			// boundary crossed on each axis, plus slack for the end-of-walk overshoot
+			Vec3 from = a.origin, to = end;
+			if (move_line_inside(g, from, to)) {
+				Key3 kf = point_to_key(g, from, a.depth), kt = point_to_key(g, to, a.depth);
+				uint32_t dx = kf.x > kt.x ? kf.x - kt.x : kt.x - kf.x;
+				uint32_t dy = kf.y > kt.y ? kf.y - kt.y : kt.y - kf.y;
+				uint32_t dz = kf.z > kt.z ? kf.z - kt.z : kt.z - kf.z;
+				bound = (dx >> 2) + (dy >> 2) + (dz >> 2) + 8u;
+			}
+		}
 	}
 	bbox_accumulate(M, lo, hi, contributes, cast);
+	if (a.seg_base) {
+		for (int o = 16; o > 0; o >>= 1) bound += __shfl_xor_sync(0xffffffffu, bound, o);
+		if ((threadIdx.x & 31) == 0 && i < a.n) {
+			unsigned long long base = atomicAdd(&M.ctr->seg_total, (unsigned long long)bound);
+			if (base + bound > a.seg_cap) {
+				atomicOr(&M.ctr->overflow, 8u);  // record buffer too small: host grows it and re-runs
+				base = 0;
+				bound = 0;
+			}
+			a.seg_base[i >> 5] = (uint32_t)base;
+			a.seg_count[i >> 5] = bound;
+		}
+	}
 }
 
 // K1b: colour maps.  The first point (lowest cloud index) of every hit voxel blends
@@ -320,178 +359,131 @@ __device__ __forceinline__ void flush_block(const DeviceMap& M, BrickCache& bc, 
 // ---------------------------------------------------------------------------
 // K2: ray walk
 // ---------------------------------------------------------------------------
-// One thread per ray, whole warp in lock-step.  A lane ORs the voxels it visits into the
-// 64-bit mask of the 4^3 block it is in; when it leaves the block the (mask, block key)
-// pair goes into a small per-lane queue in shared memory.  When any lane's queue is full
-// the whole warp drains all queues: the lookups of a lane's kQueue entries (brick hash
-// probe -> block slot -> atomicOr) are issued stage by stage so that their L2 round
-// trips overlap, instead of paying a dependent chain per block and per lane.
-#ifndef UFO_QUEUE
-#define UFO_QUEUE 4
-#endif
+// k_rays is pure arithmetic: one thread per ray, the whole warp in lock-step, each lane
+// ORs the voxels it visits into the 64-bit mask of the 4^3 block it is in and, when it
+// leaves the block, appends a (block key, mask) record to the warp's region of a
+// streaming buffer (ballot-compacted, so the warp's records of one step are contiguous).
+// k_scatter then resolves every record (brick hash -> block slot) and ORs the mask into
+// the block's per-scan miss mask with full memory-level parallelism.  Splitting the walk
+// from the lookups keeps the latency-bound pointer chasing out of the FP64 loop.
 #ifndef UFO_RAY_MINBLOCKS
-#define UFO_RAY_MINBLOCKS 7
+#define UFO_RAY_MINBLOCKS 8
 #endif
-constexpr int kQueue = UFO_QUEUE;
 constexpr int kRayThreads = 128;
 
-struct QEntry {
-	unsigned long long acc;  // visited-voxel bits of the block
-	unsigned long long key;  // packed masked block coordinates (key >> 2)
-};
-
-__device__ __forceinline__ void drain_queue(const DeviceMap& M, BrickCache& bc, const QEntry* q,
-                                            int cnt)
+// One lock-step iteration of the ray walk for the whole warp, in PTX so that everything
+// stays predicated (no divergent branches, no phi moves):
+//   mark the current voxel; computeRayTakeStep (octree.h:1227-1233: argmin with <= and
+//   x,y,z priority, vector3.h:244-251); loop condition of freeSpaceNormal
+//   (occupancy_map_base.h:1300); when the lane left its 4^3 block or finished, append
+//   (mask, voxel key of the old block) to the warp's record region via ballot compaction.
+// `active` is 1 while the lane's walk continues.  Returns true while any lane is active.
+__device__ __forceinline__ bool walk_iteration(double& tx, double& ty, double& tz, const double dx,
+                                               const double dy, const double dz, const double dist,
+                                               uint32_t& kx, uint32_t& ky, uint32_t& kz, const int sx,
+                                               const int sy, const int sz, const uint32_t ex,
+                                               const uint32_t ey, const uint32_t ez,
+                                               unsigned long long& acc, const unsigned long long bits,
+                                               uint32_t& active, uint32_t& cursor, const uint32_t cap,
+                                               QEntry* out, const uint32_t lt_mask)
 {
-	unsigned long long acc[kQueue], bkey[kQueue];
-	uint32_t cidx[kQueue], hidx[kQueue], bslot[kQueue], child[kQueue];
-	bool need[kQueue];
-	ulonglong2 ent[kQueue];
-	const unsigned long long cached = bc.slot == kNone ? kEmptyKey : pack_key(bc.bx, bc.by, bc.bz);
-	// stage 1: decode, find the entries whose brick is neither cached nor the previous entry's
-#pragma unroll
-	for (int e = 0; e < kQueue; ++e) {
-		acc[e] = 0;
-		bkey[e] = kEmptyKey;
-		cidx[e] = 0;
-		need[e] = false;
-		hidx[e] = 0;
-		if (e < cnt) {
-			QEntry v = q[e * 32];
-			acc[e] = v.acc;
-			uint32_t x, y, z;
-			unpack_key(v.key, x, y, z);
-			bkey[e] = pack_key(x >> 2, y >> 2, z >> 2);
-			cidx[e] = morton2(x, y, z);
-			need[e] = bkey[e] != cached && (e == 0 || bkey[e] != bkey[e - 1]);
-			hidx[e] = hash_u64(bkey[e]) & M.bh_mask;
-		}
-	}
-#pragma unroll
-	for (int e = 0; e < kQueue; ++e) {
-		ent[e].x = kEmptyKey;
-		ent[e].y = 0;
-		if (need[e]) ent[e] = ld_volatile_entry(&M.bh_tab[hidx[e]]);
-	}
-	// stage 2: brick slots
-#pragma unroll
-	for (int e = 0; e < kQueue; ++e) {
-		bslot[e] = kNone;
-		if (e < cnt) {
-			if (need[e]) {
-				uint32_t v = (uint32_t)ent[e].y;
-				if (ent[e].x == bkey[e] && v != kPending && v != kFailed) bslot[e] = v;
-				else bslot[e] = brick_find_or_create_from(M, bkey[e], hidx[e]);
-				if (bslot[e] != kNone) M.brick_stamp[bslot[e]] = M.scan_id;
-			} else {
-				bslot[e] = (bkey[e] == cached) ? bc.slot : (e > 0 ? bslot[e - 1] : kNone);
-			}
-		}
-	}
-	// stage 3: block slots
-#pragma unroll
-	for (int e = 0; e < kQueue; ++e) {
-		child[e] = 0;
-		if (bslot[e] != kNone) child[e] = ld_volatile_u32(&M.brick_child[(size_t)bslot[e] * 64 + cidx[e]]);
-	}
-	// stage 4: OR the masks
-#pragma unroll
-	for (int e = 0; e < kQueue; ++e) {
-		if (bslot[e] != kNone) {
-			uint32_t slot = child[e];
-			if (slot == 0 || slot == kLock) {
-				uint32_t x, y, z;
-				unpack_key(q[e * 32].key, x, y, z);
-				slot = block_find_or_create(M, bslot[e], cidx[e], pack_key(x, y, z));
-			}
-			if (slot) atomicOr(&M.rec[slot].miss, acc[e]);
-		}
-	}
-	// remember the brick of the newest entry
-#pragma unroll
-	for (int e = 0; e < kQueue; ++e) {
-		if (e == cnt - 1 && bslot[e] != kNone) {
-			uint32_t x, y, z;
-			unpack_key(bkey[e], x, y, z);
-			bc.bx = x;
-			bc.by = y;
-			bc.bz = z;
-			bc.slot = bslot[e];
-		}
-	}
-}
-
-// One voxel step of all three axes, branch-free: computeRayTakeStep (octree.h:1227-1233,
-// argmin with <= and x,y,z priority, vector3.h:244-251) followed by the loop condition
-// of freeSpaceNormal (occupancy_map_base.h:1300).  Written in PTX so the per-axis updates
-// stay predicated instead of becoming a three-way divergent branch.  Returns
-// bit0 = "walk continues", bit1 = "the 4^3 block changed".
-__device__ __forceinline__ uint32_t walk_step_pred(Walk& w, double dist)
-{
-	uint32_t flags;
+	uint32_t any;
 	asm volatile(
 	    "{\n\t"
-	    ".reg .pred px, py, pz, pt, pm, pn;\n\t"
-	    ".reg .u32 ox, oy, oz, m, l;\n\t"
-	    "setp.le.f64 px, %1, %2;\n\t"
-	    "setp.le.and.f64 px, %1, %3, px;\n\t"
-	    "setp.gt.f64 py, %1, %2;\n\t"
-	    "setp.le.and.f64 py, %2, %3, py;\n\t"
+	    ".reg .pred pa, px, py, pz, pt, pm, pn, pl, pp, pw;\n\t"
+	    ".reg .u32 ox, oy, oz, vx, vy, vz, bal, rank, idx, cnt, klo, khi, t;\n\t"
+	    ".reg .u64 key, addr;\n\t"
+	    "setp.ne.u32 pa, %8, 0;\n\t"
+	    "@pa or.b64 %7, %7, %22;\n\t"
+	    "mov.u32 ox, %3;\n\t"
+	    "mov.u32 oy, %4;\n\t"
+	    "mov.u32 oz, %5;\n\t"
+	    // axis selection
+	    "setp.le.f64 px, %0, %1;\n\t"
+	    "setp.le.and.f64 px, %0, %2, px;\n\t"
+	    "setp.gt.f64 py, %0, %1;\n\t"
+	    "setp.le.and.f64 py, %1, %2, py;\n\t"
 	    "or.pred pt, px, py;\n\t"
 	    "not.pred pz, pt;\n\t"
-	    "mov.u32 ox, %4;\n\t"
-	    "mov.u32 oy, %5;\n\t"
-	    "mov.u32 oz, %6;\n\t"
-	    "@px add.rn.f64 %1, %1, %7;\n\t"
-	    "@py add.rn.f64 %2, %2, %8;\n\t"
-	    "@pz add.rn.f64 %3, %3, %9;\n\t"
-	    "@px add.u32 %4, %4, %10;\n\t"
-	    "@py add.u32 %5, %5, %11;\n\t"
-	    "@pz add.u32 %6, %6, %12;\n\t"
+	    "and.pred px, px, pa;\n\t"
+	    "and.pred py, py, pa;\n\t"
+	    "and.pred pz, pz, pa;\n\t"
+	    "@px add.rn.f64 %0, %0, %10;\n\t"
+	    "@py add.rn.f64 %1, %1, %11;\n\t"
+	    "@pz add.rn.f64 %2, %2, %12;\n\t"
+	    "@px add.u32 %3, %3, %14;\n\t"
+	    "@py add.u32 %4, %4, %15;\n\t"
+	    "@pz add.u32 %5, %5, %16;\n\t"
 	    // more = (cur != end) && (tx <= dist || ty <= dist || tz <= dist)
-	    "setp.le.f64 pm, %1, %16;\n\t"
-	    "setp.le.or.f64 pm, %2, %16, pm;\n\t"
-	    "setp.le.or.f64 pm, %3, %16, pm;\n\t"
-	    "setp.ne.u32 pn, %4, %13;\n\t"
-	    "setp.ne.or.u32 pn, %5, %14, pn;\n\t"
-	    "setp.ne.or.u32 pn, %6, %15, pn;\n\t"
+	    "setp.le.f64 pm, %0, %13;\n\t"
+	    "setp.le.or.f64 pm, %1, %13, pm;\n\t"
+	    "setp.le.or.f64 pm, %2, %13, pm;\n\t"
+	    "setp.ne.u32 pn, %3, %17;\n\t"
+	    "setp.ne.or.u32 pn, %4, %18, pn;\n\t"
+	    "setp.ne.or.u32 pn, %5, %19, pn;\n\t"
 	    "and.pred pm, pm, pn;\n\t"
-	    "selp.u32 m, 1, 0, pm;\n\t"
 	    // left = ((cur ^ old) >> 2) != 0 on any axis
-	    "xor.b32 ox, ox, %4;\n\t"
-	    "xor.b32 oy, oy, %5;\n\t"
-	    "xor.b32 oz, oz, %6;\n\t"
-	    "or.b32 ox, ox, oy;\n\t"
-	    "or.b32 ox, ox, oz;\n\t"
-	    "setp.gt.u32 pt, ox, 3;\n\t"
-	    "selp.u32 l, 2, 0, pt;\n\t"
-	    "or.b32 %0, m, l;\n\t"
+	    "xor.b32 vx, ox, %3;\n\t"
+	    "xor.b32 vy, oy, %4;\n\t"
+	    "xor.b32 vz, oz, %5;\n\t"
+	    "or.b32 vx, vx, vy;\n\t"
+	    "or.b32 vx, vx, vz;\n\t"
+	    "setp.gt.u32 pl, vx, 3;\n\t"
+	    // push = active && (!more || left);  active' = active && more
+	    "not.pred pt, pm;\n\t"
+	    "or.pred pp, pt, pl;\n\t"
+	    "and.pred pp, pp, pa;\n\t"
+	    "and.pred pa, pa, pm;\n\t"
+	    "selp.u32 %8, 1, 0, pa;\n\t"
+	    // ballot-compacted append of {acc, voxel key of the block just left}
+	    "vote.sync.ballot.b32 bal, pp, 0xffffffff;\n\t"
+	    "and.b32 rank, bal, %21;\n\t"
+	    "popc.b32 rank, rank;\n\t"
+	    "add.u32 idx, %9, rank;\n\t"
+	    "setp.lt.and.u32 pw, idx, %20, pp;\n\t"
+	    "and.b32 ox, ox, 0x1fffff;\n\t"
+	    "and.b32 oy, oy, 0x1fffff;\n\t"
+	    "and.b32 oz, oz, 0x1fffff;\n\t"
+	    "mad.lo.u32 klo, oy, 0x200000, ox;\n\t"
+	    "shr.u32 t, oy, 11;\n\t"
+	    "mad.lo.u32 khi, oz, 1024, t;\n\t"
+	    "mov.b64 key, {klo, khi};\n\t"
+	    "mad.wide.u32 addr, idx, 16, %23;\n\t"
+	    "@pw st.global.v2.u64 [addr], {%7, key};\n\t"
+	    "@pp mov.u64 %7, 0;\n\t"
+	    "popc.b32 cnt, bal;\n\t"
+	    "add.u32 %9, %9, cnt;\n\t"
+	    "vote.sync.any.pred pt, pa, 0xffffffff;\n\t"
+	    "selp.u32 %6, 1, 0, pt;\n\t"
 	    "}"
-	    : "=r"(flags), "+d"(w.tx), "+d"(w.ty), "+d"(w.tz), "+r"(w.cur.x), "+r"(w.cur.y), "+r"(w.cur.z)
-	    : "d"(w.dx), "d"(w.dy), "d"(w.dz), "r"(w.sx), "r"(w.sy), "r"(w.sz), "r"(w.end.x), "r"(w.end.y),
-	      "r"(w.end.z), "d"(dist));
-	return flags;
+	    : "+d"(tx), "+d"(ty), "+d"(tz), "+r"(kx), "+r"(ky), "+r"(kz), "=r"(any), "+l"(acc), "+r"(active),
+	      "+r"(cursor)
+	    : "d"(dx), "d"(dy), "d"(dz), "d"(dist), "r"(sx), "r"(sy), "r"(sz), "r"(ex), "r"(ey), "r"(ez),
+	      "r"(cap), "r"(lt_mask), "l"(bits), "l"(out)
+	    : "memory");
+	return any != 0;
 }
 
 // Persistent warps: each warp fetches batches of 32 consecutive rays until the scan is
 // exhausted, so short rays do not leave SMs idle behind long ones.
-template <int DEPTH>
+template <int DEPTH, bool COUNT>
 __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceMap M, ScanArgs a, uint32_t* batch_counter)
 {
-	__shared__ QEntry queue[kRayThreads / 32][kQueue][32];
-	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t lane = threadIdx.x & 31;
 	constexpr uint32_t FULL = 0xffffffffu;
-	QEntry* myq = &queue[wid][0][lane];
-	const uint32_t kmask = M.g.key_mask;
+	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint32_t n_batches = (a.n + 31) / 32;
 	unsigned int visits = 0;
-	BrickCache bc = {0, 0, 0, kNone};
+	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;  // record buffer being regrown
 	while (true) {
 		uint32_t batch = 0;
 		if (lane == 0) batch = atomicAdd(batch_counter, 1u);
 		batch = __shfl_sync(FULL, batch, 0);
 		if (batch >= n_batches) break;
 		const uint32_t i = batch * 32 + lane;
+		QEntry* out = a.seg + a.seg_base[batch];
+		const uint32_t cap = a.seg_count[batch];
+		uint32_t cursor = 0;
 		Walk w;
 		w.tx = w.ty = w.tz = 0.0;
 		w.dx = w.dy = w.dz = 0.0;
@@ -499,9 +491,9 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 		w.cur = {0, 0, 0};
 		w.end = {0, 0, 0};
 		double dist = 0.0;
-		bool done = true;
+		uint32_t active = 0;
+		bool same = false;
 		unsigned long long acc = 0;
-		int qn = 0;
 		if (i < a.n) {
 			const double* r = a.ray_end + 3 * (size_t)i;
 			Vec3 to = {r[0], r[1], r[2]};
@@ -513,39 +505,86 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 				dist = vnorm(dir);
 				dir = vdiv(dir, dist);
 				walk_init(M.g, to, from, dir, DEPTH, w);
-				if (w.same) {
-					myq[0].acc = voxel_bits<DEPTH>(w.cur);
-					myq[0].key = pack_key((w.cur.x & kmask) >> 2, (w.cur.y & kmask) >> 2, (w.cur.z & kmask) >> 2);
-					qn = 1;
-					++visits;
-				} else {
-					done = false;
-				}
+				same = w.same;
+				active = same ? 0u : 1u;
 			}
 		}
-		while (true) {
-			if (!done) {
-				acc |= voxel_bits<DEPTH>(w.cur);
-				++visits;
-				const uint32_t ox = w.cur.x, oy = w.cur.y, oz = w.cur.z;
-				const uint32_t f = walk_step_pred(w, dist);
-				done = !(f & 1u);
-				if (f != 1u) {  // block left or walk finished: queue the block
-					myq[qn * 32].acc = acc;
-					myq[qn * 32].key = pack_key((ox & kmask) >> 2, (oy & kmask) >> 2, (oz & kmask) >> 2);
-					++qn;
-					acc = 0;
+		{
+			// rays whose two ends share a voxel mark just that voxel (occupancy_map_base.h:1281-1284)
+			const uint32_t pm = __ballot_sync(FULL, same);
+			if (same) {
+				const uint32_t idx = __popc(pm & lt_mask);
+				if (idx < cap) {
+					out[idx].acc = voxel_bits<DEPTH>(w.cur);
+					out[idx].key = pack_key(w.cur.x & 0x1fffffu, w.cur.y & 0x1fffffu, w.cur.z & 0x1fffffu);
 				}
+				if (COUNT) ++visits;
 			}
-			const bool all_done = __all_sync(FULL, done);
-			if (all_done || __any_sync(FULL, qn == kQueue)) {
-				drain_queue(M, bc, myq, qn);
-				qn = 0;
+			cursor += __popc(pm);
+		}
+		bool any = __any_sync(FULL, active != 0u);
+		while (any) {
+			if (COUNT) visits += active;
+			any = walk_iteration(w.tx, w.ty, w.tz, w.dx, w.dy, w.dz, dist, w.cur.x, w.cur.y, w.cur.z, w.sx,
+			                     w.sy, w.sz, w.end.x, w.end.y, w.end.z, acc, voxel_bits<DEPTH>(w.cur),
+			                     active, cursor, cap, out, lt_mask);
+		}
+		if (lane == 0) {
+			if (cursor > cap) {
+				atomicOr(&M.ctr->overflow, 16u);  // walk outran its bound: must never happen
+				cursor = cap;
 			}
-			if (all_done) break;
+			a.seg_count[batch] = cursor;
+			// publish the region as work items for k_scatter
+			const uint32_t nch = (cursor + kChunk - 1) / kChunk;
+			if (nch) {
+				const uint32_t pos = atomicAdd(&M.ctr->n_chunks, nch);
+				const uint32_t base = a.seg_base[batch];
+				for (uint32_t c = 0; c < nch; ++c)
+					a.chunks[pos + c] = make_uint2(base + c * kChunk, min(kChunk, cursor - c * kChunk));
+			}
 		}
 	}
-	if (a.count_visits && visits) atomicAdd(&M.ctr->visits, (unsigned long long)visits);
+	if (COUNT && visits) atomicAdd(&M.ctr->visits, (unsigned long long)visits);
+}
+
+// K2b: one thread per record.  Resolves the brick (one 16-byte hash probe in the common
+// case), the block slot, and ORs the mask into the block's miss mask.  The upper half of
+// the hash entry's value caches the scan stamp of the brick so that only the first
+// records of a brick write brick_stamp.  Work items are kChunk-record slices published by
+// k_rays; CTAs loop over them.
+__global__ void __launch_bounds__(kChunk) k_scatter(DeviceMap M, ScanArgs a)
+{
+	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;
+	const uint32_t n_chunks = ld_volatile_u32(&M.ctr->n_chunks);
+	for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+		const uint2 ch = a.chunks[c];
+		if (threadIdx.x >= ch.y) continue;
+		const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&a.seg[ch.x + threadIdx.x]);
+		uint32_t x, y, z;
+		unpack_key(v.y, x, y, z);
+		x = (x & M.g.key_mask) >> 2;  // block coordinates inside the tree
+		y = (y & M.g.key_mask) >> 2;
+		z = (z & M.g.key_mask) >> 2;
+		const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
+		const uint32_t cidx = morton2(x, y, z);
+		const uint32_t hidx = hash_u64(bkey) & M.bh_mask;
+		const ulonglong2 ent = ld_volatile_entry(&M.bh_tab[hidx]);
+		uint32_t bslot = (uint32_t)ent.y;
+		if (ent.x == bkey && bslot != kPending && bslot != kFailed) {
+			if ((uint32_t)(ent.y >> 32) != M.scan_id) {
+				M.brick_stamp[bslot] = M.scan_id;
+				reinterpret_cast<uint32_t*>(&M.bh_tab[hidx].y)[1] = M.scan_id;
+			}
+		} else {
+			bslot = brick_find_or_create_from(M, bkey, hidx);
+			if (bslot == kNone) continue;
+			M.brick_stamp[bslot] = M.scan_id;
+		}
+		uint32_t slot = ld_volatile_u32(&M.brick_child[(size_t)bslot * 64 + cidx]);
+		if (slot == 0 || slot == kLock) slot = block_find_or_create(M, bslot, cidx, pack_key(x, y, z));
+		if (slot) atomicOr(&M.rec[slot].miss, v.x);
+	}
 }
 
 // freeSpaceSimple (occupancy_map_base.h:1303-1339): samples at fixed spacing

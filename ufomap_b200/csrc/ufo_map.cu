@@ -94,13 +94,18 @@ struct ufo_b200_map {
 	uint32_t* d_tab_min = nullptr;
 	uint32_t tab_size = 0;
 	uint32_t* d_list[2] = {nullptr, nullptr};
+	QEntry* d_seg = nullptr;          // ray-walk records
+	unsigned long long seg_cap = 0;
+	uint32_t *d_seg_base = nullptr, *d_seg_count = nullptr;
+	uint2* d_chunks = nullptr;
+	size_t chunks_cap = 0;
 	// bookkeeping
 	uint32_t n_blocks = 1, n_bricks = 0, n_upper = 0;  // host view after the last sync
 	size_t device_bytes = 0;
 	int profiling = 0;
 	uint64_t launches = 0;
 	cudaEvent_t ev[8]{};
-	bool ev_valid = false;
+	bool ev_valid = false, ev7_valid = false;
 	cudaEvent_t ev_done = nullptr;
 	ufo_b200_scan_stats stats{};
 	bool stats_pending = false;
@@ -201,7 +206,7 @@ void free_pools(Map* m)
 	                M.block_key, M.sum1_rgb,
 	                M.uh_keys,   M.uh_vals,   M.up_key,      M.up_agg,      M.up_rgb,
 	                M.up_stamp,  M.ctr,       m->d_list[0], m->d_list[1], m->d_points,   m->d_ray_end,
-	                m->d_hit_tab, m->d_tab_keys, m->d_tab_min};
+	                m->d_hit_tab, m->d_tab_keys, m->d_tab_min, m->d_seg, m->d_seg_base, m->d_seg_count, m->d_chunks};
 	for (void* p : ptrs)
 		if (p) cudaFree(p);
 }
@@ -312,11 +317,15 @@ void ensure_scan_buffers(Map* m, size_t n, bool need_table)
 		if (m->d_ray_end) {
 			cudaFree(m->d_ray_end);
 			cudaFree(m->d_hit_tab);
-			tot -= m->ray_cap * (3 * sizeof(double) + sizeof(uint32_t));
+			cudaFree(m->d_seg_base);
+			cudaFree(m->d_seg_count);
+			tot -= m->ray_cap * (3 * sizeof(double) + sizeof(uint32_t)) + (m->ray_cap / 32 + 1) * 8;
 		}
 		size_t cap = std::max<size_t>(n, 1024);
 		dev_alloc(m->d_ray_end, cap * 3, 0, m->stream, tot);
 		dev_alloc(m->d_hit_tab, cap, 0xff, m->stream, tot);
+		dev_alloc(m->d_seg_base, cap / 32 + 1, 0, m->stream, tot);
+		dev_alloc(m->d_seg_count, cap / 32 + 1, 0, m->stream, tot);
 		m->ray_cap = cap;
 	}
 	if (need_table) {
@@ -368,7 +377,12 @@ void finish_stats(Map* m)
 		if (m->profiling) {
 			cudaEventElapsedTime(&st.ms_h2d, m->ev[0], m->ev[1]);
 			cudaEventElapsedTime(&st.ms_points, m->ev[1], m->ev[2]);
-			cudaEventElapsedTime(&st.ms_rays, m->ev[2], m->ev[3]);
+			if (m->ev7_valid) {
+				cudaEventElapsedTime(&st.ms_rays, m->ev[2], m->ev[7]);
+				cudaEventElapsedTime(&st.ms_scatter, m->ev[7], m->ev[3]);
+			} else {
+				cudaEventElapsedTime(&st.ms_rays, m->ev[2], m->ev[3]);
+			}
 			cudaEventElapsedTime(&st.ms_update, m->ev[4], m->ev[5]);
 			cudaEventElapsedTime(&st.ms_propagate, m->ev[5], m->ev[6]);
 		}
@@ -386,6 +400,36 @@ int sync_map(Map* m)
 	return UFO_B200_OK;
 }
 
+void ensure_seg(Map* m, unsigned long long want)
+{
+	if (want <= m->seg_cap) return;
+	CK(cudaStreamSynchronize(m->stream));
+	if (m->d_seg) {
+		cudaFree(m->d_seg);
+		m->device_bytes -= m->seg_cap * sizeof(QEntry);
+	}
+	m->d_seg = nullptr;
+	CK(cudaMalloc(reinterpret_cast<void**>(&m->d_seg), want * sizeof(QEntry)));
+	m->seg_cap = want;
+	m->device_bytes += want * sizeof(QEntry);
+}
+
+void ensure_chunks(Map* m, size_t n_points)
+{
+	// every region of 32 rays publishes ceil(count / kChunk) <= count / kChunk + 1 items
+	size_t want = (size_t)(m->seg_cap / kChunk) + n_points / 32 + 2;
+	if (want <= m->chunks_cap) return;
+	CK(cudaStreamSynchronize(m->stream));
+	if (m->d_chunks) {
+		cudaFree(m->d_chunks);
+		m->device_bytes -= m->chunks_cap * sizeof(uint2);
+	}
+	m->d_chunks = nullptr;
+	CK(cudaMalloc(reinterpret_cast<void**>(&m->d_chunks), want * sizeof(uint2)));
+	m->chunks_cap = want;
+	m->device_bytes += want * sizeof(uint2);
+}
+
 void launch_rays(Map* m, const ScanArgs& a, int simple)
 {
 	if (simple) {
@@ -397,13 +441,21 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 	CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), m->stream));
 	uint32_t need = (a.n + kRayThreads - 1) / kRayThreads;
 	uint32_t grid = std::min<uint32_t>(need, (uint32_t)m->sm_count * m->ray_blocks_per_sm);
-	if (a.depth == 0) {
-		k_rays<0><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
-	} else if (a.depth == 1) {
-		k_rays<1><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
+	if (a.count_visits) {
+		if (a.depth == 0) k_rays<0, true><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
+		else if (a.depth == 1) k_rays<1, true><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
+		else k_rays<2, true><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
 	} else {
-		k_rays<2><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
+		if (a.depth == 0) k_rays<0, false><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
+		else if (a.depth == 1) k_rays<1, false><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
+		else k_rays<2, false><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
 	}
+	if (m->profiling) {
+		CK(cudaEventRecord(m->ev[7], m->stream));
+		m->ev7_valid = true;
+	}
+	k_scatter<<<(uint32_t)m->sm_count * 8, kChunk, 0, m->stream>>>(m->M, a);
+	++m->launches;
 }
 
 int do_insert(Map* m, const double origin[3], const void* points, bool on_device, size_t n,
@@ -450,8 +502,19 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	a.tab_mask = m->tab_size ? m->tab_size - 1 : 0;
 	a.hit_tab = use_color ? m->d_hit_tab : nullptr;
 	a.count_visits = m->profiling >= 2;
+	if (!simple) {
+		// first guess for the record buffer: 48 records per ray; grown on demand
+		ensure_seg(m, std::max<unsigned long long>(m->seg_cap, std::max<unsigned long long>(n, 1024) * 48ull));
+		a.seg = m->d_seg;
+		a.seg_cap = m->seg_cap;
+		a.seg_base = m->d_seg_base;
+		a.seg_count = m->d_seg_count;
+		ensure_chunks(m, n);
+		a.chunks = m->d_chunks;
+	}
 
 	m->stats = ufo_b200_scan_stats{};
+	m->ev7_valid = false;
 	m->stats.points = n;
 	m->launches = 0;
 	M.scan_id++;
@@ -510,9 +573,21 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 			m->set_error("device pools keep overflowing");
 			return UFO_B200_E_NOMEM;
 		}
+		if (ov & 16u) {
+			m->set_error("internal error: a ray walk exceeded its record bound");
+			return UFO_B200_E_CUDA;
+		}
 		uint32_t wb = m->h_ctr->n_blocks, wk = m->h_ctr->n_bricks, wu = m->h_ctr->n_upper;
 		m->n_blocks = std::min(wb, M.block_cap);
 		m->n_bricks = std::min(wk, M.brick_cap);
+		if (ov & 8u) {
+			unsigned long long want = m->h_ctr->seg_total + m->h_ctr->seg_total / 4 + 1024;
+			ensure_seg(m, want);
+			a.seg = m->d_seg;
+			a.seg_cap = m->seg_cap;
+			ensure_chunks(m, n);
+			a.chunks = m->d_chunks;
+		}
 		try {
 			grow_pools(m, ov, wb, wk, wu);
 		} catch (std::bad_alloc&) {
@@ -639,7 +714,7 @@ int ufo_b200_create(const ufo_b200_params* p, ufo_b200_map** out)
 		cudaDeviceProp prop;
 		CK(cudaGetDeviceProperties(&prop, dev));
 		m->sm_count = prop.multiProcessorCount;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->ray_blocks_per_sm, k_rays<0>, kRayThreads, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->ray_blocks_per_sm, k_rays<0, false>, kRayThreads, 0));
 		if (m->ray_blocks_per_sm < 1) m->ray_blocks_per_sm = 1;
 		m->params = *p;
 		CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
