@@ -55,7 +55,7 @@ struct Counters {
 	uint32_t list_count[2];  // ping-pong dirty lists of the upper-level pass
 	uint32_t n_rays;
 	uint32_t ray_batch;  // next batch of 32 rays for the persistent ray-walk warps
-	uint32_t n_chunks;   // k_scatter work items published by k_rays
+	uint32_t n_chunks;   // longest ray-record region of the scan, in kChunk slices
 	uint32_t pad1;
 	unsigned long long seg_total;  // ray-walk records reserved by K1
 	unsigned long long visits;
@@ -170,7 +170,7 @@ __device__ __forceinline__ ulonglong2 ld_volatile_entry(const ulonglong2* p)
 // value field of an entry: low 32 bits = brick slot / kPending / kFailed
 __device__ __forceinline__ uint32_t brick_find(const DeviceMap& M, uint64_t key)
 {
-	uint32_t i = hash_u64(key) & M.bh_mask;
+	uint32_t i = hash_u64(key) & M.bh_mask & ~1u;  // buckets of two entries (one 32 B sector)
 	for (uint32_t probes = 0; probes <= M.bh_mask; ++probes) {
 		ulonglong2 e = ld_volatile_entry(&M.bh_tab[i]);
 		if (e.x == key) {
@@ -221,7 +221,7 @@ __device__ __forceinline__ uint32_t brick_find_or_create_from(const DeviceMap& M
 
 __device__ __forceinline__ uint32_t brick_find_or_create(const DeviceMap& M, uint64_t key)
 {
-	return brick_find_or_create_from(M, key, hash_u64(key) & M.bh_mask);
+	return brick_find_or_create_from(M, key, hash_u64(key) & M.bh_mask & ~1u);
 }
 
 // block slot of child b (0..63) of a brick; 0 when the pool overflowed

@@ -49,7 +49,7 @@ struct ScanArgs {
 	unsigned long long seg_cap;  // records
 	uint32_t* seg_base;          // [ceil(n/32)] first record of the warp's region
 	uint32_t* seg_count;         // [ceil(n/32)] K1: capacity of the region, K2: records written
-	uint2* chunks;               // work list for k_scatter: (first record, count <= kChunk)
+	uint32_t* order;             // [ceil(n/32)] ray batches sorted by estimated work, longest first
 };
 
 __device__ __forceinline__ void load_point(const ScanArgs& a, uint32_t i, Vec3& p, uint32_t& rgb)
@@ -464,8 +464,40 @@ __device__ __forceinline__ bool walk_iteration(double& tx, double& ty, double& t
 	return any != 0;
 }
 
-// Persistent warps: each warp fetches batches of 32 consecutive rays until the scan is
-// exhausted, so short rays do not leave SMs idle behind long ones.
+// Orders the batches of 32 rays by their estimated work (the record bound K1 computed,
+// which is proportional to the walk length), longest first: a counting sort over 256
+// work classes in one CTA.
+__global__ void __launch_bounds__(1024) k_order_batches(const uint32_t* work, uint32_t n, uint32_t* order)
+{
+	__shared__ uint32_t hist[256];
+	__shared__ uint32_t wmax;
+	if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+	if (threadIdx.x == 0) wmax = 1;
+	__syncthreads();
+	uint32_t m = 0;
+	for (uint32_t b = threadIdx.x; b < n; b += blockDim.x) m = max(m, work[b]);
+	atomicMax(&wmax, m);
+	__syncthreads();
+	const uint32_t top = wmax;
+	for (uint32_t b = threadIdx.x; b < n; b += blockDim.x)
+		atomicAdd(&hist[255u - (uint32_t)(((unsigned long long)work[b] * 255ull) / top)], 1u);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t run = 0;
+		for (int k = 0; k < 256; ++k) {
+			uint32_t c = hist[k];
+			hist[k] = run;
+			run += c;
+		}
+	}
+	__syncthreads();
+	for (uint32_t b = threadIdx.x; b < n; b += blockDim.x)
+		order[atomicAdd(&hist[255u - (uint32_t)(((unsigned long long)work[b] * 255ull) / top)], 1u)] = b;
+}
+
+// Warp w of CTA c walks the batches of rank c + gridDim.x * (w + 4 * round): every CTA
+// gets one batch from each work quartile, so every SM receives the same amount of work
+// whatever the hardware's CTA placement is.
 template <int DEPTH, bool COUNT>
 __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceMap M, ScanArgs a, uint32_t* batch_counter)
 {
@@ -474,12 +506,10 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint32_t n_batches = (a.n + 31) / 32;
 	unsigned int visits = 0;
+	(void)batch_counter;
 	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;  // record buffer being regrown
-	while (true) {
-		uint32_t batch = 0;
-		if (lane == 0) batch = atomicAdd(batch_counter, 1u);
-		batch = __shfl_sync(FULL, batch, 0);
-		if (batch >= n_batches) break;
+	for (uint32_t v = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; v < n_batches; v += gridDim.x * (kRayThreads / 32)) {
+		const uint32_t batch = a.order[v];
 		const uint32_t i = batch * 32 + lane;
 		QEntry* out = a.seg + a.seg_base[batch];
 		const uint32_t cap = a.seg_count[batch];
@@ -535,32 +565,33 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 				cursor = cap;
 			}
 			a.seg_count[batch] = cursor;
-			// publish the region as work items for k_scatter
-			const uint32_t nch = (cursor + kChunk - 1) / kChunk;
-			if (nch) {
-				const uint32_t pos = atomicAdd(&M.ctr->n_chunks, nch);
-				const uint32_t base = a.seg_base[batch];
-				for (uint32_t c = 0; c < nch; ++c)
-					a.chunks[pos + c] = make_uint2(base + c * kChunk, min(kChunk, cursor - c * kChunk));
-			}
+			atomicMax(&M.ctr->n_chunks, (cursor + kChunk - 1) / kChunk);  // longest region, in chunks
 		}
 	}
 	if (COUNT && visits) atomicAdd(&M.ctr->visits, (unsigned long long)visits);
 }
 
-// K2b: one thread per record.  Resolves the brick (one 16-byte hash probe in the common
-// case), the block slot, and ORs the mask into the block's miss mask.  The upper half of
-// the hash entry's value caches the scan stamp of the brick so that only the first
-// records of a brick write brick_stamp.  Work items are kChunk-record slices published by
-// k_rays; CTAs loop over them.
+// K2b: one thread per record.  Resolves the brick (one probe of a two-entry hash bucket
+// = one 32-byte sector in the common case), the block slot, and ORs the mask into the
+// block's miss mask.  The upper half of a hash entry's value caches the scan stamp of the
+// brick so that only the first records of a brick write brick_stamp.
+// Work item (j, r) = the j-th kChunk-record slice COUNTED FROM THE END of region r, and
+// items are visited j-major: the walks run from the end point towards the sensor, so the
+// tails of all regions hold the records next to the sensor, which thousands of rays share
+// -- visiting them together turns most of the mask atomics into L2 hits.
 __global__ void __launch_bounds__(kChunk) k_scatter(DeviceMap M, ScanArgs a)
 {
 	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;
-	const uint32_t n_chunks = ld_volatile_u32(&M.ctr->n_chunks);
-	for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-		const uint2 ch = a.chunks[c];
-		if (threadIdx.x >= ch.y) continue;
-		const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&a.seg[ch.x + threadIdx.x]);
+	const uint32_t n_regions = (a.n + 31) / 32;
+	const unsigned long long n_items = (unsigned long long)ld_volatile_u32(&M.ctr->n_chunks) * n_regions;
+	for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+		const uint32_t j = (uint32_t)(it / n_regions), r = (uint32_t)(it % n_regions);
+		const uint32_t cnt = a.seg_count[r];
+		if ((unsigned long long)j * kChunk >= cnt) continue;
+		const uint32_t hi = cnt - j * kChunk;                 // one past the slice's last record
+		const uint32_t lo = hi > kChunk ? hi - kChunk : 0u;
+		if (lo + threadIdx.x >= hi) continue;
+		const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&a.seg[a.seg_base[r] + lo + threadIdx.x]);
 		uint32_t x, y, z;
 		unpack_key(v.y, x, y, z);
 		x = (x & M.g.key_mask) >> 2;  // block coordinates inside the tree
@@ -568,13 +599,17 @@ __global__ void __launch_bounds__(kChunk) k_scatter(DeviceMap M, ScanArgs a)
 		z = (z & M.g.key_mask) >> 2;
 		const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
 		const uint32_t cidx = morton2(x, y, z);
-		const uint32_t hidx = hash_u64(bkey) & M.bh_mask;
-		const ulonglong2 ent = ld_volatile_entry(&M.bh_tab[hidx]);
+		const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
+		const ulonglong2 e0 = ld_volatile_entry(&M.bh_tab[hidx]);
+		const ulonglong2 e1 = ld_volatile_entry(&M.bh_tab[hidx + 1]);
+		const bool hit0 = e0.x == bkey, hit1 = e1.x == bkey;
+		const ulonglong2 ent = hit0 ? e0 : e1;
+		const uint32_t hpos = hit0 ? hidx : hidx + 1;
 		uint32_t bslot = (uint32_t)ent.y;
-		if (ent.x == bkey && bslot != kPending && bslot != kFailed) {
+		if ((hit0 || hit1) && bslot != kPending && bslot != kFailed) {
 			if ((uint32_t)(ent.y >> 32) != M.scan_id) {
 				M.brick_stamp[bslot] = M.scan_id;
-				reinterpret_cast<uint32_t*>(&M.bh_tab[hidx].y)[1] = M.scan_id;
+				reinterpret_cast<uint32_t*>(&M.bh_tab[hpos].y)[1] = M.scan_id;
 			}
 		} else {
 			bslot = brick_find_or_create_from(M, bkey, hidx);
@@ -691,6 +726,40 @@ __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, uin
 	lp[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+struct OctetLoad {
+	float4 a0, a1;
+	float s1;
+	uint32_t slot, meta, child, m8, h8;
+	bool act;
+};
+
+// issues the loads one lane needs for octet `oct` of work item e
+__device__ __forceinline__ OctetLoad load_octet(const DeviceMap& M, const WorkItem* wl, int e, int n_work,
+                                                uint32_t oct)
+{
+	OctetLoad L;
+	L.act = e < n_work;
+	L.a0 = L.a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+	L.s1 = 0.0f;
+	L.slot = L.meta = L.child = L.m8 = L.h8 = 0;
+	if (L.act) {
+		const WorkItem w = wl[e];
+		L.slot = w.slot;
+		L.meta = w.meta;
+		L.child = w.child;
+		L.m8 = octet_bits8(w.miss, oct);
+		L.h8 = octet_bits8(w.hit, oct);
+		if (L.m8 | L.h8) {
+			const float4* lp = reinterpret_cast<const float4*>(M.leaf + (size_t)w.slot * 64 + 8 * oct);
+			L.a0 = lp[0];
+			L.a1 = lp[1];
+		} else if ((w.meta >> (16 + oct)) & 1u) {
+			L.s1 = M.rec[w.slot].sum1[oct];
+		}
+	}
+	return L;
+}
+
 __global__ void __launch_bounds__(kUpdWarps * 32) k_update(DeviceMap M, float miss, uint32_t n_bricks)
 {
 	__shared__ WorkItem work[kUpdWarps][64];
@@ -744,86 +813,62 @@ __global__ void __launch_bounds__(kUpdWarps * 32) k_update(DeviceMap M, float mi
 			if (M.color) aggrgb[wid][r * 32 + lane] = hd[r].w;
 		}
 		__syncwarp();
-		// ---- phase B: 8 blocks per iteration (group g: items it*8+g and it*8+4+g)
-		for (int it = 0; it * 8 < n_work; ++it) {
-			WorkItem wi[2];
-			bool act[2];
-			uint32_t m8[2], h8[2];
-			float4 a0[2], a1[2];
-			float s1[2];
-#pragma unroll
-			for (int u = 0; u < 2; ++u) {
-				const int e = it * 8 + u * 4 + (int)grp;
-				act[u] = e < n_work;
-				m8[u] = h8[u] = 0;
-				s1[u] = 0.0f;
-				a0[u] = a1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-				if (act[u]) {
-					wi[u] = wl[e];
-					m8[u] = octet_bits8(wi[u].miss, oct);
-					h8[u] = octet_bits8(wi[u].hit, oct);
-					if (m8[u] | h8[u]) {
-						const float4* lp = reinterpret_cast<const float4*>(M.leaf + (size_t)wi[u].slot * 64 + 8 * oct);
-						a0[u] = lp[0];
-						a1[u] = lp[1];
-					} else if ((wi[u].meta >> (16 + oct)) & 1u) {
-						s1[u] = M.rec[wi[u].slot].sum1[oct];
+		// ---- phase B: four blocks per iteration (group g: item it*4+g), software-pipelined:
+		// the loads of iteration it+1 are issued before iteration it is computed
+		OctetLoad cur = load_octet(M, wl, 0 + (int)grp, n_work, oct);
+		for (int it = 0; it * 4 < n_work; ++it) {
+			OctetLoad nxt = load_octet(M, wl, (it + 1) * 4 + (int)grp, n_work, oct);
+			float omax = 0.0f;
+			uint32_t oflags = M.default_flags;  // bit8: touched by this scan
+			uint32_t orgb = 0;
+			if (cur.act) {
+				if (cur.m8 | cur.h8) {
+					update_octet(M, miss, cur.slot, oct, cur.m8, cur.h8, cur.a0, cur.a1, omax, oflags);
+					st_vox += __popc(cur.m8 | cur.h8);
+					st_hit += __popc(cur.h8);
+					++st_oct;
+					M.rec[cur.slot].sum1[oct] = omax;
+					if (M.color) {
+						const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + (size_t)cur.slot * 64 + 8 * oct);
+						uint4 c0 = cp[0], c1 = cp[1];
+						uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+						orgb = rms_rgb(cc, 8);
+						M.sum1_rgb[(size_t)cur.slot * 8 + oct] = orgb;
 					}
+				} else if ((cur.meta >> (16 + oct)) & 1u) {
+					omax = cur.s1;
+					oflags = (cur.meta >> (2 * oct)) & 3u;
+					if (M.color) orgb = M.sum1_rgb[(size_t)cur.slot * 8 + oct];
 				}
 			}
+			// depth-2 aggregate over the 8 octets of the block (8-lane groups)
+			float bmax = omax;
+			uint32_t bfl = oflags & 3u;
+			uint32_t newmeta = ((oflags & 3u) << (2 * oct)) | (((oflags >> 8) & 1u) << (16 + oct));
 #pragma unroll
-			for (int u = 0; u < 2; ++u) {
-				float omax = 0.0f;
-				uint32_t oflags = M.default_flags;  // bit8: touched by this scan
-				uint32_t orgb = 0;
-				if (act[u]) {
-					if (m8[u] | h8[u]) {
-						update_octet(M, miss, wi[u].slot, oct, m8[u], h8[u], a0[u], a1[u], omax, oflags);
-						st_vox += __popc(m8[u] | h8[u]);
-						st_hit += __popc(h8[u]);
-						++st_oct;
-						M.rec[wi[u].slot].sum1[oct] = omax;
-						if (M.color) {
-							const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + (size_t)wi[u].slot * 64 + 8 * oct);
-							uint4 c0 = cp[0], c1 = cp[1];
-							uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-							orgb = rms_rgb(cc, 8);
-							M.sum1_rgb[(size_t)wi[u].slot * 8 + oct] = orgb;
-						}
-					} else if ((wi[u].meta >> (16 + oct)) & 1u) {
-						omax = s1[u];
-						oflags = (wi[u].meta >> (2 * oct)) & 3u;
-						if (M.color) orgb = M.sum1_rgb[(size_t)wi[u].slot * 8 + oct];
-					}
-				}
-				// depth-2 aggregate over the 8 octets of the block (8-lane groups)
-				float bmax = omax;
-				uint32_t bfl = oflags & 3u;
-				uint32_t newmeta = ((oflags & 3u) << (2 * oct)) | (((oflags >> 8) & 1u) << (16 + oct));
-#pragma unroll
-				for (int o = 1; o < 8; o <<= 1) {
-					bmax = fmaxf(bmax, __shfl_xor_sync(FULL, bmax, o));
-					bfl |= __shfl_xor_sync(FULL, bfl, o);
-					newmeta |= __shfl_xor_sync(FULL, newmeta, o);
-				}
-				uint32_t brgb = 0;
-				if (M.color) {
-					uint32_t oc[8];
-#pragma unroll
-					for (int j = 0; j < 8; ++j) oc[j] = __shfl_sync(FULL, orgb, (lane & 24) + j);
-					brgb = rms_rgb(oc, 8);
-				}
-				if (act[u] && oct == 0) {
-					// new first sector of the record: masks cleared for the next scan
-					BlockRec* rp = &M.rec[wi[u].slot];
-					const uint32_t meta = (newmeta & 0xffffffu) | (wi[u].meta & 0xff0000u);
-					*reinterpret_cast<ulonglong2*>(rp) = make_ulonglong2(0ull, 0ull);
-					*reinterpret_cast<uint4*>(&rp->occ2) = make_uint4(__float_as_uint(bmax), bfl, meta, brgb);
-					agg[wid][wi[u].child] = {bmax, bfl};
-					if (M.color) aggrgb[wid][wi[u].child] = brgb;
-					++st_blk;
-				}
+			for (int o = 1; o < 8; o <<= 1) {
+				bmax = fmaxf(bmax, __shfl_xor_sync(FULL, bmax, o));
+				bfl |= __shfl_xor_sync(FULL, bfl, o);
+				newmeta |= __shfl_xor_sync(FULL, newmeta, o);
 			}
+			uint32_t brgb = 0;
+			if (M.color) {
+				uint32_t oc[8];
+#pragma unroll
+				for (int j = 0; j < 8; ++j) oc[j] = __shfl_sync(FULL, orgb, (lane & 24) + j);
+				brgb = rms_rgb(oc, 8);
+			}
+			if (cur.act && oct == 0) {
+				// new first sector of the record: masks cleared for the next scan
+				BlockRec* rp = &M.rec[cur.slot];
+				const uint32_t meta = (newmeta & 0xffffffu) | (cur.meta & 0xff0000u);
+				*reinterpret_cast<ulonglong2*>(rp) = make_ulonglong2(0ull, 0ull);
+				*reinterpret_cast<uint4*>(&rp->occ2) = make_uint4(__float_as_uint(bmax), bfl, meta, brgb);
+				agg[wid][cur.child] = {bmax, bfl};
+				if (M.color) aggrgb[wid][cur.child] = brgb;
+				++st_blk;
+			}
+			cur = nxt;
 		}
 		__syncwarp();
 		// ---- phase C: lane owns children 2*lane, 2*lane+1 (both under depth-3 node lane/4)
@@ -981,7 +1026,7 @@ __global__ void __launch_bounds__(256) k_rebuild_brick_hash(DeviceMap M, uint32_
 	uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= n_bricks) return;
 	unsigned long long key = M.brick_key[b];
-	uint32_t i = hash_u64(key) & M.bh_mask;
+	uint32_t i = hash_u64(key) & M.bh_mask & ~1u;
 	while (true) {
 		unsigned long long k = atomicCAS(&M.bh_tab[i].x, kEmptyKey, key);
 		if (k == kEmptyKey) {

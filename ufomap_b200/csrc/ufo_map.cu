@@ -97,8 +97,7 @@ struct ufo_b200_map {
 	QEntry* d_seg = nullptr;          // ray-walk records
 	unsigned long long seg_cap = 0;
 	uint32_t *d_seg_base = nullptr, *d_seg_count = nullptr;
-	uint2* d_chunks = nullptr;
-	size_t chunks_cap = 0;
+	uint32_t* d_order = nullptr;
 	// bookkeeping
 	uint32_t n_blocks = 1, n_bricks = 0, n_upper = 0;  // host view after the last sync
 	size_t device_bytes = 0;
@@ -206,7 +205,7 @@ void free_pools(Map* m)
 	                M.block_key, M.sum1_rgb,
 	                M.uh_keys,   M.uh_vals,   M.up_key,      M.up_agg,      M.up_rgb,
 	                M.up_stamp,  M.ctr,       m->d_list[0], m->d_list[1], m->d_points,   m->d_ray_end,
-	                m->d_hit_tab, m->d_tab_keys, m->d_tab_min, m->d_seg, m->d_seg_base, m->d_seg_count, m->d_chunks};
+	                m->d_hit_tab, m->d_tab_keys, m->d_tab_min, m->d_seg, m->d_seg_base, m->d_seg_count, m->d_order};
 	for (void* p : ptrs)
 		if (p) cudaFree(p);
 }
@@ -319,13 +318,15 @@ void ensure_scan_buffers(Map* m, size_t n, bool need_table)
 			cudaFree(m->d_hit_tab);
 			cudaFree(m->d_seg_base);
 			cudaFree(m->d_seg_count);
-			tot -= m->ray_cap * (3 * sizeof(double) + sizeof(uint32_t)) + (m->ray_cap / 32 + 1) * 8;
+			cudaFree(m->d_order);
+			tot -= m->ray_cap * (3 * sizeof(double) + sizeof(uint32_t)) + (m->ray_cap / 32 + 1) * 12;
 		}
 		size_t cap = std::max<size_t>(n, 1024);
 		dev_alloc(m->d_ray_end, cap * 3, 0, m->stream, tot);
 		dev_alloc(m->d_hit_tab, cap, 0xff, m->stream, tot);
 		dev_alloc(m->d_seg_base, cap / 32 + 1, 0, m->stream, tot);
 		dev_alloc(m->d_seg_count, cap / 32 + 1, 0, m->stream, tot);
+		dev_alloc(m->d_order, cap / 32 + 1, 0, m->stream, tot);
 		m->ray_cap = cap;
 	}
 	if (need_table) {
@@ -414,31 +415,17 @@ void ensure_seg(Map* m, unsigned long long want)
 	m->device_bytes += want * sizeof(QEntry);
 }
 
-void ensure_chunks(Map* m, size_t n_points)
-{
-	// every region of 32 rays publishes ceil(count / kChunk) <= count / kChunk + 1 items
-	size_t want = (size_t)(m->seg_cap / kChunk) + n_points / 32 + 2;
-	if (want <= m->chunks_cap) return;
-	CK(cudaStreamSynchronize(m->stream));
-	if (m->d_chunks) {
-		cudaFree(m->d_chunks);
-		m->device_bytes -= m->chunks_cap * sizeof(uint2);
-	}
-	m->d_chunks = nullptr;
-	CK(cudaMalloc(reinterpret_cast<void**>(&m->d_chunks), want * sizeof(uint2)));
-	m->chunks_cap = want;
-	m->device_bytes += want * sizeof(uint2);
-}
-
 void launch_rays(Map* m, const ScanArgs& a, int simple)
 {
 	if (simple) {
 		k_rays_simple<<<(a.n + 127) / 128, 128, 0, m->stream>>>(m->M, a);
 		return;
 	}
-	// persistent warps: one resident wave, batches of 32 rays fetched dynamically
+	// one resident wave; batches are ordered by work and dealt round-robin over the CTAs
 	uint32_t* counter = &m->M.ctr->ray_batch;
-	CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), m->stream));
+	uint32_t n_batches = (a.n + 31) / 32;
+	k_order_batches<<<1, 1024, 0, m->stream>>>(a.seg_count, n_batches, a.order);
+	++m->launches;
 	uint32_t need = (a.n + kRayThreads - 1) / kRayThreads;
 	uint32_t grid = std::min<uint32_t>(need, (uint32_t)m->sm_count * m->ray_blocks_per_sm);
 	if (a.count_visits) {
@@ -509,8 +496,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		a.seg_cap = m->seg_cap;
 		a.seg_base = m->d_seg_base;
 		a.seg_count = m->d_seg_count;
-		ensure_chunks(m, n);
-		a.chunks = m->d_chunks;
+		a.order = m->d_order;
 	}
 
 	m->stats = ufo_b200_scan_stats{};
@@ -585,8 +571,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 			ensure_seg(m, want);
 			a.seg = m->d_seg;
 			a.seg_cap = m->seg_cap;
-			ensure_chunks(m, n);
-			a.chunks = m->d_chunks;
+
 		}
 		try {
 			grow_pools(m, ov, wb, wk, wu);
