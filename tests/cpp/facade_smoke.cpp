@@ -1,0 +1,56 @@
+// Reads like a program written against the reference: only the include line differs
+// (#include <ufo/map/ufomap.h> there).  Built and run by tests/test_facade.py.
+#include <ufomap_b200/ufomap.hpp>
+
+#include <cstdio>
+#include <cstring>
+
+int main(int argc, char** argv)
+{
+	using namespace ufo::map;
+	bool compile_only = argc > 1 && 0 == std::strcmp(argv[1], "--no-device");
+	if (compile_only) {
+		// constructor arguments are validated before any device is touched (octree.h:931-935)
+		try {
+			OccupancyMap bad(0.1, 40);
+			return 2;
+		} catch (std::invalid_argument const&) {
+		}
+		std::puts("facade ok (no device)");
+		return 0;
+	}
+
+	OccupancyMap map(0.02);
+	PointCloud cloud;
+	cloud.push_back(Point3(1.0, 0.0, 0.0));
+	map.insertPointCloud(Point3(0, 0, 0), cloud, 5.0);
+
+	// end voxel = float(hit) + float(miss), mid voxel = float(miss), origin untouched
+	double end = map.getOccupancy(Point3(1.0, 0, 0)), mid = map.getOccupancy(Point3(0.5, 0, 0));
+	if (!map.isOccupied(Point3(1.0, 0, 0)) || !map.isFree(Point3(0.5, 0, 0)) || !map.isUnknown(Point3(0, 0, 0))) return 3;
+	if (!(end > 0.6 && end < 0.62) || !(mid > 0.39 && mid < 0.41)) return 4;
+
+	CodeRay ray = map.computeRay(Point3(0, 0, 0), Point3(0.1, 0.1, 0.1));
+	if (ray.size() != 15) return 5;
+	if (map.toCode(Point3(1.0, 0, 0)).toKey() != map.toKey(Point3(1.0, 0, 0))) return 6;
+
+	OccupancyMapColor cmap(0.02);
+	PointCloudColor ccloud;
+	ccloud.push_back(Point3Color(0.5, 0.1, 0.2, 200, 100, 50));
+	cmap.insertPointCloudDiscrete(Point3(0, 0, 0), ccloud, -1, 0, false, 0, true);
+	cmap.insertPointCloudWait();
+	if (!cmap.insertPointCloudDone()) return 7;
+	Color c = cmap.getColor(Point3(0.5, 0.1, 0.2));
+	if (c != Color(200, 100, 50)) return 8;
+
+	// early_stopping is rejected, not silently ignored
+	map.insertPointCloud(Point3(0, 0, 0), cloud, 5.0, 0, false, 3);
+	if (map.lastStatus() != UFO_B200_E_UNSUPPORTED) return 9;
+
+	ufo::math::Pose6 pose(1.0, 2.0, 3.0, 0.0, 0.0, 1.5707963267948966);
+	PointCloud moved = cloud;
+	moved.transform(pose);
+	if (std::fabs(moved[0].x() - 1.0) > 1e-12 || std::fabs(moved[0].y() - 3.0) > 1e-12) return 10;
+	std::puts("facade ok");
+	return 0;
+}

@@ -52,11 +52,10 @@ struct Counters {
 	uint32_t n_bricks;   // next free brick slot
 	uint32_t n_upper;    // next free upper-node slot
 	uint32_t overflow;   // bit0 blocks, bit1 bricks/brick hash, bit2 upper nodes, bit3 ray-record buffer, bit4 ray bound violated (bug)
-	uint32_t list_count[2];  // ping-pong dirty lists of the upper-level pass
+	uint32_t list_count[3];  // dirty-list lengths of the upper-level pass (rotating by depth % 3)
 	uint32_t n_rays;
 	uint32_t ray_batch;  // next batch of 32 rays for the persistent ray-walk warps
 	uint32_t n_chunks;   // longest ray-record region of the scan, in kChunk slices
-	uint32_t pad1;
 	unsigned long long seg_total;  // ray-walk records reserved by K1
 	unsigned long long visits;
 	unsigned long long touched_voxels;
@@ -200,9 +199,10 @@ __device__ __forceinline__ uint32_t brick_find_or_create_from(const DeviceMap& M
 					st_volatile_u32(vp, kFailed);
 					return kNone;
 				}
+				// brick_key / block_key are only read by later kernels (export, rebuild), so
+				// publishing the slot needs no fence
 				M.brick_key[s] = key;
 				vp[1] = 0;  // cached scan stamp (see k_scatter)
-				__threadfence();
 				st_volatile_u32(vp, s);
 				return s;
 			}
@@ -240,7 +240,6 @@ __device__ __forceinline__ uint32_t block_find_or_create(const DeviceMap& M, uin
 				return 0;
 			}
 			M.block_key[s] = block_key;
-			__threadfence();
 			atomicExch(p, s);
 			return s;
 		}

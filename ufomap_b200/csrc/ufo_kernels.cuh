@@ -579,46 +579,68 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 // items are visited j-major: the walks run from the end point towards the sensor, so the
 // tails of all regions hold the records next to the sensor, which thousands of rays share
 // -- visiting them together turns most of the mask atomics into L2 hits.
+constexpr int kScatterRegions = 64;  // regions one CTA can own (grid is sized accordingly)
+
 __global__ void __launch_bounds__(kChunk) k_scatter(DeviceMap M, ScanArgs a)
 {
+	__shared__ uint32_t r_cnt[kScatterRegions], r_base[kScatterRegions];
+	__shared__ uint32_t n_mine, max_cnt;
 	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;
 	const uint32_t n_regions = (a.n + 31) / 32;
-	const unsigned long long n_items = (unsigned long long)ld_volatile_u32(&M.ctr->n_chunks) * n_regions;
-	for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x) {
-		const uint32_t j = (uint32_t)(it / n_regions), r = (uint32_t)(it % n_regions);
-		const uint32_t cnt = a.seg_count[r];
-		if ((unsigned long long)j * kChunk >= cnt) continue;
-		const uint32_t hi = cnt - j * kChunk;                 // one past the slice's last record
-		const uint32_t lo = hi > kChunk ? hi - kChunk : 0u;
-		if (lo + threadIdx.x >= hi) continue;
-		const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&a.seg[a.seg_base[r] + lo + threadIdx.x]);
-		uint32_t x, y, z;
-		unpack_key(v.y, x, y, z);
-		x = (x & M.g.key_mask) >> 2;  // block coordinates inside the tree
-		y = (y & M.g.key_mask) >> 2;
-		z = (z & M.g.key_mask) >> 2;
-		const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
-		const uint32_t cidx = morton2(x, y, z);
-		const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
-		const ulonglong2 e0 = ld_volatile_entry(&M.bh_tab[hidx]);
-		const ulonglong2 e1 = ld_volatile_entry(&M.bh_tab[hidx + 1]);
-		const bool hit0 = e0.x == bkey, hit1 = e1.x == bkey;
-		const ulonglong2 ent = hit0 ? e0 : e1;
-		const uint32_t hpos = hit0 ? hidx : hidx + 1;
-		uint32_t bslot = (uint32_t)ent.y;
-		if ((hit0 || hit1) && bslot != kPending && bslot != kFailed) {
-			if ((uint32_t)(ent.y >> 32) != M.scan_id) {
-				M.brick_stamp[bslot] = M.scan_id;
-				reinterpret_cast<uint32_t*>(&M.bh_tab[hpos].y)[1] = M.scan_id;
-			}
-		} else {
-			bslot = brick_find_or_create_from(M, bkey, hidx);
-			if (bslot == kNone) continue;
-			M.brick_stamp[bslot] = M.scan_id;
+	// CTA b owns the regions of work rank b, b + G, b + 2G, ... (balanced like k_rays)
+	if (threadIdx.x == 0) {
+		n_mine = 0;
+		max_cnt = 0;
+	}
+	__syncthreads();
+	if (threadIdx.x < kScatterRegions) {
+		const uint32_t v = blockIdx.x + threadIdx.x * gridDim.x;
+		if (v < n_regions) {
+			const uint32_t r = a.order[v];
+			r_cnt[threadIdx.x] = a.seg_count[r];
+			r_base[threadIdx.x] = a.seg_base[r];
+			atomicAdd(&n_mine, 1u);
+			atomicMax(&max_cnt, r_cnt[threadIdx.x]);
 		}
-		uint32_t slot = ld_volatile_u32(&M.brick_child[(size_t)bslot * 64 + cidx]);
-		if (slot == 0 || slot == kLock) slot = block_find_or_create(M, bslot, cidx, pack_key(x, y, z));
-		if (slot) atomicOr(&M.rec[slot].miss, v.x);
+	}
+	__syncthreads();
+	const uint32_t mine = n_mine, slices = (max_cnt + kChunk - 1) / kChunk;
+	for (uint32_t j = 0; j < slices; ++j) {
+		for (uint32_t q = 0; q < mine; ++q) {
+			const uint32_t cnt = r_cnt[q];
+			if (j * kChunk >= cnt) continue;
+			const uint32_t hi = cnt - j * kChunk;  // one past the slice's last record
+			const uint32_t lo = hi > kChunk ? hi - kChunk : 0u;
+			if (lo + threadIdx.x >= hi) continue;
+			const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&a.seg[r_base[q] + lo + threadIdx.x]);
+			uint32_t x, y, z;
+			unpack_key(v.y, x, y, z);
+			x = (x & M.g.key_mask) >> 2;  // block coordinates inside the tree
+			y = (y & M.g.key_mask) >> 2;
+			z = (z & M.g.key_mask) >> 2;
+			const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
+			const uint32_t cidx = morton2(x, y, z);
+			const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
+			const ulonglong2 e0 = ld_volatile_entry(&M.bh_tab[hidx]);
+			const ulonglong2 e1 = ld_volatile_entry(&M.bh_tab[hidx + 1]);
+			const bool hit0 = e0.x == bkey, hit1 = e1.x == bkey;
+			const ulonglong2 ent = hit0 ? e0 : e1;
+			const uint32_t hpos = hit0 ? hidx : hidx + 1;
+			uint32_t bslot = (uint32_t)ent.y;
+			if ((hit0 || hit1) && bslot != kPending && bslot != kFailed) {
+				if ((uint32_t)(ent.y >> 32) != M.scan_id) {
+					M.brick_stamp[bslot] = M.scan_id;
+					reinterpret_cast<uint32_t*>(&M.bh_tab[hpos].y)[1] = M.scan_id;
+				}
+			} else {
+				bslot = brick_find_or_create_from(M, bkey, hidx);
+				if (bslot == kNone) continue;
+				M.brick_stamp[bslot] = M.scan_id;
+			}
+			uint32_t slot = ld_volatile_u32(&M.brick_child[(size_t)bslot * 64 + cidx]);
+			if (slot == 0 || slot == kLock) slot = block_find_or_create(M, bslot, cidx, pack_key(x, y, z));
+			if (slot) atomicOr(&M.rec[slot].miss, v.x);
+		}
 	}
 }
 
@@ -710,17 +732,27 @@ __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, uin
 {
 	float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 	omax = -3.402823466e+38f;
-	oflags = 0x100u;
+	float omin = 3.402823466e+38f;
+	bool unk = false;
+	// all hits of a scan are applied before its misses (occupancy_map_base.h:1351-1365);
+	// hits are rare (one voxel per ray), so their arithmetic is skipped for octets without one
+	if (h8) {
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			float hv = apply_update(M, v[j], M.hit);
+			v[j] = ((h8 >> j) & 1u) ? hv : v[j];
+		}
+	}
 #pragma unroll
 	for (int j = 0; j < 8; ++j) {
-		// all hits of a scan are applied before its misses (occupancy_map_base.h:1351-1365)
-		float hv = apply_update(M, v[j], M.hit);
-		v[j] = ((h8 >> j) & 1u) ? hv : v[j];
 		float mv = apply_update(M, v[j], miss);
 		v[j] = ((m8 >> j) & 1u) ? mv : v[j];
 		omax = fmaxf(omax, v[j]);
-		oflags |= leaf_flags(M, v[j]);
+		omin = fminf(omin, v[j]);
+		unk = unk || (v[j] >= M.free_ceil && v[j] <= M.occ_floor);
 	}
+	// contains_free = any voxel below the free threshold, contains_unknown = any in between
+	oflags = 0x100u | (omin < M.free_ceil ? 1u : 0u) | (unk ? 2u : 0u);
 	float4* lp = reinterpret_cast<float4*>(M.leaf + (size_t)slot * 64 + 8 * oct);
 	lp[0] = make_float4(v[0], v[1], v[2], v[3]);
 	lp[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -760,7 +792,7 @@ __device__ __forceinline__ OctetLoad load_octet(const DeviceMap& M, const WorkIt
 	return L;
 }
 
-__global__ void __launch_bounds__(kUpdWarps * 32) k_update(DeviceMap M, float miss, uint32_t n_bricks)
+__global__ void __launch_bounds__(kUpdWarps * 32, 4) k_update(DeviceMap M, float miss, uint32_t n_bricks)
 {
 	__shared__ WorkItem work[kUpdWarps][64];
 	__shared__ Agg agg[kUpdWarps][64];
@@ -944,31 +976,30 @@ __global__ void __launch_bounds__(256) k_upper_seed(DeviceMap M, uint32_t n_bric
 	uint32_t s = upper_find_or_create(M, upper_key(5, x >> 1, y >> 1, z >> 1));
 	if (s == kNone) return;
 	if (atomicExch(&M.up_stamp[s], M.scan_id) != M.scan_id) {
-		uint32_t idx = atomicAdd(&M.ctr->list_count[0], 1u);
+		uint32_t idx = atomicAdd(&M.ctr->list_count[5 % 3], 1u);
 		if (idx < list_cap) list[idx] = s;
 	}
 }
 
-// Recomputes the nodes of `in` (all at depth d) from their 8 children and pushes
-// their parents to `out`.  which = index of the input counter (0/1).
-__global__ void __launch_bounds__(256) k_upper_level(DeviceMap M, uint32_t depth, const uint32_t* in,
-                                                     uint32_t* out, uint32_t list_cap, int which)
+// Recomputes the nodes of `in` (all at depth d) from their 8 children and pushes their
+// parents to `out`.  Eight lanes per node, one child each.  Counters rotate three ways:
+// level d reads list_count[d % 3], appends to [(d + 1) % 3] and clears [(d + 2) % 3]
+// (the next level's output), so no separate reset launches are needed.
+__device__ __forceinline__ void upper_level_pass(const DeviceMap& M, uint32_t depth, const uint32_t* in,
+                                                 uint32_t* out, uint32_t list_cap, uint32_t n,
+                                                 uint32_t gid, uint32_t stride)
 {
-	uint32_t n = M.ctr->list_count[which];
-	if (n > list_cap) n = list_cap;
 	const uint32_t lane8 = threadIdx.x & 7;
-	uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-	uint32_t stride = (gridDim.x * blockDim.x) >> 3;
-	const uint32_t gmask = 0xffu << (threadIdx.x & 24);
+	uint32_t* out_count = &M.ctr->list_count[(depth + 1) % 3];
 	// n is uniform, groups of 8 lanes stay together
 	for (uint32_t i = gid; i < ((n + 3) & ~3u); i += stride) {
 		bool valid = i < n;
-		uint32_t s = valid ? in[i] : 0;
+		uint32_t s = valid ? ld_volatile_u32(&in[i]) : 0;
 		float occ = 0.0f;
 		uint32_t fl = M.default_flags, rgb = 0;
 		uint32_t x = 0, y = 0, z = 0;
 		if (valid) {
-			uint64_t key = M.up_key[s];
+			uint64_t key = ld_volatile_u64(&M.up_key[s]);
 			unpack_key(key, x, y, z);
 			x &= 0xffffu;  // strip the depth tag
 			uint32_t cx = 2 * x + (lane8 & 1), cy = 2 * y + ((lane8 >> 1) & 1), cz = 2 * z + (lane8 >> 2);
@@ -983,10 +1014,11 @@ __global__ void __launch_bounds__(256) k_upper_level(DeviceMap M, uint32_t depth
 			} else {
 				uint32_t c = upper_find(M, upper_key(depth - 1, cx, cy, cz));
 				if (c != kNone) {
-					Agg a = M.up_agg[c];
-					occ = a.occ;
-					fl = a.flags;
-					if (M.color) rgb = M.up_rgb[c];
+					// volatile: in k_upper_tail the child was written by this same CTA a level earlier
+					unsigned long long raw = ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&M.up_agg[c]));
+					occ = __uint_as_float((uint32_t)raw);
+					fl = (uint32_t)(raw >> 32);
+					if (M.color) rgb = ld_volatile_u32(&M.up_rgb[c]);
 				}
 			}
 		}
@@ -1000,7 +1032,6 @@ __global__ void __launch_bounds__(256) k_upper_level(DeviceMap M, uint32_t depth
 			occ = fmaxf(occ, __shfl_xor_sync(0xffffffffu, occ, o));
 			fl |= __shfl_xor_sync(0xffffffffu, fl, o);
 		}
-		(void)gmask;
 		if (valid && lane8 == 0) {
 			M.up_agg[s] = {occ, fl};
 			if (M.color) M.up_rgb[s] = rms_rgb(crgb, 8);
@@ -1008,7 +1039,7 @@ __global__ void __launch_bounds__(256) k_upper_level(DeviceMap M, uint32_t depth
 			if (depth < M.g.depth_levels) {
 				uint32_t p = upper_find_or_create(M, upper_key(depth + 1, x >> 1, y >> 1, z >> 1));
 				if (p != kNone && atomicExch(&M.up_stamp[p], M.scan_id) != M.scan_id) {
-					uint32_t idx = atomicAdd(&M.ctr->list_count[which ^ 1], 1u);
+					uint32_t idx = atomicAdd(out_count, 1u);
 					if (idx < list_cap) out[idx] = p;
 				}
 			}
@@ -1016,7 +1047,32 @@ __global__ void __launch_bounds__(256) k_upper_level(DeviceMap M, uint32_t depth
 	}
 }
 
-__global__ void k_reset_list(DeviceMap M, int which) { M.ctr->list_count[which] = 0; }
+__global__ void __launch_bounds__(256) k_upper_level(DeviceMap M, uint32_t depth, const uint32_t* in,
+                                                     uint32_t* out, uint32_t list_cap)
+{
+	uint32_t n = ld_volatile_u32(&M.ctr->list_count[depth % 3]);
+	if (n > list_cap) n = list_cap;
+	if (blockIdx.x == 0 && threadIdx.x == 0) M.ctr->list_count[(depth + 2) % 3] = 0;
+	upper_level_pass(M, depth, in, out, list_cap, n, (blockIdx.x * blockDim.x + threadIdx.x) >> 3,
+	                 (gridDim.x * blockDim.x) >> 3);
+}
+
+// Levels first..L in ONE CTA: the dirty lists above depth ~7 hold a few hundred nodes,
+// so a launch per level would be pure launch latency.
+__global__ void __launch_bounds__(1024) k_upper_tail(DeviceMap M, uint32_t first, uint32_t* list0,
+                                                     uint32_t* list1, uint32_t list_cap)
+{
+	for (uint32_t depth = first; depth <= M.g.depth_levels; ++depth) {
+		uint32_t n = ld_volatile_u32(&M.ctr->list_count[depth % 3]);
+		if (n > list_cap) n = list_cap;
+		if (threadIdx.x == 0) M.ctr->list_count[(depth + 2) % 3] = 0;
+		const uint32_t* in = (depth & 1) ? list0 : list1;
+		uint32_t* out = (depth & 1) ? list1 : list0;
+		upper_level_pass(M, depth, in, out, list_cap, n, threadIdx.x >> 3, blockDim.x >> 3);
+		__threadfence();
+		__syncthreads();
+	}
+}
 
 // ---------------------------------------------------------------------------
 // utility kernels

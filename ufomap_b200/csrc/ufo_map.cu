@@ -441,7 +441,11 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 		CK(cudaEventRecord(m->ev[7], m->stream));
 		m->ev7_valid = true;
 	}
-	k_scatter<<<(uint32_t)m->sm_count * 8, kChunk, 0, m->stream>>>(m->M, a);
+	{
+		// all CTAs resident; at most kScatterRegions regions per CTA
+		uint32_t sgrid = std::max<uint32_t>((uint32_t)m->sm_count * 8, (n_batches + kScatterRegions - 1) / kScatterRegions);
+		k_scatter<<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
+	}
 	++m->launches;
 }
 
@@ -603,18 +607,18 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 			m->h_ctr->n_upper = m->n_upper;
 			grow_pools(m, 4u, 0, 0, (uint32_t)std::min<uint64_t>(need, 0x7fffffffull));
 		}
-		k_reset_list<<<1, 1, 0, s>>>(M, 0);
-		k_reset_list<<<1, 1, 0, s>>>(M, 1);
+		// list_count[] is zero at this point (push_counters); level d reads list d&1 ? 0 : 1
 		k_upper_seed<<<(m->n_bricks + 255) / 256, 256, 0, s>>>(M, m->n_bricks, m->d_list[0], M.up_cap);
-		int which = 0;
-		for (uint32_t d = 5; d <= M.g.depth_levels; ++d) {
-			k_upper_level<<<std::max(1, m->sm_count / (d > 7 ? 16 : 1)), 256, 0, s>>>(
-			    M, d, m->d_list[which], m->d_list[which ^ 1], M.up_cap, which);
-			k_reset_list<<<1, 1, 0, s>>>(M, which);
-			which ^= 1;
-			m->launches += 2;
+		++m->launches;
+		const uint32_t L = M.g.depth_levels;
+		for (uint32_t d = 5; d <= std::min(6u, L); ++d) {
+			k_upper_level<<<m->sm_count, 256, 0, s>>>(M, d, m->d_list[(d & 1) ? 0 : 1], m->d_list[(d & 1) ? 1 : 0], M.up_cap);
+			++m->launches;
 		}
-		m->launches += 3;
+		if (L >= 7) {
+			k_upper_tail<<<1, 1024, 0, s>>>(M, 7, m->d_list[0], m->d_list[1], M.up_cap);
+			++m->launches;
+		}
 		CK(cudaGetLastError());
 	}
 	CK(cudaEventRecord(m->ev[6], s));
