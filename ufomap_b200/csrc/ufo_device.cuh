@@ -35,11 +35,13 @@ struct Agg {
 	uint32_t flags;
 };
 
-// Per-block record, one 64-byte line: the first sector is everything the ray walk and
-// the brick scan need (per-scan masks + depth-2 aggregate), the second the depth-1 maxima.
+// Per-block record, one 64-byte line: the first sector holds the per-scan hit mask and the
+// depth-2 aggregate, the second the depth-1 maxima.  The per-scan MISS masks live in their
+// own dense array (DeviceMap::miss_mask, 8 B per block) so that the ~26 M atomicOr of a
+// scan land in an L2-resident table instead of one DRAM sector per block.
 struct __align__(64) BlockRec {
-	unsigned long long miss;  // per-scan free-set bits, linear order x + 4y + 16z
-	unsigned long long hit;   // per-scan hit bits
+	unsigned long long pad0;
+	unsigned long long hit;   // per-scan hit bits, linear order x + 4y + 16z
 	float occ2;               // depth-2 aggregate: max log-odds of the 64 voxels
 	uint32_t flags2;          // bit0 contains_free, bit1 contains_unknown
 	uint32_t meta;            // bits 0..15: flags of the 8 octets, bits 16..23: octet initialised
@@ -96,7 +98,8 @@ struct DeviceMap {
 	// block pool
 	float* leaf;                    // [block][64]
 	uint32_t* leaf_rgb;             // colour maps: [block][64] packed r | g<<8 | b<<16
-	BlockRec* rec;                  // [block] masks + depth-1/2 aggregates
+	BlockRec* rec;                  // [block] hit mask + depth-1/2 aggregates
+	unsigned long long* miss_mask;  // [block] per-scan free-set bits, linear order x + 4y + 16z
 	unsigned long long* block_key;  // packed (kx>>2, ky>>2, kz>>2)
 	uint32_t* sum1_rgb;             // colour maps: [block][8]
 	uint32_t block_cap;

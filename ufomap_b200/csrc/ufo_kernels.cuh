@@ -353,7 +353,7 @@ __device__ __forceinline__ void flush_block(const DeviceMap& M, BrickCache& bc, 
 	if (bc.slot == kNone) return;
 	uint32_t slot = block_find_or_create(M, bc.slot, morton2(kx >> 2, ky >> 2, kz >> 2),
 	                                     pack_key(kx >> 2, ky >> 2, kz >> 2));
-	if (slot) atomicOr(&M.rec[slot].miss, bits);
+	if (slot) atomicOr(&M.miss_mask[slot], bits);
 }
 
 // ---------------------------------------------------------------------------
@@ -579,68 +579,123 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 // items are visited j-major: the walks run from the end point towards the sensor, so the
 // tails of all regions hold the records next to the sensor, which thousands of rays share
 // -- visiting them together turns most of the mask atomics into L2 hits.
-constexpr int kScatterRegions = 64;  // regions one CTA can own (grid is sized accordingly)
+constexpr int kScatterRegions = 16;  // regions one CTA can own (grid is sized accordingly)
+constexpr int kScatterSlices = 1024;  // slices one CTA can own; longer regions are cut by the host-side bound
+constexpr int kScatterUnroll = 4;     // records in flight per thread
 
 __global__ void __launch_bounds__(kChunk) k_scatter(DeviceMap M, ScanArgs a)
 {
 	__shared__ uint32_t r_cnt[kScatterRegions], r_base[kScatterRegions];
-	__shared__ uint32_t n_mine, max_cnt;
+	__shared__ uint2 slices[kScatterSlices];  // (first record, count), j-major over the CTA's regions
+	__shared__ uint32_t n_slices;
 	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;
 	const uint32_t n_regions = (a.n + 31) / 32;
 	// CTA b owns the regions of work rank b, b + G, b + 2G, ... (balanced like k_rays)
-	if (threadIdx.x == 0) {
-		n_mine = 0;
-		max_cnt = 0;
-	}
-	__syncthreads();
 	if (threadIdx.x < kScatterRegions) {
 		const uint32_t v = blockIdx.x + threadIdx.x * gridDim.x;
+		r_cnt[threadIdx.x] = 0;
+		r_base[threadIdx.x] = 0;
 		if (v < n_regions) {
 			const uint32_t r = a.order[v];
 			r_cnt[threadIdx.x] = a.seg_count[r];
 			r_base[threadIdx.x] = a.seg_base[r];
-			atomicAdd(&n_mine, 1u);
-			atomicMax(&max_cnt, r_cnt[threadIdx.x]);
 		}
 	}
 	__syncthreads();
-	const uint32_t mine = n_mine, slices = (max_cnt + kChunk - 1) / kChunk;
-	for (uint32_t j = 0; j < slices; ++j) {
-		for (uint32_t q = 0; q < mine; ++q) {
-			const uint32_t cnt = r_cnt[q];
-			if (j * kChunk >= cnt) continue;
+	uint32_t maxc = 0;
+	for (int q = 0; q < kScatterRegions; ++q) maxc = max(maxc, r_cnt[q]);
+	constexpr uint32_t kRound = kScatterSlices / kScatterRegions;  // slices per region and round
+	for (uint32_t j0 = 0; j0 * kChunk < maxc; j0 += kRound) {
+	__syncthreads();
+	if (threadIdx.x == 0) n_slices = 0;
+	__syncthreads();
+	// slice (j, q): the j-th kChunk-record slice counted from the END of region q; combos are
+	// enumerated j-major so the list is (nearly) ordered tail-first across the regions
+	for (uint32_t c = threadIdx.x; c < kRound * kScatterRegions; c += blockDim.x) {
+		const uint32_t j = j0 + c / kScatterRegions, q = c % kScatterRegions;
+		const uint32_t cnt = r_cnt[q];
+		if ((unsigned long long)j * kChunk < cnt) {
 			const uint32_t hi = cnt - j * kChunk;  // one past the slice's last record
 			const uint32_t lo = hi > kChunk ? hi - kChunk : 0u;
-			if (lo + threadIdx.x >= hi) continue;
-			const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&a.seg[r_base[q] + lo + threadIdx.x]);
+			slices[atomicAdd(&n_slices, 1u)] = make_uint2(r_base[q] + lo, hi - lo);
+		}
+	}
+	__syncthreads();
+	const uint32_t ns = n_slices;
+	for (uint32_t s0 = 0; s0 < ns; s0 += kScatterUnroll) {
+		unsigned long long acc[kScatterUnroll], bkey[kScatterUnroll], blk[kScatterUnroll];
+		uint32_t cidx[kScatterUnroll], hidx[kScatterUnroll], bslot[kScatterUnroll], child[kScatterUnroll];
+		ulonglong2 e0[kScatterUnroll], e1[kScatterUnroll];
+		bool act[kScatterUnroll];
+		// stage 1: records
+#pragma unroll
+		for (int u = 0; u < kScatterUnroll; ++u) {
+			act[u] = false;
+			ulonglong2 v = make_ulonglong2(0ull, 0ull);
+			if (s0 + u < ns) {
+				const uint2 d = slices[s0 + u];
+				act[u] = threadIdx.x < d.y;
+				if (act[u]) v = *reinterpret_cast<const ulonglong2*>(&a.seg[d.x + threadIdx.x]);
+			}
+			acc[u] = v.x;
 			uint32_t x, y, z;
 			unpack_key(v.y, x, y, z);
 			x = (x & M.g.key_mask) >> 2;  // block coordinates inside the tree
 			y = (y & M.g.key_mask) >> 2;
 			z = (z & M.g.key_mask) >> 2;
-			const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
-			const uint32_t cidx = morton2(x, y, z);
-			const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
-			const ulonglong2 e0 = ld_volatile_entry(&M.bh_tab[hidx]);
-			const ulonglong2 e1 = ld_volatile_entry(&M.bh_tab[hidx + 1]);
-			const bool hit0 = e0.x == bkey, hit1 = e1.x == bkey;
-			const ulonglong2 ent = hit0 ? e0 : e1;
-			const uint32_t hpos = hit0 ? hidx : hidx + 1;
-			uint32_t bslot = (uint32_t)ent.y;
-			if ((hit0 || hit1) && bslot != kPending && bslot != kFailed) {
-				if ((uint32_t)(ent.y >> 32) != M.scan_id) {
-					M.brick_stamp[bslot] = M.scan_id;
-					reinterpret_cast<uint32_t*>(&M.bh_tab[hpos].y)[1] = M.scan_id;
-				}
-			} else {
-				bslot = brick_find_or_create_from(M, bkey, hidx);
-				if (bslot == kNone) continue;
-				M.brick_stamp[bslot] = M.scan_id;
-			}
-			uint32_t slot = ld_volatile_u32(&M.brick_child[(size_t)bslot * 64 + cidx]);
-			if (slot == 0 || slot == kLock) slot = block_find_or_create(M, bslot, cidx, pack_key(x, y, z));
-			if (slot) atomicOr(&M.rec[slot].miss, v.x);
+			blk[u] = pack_key(x, y, z);
+			bkey[u] = pack_key(x >> 2, y >> 2, z >> 2);
+			cidx[u] = morton2(x, y, z);
+			hidx[u] = hash_u64(bkey[u]) & M.bh_mask & ~1u;
 		}
+		// stage 2: brick hash buckets
+#pragma unroll
+		for (int u = 0; u < kScatterUnroll; ++u) {
+			e0[u] = e1[u] = make_ulonglong2(kEmptyKey, 0ull);
+			if (act[u]) {
+				e0[u] = ld_volatile_entry(&M.bh_tab[hidx[u]]);
+				e1[u] = ld_volatile_entry(&M.bh_tab[hidx[u] + 1]);
+			}
+		}
+		// stage 3: block slots
+#pragma unroll
+		for (int u = 0; u < kScatterUnroll; ++u) {
+			bslot[u] = kNone;
+			child[u] = 0;
+			if (act[u]) {
+				const bool hit0 = e0[u].x == bkey[u], hit1 = e1[u].x == bkey[u];
+				const ulonglong2 ent = hit0 ? e0[u] : e1[u];
+				const uint32_t hpos = hit0 ? hidx[u] : hidx[u] + 1;
+				bslot[u] = (uint32_t)ent.y;
+				if ((hit0 || hit1) && bslot[u] != kPending && bslot[u] != kFailed) {
+					if ((uint32_t)(ent.y >> 32) != M.scan_id) {
+						M.brick_stamp[bslot[u]] = M.scan_id;
+						reinterpret_cast<uint32_t*>(&M.bh_tab[hpos].y)[1] = M.scan_id;
+					}
+				} else {
+					bslot[u] = brick_find_or_create_from(M, bkey[u], hidx[u]);
+					if (bslot[u] != kNone) M.brick_stamp[bslot[u]] = M.scan_id;
+				}
+				if (bslot[u] != kNone) child[u] = ld_volatile_u32(&M.brick_child[(size_t)bslot[u] * 64 + cidx[u]]);
+			}
+		}
+		// stage 4: OR the masks.  Neighbouring records of a slice come from neighbouring rays
+		// at the same step, which near the sensor sit in the same block: lanes with equal
+		// block keys merge their masks first and one of them issues the atomic.
+#pragma unroll
+		for (int u = 0; u < kScatterUnroll; ++u) {
+			uint32_t slot = 0;
+			if (act[u] && bslot[u] != kNone) {
+				slot = child[u];
+				if (slot == 0 || slot == kLock) slot = block_find_or_create(M, bslot[u], cidx[u], blk[u]);
+			}
+			const uint32_t peers = __match_any_sync(0xffffffffu, slot);
+			const uint32_t lo = __reduce_or_sync(peers, (uint32_t)acc[u]);
+			const uint32_t hi = __reduce_or_sync(peers, (uint32_t)(acc[u] >> 32));
+			if (slot && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1))
+				atomicOr(&M.miss_mask[slot], ((unsigned long long)hi << 32) | lo);
+		}
+	}
 	}
 }
 
@@ -711,24 +766,31 @@ __device__ __forceinline__ uint32_t rms_rgb(const uint32_t* c, int n)
 }
 
 // One warp per touched brick.
-//  phase A  lane l reads the block slots of children l and l+32 and the first sector of
-//           their records (masks + depth-2 aggregate); touched children are compacted
-//           into a shared-memory work list with a ballot.
-//  phase B  eight-lane groups: lane%8 owns one octet (8 voxels = one 32 B sector) of a
-//           block; each group works on two blocks per iteration so that four 16-byte leaf
-//           loads per lane are in flight.  Only touched octets are read and written.
-//  phase C  depth-3 / depth-4 aggregates of the brick from the 64 depth-2 aggregates
-//           (fresh ones from phase B, the rest already loaded in phase A).
-constexpr int kUpdWarps = 8;
+//  phase A  lane l reads the block slots of children l and l+32, their miss masks (dense,
+//           L2-resident after k_scatter) and the first sector of their records (hit mask +
+//           depth-2 aggregate); touched children are compacted into a shared-memory work
+//           list with a ballot, and their touched OCTETS into a second list.
+//  phase B  one lane per touched octet (8 voxels = one 32 B sector): only touched sectors
+//           are read and written, lanes are fully used, and the loads of the next two
+//           octets are issued before the current one is computed.
+//  phase B2 one lane per touched block: depth-2 aggregate from its 8 octets (fresh ones
+//           from shared memory, the rest from the record), new record header, masks cleared.
+//  phase C  depth-3 / depth-4 aggregates of the brick from the 64 depth-2 aggregates.
+constexpr int kUpdWarps = 4;
 
-struct WorkItem {
-	unsigned long long miss, hit;
-	uint32_t slot, meta, child, pad;
+// Work list of one warp (structure of arrays: conflict-free shared-memory access)
+struct WorkList {
+	unsigned long long miss[64], hit[64];
+	uint32_t slot[64], meta[64];
+	uint8_t child[64], touched[64];
 };
+// per-(octet, item) scratch, octet-major with a stride of 65 so that neither the
+// per-octet writes of phase B nor the per-item reads of phase B2 conflict
+constexpr int kOctStride = 65;
 
-__device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, uint32_t slot,
-                                             uint32_t oct, uint32_t m8, uint32_t h8, float4 a0,
-                                             float4 a1, float& omax, uint32_t& oflags)
+__device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, float* lp, uint32_t m8,
+                                             uint32_t h8, float4 a0, float4 a1, float& omax,
+                                             uint32_t& oflags)
 {
 	float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 	omax = -3.402823466e+38f;
@@ -752,58 +814,70 @@ __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, uin
 		unk = unk || (v[j] >= M.free_ceil && v[j] <= M.occ_floor);
 	}
 	// contains_free = any voxel below the free threshold, contains_unknown = any in between
-	oflags = 0x100u | (omin < M.free_ceil ? 1u : 0u) | (unk ? 2u : 0u);
-	float4* lp = reinterpret_cast<float4*>(M.leaf + (size_t)slot * 64 + 8 * oct);
-	lp[0] = make_float4(v[0], v[1], v[2], v[3]);
-	lp[1] = make_float4(v[4], v[5], v[6], v[7]);
+	oflags = (omin < M.free_ceil ? 1u : 0u) | (unk ? 2u : 0u);
+	reinterpret_cast<float4*>(lp)[0] = make_float4(v[0], v[1], v[2], v[3]);
+	reinterpret_cast<float4*>(lp)[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
 struct OctetLoad {
 	float4 a0, a1;
-	float s1;
-	uint32_t slot, meta, child, m8, h8;
+	float* lp;
+	uint32_t m8, h8, item, oct;
 	bool act;
 };
 
-// issues the loads one lane needs for octet `oct` of work item e
-__device__ __forceinline__ OctetLoad load_octet(const DeviceMap& M, const WorkItem* wl, int e, int n_work,
-                                                uint32_t oct)
+// issues the two 16-byte leaf loads of octet-list entry e
+__device__ __forceinline__ OctetLoad load_octet(const DeviceMap& M, const WorkList& wl, const uint16_t* ol,
+                                                int e, int n_oct)
 {
 	OctetLoad L;
-	L.act = e < n_work;
+	L.act = e < n_oct;
 	L.a0 = L.a1 = make_float4(0.f, 0.f, 0.f, 0.f);
-	L.s1 = 0.0f;
-	L.slot = L.meta = L.child = L.m8 = L.h8 = 0;
+	L.lp = nullptr;
+	L.m8 = L.h8 = L.item = L.oct = 0;
 	if (L.act) {
-		const WorkItem w = wl[e];
-		L.slot = w.slot;
-		L.meta = w.meta;
-		L.child = w.child;
-		L.m8 = octet_bits8(w.miss, oct);
-		L.h8 = octet_bits8(w.hit, oct);
-		if (L.m8 | L.h8) {
-			const float4* lp = reinterpret_cast<const float4*>(M.leaf + (size_t)w.slot * 64 + 8 * oct);
-			L.a0 = lp[0];
-			L.a1 = lp[1];
-		} else if ((w.meta >> (16 + oct)) & 1u) {
-			L.s1 = M.rec[w.slot].sum1[oct];
-		}
+		const uint32_t code = ol[e];
+		L.item = code >> 3;
+		L.oct = code & 7u;
+		L.m8 = octet_bits8(wl.miss[L.item], L.oct);
+		L.h8 = octet_bits8(wl.hit[L.item], L.oct);
+		L.lp = M.leaf + (size_t)wl.slot[L.item] * 64 + 8 * L.oct;
+		const float4* p = reinterpret_cast<const float4*>(L.lp);
+		L.a0 = p[0];
+		L.a1 = p[1];
 	}
 	return L;
 }
 
-__global__ void __launch_bounds__(kUpdWarps * 32, 4) k_update(DeviceMap M, float miss, uint32_t n_bricks)
+// bit o set <=> octet o of the block has a marked voxel (mask in linear order x + 4y + 16z)
+__device__ __forceinline__ uint32_t touched_octets(unsigned long long m)
 {
-	__shared__ WorkItem work[kUpdWarps][64];
+	uint32_t t = 0;
+#pragma unroll
+	for (uint32_t o = 0; o < 8; ++o) {
+		const uint32_t base = ((o & 1u) << 1) | ((o & 2u) << 2) | ((o & 4u) << 3);
+		t |= ((m >> base) & 0x330033ull) ? (1u << o) : 0u;
+	}
+	return t;
+}
+
+template <bool COLOR>
+__global__ void __launch_bounds__(kUpdWarps * 32, 8) k_update(DeviceMap M, float miss, uint32_t n_bricks)
+{
+	__shared__ WorkList work[kUpdWarps];
 	__shared__ Agg agg[kUpdWarps][64];
-	__shared__ uint32_t aggrgb[kUpdWarps][64];
+	__shared__ uint16_t octs[kUpdWarps][512];
+	__shared__ uint8_t oflgs[kUpdWarps][8 * kOctStride];  // flags of a touched octet
+	__shared__ float omaxs[kUpdWarps][8 * kOctStride];    // max of a touched octet
+	__shared__ uint32_t orgbs[COLOR ? kUpdWarps : 1][COLOR ? 8 * kOctStride : 1];
+	__shared__ uint32_t aggrgb[COLOR ? kUpdWarps : 1][COLOR ? 64 : 1];
 	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-	const uint32_t grp = lane >> 3, oct = lane & 7;
 	constexpr uint32_t FULL = 0xffffffffu;
 	unsigned int st_vox = 0, st_hit = 0, st_oct = 0, st_blk = 0, st_brk = 0, st_d3 = 0;
-	WorkItem* wl = work[wid];
+	WorkList& wl = work[wid];
+	uint16_t* ol = octs[wid];
 
 	for (uint32_t brick = warp; brick < n_bricks; brick += n_warps) {
 		if (M.brick_stamp[brick] != M.scan_id) continue;
@@ -812,95 +886,126 @@ __global__ void __launch_bounds__(kUpdWarps * 32, 4) k_update(DeviceMap M, float
 		uint32_t slot[2];
 		slot[0] = M.brick_child[(size_t)brick * 64 + lane];
 		slot[1] = M.brick_child[(size_t)brick * 64 + 32 + lane];
-		ulonglong2 m01[2];
+		unsigned long long mm[2], hm[2];
 		uint4 hd[2];
 #pragma unroll
 		for (int r = 0; r < 2; ++r) {
-			m01[r] = make_ulonglong2(0ull, 0ull);
+			mm[r] = hm[r] = 0ull;
 			hd[r] = make_uint4(0u, M.default_flags, 0u, 0u);
 			if (slot[r]) {
 				const BlockRec* rp = &M.rec[slot[r]];
-				m01[r] = *reinterpret_cast<const ulonglong2*>(rp);
+				mm[r] = M.miss_mask[slot[r]];
+				hm[r] = rp->hit;
 				hd[r] = *reinterpret_cast<const uint4*>(&rp->occ2);
 			}
 		}
-		int n_work = 0;
+		int n_work = 0, n_oct = 0;
 #pragma unroll
 		for (int r = 0; r < 2; ++r) {
-			const bool touched = (m01[r].x | m01[r].y) != 0ull;
+			const bool touched = (mm[r] | hm[r]) != 0ull;
 			const uint32_t ballot = __ballot_sync(FULL, touched);
 			if (lane < 4) st_d3 += ((ballot >> (8 * lane)) & 0xffu) ? 1u : 0u;
+			// octet list: inclusive warp scan of the per-item octet counts
+			const uint32_t t8 = touched ? touched_octets(mm[r] | hm[r]) : 0u;
+			uint32_t cnt = __popc(t8), incl = cnt;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				uint32_t up = __shfl_up_sync(FULL, incl, o);
+				if ((int)lane >= o) incl += up;
+			}
+			const uint32_t first = n_oct + incl - cnt;
 			if (touched) {
-				WorkItem w;
-				w.miss = m01[r].x;
-				w.hit = m01[r].y;
-				w.slot = slot[r];
-				w.meta = hd[r].z;
-				w.child = r * 32 + lane;
-				w.pad = 0;
-				wl[n_work + __popc(ballot & ((1u << lane) - 1u))] = w;
+				const int wi = n_work + __popc(ballot & ((1u << lane) - 1u));
+				wl.miss[wi] = mm[r];
+				wl.hit[wi] = hm[r];
+				wl.slot[wi] = slot[r];
+				wl.meta[wi] = hd[r].z;
+				wl.child[wi] = (uint8_t)(r * 32 + lane);
+				wl.touched[wi] = (uint8_t)t8;
+				uint32_t pos = first;
+				for (uint32_t o = 0; o < 8; ++o)
+					if ((t8 >> o) & 1u) ol[pos++] = (uint16_t)((wi << 3) | o);
 			}
 			n_work += __popc(ballot);
+			n_oct += __shfl_sync(FULL, incl, 31);
 			agg[wid][r * 32 + lane] = {__uint_as_float(hd[r].x), hd[r].y};
-			if (M.color) aggrgb[wid][r * 32 + lane] = hd[r].w;
+			if (COLOR) aggrgb[wid][r * 32 + lane] = hd[r].w;
 		}
 		__syncwarp();
-		// ---- phase B: four blocks per iteration (group g: item it*4+g), software-pipelined:
-		// the loads of iteration it+1 are issued before iteration it is computed
-		OctetLoad cur = load_octet(M, wl, 0 + (int)grp, n_work, oct);
-		for (int it = 0; it * 4 < n_work; ++it) {
-			OctetLoad nxt = load_octet(M, wl, (it + 1) * 4 + (int)grp, n_work, oct);
-			float omax = 0.0f;
-			uint32_t oflags = M.default_flags;  // bit8: touched by this scan
-			uint32_t orgb = 0;
+		// ---- phase B: one lane per touched octet, loads two entries ahead
+		OctetLoad cur = load_octet(M, wl, ol, (int)lane, n_oct);
+		OctetLoad nx1 = load_octet(M, wl, ol, 32 + (int)lane, n_oct);
+		for (int e0 = 0; e0 < n_oct; e0 += 32) {
+			OctetLoad nx2 = load_octet(M, wl, ol, e0 + 64 + (int)lane, n_oct);
 			if (cur.act) {
-				if (cur.m8 | cur.h8) {
-					update_octet(M, miss, cur.slot, oct, cur.m8, cur.h8, cur.a0, cur.a1, omax, oflags);
-					st_vox += __popc(cur.m8 | cur.h8);
-					st_hit += __popc(cur.h8);
-					++st_oct;
-					M.rec[cur.slot].sum1[oct] = omax;
-					if (M.color) {
-						const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + (size_t)cur.slot * 64 + 8 * oct);
-						uint4 c0 = cp[0], c1 = cp[1];
-						uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-						orgb = rms_rgb(cc, 8);
-						M.sum1_rgb[(size_t)cur.slot * 8 + oct] = orgb;
-					}
-				} else if ((cur.meta >> (16 + oct)) & 1u) {
-					omax = cur.s1;
-					oflags = (cur.meta >> (2 * oct)) & 3u;
-					if (M.color) orgb = M.sum1_rgb[(size_t)cur.slot * 8 + oct];
+				float omax;
+				uint32_t ofl;
+				update_octet(M, miss, cur.lp, cur.m8, cur.h8, cur.a0, cur.a1, omax, ofl);
+				st_vox += __popc(cur.m8 | cur.h8);
+				st_hit += __popc(cur.h8);
+				++st_oct;
+				omaxs[wid][cur.oct * kOctStride + cur.item] = omax;
+				oflgs[wid][cur.oct * kOctStride + cur.item] = (uint8_t)ofl;
+				if (COLOR) {
+					// depth-1 colour of the octet (getAverageChildColor, occupancy_map_color.cpp:177-194)
+					const size_t li = (size_t)wl.slot[cur.item] * 64 + 8 * cur.oct;
+					const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + li);
+					uint4 c0 = cp[0], c1 = cp[1];
+					uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+					const uint32_t orgb = rms_rgb(cc, 8);
+					M.sum1_rgb[li >> 3] = orgb;
+					orgbs[wid][cur.oct * kOctStride + cur.item] = orgb;
 				}
 			}
-			// depth-2 aggregate over the 8 octets of the block (8-lane groups)
-			float bmax = omax;
-			uint32_t bfl = oflags & 3u;
-			uint32_t newmeta = ((oflags & 3u) << (2 * oct)) | (((oflags >> 8) & 1u) << (16 + oct));
+			cur = nx1;
+			nx1 = nx2;
+		}
+		__syncwarp();
+		// ---- phase B2: one lane per touched block
+		for (int wi = (int)lane; wi < n_work; wi += 32) {
+			const uint32_t w_slot = wl.slot[wi], w_meta = wl.meta[wi];
+			const uint32_t t8 = wl.touched[wi], init8 = (w_meta >> 16) & 0xffu;
+			BlockRec* rp = &M.rec[w_slot];
+			float s1[8];
 #pragma unroll
-			for (int o = 1; o < 8; o <<= 1) {
-				bmax = fmaxf(bmax, __shfl_xor_sync(FULL, bmax, o));
-				bfl |= __shfl_xor_sync(FULL, bfl, o);
-				newmeta |= __shfl_xor_sync(FULL, newmeta, o);
+			for (int o = 0; o < 8; ++o) {
+				s1[o] = 0.0f;
+				if (!((t8 >> o) & 1u) && ((init8 >> o) & 1u)) s1[o] = rp->sum1[o];
 			}
-			uint32_t brgb = 0;
-			if (M.color) {
-				uint32_t oc[8];
+			float bmax = -3.402823466e+38f;
+			uint32_t bfl = 0, oflags16 = 0, brgb = 0;
+			uint32_t oc[8];
 #pragma unroll
-				for (int j = 0; j < 8; ++j) oc[j] = __shfl_sync(FULL, orgb, (lane & 24) + j);
-				brgb = rms_rgb(oc, 8);
+			for (int o = 0; o < 8; ++o) {
+				uint32_t f;
+				float v;
+				oc[o] = 0;
+				if ((t8 >> o) & 1u) {
+					v = omaxs[wid][o * kOctStride + wi];
+					f = oflgs[wid][o * kOctStride + wi];
+					rp->sum1[o] = v;
+					if (COLOR) oc[o] = orgbs[wid][o * kOctStride + wi];
+				} else if ((init8 >> o) & 1u) {
+					v = s1[o];
+					f = (w_meta >> (2 * o)) & 3u;
+					if (COLOR) oc[o] = M.sum1_rgb[(size_t)w_slot * 8 + o];
+				} else {
+					v = 0.0f;
+					f = M.default_flags;
+				}
+				bmax = fmaxf(bmax, v);
+				bfl |= f;
+				oflags16 |= f << (2 * o);
 			}
-			if (cur.act && oct == 0) {
-				// new first sector of the record: masks cleared for the next scan
-				BlockRec* rp = &M.rec[cur.slot];
-				const uint32_t meta = (newmeta & 0xffffffu) | (cur.meta & 0xff0000u);
-				*reinterpret_cast<ulonglong2*>(rp) = make_ulonglong2(0ull, 0ull);
-				*reinterpret_cast<uint4*>(&rp->occ2) = make_uint4(__float_as_uint(bmax), bfl, meta, brgb);
-				agg[wid][cur.child] = {bmax, bfl};
-				if (M.color) aggrgb[wid][cur.child] = brgb;
-				++st_blk;
-			}
-			cur = nxt;
+			if (COLOR) brgb = rms_rgb(oc, 8);
+			const uint32_t meta = oflags16 | ((init8 | t8) << 16);
+			// new first sector of the record; both per-scan masks cleared for the next scan
+			*reinterpret_cast<ulonglong2*>(rp) = make_ulonglong2(0ull, 0ull);
+			*reinterpret_cast<uint4*>(&rp->occ2) = make_uint4(__float_as_uint(bmax), bfl, meta, brgb);
+			M.miss_mask[w_slot] = 0ull;
+			agg[wid][wl.child[wi]] = {bmax, bfl};
+			if (COLOR) aggrgb[wid][wl.child[wi]] = brgb;
+			++st_blk;
 		}
 		__syncwarp();
 		// ---- phase C: lane owns children 2*lane, 2*lane+1 (both under depth-3 node lane/4)
@@ -912,13 +1017,6 @@ __global__ void __launch_bounds__(kUpdWarps * 32, 4) k_update(DeviceMap M, float
 			m3 = fmaxf(m3, __shfl_xor_sync(FULL, m3, o));
 			f3 |= __shfl_xor_sync(FULL, f3, o);
 		}
-		uint32_t rgb3 = 0;
-		if (M.color) {
-			uint32_t cc[8];
-#pragma unroll
-			for (int j = 0; j < 8; ++j) cc[j] = aggrgb[wid][8 * (lane >> 2) + j];
-			rgb3 = rms_rgb(cc, 8);
-		}
 		float m4 = m3;
 		uint32_t f4 = f3;
 #pragma unroll
@@ -926,20 +1024,18 @@ __global__ void __launch_bounds__(kUpdWarps * 32, 4) k_update(DeviceMap M, float
 			m4 = fmaxf(m4, __shfl_xor_sync(FULL, m4, o));
 			f4 |= __shfl_xor_sync(FULL, f4, o);
 		}
-		uint32_t rgb4 = 0;
-		if (M.color) {
+		if ((lane & 3) == 0) M.brick_sum3[(size_t)brick * 8 + (lane >> 2)] = {m3, f3};
+		if (lane == 0) M.brick_sum4[brick] = {m4, f4};
+		if (COLOR) {
 			uint32_t cc[8];
 #pragma unroll
+			for (int j = 0; j < 8; ++j) cc[j] = aggrgb[wid][8 * (lane >> 2) + j];
+			const uint32_t rgb3 = rms_rgb(cc, 8);
+#pragma unroll
 			for (int j = 0; j < 8; ++j) cc[j] = __shfl_sync(FULL, rgb3, 4 * j);
-			rgb4 = rms_rgb(cc, 8);
-		}
-		if ((lane & 3) == 0) {
-			M.brick_sum3[(size_t)brick * 8 + (lane >> 2)] = {m3, f3};
-			if (M.color) M.brick_rgb3[(size_t)brick * 8 + (lane >> 2)] = rgb3;
-		}
-		if (lane == 0) {
-			M.brick_sum4[brick] = {m4, f4};
-			if (M.color) M.brick_rgb4[brick] = rgb4;
+			const uint32_t rgb4 = rms_rgb(cc, 8);
+			if ((lane & 3) == 0) M.brick_rgb3[(size_t)brick * 8 + (lane >> 2)] = rgb3;
+			if (lane == 0) M.brick_rgb4[brick] = rgb4;
 		}
 		__syncwarp();
 	}

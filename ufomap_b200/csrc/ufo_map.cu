@@ -179,6 +179,7 @@ void alloc_pools(Map* m, uint32_t block_cap, uint32_t brick_cap, uint32_t up_cap
 	dev_alloc(M.brick_sum4, brick_cap, 0, s, tot);
 	dev_alloc(M.leaf, (size_t)block_cap * 64, 0, s, tot);
 	dev_alloc(M.rec, block_cap, 0, s, tot);
+	dev_alloc(M.miss_mask, block_cap, 0, s, tot);
 	dev_alloc(M.block_key, block_cap, 0, s, tot);
 	dev_alloc(M.uh_keys, (size_t)M.uh_mask + 1, 0xff, s, tot);
 	dev_alloc(M.uh_vals, (size_t)M.uh_mask + 1, 0xff, s, tot);
@@ -201,7 +202,7 @@ void free_pools(Map* m)
 {
 	DeviceMap& M = m->M;
 	void* ptrs[] = {M.bh_tab,   M.brick_key, M.brick_child, M.brick_stamp, M.brick_sum3,
-	                M.brick_sum4, M.brick_rgb3, M.brick_rgb4, M.leaf,       M.leaf_rgb,    M.rec,
+	                M.brick_sum4, M.brick_rgb3, M.brick_rgb4, M.leaf,       M.leaf_rgb,    M.rec, M.miss_mask,
 	                M.block_key, M.sum1_rgb,
 	                M.uh_keys,   M.uh_vals,   M.up_key,      M.up_agg,      M.up_rgb,
 	                M.up_stamp,  M.ctr,       m->d_list[0], m->d_list[1], m->d_points,   m->d_ray_end,
@@ -247,6 +248,7 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_blocks, uint32_t want_b
 		uint32_t nc = (uint32_t)nc64;
 		dev_grow(M.leaf, (size_t)oc * 64, (size_t)nc * 64, 0, s, tot);
 		dev_grow(M.rec, oc, nc, 0, s, tot);
+		dev_grow(M.miss_mask, oc, nc, 0, s, tot);
 		dev_grow(M.block_key, oc, nc, 0, s, tot);
 		dev_grow(M.leaf_rgb, (size_t)oc * 64, (size_t)nc * 64, 0, s, tot);
 		dev_grow(M.sum1_rgb, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
@@ -442,8 +444,9 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 		m->ev7_valid = true;
 	}
 	{
-		// all CTAs resident; at most kScatterRegions regions per CTA
-		uint32_t sgrid = std::max<uint32_t>((uint32_t)m->sm_count * 8, (n_batches + kScatterRegions - 1) / kScatterRegions);
+		// at most kScatterRegions regions per CTA; enough CTAs to fill the machine
+		uint32_t sgrid = std::max<uint32_t>((uint32_t)m->sm_count * 6, (n_batches + kScatterRegions - 1) / kScatterRegions);
+		sgrid = std::min<uint32_t>(sgrid, std::max<uint32_t>(n_batches, 1u));
 		k_scatter<<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
 	}
 	++m->launches;
@@ -592,8 +595,9 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	if (m->profiling) CK(cudaEventRecord(m->ev[4], s));
 	// K3
 	if (m->n_bricks) {
-		uint32_t grid = std::min<uint32_t>((m->n_bricks + kUpdWarps - 1) / kUpdWarps, (uint32_t)m->sm_count * 16);
-		k_update<<<grid, kUpdWarps * 32, 0, s>>>(M, a.miss, m->n_bricks);
+		uint32_t grid = std::min<uint32_t>((m->n_bricks + kUpdWarps - 1) / kUpdWarps, (uint32_t)m->sm_count * 32);
+		if (M.color) k_update<true><<<grid, kUpdWarps * 32, 0, s>>>(M, a.miss, m->n_bricks);
+		else k_update<false><<<grid, kUpdWarps * 32, 0, s>>>(M, a.miss, m->n_bricks);
 		++m->launches;
 	}
 	if (m->profiling) CK(cudaEventRecord(m->ev[5], s));
@@ -1060,6 +1064,7 @@ int ufo_b200_clear(ufo_b200_map* m)
 		CK(cudaMemsetAsync(M.up_stamp, 0, (size_t)m->n_upper * 4, s));
 		CK(cudaMemsetAsync(M.leaf, 0, (size_t)m->n_blocks * 64 * 4, s));
 		CK(cudaMemsetAsync(M.rec, 0, (size_t)m->n_blocks * sizeof(BlockRec), s));
+		CK(cudaMemsetAsync(M.miss_mask, 0, (size_t)m->n_blocks * sizeof(unsigned long long), s));
 		if (M.color) CK(cudaMemsetAsync(M.leaf_rgb, 0, (size_t)m->n_blocks * 64 * 4, s));
 		m->n_blocks = 1;
 		m->n_bricks = 0;
