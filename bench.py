@@ -228,7 +228,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     def fresh_map():
-        m = capi.Map(RESOLUTION, device=local_rank, initial_blocks=20 << 20, initial_bricks=1 << 20)
+        m = capi.Map(RESOLUTION, device=local_rank, initial_bricks=1 << 19)
         m.set_stream(stream.cuda_stream)
         return m
 

@@ -17,11 +17,11 @@ ap.add_argument("--range", type=float, default=30.0)
 ap.add_argument("--scans", type=int, default=8)
 ap.add_argument("--shape", default="velodyne")
 ap.add_argument("--discrete", action="store_true")
-ap.add_argument("--blocks", type=int, default=20 << 20)
+ap.add_argument("--bricks", type=int, default=1 << 19)
 args = ap.parse_args()
 
 color = args.shape == "rgbd"
-m = capi.Map(args.res, color=color, initial_blocks=args.blocks, initial_bricks=1 << 20)
+m = capi.Map(args.res, color=color, initial_bricks=args.bricks)
 m.set_profiling(1)
 rows = []
 for k in range(args.scans):

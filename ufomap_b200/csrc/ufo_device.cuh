@@ -6,8 +6,11 @@
 //   block  = 4^3 voxels  (depth 2)   64 floats = 256 B, Morton order inside the block, so
 //                                    one 2^3 octet (depth-1 node) = 8 consecutive floats = one
 //                                    32 B sector; per-scan miss/hit bit masks are one u64 each
-//   brick  = 4^3 blocks  (depth 4)   hashed by packed (kx>>4, ky>>4, kz>>4); holds the 64
-//                                    block slots and the depth-3/4 aggregates
+//   brick  = 4^3 blocks  (depth 4)   hashed by packed (kx>>4, ky>>4, kz>>4).  A brick owns 64
+//                                    CONSECUTIVE block slots (slot = brick*64 + Morton child), so
+//                                    everything one warp of the update kernel touches is
+//                                    contiguous (16 KB of leaves, 512 B of masks, ...), there is
+//                                    no per-block allocation and no child-pointer indirection
 //   upper  = depth >= 5 nodes        hashed by (depth, key>>depth); aggregates only
 // This replaces the reference's pointer octree (octree_node.h:52-111,
 // occupancy_map_node.h:55-185) with flat SoA pools addressed by slot index.
@@ -26,7 +29,6 @@ constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint32_t kPending = 0xffffffffu;  // hash value not published yet
 constexpr uint32_t kFailed = 0xfffffffeu;   // allocation behind this key overflowed
 constexpr uint32_t kNone = 0xffffffffu;     // "no such brick / node"
-constexpr uint32_t kLock = 0xffffffffu;     // child pointer being allocated
 
 // aggregate of an inner node: max log-odds of the subtree + contains_* flags
 // (occupancy_map_base.h:1179-1224).  flags: bit0 contains_free, bit1 contains_unknown.
@@ -35,22 +37,8 @@ struct Agg {
 	uint32_t flags;
 };
 
-// Per-block record, one 64-byte line: the first sector holds the per-scan hit mask and the
-// depth-2 aggregate, the second the depth-1 maxima.  The per-scan MISS masks live in their
-// own dense array (DeviceMap::miss_mask, 8 B per block) so that the ~26 M atomicOr of a
-// scan land in an L2-resident table instead of one DRAM sector per block.
-struct __align__(64) BlockRec {
-	unsigned long long pad0;
-	unsigned long long hit;   // per-scan hit bits, linear order x + 4y + 16z
-	float occ2;               // depth-2 aggregate: max log-odds of the 64 voxels
-	uint32_t flags2;          // bit0 contains_free, bit1 contains_unknown
-	uint32_t meta;            // bits 0..15: flags of the 8 octets, bits 16..23: octet initialised
-	uint32_t rgb2;            // colour maps: depth-2 colour
-	float sum1[8];            // depth-1 aggregates: max log-odds per octet
-};
-
 struct Counters {
-	uint32_t n_blocks;   // next free block slot (slot 0 is the null block)
+	uint32_t n_blocks;   // blocks that ever received an update (statistics only)
 	uint32_t n_bricks;   // next free brick slot
 	uint32_t n_upper;    // next free upper-node slot
 	uint32_t overflow;   // bit0 blocks, bit1 bricks/brick hash, bit2 upper nodes, bit3 ray-record buffer, bit4 ray bound violated (bug)
@@ -88,21 +76,22 @@ struct DeviceMap {
 	uint32_t bh_mask;
 	// brick pool
 	unsigned long long* brick_key;
-	uint32_t* brick_child;  // [brick][64] block slots, 0 = none
 	uint32_t* brick_stamp;  // scan id of the last scan that touched the brick
 	Agg* brick_sum3;        // [brick][8]
 	Agg* brick_sum4;        // [brick]
 	uint32_t* brick_rgb3;   // colour maps: [brick][8] packed rgb of depth-3 nodes
 	uint32_t* brick_rgb4;
 	uint32_t brick_cap;
-	// block pool
-	float* leaf;                    // [block][64]
-	uint32_t* leaf_rgb;             // colour maps: [block][64] packed r | g<<8 | b<<16
-	BlockRec* rec;                  // [block] hit mask + depth-1/2 aggregates
-	unsigned long long* miss_mask;  // [block] per-scan free-set bits, linear order x + 4y + 16z
-	unsigned long long* block_key;  // packed (kx>>2, ky>>2, kz>>2)
-	uint32_t* sum1_rgb;             // colour maps: [block][8]
-	uint32_t block_cap;
+	// block arrays, index b = brick * 64 + Morton child index (brick-contiguous)
+	float* leaf;                    // [b][64] log-odds, Morton order inside the block
+	uint32_t* leaf_rgb;             // colour maps: [b][64] packed r | g<<8 | b<<16
+	unsigned long long* miss_mask;  // [b] per-scan free-set bits, linear order x + 4y + 16z
+	unsigned long long* hit_mask;   // [b] per-scan hit bits
+	Agg* agg2;                      // [b] depth-2 aggregate
+	uint32_t* meta;                 // [b] bits 0..15: flags of the 8 octets, bits 16..23: octet initialised
+	float* sum1;                    // [b][8] depth-1 maxima
+	uint32_t* rgb2;                 // colour maps: [b]
+	uint32_t* sum1_rgb;             // colour maps: [b][8]
 	// upper nodes
 	unsigned long long* uh_keys;
 	uint32_t* uh_vals;
@@ -225,31 +214,6 @@ __device__ __forceinline__ uint32_t brick_find_or_create_from(const DeviceMap& M
 __device__ __forceinline__ uint32_t brick_find_or_create(const DeviceMap& M, uint64_t key)
 {
 	return brick_find_or_create_from(M, key, hash_u64(key) & M.bh_mask & ~1u);
-}
-
-// block slot of child b (0..63) of a brick; 0 when the pool overflowed
-__device__ __forceinline__ uint32_t block_find_or_create(const DeviceMap& M, uint32_t brick,
-                                                         uint32_t b, uint64_t block_key)
-{
-	uint32_t* p = &M.brick_child[(size_t)brick * 64 + b];
-	uint32_t s = ld_volatile_u32(p);
-	if (s == 0) {
-		uint32_t prev = atomicCAS(p, 0u, kLock);
-		if (prev == 0) {
-			s = atomicAdd(&M.ctr->n_blocks, 1u);
-			if (s >= M.block_cap) {
-				atomicOr(&M.ctr->overflow, 1u);
-				atomicExch(p, 0u);
-				return 0;
-			}
-			M.block_key[s] = block_key;
-			atomicExch(p, s);
-			return s;
-		}
-		s = prev;
-	}
-	while (s == kLock) s = ld_volatile_u32(p);
-	return s;
 }
 
 __device__ __forceinline__ uint32_t upper_find(const DeviceMap& M, uint64_t key)

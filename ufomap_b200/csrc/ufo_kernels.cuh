@@ -130,10 +130,8 @@ __device__ __forceinline__ void mark_hit(const DeviceMap& M, Key3 k)
 	uint32_t brick = brick_find_or_create(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
 	if (brick == kNone) return;
 	M.brick_stamp[brick] = M.scan_id;
-	uint32_t slot = block_find_or_create(M, brick, morton2(k.x >> 2, k.y >> 2, k.z >> 2),
-	                                     pack_key(k.x >> 2, k.y >> 2, k.z >> 2));
-	if (!slot) return;
-	atomicOr(&M.rec[slot].hit, 1ull << linear2(k.x, k.y, k.z));
+	const size_t b = (size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2);
+	atomicOr(&M.hit_mask[b], 1ull << linear2(k.x, k.y, k.z));
 }
 
 // ---------------------------------------------------------------------------
@@ -290,17 +288,15 @@ __global__ void __launch_bounds__(256) k_hits(DeviceMap M, ScanArgs a)
 	uint32_t brick = brick_find_or_create(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
 	if (brick == kNone) return;
 	M.brick_stamp[brick] = M.scan_id;
-	uint32_t slot = block_find_or_create(M, brick, morton2(k.x >> 2, k.y >> 2, k.z >> 2),
-	                                     pack_key(k.x >> 2, k.y >> 2, k.z >> 2));
-	if (!slot) return;
+	const size_t slot = (size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2);
 	uint32_t v = morton2(k.x, k.y, k.z);
 	const unsigned long long hbit = 1ull << linear2(k.x, k.y, k.z);
-	unsigned long long old = atomicOr(&M.rec[slot].hit, hbit);
+	unsigned long long old = atomicOr(&M.hit_mask[slot], hbit);
 	if (old & hbit) return;  // re-run after a pool regrow: colour already blended
 	Vec3 p;
 	uint32_t upd;
 	load_point(a, i, p, upd);
-	size_t li = (size_t)slot * 64 + v;
+	size_t li = slot * 64 + v;
 	uint32_t cur = M.leaf_rgb[li];
 	if (cur == upd) return;
 	if (cur == 0) {
@@ -351,9 +347,7 @@ __device__ __forceinline__ void flush_block(const DeviceMap& M, BrickCache& bc, 
 		if (bc.slot != kNone) M.brick_stamp[bc.slot] = M.scan_id;
 	}
 	if (bc.slot == kNone) return;
-	uint32_t slot = block_find_or_create(M, bc.slot, morton2(kx >> 2, ky >> 2, kz >> 2),
-	                                     pack_key(kx >> 2, ky >> 2, kz >> 2));
-	if (slot) atomicOr(&M.miss_mask[slot], bits);
+	atomicOr(&M.miss_mask[(size_t)bc.slot * 64 + morton2(kx >> 2, ky >> 2, kz >> 2)], bits);
 }
 
 // ---------------------------------------------------------------------------
@@ -579,123 +573,43 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 // items are visited j-major: the walks run from the end point towards the sensor, so the
 // tails of all regions hold the records next to the sensor, which thousands of rays share
 // -- visiting them together turns most of the mask atomics into L2 hits.
-constexpr int kScatterRegions = 16;  // regions one CTA can own (grid is sized accordingly)
-constexpr int kScatterSlices = 1024;  // slices one CTA can own; longer regions are cut by the host-side bound
-constexpr int kScatterUnroll = 4;     // records in flight per thread
-
 __global__ void __launch_bounds__(kChunk) k_scatter(DeviceMap M, ScanArgs a)
 {
-	__shared__ uint32_t r_cnt[kScatterRegions], r_base[kScatterRegions];
-	__shared__ uint2 slices[kScatterSlices];  // (first record, count), j-major over the CTA's regions
-	__shared__ uint32_t n_slices;
 	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;
 	const uint32_t n_regions = (a.n + 31) / 32;
-	// CTA b owns the regions of work rank b, b + G, b + 2G, ... (balanced like k_rays)
-	if (threadIdx.x < kScatterRegions) {
-		const uint32_t v = blockIdx.x + threadIdx.x * gridDim.x;
-		r_cnt[threadIdx.x] = 0;
-		r_base[threadIdx.x] = 0;
-		if (v < n_regions) {
-			const uint32_t r = a.order[v];
-			r_cnt[threadIdx.x] = a.seg_count[r];
-			r_base[threadIdx.x] = a.seg_base[r];
-		}
-	}
-	__syncthreads();
-	uint32_t maxc = 0;
-	for (int q = 0; q < kScatterRegions; ++q) maxc = max(maxc, r_cnt[q]);
-	constexpr uint32_t kRound = kScatterSlices / kScatterRegions;  // slices per region and round
-	for (uint32_t j0 = 0; j0 * kChunk < maxc; j0 += kRound) {
-	__syncthreads();
-	if (threadIdx.x == 0) n_slices = 0;
-	__syncthreads();
-	// slice (j, q): the j-th kChunk-record slice counted from the END of region q; combos are
-	// enumerated j-major so the list is (nearly) ordered tail-first across the regions
-	for (uint32_t c = threadIdx.x; c < kRound * kScatterRegions; c += blockDim.x) {
-		const uint32_t j = j0 + c / kScatterRegions, q = c % kScatterRegions;
-		const uint32_t cnt = r_cnt[q];
-		if ((unsigned long long)j * kChunk < cnt) {
-			const uint32_t hi = cnt - j * kChunk;  // one past the slice's last record
-			const uint32_t lo = hi > kChunk ? hi - kChunk : 0u;
-			slices[atomicAdd(&n_slices, 1u)] = make_uint2(r_base[q] + lo, hi - lo);
-		}
-	}
-	__syncthreads();
-	const uint32_t ns = n_slices;
-	for (uint32_t s0 = 0; s0 < ns; s0 += kScatterUnroll) {
-		unsigned long long acc[kScatterUnroll], bkey[kScatterUnroll], blk[kScatterUnroll];
-		uint32_t cidx[kScatterUnroll], hidx[kScatterUnroll], bslot[kScatterUnroll], child[kScatterUnroll];
-		ulonglong2 e0[kScatterUnroll], e1[kScatterUnroll];
-		bool act[kScatterUnroll];
-		// stage 1: records
-#pragma unroll
-		for (int u = 0; u < kScatterUnroll; ++u) {
-			act[u] = false;
-			ulonglong2 v = make_ulonglong2(0ull, 0ull);
-			if (s0 + u < ns) {
-				const uint2 d = slices[s0 + u];
-				act[u] = threadIdx.x < d.y;
-				if (act[u]) v = *reinterpret_cast<const ulonglong2*>(&a.seg[d.x + threadIdx.x]);
+	const unsigned long long n_items = (unsigned long long)ld_volatile_u32(&M.ctr->n_chunks) * n_regions;
+	for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+		const uint32_t j = (uint32_t)(it / n_regions), r = (uint32_t)(it % n_regions);
+		const uint32_t cnt = a.seg_count[r];
+		if ((unsigned long long)j * kChunk >= cnt) continue;
+		const uint32_t hi = cnt - j * kChunk;  // one past the slice's last record
+		const uint32_t lo = hi > kChunk ? hi - kChunk : 0u;
+		if (lo + threadIdx.x >= hi) continue;
+		const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&a.seg[a.seg_base[r] + lo + threadIdx.x]);
+		uint32_t x, y, z;
+		unpack_key(v.y, x, y, z);
+		x = (x & M.g.key_mask) >> 2;  // block coordinates inside the tree
+		y = (y & M.g.key_mask) >> 2;
+		z = (z & M.g.key_mask) >> 2;
+		const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
+		const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
+		const ulonglong2 e0 = ld_volatile_entry(&M.bh_tab[hidx]);
+		const ulonglong2 e1 = ld_volatile_entry(&M.bh_tab[hidx + 1]);
+		const bool hit0 = e0.x == bkey, hit1 = e1.x == bkey;
+		const ulonglong2 ent = hit0 ? e0 : e1;
+		const uint32_t hpos = hit0 ? hidx : hidx + 1;
+		uint32_t brick = (uint32_t)ent.y;
+		if ((hit0 || hit1) && brick != kPending && brick != kFailed) {
+			if ((uint32_t)(ent.y >> 32) != M.scan_id) {
+				M.brick_stamp[brick] = M.scan_id;
+				reinterpret_cast<uint32_t*>(&M.bh_tab[hpos].y)[1] = M.scan_id;
 			}
-			acc[u] = v.x;
-			uint32_t x, y, z;
-			unpack_key(v.y, x, y, z);
-			x = (x & M.g.key_mask) >> 2;  // block coordinates inside the tree
-			y = (y & M.g.key_mask) >> 2;
-			z = (z & M.g.key_mask) >> 2;
-			blk[u] = pack_key(x, y, z);
-			bkey[u] = pack_key(x >> 2, y >> 2, z >> 2);
-			cidx[u] = morton2(x, y, z);
-			hidx[u] = hash_u64(bkey[u]) & M.bh_mask & ~1u;
+		} else {
+			brick = brick_find_or_create_from(M, bkey, hidx);
+			if (brick == kNone) continue;
+			M.brick_stamp[brick] = M.scan_id;
 		}
-		// stage 2: brick hash buckets
-#pragma unroll
-		for (int u = 0; u < kScatterUnroll; ++u) {
-			e0[u] = e1[u] = make_ulonglong2(kEmptyKey, 0ull);
-			if (act[u]) {
-				e0[u] = ld_volatile_entry(&M.bh_tab[hidx[u]]);
-				e1[u] = ld_volatile_entry(&M.bh_tab[hidx[u] + 1]);
-			}
-		}
-		// stage 3: block slots
-#pragma unroll
-		for (int u = 0; u < kScatterUnroll; ++u) {
-			bslot[u] = kNone;
-			child[u] = 0;
-			if (act[u]) {
-				const bool hit0 = e0[u].x == bkey[u], hit1 = e1[u].x == bkey[u];
-				const ulonglong2 ent = hit0 ? e0[u] : e1[u];
-				const uint32_t hpos = hit0 ? hidx[u] : hidx[u] + 1;
-				bslot[u] = (uint32_t)ent.y;
-				if ((hit0 || hit1) && bslot[u] != kPending && bslot[u] != kFailed) {
-					if ((uint32_t)(ent.y >> 32) != M.scan_id) {
-						M.brick_stamp[bslot[u]] = M.scan_id;
-						reinterpret_cast<uint32_t*>(&M.bh_tab[hpos].y)[1] = M.scan_id;
-					}
-				} else {
-					bslot[u] = brick_find_or_create_from(M, bkey[u], hidx[u]);
-					if (bslot[u] != kNone) M.brick_stamp[bslot[u]] = M.scan_id;
-				}
-				if (bslot[u] != kNone) child[u] = ld_volatile_u32(&M.brick_child[(size_t)bslot[u] * 64 + cidx[u]]);
-			}
-		}
-		// stage 4: OR the masks.  Neighbouring records of a slice come from neighbouring rays
-		// at the same step, which near the sensor sit in the same block: lanes with equal
-		// block keys merge their masks first and one of them issues the atomic.
-#pragma unroll
-		for (int u = 0; u < kScatterUnroll; ++u) {
-			uint32_t slot = 0;
-			if (act[u] && bslot[u] != kNone) {
-				slot = child[u];
-				if (slot == 0 || slot == kLock) slot = block_find_or_create(M, bslot[u], cidx[u], blk[u]);
-			}
-			const uint32_t peers = __match_any_sync(0xffffffffu, slot);
-			const uint32_t lo = __reduce_or_sync(peers, (uint32_t)acc[u]);
-			const uint32_t hi = __reduce_or_sync(peers, (uint32_t)(acc[u] >> 32));
-			if (slot && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1))
-				atomicOr(&M.miss_mask[slot], ((unsigned long long)hi << 32) | lo);
-		}
-	}
+		atomicOr(&M.miss_mask[(size_t)brick * 64 + morton2(x, y, z)], v.x);
 	}
 }
 
@@ -781,7 +695,7 @@ constexpr int kUpdWarps = 4;
 // Work list of one warp (structure of arrays: conflict-free shared-memory access)
 struct WorkList {
 	unsigned long long miss[64], hit[64];
-	uint32_t slot[64], meta[64];
+	uint32_t meta[64];
 	uint8_t child[64], touched[64];
 };
 // per-(octet, item) scratch, octet-major with a stride of 65 so that neither the
@@ -828,7 +742,7 @@ struct OctetLoad {
 
 // issues the two 16-byte leaf loads of octet-list entry e
 __device__ __forceinline__ OctetLoad load_octet(const DeviceMap& M, const WorkList& wl, const uint16_t* ol,
-                                                int e, int n_oct)
+                                                size_t brick64, int e, int n_oct)
 {
 	OctetLoad L;
 	L.act = e < n_oct;
@@ -841,7 +755,7 @@ __device__ __forceinline__ OctetLoad load_octet(const DeviceMap& M, const WorkLi
 		L.oct = code & 7u;
 		L.m8 = octet_bits8(wl.miss[L.item], L.oct);
 		L.h8 = octet_bits8(wl.hit[L.item], L.oct);
-		L.lp = M.leaf + (size_t)wl.slot[L.item] * 64 + 8 * L.oct;
+		L.lp = M.leaf + (brick64 + wl.child[L.item]) * 64 + 8 * L.oct;
 		const float4* p = reinterpret_cast<const float4*>(L.lp);
 		L.a0 = p[0];
 		L.a1 = p[1];
@@ -875,29 +789,27 @@ __global__ void __launch_bounds__(kUpdWarps * 32, 8) k_update(DeviceMap M, float
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
 	constexpr uint32_t FULL = 0xffffffffu;
-	unsigned int st_vox = 0, st_hit = 0, st_oct = 0, st_blk = 0, st_brk = 0, st_d3 = 0;
+	unsigned int st_vox = 0, st_hit = 0, st_oct = 0, st_blk = 0, st_brk = 0, st_d3 = 0, st_new = 0;
 	WorkList& wl = work[wid];
 	uint16_t* ol = octs[wid];
 
 	for (uint32_t brick = warp; brick < n_bricks; brick += n_warps) {
 		if (M.brick_stamp[brick] != M.scan_id) continue;
 		if (lane == 0) ++st_brk;
-		// ---- phase A
-		uint32_t slot[2];
-		slot[0] = M.brick_child[(size_t)brick * 64 + lane];
-		slot[1] = M.brick_child[(size_t)brick * 64 + 32 + lane];
+		// ---- phase A: everything per child is contiguous per brick -> coalesced loads
+		const size_t brick64 = (size_t)brick * 64;
 		unsigned long long mm[2], hm[2];
-		uint4 hd[2];
+		uint32_t mt[2];
+		Agg a2[2];
 #pragma unroll
 		for (int r = 0; r < 2; ++r) {
-			mm[r] = hm[r] = 0ull;
-			hd[r] = make_uint4(0u, M.default_flags, 0u, 0u);
-			if (slot[r]) {
-				const BlockRec* rp = &M.rec[slot[r]];
-				mm[r] = M.miss_mask[slot[r]];
-				hm[r] = rp->hit;
-				hd[r] = *reinterpret_cast<const uint4*>(&rp->occ2);
-			}
+			const size_t b = brick64 + r * 32 + lane;
+			mm[r] = M.miss_mask[b];
+			hm[r] = M.hit_mask[b];
+			mt[r] = M.meta[b];
+			a2[r] = M.agg2[b];
+			// a block nothing was ever written to is plain unknown space
+			if (!(mt[r] >> 16)) a2[r] = {0.0f, M.default_flags};
 		}
 		int n_work = 0, n_oct = 0;
 #pragma unroll
@@ -918,8 +830,7 @@ __global__ void __launch_bounds__(kUpdWarps * 32, 8) k_update(DeviceMap M, float
 				const int wi = n_work + __popc(ballot & ((1u << lane) - 1u));
 				wl.miss[wi] = mm[r];
 				wl.hit[wi] = hm[r];
-				wl.slot[wi] = slot[r];
-				wl.meta[wi] = hd[r].z;
+				wl.meta[wi] = mt[r];
 				wl.child[wi] = (uint8_t)(r * 32 + lane);
 				wl.touched[wi] = (uint8_t)t8;
 				uint32_t pos = first;
@@ -928,15 +839,15 @@ __global__ void __launch_bounds__(kUpdWarps * 32, 8) k_update(DeviceMap M, float
 			}
 			n_work += __popc(ballot);
 			n_oct += __shfl_sync(FULL, incl, 31);
-			agg[wid][r * 32 + lane] = {__uint_as_float(hd[r].x), hd[r].y};
-			if (COLOR) aggrgb[wid][r * 32 + lane] = hd[r].w;
+			agg[wid][r * 32 + lane] = a2[r];
+			if (COLOR) aggrgb[wid][r * 32 + lane] = (mt[r] >> 16) ? M.rgb2[brick64 + r * 32 + lane] : 0u;
 		}
 		__syncwarp();
 		// ---- phase B: one lane per touched octet, loads two entries ahead
-		OctetLoad cur = load_octet(M, wl, ol, (int)lane, n_oct);
-		OctetLoad nx1 = load_octet(M, wl, ol, 32 + (int)lane, n_oct);
+		OctetLoad cur = load_octet(M, wl, ol, brick64, (int)lane, n_oct);
+		OctetLoad nx1 = load_octet(M, wl, ol, brick64, 32 + (int)lane, n_oct);
 		for (int e0 = 0; e0 < n_oct; e0 += 32) {
-			OctetLoad nx2 = load_octet(M, wl, ol, e0 + 64 + (int)lane, n_oct);
+			OctetLoad nx2 = load_octet(M, wl, ol, brick64, e0 + 64 + (int)lane, n_oct);
 			if (cur.act) {
 				float omax;
 				uint32_t ofl;
@@ -948,7 +859,7 @@ __global__ void __launch_bounds__(kUpdWarps * 32, 8) k_update(DeviceMap M, float
 				oflgs[wid][cur.oct * kOctStride + cur.item] = (uint8_t)ofl;
 				if (COLOR) {
 					// depth-1 colour of the octet (getAverageChildColor, occupancy_map_color.cpp:177-194)
-					const size_t li = (size_t)wl.slot[cur.item] * 64 + 8 * cur.oct;
+					const size_t li = (brick64 + wl.child[cur.item]) * 64 + 8 * cur.oct;
 					const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + li);
 					uint4 c0 = cp[0], c1 = cp[1];
 					uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
@@ -963,14 +874,15 @@ __global__ void __launch_bounds__(kUpdWarps * 32, 8) k_update(DeviceMap M, float
 		__syncwarp();
 		// ---- phase B2: one lane per touched block
 		for (int wi = (int)lane; wi < n_work; wi += 32) {
-			const uint32_t w_slot = wl.slot[wi], w_meta = wl.meta[wi];
+			const size_t w_slot = brick64 + wl.child[wi];
+			const uint32_t w_meta = wl.meta[wi];
 			const uint32_t t8 = wl.touched[wi], init8 = (w_meta >> 16) & 0xffu;
-			BlockRec* rp = &M.rec[w_slot];
+			float* sp = M.sum1 + w_slot * 8;
 			float s1[8];
 #pragma unroll
 			for (int o = 0; o < 8; ++o) {
 				s1[o] = 0.0f;
-				if (!((t8 >> o) & 1u) && ((init8 >> o) & 1u)) s1[o] = rp->sum1[o];
+				if (!((t8 >> o) & 1u) && ((init8 >> o) & 1u)) s1[o] = sp[o];
 			}
 			float bmax = -3.402823466e+38f;
 			uint32_t bfl = 0, oflags16 = 0, brgb = 0;
@@ -983,12 +895,12 @@ __global__ void __launch_bounds__(kUpdWarps * 32, 8) k_update(DeviceMap M, float
 				if ((t8 >> o) & 1u) {
 					v = omaxs[wid][o * kOctStride + wi];
 					f = oflgs[wid][o * kOctStride + wi];
-					rp->sum1[o] = v;
+					sp[o] = v;
 					if (COLOR) oc[o] = orgbs[wid][o * kOctStride + wi];
 				} else if ((init8 >> o) & 1u) {
 					v = s1[o];
 					f = (w_meta >> (2 * o)) & 3u;
-					if (COLOR) oc[o] = M.sum1_rgb[(size_t)w_slot * 8 + o];
+					if (COLOR) oc[o] = M.sum1_rgb[w_slot * 8 + o];
 				} else {
 					v = 0.0f;
 					f = M.default_flags;
@@ -999,10 +911,13 @@ __global__ void __launch_bounds__(kUpdWarps * 32, 8) k_update(DeviceMap M, float
 			}
 			if (COLOR) brgb = rms_rgb(oc, 8);
 			const uint32_t meta = oflags16 | ((init8 | t8) << 16);
-			// new first sector of the record; both per-scan masks cleared for the next scan
-			*reinterpret_cast<ulonglong2*>(rp) = make_ulonglong2(0ull, 0ull);
-			*reinterpret_cast<uint4*>(&rp->occ2) = make_uint4(__float_as_uint(bmax), bfl, meta, brgb);
+			// new block aggregate; both per-scan masks cleared for the next scan
+			M.agg2[w_slot] = {bmax, bfl};
+			M.meta[w_slot] = meta;
+			if (COLOR) M.rgb2[w_slot] = brgb;
 			M.miss_mask[w_slot] = 0ull;
+			if (wl.hit[wi]) M.hit_mask[w_slot] = 0ull;
+			if (!init8) ++st_new;
 			agg[wid][wl.child[wi]] = {bmax, bfl};
 			if (COLOR) aggrgb[wid][wl.child[wi]] = brgb;
 			++st_blk;
@@ -1047,8 +962,10 @@ __global__ void __launch_bounds__(kUpdWarps * 32, 8) k_update(DeviceMap M, float
 		st_blk += __shfl_xor_sync(FULL, st_blk, o);
 		st_brk += __shfl_xor_sync(FULL, st_brk, o);
 		st_d3 += __shfl_xor_sync(FULL, st_d3, o);
+		st_new += __shfl_xor_sync(FULL, st_new, o);
 	}
 	if (lane == 0 && st_brk) {
+		if (st_new) atomicAdd(&M.ctr->n_blocks, st_new);
 		atomicAdd(&M.ctr->touched_voxels, (unsigned long long)st_vox);
 		atomicAdd(&M.ctr->hit_voxels, (unsigned long long)st_hit);
 		atomicAdd(&M.ctr->touched_octets, (unsigned long long)st_oct);
@@ -1205,19 +1122,20 @@ __global__ void __launch_bounds__(256) k_rebuild_upper_hash(DeviceMap M, uint32_
 	}
 }
 
-// value-field export: one thread per voxel of every block
-__global__ void __launch_bounds__(256) k_export(DeviceMap M, uint32_t n_blocks, unsigned long long* codes,
+// value-field export: one thread per voxel of every block of every brick
+__global__ void __launch_bounds__(256) k_export(DeviceMap M, uint32_t n_bricks, unsigned long long* codes,
                                                 float* occ, uint32_t* rgb, unsigned long long cap,
                                                 unsigned long long* count)
 {
 	size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t slot = (uint32_t)(t >> 6) + 1, v = (uint32_t)(t & 63);
+	const size_t blk = t >> 6;
+	const uint32_t v = (uint32_t)(t & 63);
 	bool emit = false;
 	float o = 0.0f;
 	uint32_t c = 0;
-	if (slot < n_blocks) {
-		o = M.leaf[(size_t)slot * 64 + v];
-		c = M.color ? M.leaf_rgb[(size_t)slot * 64 + v] : 0u;
+	if (blk < (size_t)n_bricks * 64 && (M.meta[blk] >> 16)) {
+		o = M.leaf[blk * 64 + v];
+		c = M.color ? M.leaf_rgb[blk * 64 + v] : 0u;
 		emit = (o != 0.0f) || (c != 0u);
 	}
 	uint32_t ballot = __ballot_sync(0xffffffffu, emit);
@@ -1230,11 +1148,14 @@ __global__ void __launch_bounds__(256) k_export(DeviceMap M, uint32_t n_blocks, 
 	unsigned long long idx = base + __popc(ballot & ((1u << lane) - 1u));
 	if (idx >= cap) return;
 	uint32_t bx, by, bz;
-	unpack_key(M.block_key[slot], bx, by, bz);
-	// v is the Morton index inside the block: de-interleave 2 bits per axis
+	unpack_key(M.brick_key[blk >> 6], bx, by, bz);
+	// child and voxel indices are Morton: de-interleave 2 bits per axis
+	const uint32_t ch = (uint32_t)(blk & 63);
+	uint32_t cx = (ch & 1u) | ((ch >> 2) & 2u), cy = ((ch >> 1) & 1u) | ((ch >> 3) & 2u),
+	         cz = ((ch >> 2) & 1u) | ((ch >> 4) & 2u);
 	uint32_t vx = (v & 1u) | ((v >> 2) & 2u), vy = ((v >> 1) & 1u) | ((v >> 3) & 2u),
 	         vz = ((v >> 2) & 1u) | ((v >> 4) & 2u);
-	codes[idx] = key_to_code({(bx << 2) | vx, (by << 2) | vy, (bz << 2) | vz});
+	codes[idx] = key_to_code({(bx << 4) | (cx << 2) | vx, (by << 4) | (cy << 2) | vy, (bz << 4) | (cz << 2) | vz});
 	occ[idx] = o;
 	if (rgb) rgb[idx] = c;
 }
@@ -1275,25 +1196,25 @@ __global__ void __launch_bounds__(256) k_query(DeviceMap M, const unsigned long 
 				f = M.brick_sum3[(size_t)brick * 8 + j].flags;
 				if (M.color) c = M.brick_rgb3[(size_t)brick * 8 + j];
 			} else {
-				uint32_t slot = M.brick_child[(size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2)];
-				if (slot && slot != kLock) {
+				const size_t slot = (size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2);
+				const uint32_t meta = M.meta[slot];
+				if (meta >> 16) {
 					if (d == 2) {
-						o = M.rec[slot].occ2;
-						f = M.rec[slot].flags2;
-						if (M.color) c = M.rec[slot].rgb2;
+						o = M.agg2[slot].occ;
+						f = M.agg2[slot].flags;
+						if (M.color) c = M.rgb2[slot];
 					} else if (d == 1) {
 						uint32_t j = ((k.x >> 1) & 1u) | (((k.y >> 1) & 1u) << 1) | (((k.z >> 1) & 1u) << 2);
-						uint32_t meta = M.rec[slot].meta;
 						if ((meta >> (16 + j)) & 1u) {
-							o = M.rec[slot].sum1[j];
+							o = M.sum1[slot * 8 + j];
 							f = (meta >> (2 * j)) & 3u;
-							if (M.color) c = M.sum1_rgb[(size_t)slot * 8 + j];
+							if (M.color) c = M.sum1_rgb[slot * 8 + j];
 						}
 					} else {
 						uint32_t v = morton2(k.x, k.y, k.z);
-						o = M.leaf[(size_t)slot * 64 + v];
+						o = M.leaf[slot * 64 + v];
 						f = leaf_flags(M, o);
-						if (M.color) c = M.leaf_rgb[(size_t)slot * 64 + v];
+						if (M.color) c = M.leaf_rgb[slot * 64 + v];
 					}
 				}
 			}

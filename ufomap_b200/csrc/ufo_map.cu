@@ -99,7 +99,7 @@ struct ufo_b200_map {
 	uint32_t *d_seg_base = nullptr, *d_seg_count = nullptr;
 	uint32_t* d_order = nullptr;
 	// bookkeeping
-	uint32_t n_blocks = 1, n_bricks = 0, n_upper = 0;  // host view after the last sync
+	uint32_t n_blocks = 0, n_bricks = 0, n_upper = 0;  // host view after the last sync
 	size_t device_bytes = 0;
 	int profiling = 0;
 	uint64_t launches = 0;
@@ -161,26 +161,27 @@ void reset_bbox(Map* m)
 	}
 }
 
-void alloc_pools(Map* m, uint32_t block_cap, uint32_t brick_cap, uint32_t up_cap)
+void alloc_pools(Map* m, uint32_t brick_cap, uint32_t up_cap)
 {
 	DeviceMap& M = m->M;
 	cudaStream_t s = m->stream;
 	size_t& tot = m->device_bytes;
-	M.block_cap = block_cap;
+	const size_t nb = (size_t)brick_cap * 64;  // block slots: 64 consecutive per brick
 	M.brick_cap = brick_cap;
 	M.up_cap = up_cap;
 	M.bh_mask = std::max(kMinHash, next_pow2(2ull * brick_cap)) - 1;
 	M.uh_mask = std::max(kMinHash, next_pow2(2ull * up_cap)) - 1;
 	dev_alloc(M.bh_tab, (size_t)M.bh_mask + 1, 0xff, s, tot);
 	dev_alloc(M.brick_key, brick_cap, 0, s, tot);
-	dev_alloc(M.brick_child, (size_t)brick_cap * 64, 0, s, tot);
 	dev_alloc(M.brick_stamp, brick_cap, 0, s, tot);
 	dev_alloc(M.brick_sum3, (size_t)brick_cap * 8, 0, s, tot);
 	dev_alloc(M.brick_sum4, brick_cap, 0, s, tot);
-	dev_alloc(M.leaf, (size_t)block_cap * 64, 0, s, tot);
-	dev_alloc(M.rec, block_cap, 0, s, tot);
-	dev_alloc(M.miss_mask, block_cap, 0, s, tot);
-	dev_alloc(M.block_key, block_cap, 0, s, tot);
+	dev_alloc(M.leaf, nb * 64, 0, s, tot);
+	dev_alloc(M.miss_mask, nb, 0, s, tot);
+	dev_alloc(M.hit_mask, nb, 0, s, tot);
+	dev_alloc(M.agg2, nb, 0, s, tot);
+	dev_alloc(M.meta, nb, 0, s, tot);
+	dev_alloc(M.sum1, nb * 8, 0, s, tot);
 	dev_alloc(M.uh_keys, (size_t)M.uh_mask + 1, 0xff, s, tot);
 	dev_alloc(M.uh_vals, (size_t)M.uh_mask + 1, 0xff, s, tot);
 	dev_alloc(M.up_key, up_cap, 0, s, tot);
@@ -191,8 +192,9 @@ void alloc_pools(Map* m, uint32_t block_cap, uint32_t brick_cap, uint32_t up_cap
 	if (M.color) {
 		dev_alloc(M.brick_rgb3, (size_t)brick_cap * 8, 0, s, tot);
 		dev_alloc(M.brick_rgb4, brick_cap, 0, s, tot);
-		dev_alloc(M.leaf_rgb, (size_t)block_cap * 64, 0, s, tot);
-		dev_alloc(M.sum1_rgb, (size_t)block_cap * 8, 0, s, tot);
+		dev_alloc(M.leaf_rgb, nb * 64, 0, s, tot);
+		dev_alloc(M.sum1_rgb, nb * 8, 0, s, tot);
+		dev_alloc(M.rgb2, nb, 0, s, tot);
 		dev_alloc(M.up_rgb, up_cap, 0, s, tot);
 	}
 	dev_alloc(M.ctr, 1, 0, s, tot);
@@ -201,12 +203,11 @@ void alloc_pools(Map* m, uint32_t block_cap, uint32_t brick_cap, uint32_t up_cap
 void free_pools(Map* m)
 {
 	DeviceMap& M = m->M;
-	void* ptrs[] = {M.bh_tab,   M.brick_key, M.brick_child, M.brick_stamp, M.brick_sum3,
-	                M.brick_sum4, M.brick_rgb3, M.brick_rgb4, M.leaf,       M.leaf_rgb,    M.rec, M.miss_mask,
-	                M.block_key, M.sum1_rgb,
-	                M.uh_keys,   M.uh_vals,   M.up_key,      M.up_agg,      M.up_rgb,
-	                M.up_stamp,  M.ctr,       m->d_list[0], m->d_list[1], m->d_points,   m->d_ray_end,
-	                m->d_hit_tab, m->d_tab_keys, m->d_tab_min, m->d_seg, m->d_seg_base, m->d_seg_count, m->d_order};
+	void* ptrs[] = {M.bh_tab, M.brick_key, M.brick_stamp, M.brick_sum3, M.brick_sum4, M.brick_rgb3, M.brick_rgb4,
+	                M.leaf, M.leaf_rgb, M.miss_mask, M.hit_mask, M.agg2, M.meta, M.sum1, M.rgb2, M.sum1_rgb,
+	                M.uh_keys, M.uh_vals, M.up_key, M.up_agg, M.up_rgb, M.up_stamp, M.ctr, m->d_list[0],
+	                m->d_list[1], m->d_points, m->d_ray_end, m->d_hit_tab, m->d_tab_keys, m->d_tab_min,
+	                m->d_seg, m->d_seg_base, m->d_seg_count, m->d_order};
 	for (void* p : ptrs)
 		if (p) cudaFree(p);
 }
@@ -241,24 +242,21 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_blocks, uint32_t want_b
 	cudaStream_t s = m->stream;
 	size_t& tot = m->device_bytes;
 	CK(cudaStreamSynchronize(s));
-	if (overflow & 1u) {
-		uint32_t oc = M.block_cap;
-		uint64_t nc64 = std::max<uint64_t>(2ull * oc, (uint64_t)want_blocks + want_blocks / 4);
-		if (nc64 > 0xfffffff0ull) throw std::bad_alloc();
-		uint32_t nc = (uint32_t)nc64;
-		dev_grow(M.leaf, (size_t)oc * 64, (size_t)nc * 64, 0, s, tot);
-		dev_grow(M.rec, oc, nc, 0, s, tot);
-		dev_grow(M.miss_mask, oc, nc, 0, s, tot);
-		dev_grow(M.block_key, oc, nc, 0, s, tot);
-		dev_grow(M.leaf_rgb, (size_t)oc * 64, (size_t)nc * 64, 0, s, tot);
-		dev_grow(M.sum1_rgb, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
-		M.block_cap = nc;
-	}
 	if (overflow & 2u) {
 		uint32_t oc = M.brick_cap;
 		uint32_t nc = (uint32_t)std::max<uint64_t>(2ull * oc, (uint64_t)want_bricks + want_bricks / 4);
+		if ((uint64_t)nc * 64 > 0xfffffff0ull) throw std::bad_alloc();
+		const size_t ob = (size_t)oc * 64, nb = (size_t)nc * 64;
+		dev_grow(M.leaf, ob * 64, nb * 64, 0, s, tot);
+		dev_grow(M.miss_mask, ob, nb, 0, s, tot);
+		dev_grow(M.hit_mask, ob, nb, 0, s, tot);
+		dev_grow(M.agg2, ob, nb, 0, s, tot);
+		dev_grow(M.meta, ob, nb, 0, s, tot);
+		dev_grow(M.sum1, ob * 8, nb * 8, 0, s, tot);
+		dev_grow(M.leaf_rgb, ob * 64, nb * 64, 0, s, tot);
+		dev_grow(M.sum1_rgb, ob * 8, nb * 8, 0, s, tot);
+		dev_grow(M.rgb2, ob, nb, 0, s, tot);
 		dev_grow(M.brick_key, oc, nc, 0, s, tot);
-		dev_grow(M.brick_child, (size_t)oc * 64, (size_t)nc * 64, 0, s, tot);
 		dev_grow(M.brick_stamp, oc, nc, 0, s, tot);
 		dev_grow(M.brick_sum3, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
 		dev_grow(M.brick_sum4, oc, nc, 0, s, tot);
@@ -272,8 +270,8 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_blocks, uint32_t want_b
 		tot -= old_tab * sizeof(ulonglong2);
 		M.bh_mask = new_tab - 1;
 		dev_alloc(M.bh_tab, new_tab, 0xff, s, tot);
-		uint32_t nb = std::min(m->h_ctr->n_bricks, oc);
-		if (nb) k_rebuild_brick_hash<<<(nb + 255) / 256, 256, 0, s>>>(M, nb);
+		uint32_t live = std::min(m->h_ctr->n_bricks, oc);
+		if (live) k_rebuild_brick_hash<<<(live + 255) / 256, 256, 0, s>>>(M, live);
 	}
 	if (overflow & 4u) {
 		uint32_t oc = M.up_cap;
@@ -362,10 +360,10 @@ void finish_stats(Map* m)
 	st.touched_d3 = c.touched_d3;
 	st.touched_bricks = c.touched_bricks;
 	st.upper_nodes = c.upper_nodes;
-	m->n_blocks = std::min(c.n_blocks, m->M.block_cap);
+	m->n_blocks = c.n_blocks;
 	m->n_bricks = std::min(c.n_bricks, m->M.brick_cap);
 	m->n_upper = std::min(c.n_upper, m->M.up_cap);
-	st.blocks_in_map = m->n_blocks - 1;
+	st.blocks_in_map = m->n_blocks;
 	st.bricks_in_map = m->n_bricks;
 	st.device_bytes = m->device_bytes;
 	if (c.n_rays || c.touched_voxels) {
@@ -444,9 +442,7 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 		m->ev7_valid = true;
 	}
 	{
-		// at most kScatterRegions regions per CTA; enough CTAs to fill the machine
-		uint32_t sgrid = std::max<uint32_t>((uint32_t)m->sm_count * 6, (n_batches + kScatterRegions - 1) / kScatterRegions);
-		sgrid = std::min<uint32_t>(sgrid, std::max<uint32_t>(n_batches, 1u));
+		uint32_t sgrid = (uint32_t)m->sm_count * 8;  // all CTAs resident, looping over the work items
 		k_scatter<<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
 	}
 	++m->launches;
@@ -570,8 +566,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 			m->set_error("internal error: a ray walk exceeded its record bound");
 			return UFO_B200_E_CUDA;
 		}
-		uint32_t wb = m->h_ctr->n_blocks, wk = m->h_ctr->n_bricks, wu = m->h_ctr->n_upper;
-		m->n_blocks = std::min(wb, M.block_cap);
+		uint32_t wb = 0, wk = m->h_ctr->n_bricks, wu = m->h_ctr->n_upper;
 		m->n_bricks = std::min(wk, M.brick_cap);
 		if (ov & 8u) {
 			unsigned long long want = m->h_ctr->seg_total + m->h_ctr->seg_total / 4 + 1024;
@@ -588,7 +583,6 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		}
 		push_counters(m);  // resets the per-scan counters; n_rays/bbox are recomputed by the re-run
 	}
-	m->n_blocks = m->h_ctr->n_blocks;
 	m->n_bricks = m->h_ctr->n_bricks;
 	m->stats.regrows = regrows;
 
@@ -723,13 +717,14 @@ int ufo_b200_create(const ufo_b200_params* p, ufo_b200_map** out)
 		m->cmin_log = to_logit(p->clamping_thres_min);
 		m->cmax_log = to_logit(p->clamping_thres_max);
 		refresh_model(m);
-		uint32_t blocks = (uint32_t)std::min<uint64_t>(p->initial_blocks ? p->initial_blocks : (1ull << 20), 0xfffffff0ull);
-		uint32_t bricks = (uint32_t)std::min<uint64_t>(p->initial_bricks ? p->initial_bricks : std::max<uint64_t>(blocks / 16, 4096), 0x7ffffff0ull);
-		blocks = std::max(blocks, 64u);
-		bricks = std::max(bricks, 16u);
+		// a brick owns 64 block slots; the block hint is honoured through its brick equivalent
+		// (a touched brick of a lidar scan holds ~32 touched blocks)
+		uint64_t bricks64 = p->initial_bricks ? p->initial_bricks
+		                                      : (p->initial_blocks ? p->initial_blocks / 32 : (1ull << 15));
+		uint32_t bricks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(bricks64, 16), 0x3ffffffull);
 		uint32_t upper = std::max(bricks / 2, 4096u);
-		alloc_pools(m, blocks, bricks, upper);
-		m->n_blocks = 1;
+		alloc_pools(m, bricks, upper);
+		m->n_blocks = 0;
 		m->n_bricks = 0;
 		m->n_upper = 0;
 		reset_bbox(m);
@@ -952,9 +947,9 @@ int ufo_b200_export_leaves(ufo_b200_map* m, uint64_t* codes, float* logodds, uin
 			CK(cudaMalloc(&d_occ, cap * 4));
 			if (rgb) CK(cudaMalloc(&d_rgb, cap * 4));
 		}
-		size_t threads = (size_t)(m->n_blocks > 1 ? m->n_blocks - 1 : 0) * 64;
+		size_t threads = (size_t)m->n_bricks * 64 * 64;
 		if (threads)
-			k_export<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>(m->M, m->n_blocks, d_codes, d_occ, d_rgb, fill ? cap : 0, d_count);
+			k_export<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>(m->M, m->n_bricks, d_codes, d_occ, d_rgb, fill ? cap : 0, d_count);
 		CK(cudaGetLastError());
 		unsigned long long cnt = 0;
 		CK(cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, s));
@@ -1059,14 +1054,16 @@ int ufo_b200_clear(ufo_b200_map* m)
 		CK(cudaMemsetAsync(M.bh_tab, 0xff, ((size_t)M.bh_mask + 1) * sizeof(ulonglong2), s));
 		CK(cudaMemsetAsync(M.uh_keys, 0xff, ((size_t)M.uh_mask + 1) * 8, s));
 		CK(cudaMemsetAsync(M.uh_vals, 0xff, ((size_t)M.uh_mask + 1) * 4, s));
-		CK(cudaMemsetAsync(M.brick_child, 0, (size_t)m->n_bricks * 64 * 4, s));
 		CK(cudaMemsetAsync(M.brick_stamp, 0, (size_t)m->n_bricks * 4, s));
 		CK(cudaMemsetAsync(M.up_stamp, 0, (size_t)m->n_upper * 4, s));
-		CK(cudaMemsetAsync(M.leaf, 0, (size_t)m->n_blocks * 64 * 4, s));
-		CK(cudaMemsetAsync(M.rec, 0, (size_t)m->n_blocks * sizeof(BlockRec), s));
-		CK(cudaMemsetAsync(M.miss_mask, 0, (size_t)m->n_blocks * sizeof(unsigned long long), s));
-		if (M.color) CK(cudaMemsetAsync(M.leaf_rgb, 0, (size_t)m->n_blocks * 64 * 4, s));
-		m->n_blocks = 1;
+		const size_t nb = (size_t)m->n_bricks * 64;
+		CK(cudaMemsetAsync(M.leaf, 0, nb * 64 * 4, s));
+		CK(cudaMemsetAsync(M.miss_mask, 0, nb * 8, s));
+		CK(cudaMemsetAsync(M.hit_mask, 0, nb * 8, s));
+		CK(cudaMemsetAsync(M.agg2, 0, nb * sizeof(Agg), s));
+		CK(cudaMemsetAsync(M.meta, 0, nb * 4, s));
+		if (M.color) CK(cudaMemsetAsync(M.leaf_rgb, 0, nb * 64 * 4, s));
+		m->n_blocks = 0;
 		m->n_bricks = 0;
 		m->n_upper = 0;
 		M.scan_id = 0;
