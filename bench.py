@@ -308,7 +308,7 @@ def main():
                        "l2": "per-scan working set (%.1f GB leaf data touched, map %.1f GB) exceeds the 126 MB L2; no flush"
                              % (last["touched_blocks"] * 256 / 1e9, dev_bytes / 1e9)},
             "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e / steps,
-                    "h2d_bytes_per_step": int(n_pts * 12), "d2h_bytes_per_step": 160},
+                    "h2d_bytes_per_step": int(n_pts * 12), "d2h_bytes_per_step": int(last["result_bytes"])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "kernel": "insert pipeline K1..K4 (SURVEY.md 8(d)); dominant kernels in `kernels_ms`",

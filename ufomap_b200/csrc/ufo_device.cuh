@@ -56,6 +56,9 @@ struct Counters {
 	unsigned long long touched_bricks;
 	unsigned long long upper_nodes;
 	unsigned long long bbox[6];  // order-preserving encoding of min xyz / max xyz of this scan
+	// k_update statistics spread over slots: [slot][0 voxels, 1 hit voxels, 2 octets, 3 blocks,
+	// 4 first-touched blocks, 5 bricks, 6 depth-3 nodes, 7 unused]
+	unsigned long long stat[64][8];
 };
 
 struct DeviceMap {

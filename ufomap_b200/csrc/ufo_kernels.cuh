@@ -679,28 +679,15 @@ __device__ __forceinline__ uint32_t rms_rgb(const uint32_t* c, int n)
 	return out;
 }
 
-// One warp per touched brick.
-//  phase A  lane l reads the block slots of children l and l+32, their miss masks (dense,
-//           L2-resident after k_scatter) and the first sector of their records (hit mask +
-//           depth-2 aggregate); touched children are compacted into a shared-memory work
-//           list with a ballot, and their touched OCTETS into a second list.
-//  phase B  one lane per touched octet (8 voxels = one 32 B sector): only touched sectors
-//           are read and written, lanes are fully used, and the loads of the next two
-//           octets are issued before the current one is computed.
-//  phase B2 one lane per touched block: depth-2 aggregate from its 8 octets (fresh ones
-//           from shared memory, the rest from the record), new record header, masks cleared.
-//  phase C  depth-3 / depth-4 aggregates of the brick from the 64 depth-2 aggregates.
-constexpr int kUpdWarps = 4;
-
-// Work list of one warp (structure of arrays: conflict-free shared-memory access)
-struct WorkList {
-	unsigned long long miss[64], hit[64];
-	uint32_t meta[64];
-	uint8_t child[64], touched[64];
-};
-// per-(octet, item) scratch, octet-major with a stride of 65 so that neither the
-// per-octet writes of phase B nor the per-item reads of phase B2 conflict
-constexpr int kOctStride = 65;
+// K3 is flat: one eight-lane group per (brick, child block) pair, lane%8 owns one octet
+// (8 voxels = one 32 B sector).  A group reads its block's two masks, and if the block was
+// marked, only the touched leaf sectors; it writes them back, the block's depth-1 maxima
+// (a full sector) and its depth-2 aggregate.  There is no cross-group dependency, so
+// millions of independent groups hide the DRAM latency; groups of unmarked blocks retire
+// after one coalesced mask read.  The brick-level aggregates follow in k_brick_agg.
+//   hit-then-miss float log-odds update   updateOccupancy, occupancy_map_base.h:1139-1145
+//   depth-1/2 aggregates per block, depth-3/4 per brick   updateNode, :1179-1224
+constexpr int kUpdThreads = 256;
 
 __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, float* lp, uint32_t m8,
                                              uint32_t h8, float4 a0, float4 a1, float& omax,
@@ -733,245 +720,153 @@ __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, flo
 	reinterpret_cast<float4*>(lp)[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
-struct OctetLoad {
-	float4 a0, a1;
-	float* lp;
-	uint32_t m8, h8, item, oct;
-	bool act;
-};
-
-// issues the two 16-byte leaf loads of octet-list entry e
-__device__ __forceinline__ OctetLoad load_octet(const DeviceMap& M, const WorkList& wl, const uint16_t* ol,
-                                                size_t brick64, int e, int n_oct)
-{
-	OctetLoad L;
-	L.act = e < n_oct;
-	L.a0 = L.a1 = make_float4(0.f, 0.f, 0.f, 0.f);
-	L.lp = nullptr;
-	L.m8 = L.h8 = L.item = L.oct = 0;
-	if (L.act) {
-		const uint32_t code = ol[e];
-		L.item = code >> 3;
-		L.oct = code & 7u;
-		L.m8 = octet_bits8(wl.miss[L.item], L.oct);
-		L.h8 = octet_bits8(wl.hit[L.item], L.oct);
-		L.lp = M.leaf + (brick64 + wl.child[L.item]) * 64 + 8 * L.oct;
-		const float4* p = reinterpret_cast<const float4*>(L.lp);
-		L.a0 = p[0];
-		L.a1 = p[1];
-	}
-	return L;
-}
-
-// bit o set <=> octet o of the block has a marked voxel (mask in linear order x + 4y + 16z)
-__device__ __forceinline__ uint32_t touched_octets(unsigned long long m)
-{
-	uint32_t t = 0;
-#pragma unroll
-	for (uint32_t o = 0; o < 8; ++o) {
-		const uint32_t base = ((o & 1u) << 1) | ((o & 2u) << 2) | ((o & 4u) << 3);
-		t |= ((m >> base) & 0x330033ull) ? (1u << o) : 0u;
-	}
-	return t;
-}
+constexpr int kStatSlots = 64;  // per-scan counters are spread over slots to avoid same-address atomics
 
 template <bool COLOR>
-__global__ void __launch_bounds__(kUpdWarps * 32, 8) k_update(DeviceMap M, float miss, uint32_t n_bricks)
+__global__ void __launch_bounds__(kUpdThreads, 8) k_update(DeviceMap M, float miss, uint32_t n_bricks)
 {
-	__shared__ WorkList work[kUpdWarps];
-	__shared__ Agg agg[kUpdWarps][64];
-	__shared__ uint16_t octs[kUpdWarps][512];
-	__shared__ uint8_t oflgs[kUpdWarps][8 * kOctStride];  // flags of a touched octet
-	__shared__ float omaxs[kUpdWarps][8 * kOctStride];    // max of a touched octet
-	__shared__ uint32_t orgbs[COLOR ? kUpdWarps : 1][COLOR ? 8 * kOctStride : 1];
-	__shared__ uint32_t aggrgb[COLOR ? kUpdWarps : 1][COLOR ? 64 : 1];
-	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-	constexpr uint32_t FULL = 0xffffffffu;
-	unsigned int st_vox = 0, st_hit = 0, st_oct = 0, st_blk = 0, st_brk = 0, st_d3 = 0, st_new = 0;
-	WorkList& wl = work[wid];
-	uint16_t* ol = octs[wid];
-
-	for (uint32_t brick = warp; brick < n_bricks; brick += n_warps) {
-		if (M.brick_stamp[brick] != M.scan_id) continue;
-		if (lane == 0) ++st_brk;
-		// ---- phase A: everything per child is contiguous per brick -> coalesced loads
-		const size_t brick64 = (size_t)brick * 64;
-		unsigned long long mm[2], hm[2];
-		uint32_t mt[2];
-		Agg a2[2];
-#pragma unroll
-		for (int r = 0; r < 2; ++r) {
-			const size_t b = brick64 + r * 32 + lane;
-			mm[r] = M.miss_mask[b];
-			hm[r] = M.hit_mask[b];
-			mt[r] = M.meta[b];
-			a2[r] = M.agg2[b];
-			// a block nothing was ever written to is plain unknown space
-			if (!(mt[r] >> 16)) a2[r] = {0.0f, M.default_flags};
+	const uint32_t lane = threadIdx.x & 31, oct = threadIdx.x & 7;
+	const size_t b = (size_t)blockIdx.x * (kUpdThreads / 8) + (threadIdx.x >> 3);  // = brick * 64 + child
+	const uint32_t brick = (uint32_t)(b >> 6);
+	if (brick >= n_bricks) return;
+	if (M.brick_stamp[brick] != M.scan_id) return;
+	// the four groups of a warp belong to the same brick, so everything above is warp-uniform
+	const unsigned long long mm = M.miss_mask[b], hm = M.hit_mask[b];
+	const bool marked = (mm | hm) != 0ull;
+	if (!__any_sync(0xffffffffu, marked)) return;
+	const uint32_t gmask = 0xffu << (lane & 24);
+	unsigned int s_vox = 0, s_hit = 0, s_oct = 0, s_blk = 0, s_new = 0;
+	if (marked) {
+		const uint32_t mt = M.meta[b];
+		const uint32_t m8 = octet_bits8(mm, oct), h8 = octet_bits8(hm, oct);
+		float omax = 0.0f;
+		uint32_t ofl = M.default_flags, touched = 0, orgb = 0;
+		if (m8 | h8) {
+			float* lp = M.leaf + b * 64 + 8 * oct;
+			const float4 a0 = reinterpret_cast<const float4*>(lp)[0], a1 = reinterpret_cast<const float4*>(lp)[1];
+			update_octet(M, miss, lp, m8, h8, a0, a1, omax, ofl);
+			touched = 1;
+			s_vox = __popc(m8 | h8);
+			s_hit = __popc(h8);
+			s_oct = 1;
+			if (COLOR) {
+				// depth-1 colour of the octet (getAverageChildColor, occupancy_map_color.cpp:177-194)
+				const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + b * 64 + 8 * oct);
+				uint4 c0 = cp[0], c1 = cp[1];
+				uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+				orgb = rms_rgb(cc, 8);
+			}
+		} else if ((mt >> (16 + oct)) & 1u) {
+			omax = M.sum1[b * 8 + oct];
+			ofl = (mt >> (2 * oct)) & 3u;
+			if (COLOR) orgb = M.sum1_rgb[b * 8 + oct];
 		}
-		int n_work = 0, n_oct = 0;
+		// the group rewrites the whole 32 B sector of depth-1 maxima (no partial-sector write)
+		M.sum1[b * 8 + oct] = omax;
+		if (COLOR) M.sum1_rgb[b * 8 + oct] = orgb;
+		// depth-2 aggregate over the 8 octets of the block
+		float bmax = omax;
+		uint32_t bfl = ofl;
+		uint32_t newmeta = (ofl << (2 * oct)) | (touched << (16 + oct));
 #pragma unroll
-		for (int r = 0; r < 2; ++r) {
-			const bool touched = (mm[r] | hm[r]) != 0ull;
-			const uint32_t ballot = __ballot_sync(FULL, touched);
-			if (lane < 4) st_d3 += ((ballot >> (8 * lane)) & 0xffu) ? 1u : 0u;
-			// octet list: inclusive warp scan of the per-item octet counts
-			const uint32_t t8 = touched ? touched_octets(mm[r] | hm[r]) : 0u;
-			uint32_t cnt = __popc(t8), incl = cnt;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				uint32_t up = __shfl_up_sync(FULL, incl, o);
-				if ((int)lane >= o) incl += up;
-			}
-			const uint32_t first = n_oct + incl - cnt;
-			if (touched) {
-				const int wi = n_work + __popc(ballot & ((1u << lane) - 1u));
-				wl.miss[wi] = mm[r];
-				wl.hit[wi] = hm[r];
-				wl.meta[wi] = mt[r];
-				wl.child[wi] = (uint8_t)(r * 32 + lane);
-				wl.touched[wi] = (uint8_t)t8;
-				uint32_t pos = first;
-				for (uint32_t o = 0; o < 8; ++o)
-					if ((t8 >> o) & 1u) ol[pos++] = (uint16_t)((wi << 3) | o);
-			}
-			n_work += __popc(ballot);
-			n_oct += __shfl_sync(FULL, incl, 31);
-			agg[wid][r * 32 + lane] = a2[r];
-			if (COLOR) aggrgb[wid][r * 32 + lane] = (mt[r] >> 16) ? M.rgb2[brick64 + r * 32 + lane] : 0u;
+		for (int o = 1; o < 8; o <<= 1) {
+			bmax = fmaxf(bmax, __shfl_xor_sync(gmask, bmax, o));
+			bfl |= __shfl_xor_sync(gmask, bfl, o);
+			newmeta |= __shfl_xor_sync(gmask, newmeta, o);
 		}
-		__syncwarp();
-		// ---- phase B: one lane per touched octet, loads two entries ahead
-		OctetLoad cur = load_octet(M, wl, ol, brick64, (int)lane, n_oct);
-		OctetLoad nx1 = load_octet(M, wl, ol, brick64, 32 + (int)lane, n_oct);
-		for (int e0 = 0; e0 < n_oct; e0 += 32) {
-			OctetLoad nx2 = load_octet(M, wl, ol, brick64, e0 + 64 + (int)lane, n_oct);
-			if (cur.act) {
-				float omax;
-				uint32_t ofl;
-				update_octet(M, miss, cur.lp, cur.m8, cur.h8, cur.a0, cur.a1, omax, ofl);
-				st_vox += __popc(cur.m8 | cur.h8);
-				st_hit += __popc(cur.h8);
-				++st_oct;
-				omaxs[wid][cur.oct * kOctStride + cur.item] = omax;
-				oflgs[wid][cur.oct * kOctStride + cur.item] = (uint8_t)ofl;
-				if (COLOR) {
-					// depth-1 colour of the octet (getAverageChildColor, occupancy_map_color.cpp:177-194)
-					const size_t li = (brick64 + wl.child[cur.item]) * 64 + 8 * cur.oct;
-					const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + li);
-					uint4 c0 = cp[0], c1 = cp[1];
-					uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-					const uint32_t orgb = rms_rgb(cc, 8);
-					M.sum1_rgb[li >> 3] = orgb;
-					orgbs[wid][cur.oct * kOctStride + cur.item] = orgb;
-				}
-			}
-			cur = nx1;
-			nx1 = nx2;
-		}
-		__syncwarp();
-		// ---- phase B2: one lane per touched block
-		for (int wi = (int)lane; wi < n_work; wi += 32) {
-			const size_t w_slot = brick64 + wl.child[wi];
-			const uint32_t w_meta = wl.meta[wi];
-			const uint32_t t8 = wl.touched[wi], init8 = (w_meta >> 16) & 0xffu;
-			float* sp = M.sum1 + w_slot * 8;
-			float s1[8];
-#pragma unroll
-			for (int o = 0; o < 8; ++o) {
-				s1[o] = 0.0f;
-				if (!((t8 >> o) & 1u) && ((init8 >> o) & 1u)) s1[o] = sp[o];
-			}
-			float bmax = -3.402823466e+38f;
-			uint32_t bfl = 0, oflags16 = 0, brgb = 0;
+		uint32_t brgb = 0;
+		if (COLOR) {
 			uint32_t oc[8];
 #pragma unroll
-			for (int o = 0; o < 8; ++o) {
-				uint32_t f;
-				float v;
-				oc[o] = 0;
-				if ((t8 >> o) & 1u) {
-					v = omaxs[wid][o * kOctStride + wi];
-					f = oflgs[wid][o * kOctStride + wi];
-					sp[o] = v;
-					if (COLOR) oc[o] = orgbs[wid][o * kOctStride + wi];
-				} else if ((init8 >> o) & 1u) {
-					v = s1[o];
-					f = (w_meta >> (2 * o)) & 3u;
-					if (COLOR) oc[o] = M.sum1_rgb[w_slot * 8 + o];
-				} else {
-					v = 0.0f;
-					f = M.default_flags;
-				}
-				bmax = fmaxf(bmax, v);
-				bfl |= f;
-				oflags16 |= f << (2 * o);
-			}
-			if (COLOR) brgb = rms_rgb(oc, 8);
-			const uint32_t meta = oflags16 | ((init8 | t8) << 16);
-			// new block aggregate; both per-scan masks cleared for the next scan
-			M.agg2[w_slot] = {bmax, bfl};
-			M.meta[w_slot] = meta;
-			if (COLOR) M.rgb2[w_slot] = brgb;
-			M.miss_mask[w_slot] = 0ull;
-			if (wl.hit[wi]) M.hit_mask[w_slot] = 0ull;
-			if (!init8) ++st_new;
-			agg[wid][wl.child[wi]] = {bmax, bfl};
-			if (COLOR) aggrgb[wid][wl.child[wi]] = brgb;
-			++st_blk;
+			for (int j = 0; j < 8; ++j) oc[j] = __shfl_sync(gmask, orgb, (lane & 24) + j);
+			brgb = rms_rgb(oc, 8);
 		}
-		__syncwarp();
-		// ---- phase C: lane owns children 2*lane, 2*lane+1 (both under depth-3 node lane/4)
-		const Agg c0 = agg[wid][2 * lane], c1 = agg[wid][2 * lane + 1];
-		float m3 = fmaxf(c0.occ, c1.occ);
-		uint32_t f3 = c0.flags | c1.flags;
-#pragma unroll
-		for (int o = 1; o < 4; o <<= 1) {
-			m3 = fmaxf(m3, __shfl_xor_sync(FULL, m3, o));
-			f3 |= __shfl_xor_sync(FULL, f3, o);
+		if (oct == 0) {
+			M.agg2[b] = {bmax, bfl};
+			// bits 24..31: low byte of the scan that last updated the block (read by k_brick_agg)
+			M.meta[b] = (newmeta & 0xffffffu) | (mt & 0xff0000u) | (M.scan_id << 24);
+			if (COLOR) M.rgb2[b] = brgb;
+			M.miss_mask[b] = 0ull;  // masks cleared for the next scan
+			if (hm) M.hit_mask[b] = 0ull;
+			s_blk = 1;
+			s_new = (mt & 0xff0000u) ? 0u : 1u;
 		}
-		float m4 = m3;
-		uint32_t f4 = f3;
-#pragma unroll
-		for (int o = 4; o < 32; o <<= 1) {
-			m4 = fmaxf(m4, __shfl_xor_sync(FULL, m4, o));
-			f4 |= __shfl_xor_sync(FULL, f4, o);
-		}
-		if ((lane & 3) == 0) M.brick_sum3[(size_t)brick * 8 + (lane >> 2)] = {m3, f3};
-		if (lane == 0) M.brick_sum4[brick] = {m4, f4};
-		if (COLOR) {
-			uint32_t cc[8];
-#pragma unroll
-			for (int j = 0; j < 8; ++j) cc[j] = aggrgb[wid][8 * (lane >> 2) + j];
-			const uint32_t rgb3 = rms_rgb(cc, 8);
-#pragma unroll
-			for (int j = 0; j < 8; ++j) cc[j] = __shfl_sync(FULL, rgb3, 4 * j);
-			const uint32_t rgb4 = rms_rgb(cc, 8);
-			if ((lane & 3) == 0) M.brick_rgb3[(size_t)brick * 8 + (lane >> 2)] = rgb3;
-			if (lane == 0) M.brick_rgb4[brick] = rgb4;
-		}
-		__syncwarp();
 	}
-	// statistics: one atomic per warp and counter
+	// counters: one set of atomics per warp
 	for (int o = 16; o > 0; o >>= 1) {
-		st_vox += __shfl_xor_sync(FULL, st_vox, o);
-		st_hit += __shfl_xor_sync(FULL, st_hit, o);
-		st_oct += __shfl_xor_sync(FULL, st_oct, o);
-		st_blk += __shfl_xor_sync(FULL, st_blk, o);
-		st_brk += __shfl_xor_sync(FULL, st_brk, o);
-		st_d3 += __shfl_xor_sync(FULL, st_d3, o);
-		st_new += __shfl_xor_sync(FULL, st_new, o);
+		s_vox += __shfl_xor_sync(0xffffffffu, s_vox, o);
+		s_hit += __shfl_xor_sync(0xffffffffu, s_hit, o);
+		s_oct += __shfl_xor_sync(0xffffffffu, s_oct, o);
+		s_blk += __shfl_xor_sync(0xffffffffu, s_blk, o);
+		s_new += __shfl_xor_sync(0xffffffffu, s_new, o);
 	}
-	if (lane == 0 && st_brk) {
-		if (st_new) atomicAdd(&M.ctr->n_blocks, st_new);
-		atomicAdd(&M.ctr->touched_voxels, (unsigned long long)st_vox);
-		atomicAdd(&M.ctr->hit_voxels, (unsigned long long)st_hit);
-		atomicAdd(&M.ctr->touched_octets, (unsigned long long)st_oct);
-		atomicAdd(&M.ctr->touched_blocks, (unsigned long long)st_blk);
-		atomicAdd(&M.ctr->touched_bricks, (unsigned long long)st_brk);
-		atomicAdd(&M.ctr->touched_d3, (unsigned long long)st_d3);
+	if (lane == 0) {
+		unsigned long long* slot = M.ctr->stat[(blockIdx.x * 8 + (threadIdx.x >> 5)) % kStatSlots];
+		atomicAdd(&slot[0], (unsigned long long)s_vox);
+		if (s_hit) atomicAdd(&slot[1], (unsigned long long)s_hit);
+		atomicAdd(&slot[2], (unsigned long long)s_oct);
+		atomicAdd(&slot[3], (unsigned long long)s_blk);
+		if (s_new) atomicAdd(&slot[4], (unsigned long long)s_new);
+	}
+}
+
+// depth-3 / depth-4 aggregates of every touched brick from its 64 depth-2 aggregates:
+// one warp per brick, lane owns children 2*lane and 2*lane+1 (both under depth-3 node lane/4)
+template <bool COLOR>
+__global__ void __launch_bounds__(256) k_brick_agg(DeviceMap M, uint32_t n_bricks)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t brick = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (brick >= n_bricks || M.brick_stamp[brick] != M.scan_id) return;
+	constexpr uint32_t FULL = 0xffffffffu;
+	const size_t b = (size_t)brick * 64 + 2 * lane;
+	const uint2 mt = *reinterpret_cast<const uint2*>(&M.meta[b]);
+	const uint4 ag = *reinterpret_cast<const uint4*>(&M.agg2[b]);
+	Agg c0 = {__uint_as_float(ag.x), ag.y}, c1 = {__uint_as_float(ag.z), ag.w};
+	if (!(mt.x & 0xff0000u)) c0 = {0.0f, M.default_flags};  // never written: unknown space
+	if (!(mt.y & 0xff0000u)) c1 = {0.0f, M.default_flags};
+	const uint32_t tag = M.scan_id & 0xffu;
+	const bool upd = ((mt.x & 0xff0000u) && (mt.x >> 24) == tag) || ((mt.y & 0xff0000u) && (mt.y >> 24) == tag);
+	float m3 = fmaxf(c0.occ, c1.occ);
+	uint32_t f3 = c0.flags | c1.flags;
+#pragma unroll
+	for (int o = 1; o < 4; o <<= 1) {
+		m3 = fmaxf(m3, __shfl_xor_sync(FULL, m3, o));
+		f3 |= __shfl_xor_sync(FULL, f3, o);
+	}
+	float m4 = m3;
+	uint32_t f4 = f3;
+#pragma unroll
+	for (int o = 4; o < 32; o <<= 1) {
+		m4 = fmaxf(m4, __shfl_xor_sync(FULL, m4, o));
+		f4 |= __shfl_xor_sync(FULL, f4, o);
+	}
+	if ((lane & 3) == 0) M.brick_sum3[(size_t)brick * 8 + (lane >> 2)] = {m3, f3};
+	if (lane == 0) M.brick_sum4[brick] = {m4, f4};
+	if (COLOR) {
+		const uint2 cr = *reinterpret_cast<const uint2*>(&M.rgb2[b]);
+		const uint32_t r0 = (mt.x & 0xff0000u) ? cr.x : 0u, r1 = (mt.y & 0xff0000u) ? cr.y : 0u;
+		uint32_t cc[8];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			cc[2 * j] = __shfl_sync(FULL, r0, (lane & 28) + j);
+			cc[2 * j + 1] = __shfl_sync(FULL, r1, (lane & 28) + j);
+		}
+		const uint32_t rgb3 = rms_rgb(cc, 8);
+#pragma unroll
+		for (int j = 0; j < 8; ++j) cc[j] = __shfl_sync(FULL, rgb3, 4 * j);
+		const uint32_t rgb4 = rms_rgb(cc, 8);
+		if ((lane & 3) == 0) M.brick_rgb3[(size_t)brick * 8 + (lane >> 2)] = rgb3;
+		if (lane == 0) M.brick_rgb4[brick] = rgb4;
+	}
+	// D_3 / D_4 counters: depth-3 node touched <=> any of its 8 children updated this scan
+	const uint32_t ub = __ballot_sync(FULL, upd);
+	if (lane == 0) {
+		uint32_t d3 = 0;
+		for (int k = 0; k < 8; ++k) d3 += ((ub >> (4 * k)) & 0xfu) ? 1u : 0u;
+		unsigned long long* slot = M.ctr->stat[brick % kStatSlots];
+		atomicAdd(&slot[5], 1ull);
+		atomicAdd(&slot[6], (unsigned long long)d3);
 	}
 }
 

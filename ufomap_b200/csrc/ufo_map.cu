@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -351,22 +352,25 @@ void finish_stats(Map* m)
 	if (!m->stats_pending) return;
 	const Counters& c = *m->h_ctr;
 	ufo_b200_scan_stats& st = m->stats;
+	unsigned long long sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	for (int sl = 0; sl < kStatSlots; ++sl)
+		for (int k = 0; k < 8; ++k) sum[k] += c.stat[sl][k];
 	st.rays = c.n_rays;
 	st.visits = c.visits;
-	st.touched_voxels = c.touched_voxels;
-	st.hit_voxels = c.hit_voxels;
-	st.touched_octets = c.touched_octets;
-	st.touched_blocks = c.touched_blocks;
-	st.touched_d3 = c.touched_d3;
-	st.touched_bricks = c.touched_bricks;
+	st.touched_voxels = sum[0];
+	st.hit_voxels = sum[1];
+	st.touched_octets = sum[2];
+	st.touched_blocks = sum[3];
+	st.touched_d3 = sum[6];
+	st.touched_bricks = sum[5];
 	st.upper_nodes = c.upper_nodes;
-	m->n_blocks = c.n_blocks;
+	m->n_blocks += (uint32_t)sum[4];
 	m->n_bricks = std::min(c.n_bricks, m->M.brick_cap);
 	m->n_upper = std::min(c.n_upper, m->M.up_cap);
 	st.blocks_in_map = m->n_blocks;
 	st.bricks_in_map = m->n_bricks;
 	st.device_bytes = m->device_bytes;
-	if (c.n_rays || c.touched_voxels) {
+	if (c.n_rays || sum[0]) {
 		for (int i = 0; i < 3; ++i) {
 			if (c.bbox[i] != ~0ull) m->min_change[i] = std::min(m->min_change[i], decode_ordered(c.bbox[i]));
 			if (c.bbox[3 + i] != 0ull)
@@ -589,9 +593,16 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	if (m->profiling) CK(cudaEventRecord(m->ev[4], s));
 	// K3
 	if (m->n_bricks) {
-		uint32_t grid = std::min<uint32_t>((m->n_bricks + kUpdWarps - 1) / kUpdWarps, (uint32_t)m->sm_count * 32);
-		if (M.color) k_update<true><<<grid, kUpdWarps * 32, 0, s>>>(M, a.miss, m->n_bricks);
-		else k_update<false><<<grid, kUpdWarps * 32, 0, s>>>(M, a.miss, m->n_bricks);
+		const uint32_t groups = m->n_bricks * 64u;  // one eight-lane group per (brick, child)
+		const uint32_t ugrid = (groups + kUpdThreads / 8 - 1) / (kUpdThreads / 8);
+		const uint32_t agrid = (m->n_bricks + 7) / 8;
+		if (M.color) {
+			k_update<true><<<ugrid, kUpdThreads, 0, s>>>(M, a.miss, m->n_bricks);
+			k_brick_agg<true><<<agrid, 256, 0, s>>>(M, m->n_bricks);
+		} else {
+			k_update<false><<<ugrid, kUpdThreads, 0, s>>>(M, a.miss, m->n_bricks);
+			k_brick_agg<false><<<agrid, 256, 0, s>>>(M, m->n_bricks);
+		}
 		++m->launches;
 	}
 	if (m->profiling) CK(cudaEventRecord(m->ev[5], s));
@@ -622,6 +633,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	CK(cudaEventRecord(m->ev[6], s));
 	m->ev_valid = true;
 	m->stats.launches = m->launches;
+	m->stats.result_bytes = sizeof(Counters) * (1 + regrows + 1);  // mid-scan check(s) + end-of-scan copy
 	CK(cudaMemcpyAsync(m->h_ctr, M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
 	m->stats_pending = true;
 	if (!async) return sync_map(m);
