@@ -128,6 +128,17 @@ def make_scans(count, rank):
     return origins, clouds
 
 
+def max_over_ranks(value, world, device=None):
+    """MAX-reduce a per-rank scalar (the timed region of the slowest rank is the job's time)."""
+    if world <= 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU insertPointCloud on the host cores,
     each step a bounded sample (every `stride`-th point of scan k) of the same workload."""
@@ -250,11 +261,7 @@ def main():
         e1.record(stream)
         barrier()
         clocks = sampler.stop()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
         return ms, per_scan, launches, clocks
 
     # ---- device-resident inputs: `value` ---------------------------------

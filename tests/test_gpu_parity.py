@@ -148,13 +148,15 @@ def test_rays_leaving_the_map_and_degenerate_points():
               [dict(origin=[-30.0, 2.0, 1.0], xyz=p[:500], max_range=-1.0)], levels=(1, 2, 3, 4, 5, 6))
 
 
-@pytest.mark.xfail(reason="known deviation (DESIGN.md): a coordinate exactly on the +boundary maps to key "
-                          "2^L, which the reference's tree aliases onto the opposite face while its per-scan "
-                          "sets still treat it as a distinct voxel (octree.h:321 FIXME) -- the aliased voxel is "
-                          "updated twice per scan there, once here", strict=False)
 def test_rays_leaving_through_plus_faces_alias():
+    """A coordinate exactly on the + face maps to key 2^L, which the reference's tree wraps onto
+    the opposite face while its per-scan sets keep it distinct (octree.h:321 FIXME): the
+    wrapped voxel is updated once more in the same scan.  Reproduced exactly (k_alias_*)."""
     o, p = _boundary_cloud(40.0)
-    _run_case(dict(resolution=0.5, depth_levels=6), [dict(origin=o, xyz=p, max_range=-1.0)],
+    for disc in (False, True):
+        _run_case(dict(resolution=0.5, depth_levels=6), [dict(origin=o, xyz=p, max_range=-1.0, discrete=disc)] * 2,
+                  levels=(1, 2, 3, 4, 5, 6))
+    _run_case(dict(resolution=0.5, depth_levels=6), [dict(origin=[30.0, 2.0, 1.0], xyz=p[:800], max_range=-1.0)],
               levels=(1, 2, 3, 4, 5, 6))
 
 

@@ -41,11 +41,12 @@ struct Counters {
 	uint32_t n_blocks;   // blocks that ever received an update (statistics only)
 	uint32_t n_bricks;   // next free brick slot
 	uint32_t n_upper;    // next free upper-node slot
-	uint32_t overflow;   // bit0 blocks, bit1 bricks/brick hash, bit2 upper nodes, bit3 ray-record buffer, bit4 ray bound violated (bug)
+	uint32_t overflow;   // bit1 bricks/brick hash, bit2 upper nodes, bit3 ray-record buffer, bit4 ray bound violated (bug), bit5 alias arrays needed
 	uint32_t list_count[3];  // dirty-list lengths of the upper-level pass (rotating by depth % 3)
 	uint32_t n_rays;
 	uint32_t ray_batch;  // next batch of 32 rays for the persistent ray-walk warps
 	uint32_t n_chunks;   // longest ray-record region of the scan, in kChunk slices
+	uint32_t alias_marks;  // out-of-range keys marked this scan (0 almost always)
 	unsigned long long seg_total;  // ray-walk records reserved by K1
 	unsigned long long visits;
 	unsigned long long touched_voxels;
@@ -95,6 +96,13 @@ struct DeviceMap {
 	float* sum1;                    // [b][8] depth-1 maxima
 	uint32_t* rgb2;                 // colour maps: [b]
 	uint32_t* sum1_rgb;             // colour maps: [b][8]
+	// Keys outside [0, 2^L) (a coordinate exactly on the + face of the map, or a walk that
+	// overshoots the - face): the reference's per-scan sets keep them as distinct voxels
+	// (code.h keeps 21 bits per axis) while its tree only consumes L bits, so the wrapped
+	// voxel is updated once more.  Such marks are collected under their UNWRAPPED brick key
+	// in these two arrays (allocated on first use) and applied by k_alias_* (see there).
+	unsigned long long* alias_miss;  // [b]
+	unsigned long long* alias_hit;   // [b]
 	// upper nodes
 	unsigned long long* uh_keys;
 	uint32_t* uh_vals;

@@ -121,12 +121,37 @@ __device__ __forceinline__ uint32_t table_insert(const ScanArgs& a, uint64_t key
 	}
 }
 
+// Slow path for a voxel key (21 bits per axis, block coordinates bx..bz) with a component
+// outside the tree: the mark is kept under the UNWRAPPED brick (own set semantics, like the
+// reference's CodeSet/CodeMap) and the wrapped target brick is created right away so that
+// the host's brick count is final after this kernel.  is_hit selects the mask array.
+__device__ __noinline__ void mark_alias(const DeviceMap& M, uint32_t bx, uint32_t by, uint32_t bz,
+                                        unsigned long long bits, bool is_hit)
+{
+	if (!M.alias_miss) {
+		atomicOr(&M.ctr->overflow, 32u);  // host allocates the alias arrays and re-runs
+		return;
+	}
+	const uint32_t km = M.g.key_mask >> 2;
+	const uint32_t src = brick_find_or_create(M, pack_key(bx >> 2, by >> 2, bz >> 2));
+	const uint32_t dst = brick_find_or_create(M, pack_key((bx & km) >> 2, (by & km) >> 2, (bz & km) >> 2));
+	if (src == kNone || dst == kNone) return;
+	M.brick_stamp[src] = M.scan_id;
+	M.brick_stamp[dst] = M.scan_id;
+	atomicOr(&(is_hit ? M.alias_hit : M.alias_miss)[(size_t)src * 64 + morton2(bx, by, bz)], bits);
+	atomicAdd(&M.ctr->alias_marks, 1u);
+}
+
 // mark a depth-0 hit voxel directly (mono maps)
 __device__ __forceinline__ void mark_hit(const DeviceMap& M, Key3 k)
 {
-	k.x &= M.g.key_mask;
-	k.y &= M.g.key_mask;
-	k.z &= M.g.key_mask;
+	k.x &= 0x1fffffu;  // a Code keeps 21 bits per axis (code.h:336-347)
+	k.y &= 0x1fffffu;
+	k.z &= 0x1fffffu;
+	if ((k.x | k.y | k.z) & ~M.g.key_mask) {
+		mark_alias(M, k.x >> 2, k.y >> 2, k.z >> 2, 1ull << linear2(k.x, k.y, k.z), true);
+		return;
+	}
 	uint32_t brick = brick_find_or_create(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
 	if (brick == kNone) return;
 	M.brick_stamp[brick] = M.scan_id;
@@ -249,9 +274,10 @@ __global__ void __launch_bounds__(256) k_points(DeviceMap M, ScanArgs a)
 			Vec3 from = a.origin, to = end;
 			if (move_line_inside(g, from, to)) {
 				Key3 kf = point_to_key(g, from, a.depth), kt = point_to_key(g, to, a.depth);
-				uint32_t dx = kf.x > kt.x ? kf.x - kt.x : kt.x - kf.x;
-				uint32_t dy = kf.y > kt.y ? kf.y - kt.y : kt.y - kf.y;
-				uint32_t dz = kf.z > kt.z ? kf.z - kt.z : kt.z - kf.z;
+				// keys are u32 and may wrap below zero at the - faces (the walk wraps the same way)
+				uint32_t dx = (uint32_t)abs((int)(kf.x - kt.x));
+				uint32_t dy = (uint32_t)abs((int)(kf.y - kt.y));
+				uint32_t dz = (uint32_t)abs((int)(kf.z - kt.z));
 				bound = (dx >> 2) + (dy >> 2) + (dz >> 2) + 8u;
 			}
 		}
@@ -282,9 +308,22 @@ __global__ void __launch_bounds__(256) k_hits(DeviceMap M, ScanArgs a)
 	uint32_t t = a.hit_tab[i];
 	if (t == kNone || a.tab_min[t] != i) return;
 	Key3 k = code_to_key(a.tab_keys[t]);
-	k.x &= M.g.key_mask;
-	k.y &= M.g.key_mask;
-	k.z &= M.g.key_mask;
+	if ((k.x | k.y | k.z) & ~M.g.key_mask) {
+		// out-of-tree hit voxel: occupancy goes through the alias path; its colour is blended
+		// into the wrapped voxel below with the occupancy the voxel has at this point
+		mark_alias(M, k.x >> 2, k.y >> 2, k.z >> 2, 1ull << linear2(k.x, k.y, k.z), true);
+		k.x &= M.g.key_mask;
+		k.y &= M.g.key_mask;
+		k.z &= M.g.key_mask;
+		uint32_t tb = brick_find(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
+		if (tb == kNone) return;
+		const size_t tl = ((size_t)tb * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2)) * 64 + morton2(k.x, k.y, k.z);
+		Vec3 tp;
+		uint32_t tu;
+		load_point(a, i, tp, tu);
+		if (M.leaf_rgb[tl] == 0) M.leaf_rgb[tl] = tu;
+		return;
+	}
 	uint32_t brick = brick_find_or_create(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
 	if (brick == kNone) return;
 	M.brick_stamp[brick] = M.scan_id;
@@ -335,9 +374,13 @@ struct BrickCache {
 __device__ __forceinline__ void flush_block(const DeviceMap& M, BrickCache& bc, uint32_t kx,
                                             uint32_t ky, uint32_t kz, unsigned long long bits)
 {
-	kx &= M.g.key_mask;
-	ky &= M.g.key_mask;
-	kz &= M.g.key_mask;
+	kx &= 0x1fffffu;
+	ky &= 0x1fffffu;
+	kz &= 0x1fffffu;
+	if ((kx | ky | kz) & ~M.g.key_mask) {
+		mark_alias(M, kx >> 2, ky >> 2, kz >> 2, bits, false);
+		return;
+	}
 	uint32_t bx = kx >> 4, by = ky >> 4, bz = kz >> 4;
 	if (bc.slot == kNone || bx != bc.bx || by != bc.by || bz != bc.bz) {
 		bc.bx = bx;
@@ -588,9 +631,13 @@ __global__ void __launch_bounds__(kChunk) k_scatter(DeviceMap M, ScanArgs a)
 		const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&a.seg[a.seg_base[r] + lo + threadIdx.x]);
 		uint32_t x, y, z;
 		unpack_key(v.y, x, y, z);
-		x = (x & M.g.key_mask) >> 2;  // block coordinates inside the tree
-		y = (y & M.g.key_mask) >> 2;
-		z = (z & M.g.key_mask) >> 2;
+		if ((x | y | z) & ~M.g.key_mask) {  // key outside the tree: see DeviceMap::alias_miss
+			mark_alias(M, x >> 2, y >> 2, z >> 2, v.x, false);
+			continue;
+		}
+		x >>= 2;  // block coordinates
+		y >>= 2;
+		z >>= 2;
 		const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
 		const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
 		const ulonglong2 e0 = ld_volatile_entry(&M.bh_tab[hidx]);
@@ -729,8 +776,9 @@ __global__ void __launch_bounds__(kUpdThreads, 8) k_update(DeviceMap M, float mi
 	const size_t b = (size_t)blockIdx.x * (kUpdThreads / 8) + (threadIdx.x >> 3);  // = brick * 64 + child
 	const uint32_t brick = (uint32_t)(b >> 6);
 	if (brick >= n_bricks) return;
-	if (M.brick_stamp[brick] != M.scan_id) return;
-	// the four groups of a warp belong to the same brick, so everything above is warp-uniform
+	// No brick_stamp check: the masks of a brick nothing marked this scan are all zero
+	// (every scan clears what it consumed), so the mask read itself is the filter.
+	// The four groups of a warp belong to the same brick: `brick` is warp-uniform.
 	const unsigned long long mm = M.miss_mask[b], hm = M.hit_mask[b];
 	const bool marked = (mm | hm) != 0ull;
 	if (!__any_sync(0xffffffffu, marked)) return;
@@ -810,6 +858,9 @@ __global__ void __launch_bounds__(kUpdThreads, 8) k_update(DeviceMap M, float mi
 	}
 }
 
+__device__ __forceinline__ bool alias_source(const DeviceMap& M, uint32_t brick, uint32_t& tx, uint32_t& ty,
+                                             uint32_t& tz);
+
 // depth-3 / depth-4 aggregates of every touched brick from its 64 depth-2 aggregates:
 // one warp per brick, lane owns children 2*lane and 2*lane+1 (both under depth-3 node lane/4)
 template <bool COLOR>
@@ -819,6 +870,10 @@ __global__ void __launch_bounds__(256) k_brick_agg(DeviceMap M, uint32_t n_brick
 	const uint32_t brick = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (brick >= n_bricks || M.brick_stamp[brick] != M.scan_id) return;
 	constexpr uint32_t FULL = 0xffffffffu;
+	if (M.alias_miss) {  // bricks that only collect out-of-tree marks own no voxels
+		uint32_t ax, ay, az;
+		if (alias_source(M, brick, ax, ay, az)) return;
+	}
 	const size_t b = (size_t)brick * 64 + 2 * lane;
 	const uint2 mt = *reinterpret_cast<const uint2*>(&M.meta[b]);
 	const uint4 ag = *reinterpret_cast<const uint4*>(&M.agg2[b]);
@@ -871,6 +926,97 @@ __global__ void __launch_bounds__(256) k_brick_agg(DeviceMap M, uint32_t n_brick
 }
 
 // ---------------------------------------------------------------------------
+// Out-of-tree keys (rare; launched only when a scan produced any)
+// ---------------------------------------------------------------------------
+// The reference applies to a voxel every hit of the scan first and every miss afterwards
+// (occupancy_map_base.h:1351-1365).  With aliases a voxel can receive several of each, so
+//   k_alias_apply(hits)   runs BEFORE k_update  (alias hits, then the voxel's own hit),
+//   k_alias_apply(misses) runs AFTER  k_update  (the voxel's own miss, then alias misses),
+// which is "all hits, then all misses" again; equal updates commute.  k_alias_refresh then
+// recomputes the aggregates of the wrapped blocks from their leaves and clears the masks.
+__device__ __forceinline__ void atomic_apply(const DeviceMap& M, float* addr, float u)
+{
+	uint32_t* p = reinterpret_cast<uint32_t*>(addr);
+	uint32_t old = *reinterpret_cast<volatile uint32_t*>(p);
+	while (true) {
+		const uint32_t nv = __float_as_uint(apply_update(M, __uint_as_float(old), u));
+		const uint32_t prev = atomicCAS(p, old, nv);
+		if (prev == old) break;
+		old = prev;
+	}
+}
+
+__device__ __forceinline__ bool alias_source(const DeviceMap& M, uint32_t brick, uint32_t& tx, uint32_t& ty,
+                                             uint32_t& tz)
+{
+	uint32_t x, y, z;
+	unpack_key(M.brick_key[brick], x, y, z);
+	const uint32_t km = M.g.key_mask >> 4;
+	tx = x & km;
+	ty = y & km;
+	tz = z & km;
+	return ((x | y | z) & ~km) != 0;
+}
+
+// one thread per (alias brick, child block)
+__global__ void __launch_bounds__(256) k_alias_apply(DeviceMap M, uint32_t n_bricks, float upd, int hits)
+{
+	const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t brick = (uint32_t)(b >> 6);
+	if (brick >= n_bricks || M.brick_stamp[brick] != M.scan_id) return;
+	uint32_t tx, ty, tz;
+	if (!alias_source(M, brick, tx, ty, tz)) return;
+	unsigned long long m = (hits ? M.alias_hit : M.alias_miss)[b];
+	if (!m) return;
+	const uint32_t dst = brick_find(M, pack_key(tx, ty, tz));
+	if (dst == kNone) return;
+	float* leaf = M.leaf + ((size_t)dst * 64 + (b & 63)) * 64;
+	while (m) {
+		const uint32_t bit = __ffsll((long long)m) - 1;
+		m &= m - 1;
+		// mask bit order is linear (x + 4y + 16z), leaves are in Morton order
+		atomic_apply(M, leaf + morton2(bit & 3u, (bit >> 2) & 3u, bit >> 4), upd);
+	}
+}
+
+// one thread per (alias brick, child block): recompute the wrapped block's aggregates
+__global__ void __launch_bounds__(256) k_alias_refresh(DeviceMap M, uint32_t n_bricks)
+{
+	const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t brick = (uint32_t)(b >> 6);
+	if (brick >= n_bricks || M.brick_stamp[brick] != M.scan_id) return;
+	uint32_t tx, ty, tz;
+	if (!alias_source(M, brick, tx, ty, tz)) return;
+	if (!(M.alias_hit[b] | M.alias_miss[b])) return;
+	M.alias_hit[b] = 0ull;
+	M.alias_miss[b] = 0ull;
+	const uint32_t dst = brick_find(M, pack_key(tx, ty, tz));
+	if (dst == kNone) return;
+	const size_t tb = (size_t)dst * 64 + (b & 63);
+	const float* leaf = M.leaf + tb * 64;
+	const uint32_t old = M.meta[tb];
+	float bmax = -3.402823466e+38f;
+	uint32_t bfl = 0, meta = 0;
+	for (int o = 0; o < 8; ++o) {
+		float omax = -3.402823466e+38f;
+		uint32_t ofl = 0;
+		for (int j = 0; j < 8; ++j) {
+			const float v = *reinterpret_cast<const volatile float*>(&leaf[8 * o + j]);
+			omax = fmaxf(omax, v);
+			ofl |= leaf_flags(M, v);
+		}
+		M.sum1[tb * 8 + o] = omax;
+		bmax = fmaxf(bmax, omax);
+		bfl |= ofl;
+		meta |= ofl << (2 * o);
+	}
+	// every octet now holds real values; several sources refreshing one target write the same
+	M.agg2[tb] = {bmax, bfl};
+	M.meta[tb] = meta | 0xff0000u | (M.scan_id << 24);
+	(void)old;
+}
+
+// ---------------------------------------------------------------------------
 // K4: upper levels (depth >= 5)
 // ---------------------------------------------------------------------------
 // Seeds the depth-5 dirty list with the parents of the bricks touched this scan.
@@ -881,6 +1027,7 @@ __global__ void __launch_bounds__(256) k_upper_seed(DeviceMap M, uint32_t n_bric
 	if (b >= n_bricks || M.brick_stamp[b] != M.scan_id) return;
 	uint32_t x, y, z;
 	unpack_key(M.brick_key[b], x, y, z);
+	if ((x | y | z) & ~(M.g.key_mask >> 4)) return;  // alias collector brick
 	uint32_t s = upper_find_or_create(M, upper_key(5, x >> 1, y >> 1, z >> 1));
 	if (s == kNone) return;
 	if (atomicExch(&M.up_stamp[s], M.scan_id) != M.scan_id) {

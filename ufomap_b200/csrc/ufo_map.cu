@@ -206,7 +206,7 @@ void free_pools(Map* m)
 	DeviceMap& M = m->M;
 	void* ptrs[] = {M.bh_tab, M.brick_key, M.brick_stamp, M.brick_sum3, M.brick_sum4, M.brick_rgb3, M.brick_rgb4,
 	                M.leaf, M.leaf_rgb, M.miss_mask, M.hit_mask, M.agg2, M.meta, M.sum1, M.rgb2, M.sum1_rgb,
-	                M.uh_keys, M.uh_vals, M.up_key, M.up_agg, M.up_rgb, M.up_stamp, M.ctr, m->d_list[0],
+	                M.alias_miss, M.alias_hit, M.uh_keys, M.uh_vals, M.up_key, M.up_agg, M.up_rgb, M.up_stamp, M.ctr, m->d_list[0],
 	                m->d_list[1], m->d_points, m->d_ray_end, m->d_hit_tab, m->d_tab_keys, m->d_tab_min,
 	                m->d_seg, m->d_seg_base, m->d_seg_count, m->d_order};
 	for (void* p : ptrs)
@@ -257,6 +257,8 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_blocks, uint32_t want_b
 		dev_grow(M.leaf_rgb, ob * 64, nb * 64, 0, s, tot);
 		dev_grow(M.sum1_rgb, ob * 8, nb * 8, 0, s, tot);
 		dev_grow(M.rgb2, ob, nb, 0, s, tot);
+		dev_grow(M.alias_miss, ob, nb, 0, s, tot);
+		dev_grow(M.alias_hit, ob, nb, 0, s, tot);
 		dev_grow(M.brick_key, oc, nc, 0, s, tot);
 		dev_grow(M.brick_stamp, oc, nc, 0, s, tot);
 		dev_grow(M.brick_sum3, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
@@ -572,6 +574,14 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		}
 		uint32_t wb = 0, wk = m->h_ctr->n_bricks, wu = m->h_ctr->n_upper;
 		m->n_bricks = std::min(wk, M.brick_cap);
+		if (ov & 32u) {
+			// first out-of-tree key ever seen by this map: allocate the alias mask arrays
+			CK(cudaStreamSynchronize(s));
+			if (!M.alias_miss) {
+				dev_alloc(M.alias_miss, (size_t)M.brick_cap * 64, 0, s, m->device_bytes);
+				dev_alloc(M.alias_hit, (size_t)M.brick_cap * 64, 0, s, m->device_bytes);
+			}
+		}
 		if (ov & 8u) {
 			unsigned long long want = m->h_ctr->seg_total + m->h_ctr->seg_total / 4 + 1024;
 			ensure_seg(m, want);
@@ -590,19 +600,27 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	m->n_bricks = m->h_ctr->n_bricks;
 	m->stats.regrows = regrows;
 
+	const bool aliases = m->h_ctr->alias_marks != 0 && M.alias_miss;
+	const uint32_t alias_grid = (uint32_t)(((size_t)m->n_bricks * 64 + 255) / 256);
 	if (m->profiling) CK(cudaEventRecord(m->ev[4], s));
+	if (aliases) {
+		k_alias_apply<<<alias_grid, 256, 0, s>>>(M, m->n_bricks, M.hit, 1);
+		++m->launches;
+	}
 	// K3
 	if (m->n_bricks) {
 		const uint32_t groups = m->n_bricks * 64u;  // one eight-lane group per (brick, child)
 		const uint32_t ugrid = (groups + kUpdThreads / 8 - 1) / (kUpdThreads / 8);
 		const uint32_t agrid = (m->n_bricks + 7) / 8;
-		if (M.color) {
-			k_update<true><<<ugrid, kUpdThreads, 0, s>>>(M, a.miss, m->n_bricks);
-			k_brick_agg<true><<<agrid, 256, 0, s>>>(M, m->n_bricks);
-		} else {
-			k_update<false><<<ugrid, kUpdThreads, 0, s>>>(M, a.miss, m->n_bricks);
-			k_brick_agg<false><<<agrid, 256, 0, s>>>(M, m->n_bricks);
+		if (M.color) k_update<true><<<ugrid, kUpdThreads, 0, s>>>(M, a.miss, m->n_bricks);
+		else k_update<false><<<ugrid, kUpdThreads, 0, s>>>(M, a.miss, m->n_bricks);
+		if (aliases) {
+			k_alias_apply<<<alias_grid, 256, 0, s>>>(M, m->n_bricks, a.miss, 0);
+			k_alias_refresh<<<alias_grid, 256, 0, s>>>(M, m->n_bricks);
+			m->launches += 2;
 		}
+		if (M.color) k_brick_agg<true><<<agrid, 256, 0, s>>>(M, m->n_bricks);
+		else k_brick_agg<false><<<agrid, 256, 0, s>>>(M, m->n_bricks);
 		++m->launches;
 	}
 	if (m->profiling) CK(cudaEventRecord(m->ev[5], s));
@@ -1075,6 +1093,10 @@ int ufo_b200_clear(ufo_b200_map* m)
 		CK(cudaMemsetAsync(M.agg2, 0, nb * sizeof(Agg), s));
 		CK(cudaMemsetAsync(M.meta, 0, nb * 4, s));
 		if (M.color) CK(cudaMemsetAsync(M.leaf_rgb, 0, nb * 64 * 4, s));
+		if (M.alias_miss) {
+			CK(cudaMemsetAsync(M.alias_miss, 0, nb * 8, s));
+			CK(cudaMemsetAsync(M.alias_hit, 0, nb * 8, s));
+		}
 		m->n_blocks = 0;
 		m->n_bricks = 0;
 		m->n_upper = 0;
