@@ -47,15 +47,29 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def algorithmic_bytes(st, color=False, p_in=12):
-    """N*P_in + U*S_leaf + D1*8*S_leaf + sum_{l>=1} D_l*S_inner + sum_{l>=2} D_l*8*S_inner."""
+def algorithmic_bytes(st, color=False, p_in=12, part="scan"):
+    """N*P_in + U*S_leaf + D1*8*S_leaf + sum_{l>=1} D_l*S_inner + sum_{l>=2} D_l*8*S_inner.
+    part="update" keeps the terms the leaf-update kernels (k_update + k_brick_agg) are responsible
+    for: everything except the point input and the levels above the brick (depth >= 5)."""
     s_leaf, s_inner = (8, 12) if color else (4, 8)
     n, u = st["points"], st["touched_voxels"]
     d1, d2, d3, d4, up = (st["touched_octets"], st["touched_blocks"], st["touched_d3"],
                           st["touched_bricks"], st["upper_nodes"])
+    if part == "update":
+        n, up = 0, 0
     inner_all = d1 + d2 + d3 + d4 + up
     inner_ge2 = d2 + d3 + d4 + up
     return n * p_in + u * s_leaf + d1 * 8 * s_leaf + inner_all * s_inner + inner_ge2 * 8 * s_inner
+
+
+def measured_traffic():
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        d = json.load(open(path))
+        return float(d["traffic_bytes_per_launch"]), d["source"]
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -298,10 +312,14 @@ def main():
     # roofline of the device work of one insert (K1..K4), averaged over the timed scans
     peak, peak_src = measured_peak()
     alg = float(np.mean([algorithmic_bytes(s) for s in per_scan]))
+    alg_upd = float(np.mean([algorithmic_bytes(s, part="update") for s in per_scan]))
     t_scan_ms = float(np.mean([s["ms_total"] for s in per_scan]))
     kern = {k: float(np.mean([s[k] for s in per_scan])) for k in
             ("ms_h2d", "ms_points", "ms_rays", "ms_scatter", "ms_update", "ms_propagate")}
-    achieved = alg / (t_scan_ms * 1e-3) / 1e9
+    # dominant kernel: the leaf update (k_update + k_brick_agg between two CUDA events)
+    achieved = alg_upd / (kern["ms_update"] * 1e-3) / 1e9
+    pipeline = alg / (t_scan_ms * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic()
     last = per_scan[-1]
 
     if rank == 0:
@@ -317,9 +335,16 @@ def main():
             "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": int(n_pts * 12), "d2h_bytes_per_step": int(last["result_bytes"])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "insert pipeline K1..K4 (SURVEY.md 8(d)); dominant kernels in `kernels_ms`",
-                         "algorithmic_bytes_per_scan": alg, "device_ms_per_scan": t_scan_ms},
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "k_update (+k_brick_agg): hit/miss log-odds update of the marked voxels and "
+                                   "depth 1-4 aggregates; CUDA events on the map's stream around every launch "
+                                   "of the timed region",
+                         "algorithmic_bytes_per_launch": alg_upd, "ms_per_launch": kern["ms_update"],
+                         "traffic_source": traffic_src,
+                         # SURVEY.md 8(d)'s whole-pipeline figure: all algorithmic bytes of a scan over the
+                         # device time of the whole insert (K1..K4)
+                         "pipeline": {"algorithmic_bytes_per_scan": alg, "device_ms_per_scan": t_scan_ms,
+                                      "achieved": pipeline, "frac": pipeline / peak}},
             "kernels_ms": kern,
             "counters": {k: int(last[k]) for k in ("rays", "touched_voxels", "hit_voxels", "touched_octets",
                                                     "touched_blocks", "touched_d3", "touched_bricks",

@@ -621,7 +621,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		}
 		if (M.color) k_brick_agg<true><<<agrid, 256, 0, s>>>(M, m->n_bricks);
 		else k_brick_agg<false><<<agrid, 256, 0, s>>>(M, m->n_bricks);
-		++m->launches;
+		m->launches += 2;  // k_update + k_brick_agg
 	}
 	if (m->profiling) CK(cudaEventRecord(m->ev[5], s));
 	// K4: upper levels, depth 5 .. L.  Only bricks created by this scan can create upper
