@@ -167,6 +167,13 @@ int ufo_b200_last_scan_stats(ufo_b200_map* m, ufo_b200_scan_stats* out);
  * (one extra atomic per ray). */
 int ufo_b200_set_profiling(ufo_b200_map* m, int enable);
 
+/* Spatial sharding over several GPUs (variant 1): every rank is given the same
+ * scans (broadcast) and keeps only the bricks (16^3-voxel nodes) it owns -- ownership is a hash of
+ * the brick key, so the touched space splits evenly wherever the sensor is.  The union of the
+ * ranks' value fields is the single-GPU map; no state is exchanged.  Aggregates of depth >= 5 are
+ * per rank (partial) in this mode.  Must be called on an empty map.  world <= 1 turns it off. */
+int ufo_b200_set_shard(ufo_b200_map* m, uint32_t rank, uint32_t world);
+
 /* Forget everything (Octree::clear, octree.h:541-560): keeps device pools. */
 int ufo_b200_clear(ufo_b200_map* m);
 

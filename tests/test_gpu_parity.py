@@ -119,6 +119,25 @@ def test_insert_depth_1_and_2():
               [dict(origin=o, xyz=p, max_range=3.0, depth=1), dict(origin=o2, xyz=p2, max_range=4.0, depth=2)])
 
 
+def test_insert_depth_3_and_4():
+    """Free-space nodes of 8^3 and 16^3 voxels (updateAllChildren, occupancy_map_base.h:1085-1120),
+    mixed with depth-0 scans so that lazily shared values get split again."""
+    o, p, c = scans.rgbd(width=80, height=60)
+    o2, p2, c2 = scans.rgbd(k=3, width=80, height=60)
+    _run_case(dict(resolution=0.02),
+              [dict(origin=o, xyz=p, rgb=c, max_range=3.0, discrete=True, depth=3),
+               dict(origin=o2, xyz=p2, rgb=c2, max_range=3.0, discrete=True, depth=0),
+               dict(origin=o2, xyz=p2, rgb=c2, max_range=3.0, discrete=True, depth=4)], color=True)
+    _run_case(dict(resolution=0.05),
+              [dict(origin=o, xyz=p, max_range=3.0, depth=4), dict(origin=o2, xyz=p2, max_range=4.0, depth=3),
+               dict(origin=o, xyz=p, max_range=4.0, depth=3, simple=True)])
+    gpu = Map(0.05)
+    with pytest.raises(UfoError) as e:
+        gpu.insert(o, p, depth=5)
+    assert e.value.status == E_UNSUPPORTED
+    gpu.close()
+
+
 def test_simple_ray_casting():
     o, p, _ = scans.rgbd(width=80, height=60)
     _run_case(dict(resolution=0.05), [dict(origin=o, xyz=p, max_range=4.0, simple=True)])
@@ -180,6 +199,37 @@ def test_empty_and_unsupported():
         gpu.insert([0, 0, 0], [[1.0, 0, 0]], early_stopping=3)
     assert e.value.status == E_UNSUPPORTED
     gpu.close()
+
+
+def test_spatial_shards_partition_the_map():
+    """SURVEY.md 8(e) variant 1: every rank sees the whole scan and keeps the bricks it owns.
+    Emulated here with three maps on one device: the shards are disjoint and their union is the
+    unsharded map, bit for bit (the multi-GPU run only adds the broadcast of the scan)."""
+    world = 3
+    full = Map(0.05, initial_blocks=1 << 14)
+    shards = [Map(0.05, initial_blocks=1 << 14) for _ in range(world)]
+    for r, m in enumerate(shards):
+        m.set_shard(r, world)
+    for k in range(3):
+        o, p = scans.velodyne64(k=k, rings=16, azimuths=512)
+        for m in [full] + shards:
+            m.insert(o, p, max_range=20.0)
+    fields = [m.value_field() for m in shards]
+    codes = np.concatenate([f[0] for f in fields])
+    assert len(np.unique(codes)) == len(codes), "shards overlap"
+    assert min(len(f[0]) for f in fields) > 0.2 * len(codes) / world, "ownership is badly unbalanced"
+    order = np.argsort(codes, kind="stable")
+    union = (codes[order], np.concatenate([f[1] for f in fields])[order], np.concatenate([f[2] for f in fields])[order])
+    assert_value_fields_equal(union, full.value_field(), what="union of shards")
+    # a brick is wholly owned by one rank, so aggregates up to depth 4 are exact on the owner
+    c = fields[0][0][:: max(1, len(fields[0][0]) // 500)]
+    for lvl in (2, 4):
+        q = (c >> np.uint64(3 * lvl)) << np.uint64(3 * lvl)
+        a = shards[0].query(q, lvl)
+        b = full.query(q, lvl)
+        assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1])
+    with pytest.raises(UfoError):
+        full.set_shard(0, 2)  # not empty any more
 
 
 def test_async_matches_sync_and_determinism():

@@ -55,7 +55,7 @@ SYMBOLS = [
     "ufo_b200_key_to_coord", "ufo_b200_key_to_code", "ufo_b200_code_to_key", "ufo_b200_query",
     "ufo_b200_export_leaves", "ufo_b200_set_sensor_model", "ufo_b200_sensor_model_logit",
     "ufo_b200_change_bbox", "ufo_b200_reset_change_bbox", "ufo_b200_last_scan_stats",
-    "ufo_b200_set_profiling", "ufo_b200_clear", "ufo_b200_version",
+    "ufo_b200_set_profiling", "ufo_b200_clear", "ufo_b200_version", "ufo_b200_set_shard",
 ]
 
 _lib = None
@@ -101,6 +101,7 @@ def load():
     lib.ufo_b200_last_scan_stats.argtypes = [vp, C.POINTER(ScanStats)]
     lib.ufo_b200_set_profiling.argtypes = [vp, i32]
     lib.ufo_b200_clear.argtypes = [vp]
+    lib.ufo_b200_set_shard.argtypes = [vp, u32, u32]
     lib.ufo_b200_version.restype = C.c_char_p
     _lib = lib
     return lib
@@ -213,6 +214,10 @@ class Map:
 
     def clear(self):
         self._check(self.lib.ufo_b200_clear(self.h))
+
+    def set_shard(self, rank, world):
+        """Keep only the bricks this rank owns (spatial sharding over several GPUs)."""
+        self._check(self.lib.ufo_b200_set_shard(self.h, int(rank), int(world)))
 
     # -- state ----------------------------------------------------------------
     def value_field(self):

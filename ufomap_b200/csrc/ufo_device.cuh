@@ -73,6 +73,8 @@ struct DeviceMap {
 	uint32_t default_flags;  // flags of a never-touched voxel / subtree (value 0.0)
 	uint32_t color;
 	uint32_t scan_id;
+	// spatial sharding over several GPUs: this map only keeps the bricks it owns
+	uint32_t shard_rank, shard_world;  // world <= 1: owns everything
 
 	// brick hash (open addressing, linear probing): 16-byte entries {key, slot} so one
 	// 128-bit load resolves a probe
@@ -138,6 +140,13 @@ UFO_HD uint32_t hash_u64(uint64_t k)
 	k *= 0xc4ceb9fe1a85ec53ull;
 	k ^= k >> 33;
 	return (uint32_t)k;
+}
+
+// Owner rank of a brick when a map is sharded over several GPUs: a hash of the brick key, so
+// that every rank gets an equal share of the touched space wherever the sensor is.
+UFO_HD uint32_t brick_owner(uint64_t brick_key, uint32_t world)
+{
+	return (uint32_t)((hash_u64(brick_key ^ 0x9e3779b97f4a7c15ull) >> 7) % world);
 }
 
 // 21 bits per axis

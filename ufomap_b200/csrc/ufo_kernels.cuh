@@ -125,7 +125,7 @@ __device__ __forceinline__ uint32_t table_insert(const ScanArgs& a, uint64_t key
 // outside the tree: the mark is kept under the UNWRAPPED brick (own set semantics, like the
 // reference's CodeSet/CodeMap) and the wrapped target brick is created right away so that
 // the host's brick count is final after this kernel.  is_hit selects the mask array.
-__device__ __noinline__ void mark_alias(const DeviceMap& M, uint32_t bx, uint32_t by, uint32_t bz,
+__device__ __noinline__ void mark_alias(const DeviceMap M, uint32_t bx, uint32_t by, uint32_t bz,
                                         unsigned long long bits, bool is_hit)
 {
 	if (!M.alias_miss) {
@@ -133,6 +133,10 @@ __device__ __noinline__ void mark_alias(const DeviceMap& M, uint32_t bx, uint32_
 		return;
 	}
 	const uint32_t km = M.g.key_mask >> 2;
+	// owned by the rank that owns the WRAPPED brick the mark lands in
+	if (M.shard_world > 1 &&
+	    brick_owner(pack_key((bx & km) >> 2, (by & km) >> 2, (bz & km) >> 2), M.shard_world) != M.shard_rank)
+		return;
 	const uint32_t src = brick_find_or_create(M, pack_key(bx >> 2, by >> 2, bz >> 2));
 	const uint32_t dst = brick_find_or_create(M, pack_key((bx & km) >> 2, (by & km) >> 2, (bz & km) >> 2));
 	if (src == kNone || dst == kNone) return;
@@ -140,6 +144,39 @@ __device__ __noinline__ void mark_alias(const DeviceMap& M, uint32_t bx, uint32_
 	M.brick_stamp[dst] = M.scan_id;
 	atomicOr(&(is_hit ? M.alias_hit : M.alias_miss)[(size_t)src * 64 + morton2(bx, by, bz)], bits);
 	atomicAdd(&M.ctr->alias_marks, 1u);
+}
+
+// Free-space node of depth 3 (8^3 voxels = 8 blocks) or 4 (16^3 = the whole brick): every
+// voxel below it is marked.  (x, y, z) is any voxel key inside the node, 21 bits per axis.
+// updateAllChildren (occupancy_map_base.h:1085-1120) applies the miss to every leaf below
+// the node; in the value-field representation that is a full mask on each of its blocks.
+__device__ __noinline__ void mark_node_miss(const DeviceMap M, uint32_t x, uint32_t y, uint32_t z,
+                                               uint32_t depth)
+{
+	const uint32_t side = 1u << (depth - 2);  // blocks per axis: 2 or 4
+	const uint32_t bx0 = (x >> depth) << (depth - 2), by0 = (y >> depth) << (depth - 2),
+	               bz0 = (z >> depth) << (depth - 2);
+	if ((x | y | z) & ~M.g.key_mask) {
+		for (uint32_t k = 0; k < side; ++k)
+			for (uint32_t j = 0; j < side; ++j)
+				for (uint32_t i = 0; i < side; ++i) mark_alias(M, bx0 + i, by0 + j, bz0 + k, ~0ull, false);
+		return;
+	}
+	if (M.shard_world > 1 && brick_owner(pack_key(bx0 >> 2, by0 >> 2, bz0 >> 2), M.shard_world) != M.shard_rank) return;
+	const uint32_t brick = brick_find_or_create(M, pack_key(bx0 >> 2, by0 >> 2, bz0 >> 2));
+	if (brick == kNone) return;
+	M.brick_stamp[brick] = M.scan_id;
+	// the blocks of a depth-3 node are 8 consecutive Morton children, a depth-4 node is all 64
+	const uint32_t first = depth == 3 ? (morton2(bx0, by0, bz0) & ~7u) : 0u;
+	const uint32_t count = depth == 3 ? 8u : 64u;
+	for (uint32_t c = 0; c < count; ++c) atomicOr(&M.miss_mask[(size_t)brick * 64 + first + c], ~0ull);
+}
+
+__device__ __noinline__ void scatter_slow(const DeviceMap M, uint32_t x, uint32_t y, uint32_t z,
+                                          unsigned long long bits, uint32_t depth)
+{
+	if (depth >= 3) mark_node_miss(M, x, y, z, depth);
+	else mark_alias(M, x >> 2, y >> 2, z >> 2, bits, false);
 }
 
 // mark a depth-0 hit voxel directly (mono maps)
@@ -152,7 +189,9 @@ __device__ __forceinline__ void mark_hit(const DeviceMap& M, Key3 k)
 		mark_alias(M, k.x >> 2, k.y >> 2, k.z >> 2, 1ull << linear2(k.x, k.y, k.z), true);
 		return;
 	}
-	uint32_t brick = brick_find_or_create(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
+	const uint64_t bkey = pack_key(k.x >> 4, k.y >> 4, k.z >> 4);
+	if (M.shard_world > 1 && brick_owner(bkey, M.shard_world) != M.shard_rank) return;
+	uint32_t brick = brick_find_or_create(M, bkey);
 	if (brick == kNone) return;
 	M.brick_stamp[brick] = M.scan_id;
 	const size_t b = (size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2);
@@ -324,6 +363,7 @@ __global__ void __launch_bounds__(256) k_hits(DeviceMap M, ScanArgs a)
 		if (M.leaf_rgb[tl] == 0) M.leaf_rgb[tl] = tu;
 		return;
 	}
+	if (M.shard_world > 1 && brick_owner(pack_key(k.x >> 4, k.y >> 4, k.z >> 4), M.shard_world) != M.shard_rank) return;
 	uint32_t brick = brick_find_or_create(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
 	if (brick == kNone) return;
 	M.brick_stamp[brick] = M.scan_id;
@@ -382,6 +422,7 @@ __device__ __forceinline__ void flush_block(const DeviceMap& M, BrickCache& bc, 
 		return;
 	}
 	uint32_t bx = kx >> 4, by = ky >> 4, bz = kz >> 4;
+	if (M.shard_world > 1 && brick_owner(pack_key(bx, by, bz), M.shard_world) != M.shard_rank) return;
 	if (bc.slot == kNone || bx != bc.bx || by != bc.by || bz != bc.bz) {
 		bc.bx = bx;
 		bc.by = by;
@@ -571,7 +612,7 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 				Vec3 dir = vsub(from, to);
 				dist = vnorm(dir);
 				dir = vdiv(dir, dist);
-				walk_init(M.g, to, from, dir, DEPTH, w);
+				walk_init(M.g, to, from, dir, a.depth, w);  // DEPTH only selects the mark pattern
 				same = w.same;
 				active = same ? 0u : 1u;
 			}
@@ -616,7 +657,7 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 // items are visited j-major: the walks run from the end point towards the sensor, so the
 // tails of all regions hold the records next to the sensor, which thousands of rays share
 // -- visiting them together turns most of the mask atomics into L2 hits.
-__global__ void __launch_bounds__(kChunk) k_scatter(DeviceMap M, ScanArgs a)
+__global__ void __launch_bounds__(kChunk, 8) k_scatter(DeviceMap M, ScanArgs a)
 {
 	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;
 	const uint32_t n_regions = (a.n + 31) / 32;
@@ -631,14 +672,16 @@ __global__ void __launch_bounds__(kChunk) k_scatter(DeviceMap M, ScanArgs a)
 		const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&a.seg[a.seg_base[r] + lo + threadIdx.x]);
 		uint32_t x, y, z;
 		unpack_key(v.y, x, y, z);
-		if ((x | y | z) & ~M.g.key_mask) {  // key outside the tree: see DeviceMap::alias_miss
-			mark_alias(M, x >> 2, y >> 2, z >> 2, v.x, false);
+		if (a.depth >= 3 || ((x | y | z) & ~M.g.key_mask)) {
+			// rare: free-space nodes larger than a block, or a key outside the tree
+			scatter_slow(M, x, y, z, v.x, a.depth);
 			continue;
 		}
 		x >>= 2;  // block coordinates
 		y >>= 2;
 		z >>= 2;
 		const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
+		if (M.shard_world > 1 && brick_owner(bkey, M.shard_world) != M.shard_rank) continue;  // another GPU's brick
 		const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
 		const ulonglong2 e0 = ld_volatile_entry(&M.bh_tab[hidx]);
 		const ulonglong2 e1 = ld_volatile_entry(&M.bh_tab[hidx + 1]);
@@ -684,6 +727,12 @@ __global__ void __launch_bounds__(128) k_rays_simple(DeviceMap M, ScanArgs a)
 	unsigned int visits = 0;
 	for (int s = 0; s <= num_steps; ++s) {
 		Key3 k = point_to_key(M.g, cur, a.depth);
+		if (a.depth >= 3) {
+			mark_node_miss(M, k.x & 0x1fffffu, k.y & 0x1fffffu, k.z & 0x1fffffu, a.depth);
+			++visits;
+			cur = vadd(cur, step);
+			continue;
+		}
 		if (have && ((((k.x ^ ox) | (k.y ^ oy) | (k.z ^ oz)) >> 2) != 0)) {
 			flush_block(M, bc, ox, oy, oz, acc);
 			acc = 0;
@@ -734,6 +783,9 @@ __device__ __forceinline__ uint32_t rms_rgb(const uint32_t* c, int n)
 // after one coalesced mask read.  The brick-level aggregates follow in k_brick_agg.
 //   hit-then-miss float log-odds update   updateOccupancy, occupancy_map_base.h:1139-1145
 //   depth-1/2 aggregates per block, depth-3/4 per brick   updateNode, :1179-1224
+#ifndef UFO_UPD_MINBLOCKS
+#define UFO_UPD_MINBLOCKS 8
+#endif
 constexpr int kUpdThreads = 256;
 
 __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, float* lp, uint32_t m8,
@@ -770,12 +822,19 @@ __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, flo
 constexpr int kStatSlots = 64;  // per-scan counters are spread over slots to avoid same-address atomics
 
 template <bool COLOR>
-__global__ void __launch_bounds__(kUpdThreads, 8) k_update(DeviceMap M, float miss, uint32_t n_bricks)
+__global__ void __launch_bounds__(kUpdThreads, UFO_UPD_MINBLOCKS) k_update(DeviceMap M, float miss, uint32_t first_brick,
+                                                           uint32_t n_bricks)
 {
 	const uint32_t lane = threadIdx.x & 31, oct = threadIdx.x & 7;
-	const size_t b = (size_t)blockIdx.x * (kUpdThreads / 8) + (threadIdx.x >> 3);  // = brick * 64 + child
+	// = brick * 64 + child
+	const size_t b = (size_t)first_brick * 64 + (size_t)blockIdx.x * (kUpdThreads / 8) + (threadIdx.x >> 3);
 	const uint32_t brick = (uint32_t)(b >> 6);
 	if (brick >= n_bricks) return;
+	// launched before the host has seen this scan's allocation counters: if a pool overflowed,
+	// the marking kernels are re-run and nothing may be consumed yet
+	// (plain cached load: the flag is final before this kernel starts, and a volatile load from
+	// every thread would hammer one L2 slice)
+	if (__ldg(&M.ctr->overflow)) return;
 	// No brick_stamp check: the masks of a brick nothing marked this scan are all zero
 	// (every scan clears what it consumed), so the mask read itself is the filter.
 	// The four groups of a warp belong to the same brick: `brick` is warp-uniform.

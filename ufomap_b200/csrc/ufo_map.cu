@@ -80,7 +80,8 @@ struct ufo_b200_map {
 	ufo_b200_params params{};
 	DeviceMap M{};
 	int device = 0;
-	cudaStream_t own_stream = nullptr, stream = nullptr;
+	cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+	cudaEvent_t ev_marked = nullptr;
 	// sensor model as the reference stores it (double log-odds)
 	double occ_thr_log = 0, free_thr_log = 0, hit_log = 0, miss_log = 0, cmin_log = 0, cmax_log = 0;
 	// host mirror of the counters (pinned)
@@ -226,12 +227,6 @@ void push_counters(Map* m)
 	}
 	*m->h_ctr = c;
 	CK(cudaMemcpyAsync(m->M.ctr, m->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice, m->stream));
-}
-
-void pull_counters(Map* m)
-{
-	CK(cudaMemcpyAsync(m->h_ctr, m->M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
-	CK(cudaStreamSynchronize(m->stream));
 }
 
 // grow whichever pool overflowed; `want_*` are the allocation counters the failed
@@ -421,6 +416,16 @@ void ensure_seg(Map* m, unsigned long long want)
 	m->device_bytes += want * sizeof(QEntry);
 }
 
+// k_update over the bricks [first, last)
+void launch_update(Map* m, float miss, uint32_t first, uint32_t last)
+{
+	const uint32_t groups = (last - first) * 64u;  // one eight-lane group per (brick, child)
+	const uint32_t grid = (groups + kUpdThreads / 8 - 1) / (kUpdThreads / 8);
+	if (m->M.color) k_update<true><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
+	else k_update<false><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
+	++m->launches;
+}
+
 void launch_rays(Map* m, const ScanArgs& a, int simple)
 {
 	if (simple) {
@@ -468,8 +473,8 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		m->set_error("early_stopping is order-dependent in the reference (occupancy_map_base.h:1289-1298) and is not supported");
 		return UFO_B200_E_UNSUPPORTED;
 	}
-	if (depth > 2) {
-		m->set_error("insert depth %u > 2 is not supported yet", depth);
+	if (depth > 4) {
+		m->set_error("insert depth %u > 4 (free-space nodes larger than a brick) is not supported", depth);
 		return UFO_B200_E_UNSUPPORTED;
 	}
 	CK(cudaSetDevice(m->device));
@@ -537,6 +542,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	push_counters(m);
 	const uint32_t bricks_before = m->n_bricks;
 	uint32_t regrows = 0;
+	bool speculated = false;
 	while (true) {
 		if (need_table) {
 			CK(cudaMemsetAsync(m->d_tab_keys, 0xff, (size_t)m->tab_size * sizeof(unsigned long long), s));
@@ -558,7 +564,20 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		}
 		if (m->profiling) CK(cudaEventRecord(m->ev[3], s));
 		CK(cudaGetLastError());
-		pull_counters(m);
+		// The counters of the marking kernels are read back on a second stream while the update
+		// of the bricks that existed before this scan already runs (it backs off by itself if a
+		// pool overflowed); bricks created by this scan follow once their number is known.
+		CK(cudaEventRecord(m->ev_marked, s));
+		const bool aliases_possible = M.alias_miss != nullptr;
+		const bool speculate = !aliases_possible && bricks_before > 0;
+		if (speculate) {
+			if (m->profiling) CK(cudaEventRecord(m->ev[4], s));
+			launch_update(m, a.miss, 0, bricks_before);
+		}
+		CK(cudaStreamWaitEvent(m->copy_stream, m->ev_marked, 0));
+		CK(cudaMemcpyAsync(m->h_ctr, M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->copy_stream));
+		CK(cudaStreamSynchronize(m->copy_stream));
+		speculated = speculate;
 		uint32_t ov = m->h_ctr->overflow;
 		if (!ov) break;
 		// an allocation failed: grow, restore consistent counters, run K1/K2 again
@@ -602,18 +621,16 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 
 	const bool aliases = m->h_ctr->alias_marks != 0 && M.alias_miss;
 	const uint32_t alias_grid = (uint32_t)(((size_t)m->n_bricks * 64 + 255) / 256);
-	if (m->profiling) CK(cudaEventRecord(m->ev[4], s));
+	if (m->profiling && !speculated) CK(cudaEventRecord(m->ev[4], s));
 	if (aliases) {
 		k_alias_apply<<<alias_grid, 256, 0, s>>>(M, m->n_bricks, M.hit, 1);
 		++m->launches;
 	}
-	// K3
+	// K3 (the part not launched speculatively above)
 	if (m->n_bricks) {
-		const uint32_t groups = m->n_bricks * 64u;  // one eight-lane group per (brick, child)
-		const uint32_t ugrid = (groups + kUpdThreads / 8 - 1) / (kUpdThreads / 8);
+		const uint32_t first = speculated ? bricks_before : 0u;
+		if (first < m->n_bricks) launch_update(m, a.miss, first, m->n_bricks);
 		const uint32_t agrid = (m->n_bricks + 7) / 8;
-		if (M.color) k_update<true><<<ugrid, kUpdThreads, 0, s>>>(M, a.miss, m->n_bricks);
-		else k_update<false><<<ugrid, kUpdThreads, 0, s>>>(M, a.miss, m->n_bricks);
 		if (aliases) {
 			k_alias_apply<<<alias_grid, 256, 0, s>>>(M, m->n_bricks, a.miss, 0);
 			k_alias_refresh<<<alias_grid, 256, 0, s>>>(M, m->n_bricks);
@@ -621,7 +638,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		}
 		if (M.color) k_brick_agg<true><<<agrid, 256, 0, s>>>(M, m->n_bricks);
 		else k_brick_agg<false><<<agrid, 256, 0, s>>>(M, m->n_bricks);
-		m->launches += 2;  // k_update + k_brick_agg
+		++m->launches;
 	}
 	if (m->profiling) CK(cudaEventRecord(m->ev[5], s));
 	// K4: upper levels, depth 5 .. L.  Only bricks created by this scan can create upper
@@ -735,11 +752,15 @@ int ufo_b200_create(const ufo_b200_params* p, ufo_b200_map** out)
 		if (m->ray_blocks_per_sm < 1) m->ray_blocks_per_sm = 1;
 		m->params = *p;
 		CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&m->ev_marked, cudaEventDisableTiming));
 		m->stream = m->own_stream;
 		for (auto& e : m->ev) CK(cudaEventCreate(&e));
 		CK(cudaHostAlloc(reinterpret_cast<void**>(&m->h_ctr), sizeof(Counters), cudaHostAllocDefault));
 		m->M.g = make_geometry(p->resolution, p->depth_levels);
 		m->M.color = p->color ? 1u : 0u;
+		m->M.shard_rank = 0;
+		m->M.shard_world = 1;
 		m->occ_thr_log = to_logit(p->occupied_thres);
 		m->free_thr_log = to_logit(p->free_thres);
 		m->hit_log = to_logit(p->prob_hit);
@@ -785,6 +806,8 @@ void ufo_b200_destroy(ufo_b200_map* m)
 		if (e) cudaEventDestroy(e);
 	if (m->h_ctr) cudaFreeHost(m->h_ctr);
 	if (m->own_stream) cudaStreamDestroy(m->own_stream);
+	if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+	if (m->ev_marked) cudaEventDestroy(m->ev_marked);
 	delete m;
 }
 
@@ -1071,6 +1094,21 @@ int ufo_b200_set_profiling(ufo_b200_map* m, int enable)
 	if (!m) return UFO_B200_E_INVALID;
 	m->profiling = enable < 0 ? 0 : enable;
 	return UFO_B200_OK;
+}
+
+int ufo_b200_set_shard(ufo_b200_map* m, uint32_t rank, uint32_t world)
+{
+	if (!m || (world > 1 && rank >= world)) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		sync_map(m);
+		if (m->n_bricks != 0) {
+			m->set_error("ufo_b200_set_shard must be called on an empty map");
+			return (int)UFO_B200_E_INVALID;
+		}
+		m->M.shard_rank = world > 1 ? rank : 0;
+		m->M.shard_world = world > 1 ? world : 1;
+		return (int)UFO_B200_OK;
+	});
 }
 
 int ufo_b200_clear(ufo_b200_map* m)
