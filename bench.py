@@ -221,6 +221,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="sensors", choices=["sensors", "shard"],
+                    help="N>1: 'sensors' = one sensor stream + map per GPU (weak scaling, default); "
+                         "'shard' = ONE scan stream, broadcast over NCCL, map sharded by brick ownership "
+                         "(strong scaling, SURVEY.md 8(e) variant 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -243,7 +247,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     total = args.steps + args.warmup
-    origins, clouds = make_scans(total, rank)
+    shard = args.mode == "shard" and world > 1
+    origins, clouds = make_scans(total, 0 if shard else rank)
     n_pts = clouds[0].shape[0]
     stream = torch.cuda.current_stream(dev)
 
@@ -255,6 +260,8 @@ def main():
     def fresh_map():
         m = capi.Map(RESOLUTION, device=local_rank, initial_bricks=1 << 19)
         m.set_stream(stream.cuda_stream)
+        if shard:
+            m.set_shard(rank, world)
         return m
 
     def timed_loop(m, feed):
@@ -284,8 +291,17 @@ def main():
     m = fresh_map()
     m.set_profiling(1)
 
+    bcast = torch.empty_like(d_clouds[0]) if shard else None
+
     def feed_device(mm, k):
-        mm.insert_packed(origins[k], d_clouds[k].data_ptr(), n_pts, capi.XYZ_F32, max_range=MAX_RANGE,
+        src = d_clouds[k]
+        if shard:
+            # the one collective of the sharded mode: rank 0's scan goes to every GPU (1.5 MB)
+            if rank == 0:
+                bcast.copy_(src)
+            dist.broadcast(bcast, src=0)
+            src = bcast
+        mm.insert_packed(origins[k], src.data_ptr(), n_pts, capi.XYZ_F32, max_range=MAX_RANGE,
                          on_device=True, async_=True)
 
     ms_dev, per_scan, launches, clocks = timed_loop(m, feed_device)
@@ -298,7 +314,16 @@ def main():
     h_clouds = [torch.from_numpy(c).pin_memory() for c in clouds]
     m = fresh_map()
 
+    stage = torch.empty(n_pts, 3, dtype=torch.float32, device=dev) if shard else None
+
     def feed_host(mm, k):
+        if shard:
+            if rank == 0:
+                stage.copy_(h_clouds[k], non_blocking=True)  # H2D once, on rank 0
+            dist.broadcast(stage, src=0)
+            mm.insert_packed(origins[k], stage.data_ptr(), n_pts, capi.XYZ_F32, max_range=MAX_RANGE,
+                             on_device=True, async_=True)
+            return
         mm.insert_packed(origins[k], h_clouds[k].data_ptr(), n_pts, capi.XYZ_F32, max_range=MAX_RANGE,
                          on_device=False, async_=True)
 
@@ -306,8 +331,9 @@ def main():
     m.close()
 
     steps = args.steps
-    value = world * steps * n_pts / (ms_dev * 1e-3)
-    e2e = world * steps * n_pts / (ms_e2e * 1e-3)
+    streams = 1 if shard else world  # sharded mode integrates ONE stream with all GPUs
+    value = streams * steps * n_pts / (ms_dev * 1e-3)
+    e2e = streams * steps * n_pts / (ms_e2e * 1e-3)
 
     # roofline of the device work of one insert (K1..K4), averaged over the timed scans
     peak, peak_src = measured_peak()
@@ -326,10 +352,12 @@ def main():
         line = {
             "metric": "points_integrated_per_s", "value": value, "unit": "points/s",
             "scans_per_s": value / n_pts, "n_gpus": world, "steps": steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "strong" if shard else "weak",
             "vs_baseline": None, "dtype": "f64 geometry + f32 log-odds", "data": "synthetic",
             "config": {"workload": WORKLOAD, "points_per_scan": n_pts, "input": "float32 xyz",
-                       "parallelism": "1 map per GPU" if world == 1 else "one sensor stream + map per GPU, no merge",
+                       "parallelism": ("1 map per GPU" if world == 1 else
+                                       ("one scan stream broadcast over NCCL, map sharded by brick ownership"
+                                        if shard else "one sensor stream + map per GPU, no merge")),
                        "l2": "per-scan working set (%.1f GB leaf data touched, map %.1f GB) exceeds the 126 MB L2; no flush"
                              % (last["touched_blocks"] * 256 / 1e9, dev_bytes / 1e9)},
             "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e / steps,

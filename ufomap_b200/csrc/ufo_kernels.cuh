@@ -657,7 +657,13 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 // items are visited j-major: the walks run from the end point towards the sensor, so the
 // tails of all regions hold the records next to the sensor, which thousands of rays share
 // -- visiting them together turns most of the mask atomics into L2 hits.
-__global__ void __launch_bounds__(kChunk, 8) k_scatter(DeviceMap M, ScanArgs a)
+#ifndef UFO_SCATTER_MINBLOCKS
+#define UFO_SCATTER_MINBLOCKS 8
+#endif
+// GENERIC = false is the common case (insert depth <= 2, unsharded map): the extra tests are
+// compiled out so that the hot path keeps to 32 registers without spills.
+template <bool GENERIC>
+__global__ void __launch_bounds__(kChunk, UFO_SCATTER_MINBLOCKS) k_scatter(DeviceMap M, ScanArgs a)
 {
 	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;
 	const uint32_t n_regions = (a.n + 31) / 32;
@@ -672,16 +678,19 @@ __global__ void __launch_bounds__(kChunk, 8) k_scatter(DeviceMap M, ScanArgs a)
 		const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&a.seg[a.seg_base[r] + lo + threadIdx.x]);
 		uint32_t x, y, z;
 		unpack_key(v.y, x, y, z);
-		if (a.depth >= 3 || ((x | y | z) & ~M.g.key_mask)) {
-			// rare: free-space nodes larger than a block, or a key outside the tree
-			scatter_slow(M, x, y, z, v.x, a.depth);
+		if ((GENERIC && a.depth >= 3) || ((x | y | z) & ~M.g.key_mask)) {
+			// rare: free-space nodes larger than a block, or a key outside the tree.  The lean
+			// variant has no slow path: it asks the host for the alias arrays (bit 5), and the
+			// re-run -- like every later scan of this map -- uses the generic variant.
+			if (GENERIC) scatter_slow(M, x, y, z, v.x, a.depth);
+			else atomicOr(&M.ctr->overflow, 32u);
 			continue;
 		}
 		x >>= 2;  // block coordinates
 		y >>= 2;
 		z >>= 2;
 		const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
-		if (M.shard_world > 1 && brick_owner(bkey, M.shard_world) != M.shard_rank) continue;  // another GPU's brick
+		if (GENERIC && M.shard_world > 1 && brick_owner(bkey, M.shard_world) != M.shard_rank) continue;  // another GPU's brick
 		const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
 		const ulonglong2 e0 = ld_volatile_entry(&M.bh_tab[hidx]);
 		const ulonglong2 e1 = ld_volatile_entry(&M.bh_tab[hidx + 1]);

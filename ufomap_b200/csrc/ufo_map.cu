@@ -454,7 +454,8 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 	}
 	{
 		uint32_t sgrid = (uint32_t)m->sm_count * 8;  // all CTAs resident, looping over the work items
-		k_scatter<<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
+		if (a.depth >= 3 || m->M.shard_world > 1 || m->M.alias_miss) k_scatter<true><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
+		else k_scatter<false><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
 	}
 	++m->launches;
 }
