@@ -668,6 +668,8 @@ __global__ void __launch_bounds__(kChunk, UFO_SCATTER_MINBLOCKS) k_scatter(Devic
 	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;
 	const uint32_t n_regions = (a.n + 31) / 32;
 	const unsigned long long n_items = (unsigned long long)ld_volatile_u32(&M.ctr->n_chunks) * n_regions;
+	// (keeping the region lengths in shared memory to skip empty items without a load was
+	// measured slightly slower than this plain loop: 0.537 vs 0.513 ms)
 	for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x) {
 		const uint32_t j = (uint32_t)(it / n_regions), r = (uint32_t)(it % n_regions);
 		const uint32_t cnt = a.seg_count[r];
@@ -908,21 +910,17 @@ __global__ void __launch_bounds__(kUpdThreads, UFO_UPD_MINBLOCKS) k_update(Devic
 			s_new = (mt & 0xff0000u) ? 0u : 1u;
 		}
 	}
-	// counters: one set of atomics per warp
-	for (int o = 16; o > 0; o >>= 1) {
-		s_vox += __shfl_xor_sync(0xffffffffu, s_vox, o);
-		s_hit += __shfl_xor_sync(0xffffffffu, s_hit, o);
-		s_oct += __shfl_xor_sync(0xffffffffu, s_oct, o);
-		s_blk += __shfl_xor_sync(0xffffffffu, s_blk, o);
-		s_new += __shfl_xor_sync(0xffffffffu, s_new, o);
-	}
+	// counters: packed into one word (per warp: voxels <= 256, hits <= 256, octets <= 32,
+	// blocks <= 4, new blocks <= 4), one shuffle reduction and one set of atomics per warp
+	uint32_t packed = s_vox | (s_hit << 10) | (s_oct << 20) | (s_blk << 26) | (s_new << 29);
+	for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
 	if (lane == 0) {
 		unsigned long long* slot = M.ctr->stat[(blockIdx.x * 8 + (threadIdx.x >> 5)) % kStatSlots];
-		atomicAdd(&slot[0], (unsigned long long)s_vox);
-		if (s_hit) atomicAdd(&slot[1], (unsigned long long)s_hit);
-		atomicAdd(&slot[2], (unsigned long long)s_oct);
-		atomicAdd(&slot[3], (unsigned long long)s_blk);
-		if (s_new) atomicAdd(&slot[4], (unsigned long long)s_new);
+		atomicAdd(&slot[0], (unsigned long long)(packed & 0x3ffu));
+		if ((packed >> 10) & 0x3ffu) atomicAdd(&slot[1], (unsigned long long)((packed >> 10) & 0x3ffu));
+		atomicAdd(&slot[2], (unsigned long long)((packed >> 20) & 0x3fu));
+		atomicAdd(&slot[3], (unsigned long long)((packed >> 26) & 0x7u));
+		if (packed >> 29) atomicAdd(&slot[4], (unsigned long long)(packed >> 29));
 	}
 }
 
