@@ -94,6 +94,25 @@ int ufo_b200_insert_device(ufo_b200_map* m, const double origin[3], const void* 
                            int simple_ray_casting, uint32_t early_stopping, int discrete,
                            int async);
 
+/* insertPointCloud[Discrete](sensor_origin, cloud, frame_origin, ...) -- the overloads that
+ * first move the cloud into the map frame (occupancy_map_base.h:313-327, 403-417;
+ * occupancy_map_color.h:146-160, 253-267 -> PointCloudT::transform point_cloud.h:157-166 ->
+ * Pose6::transform math/pose6.h:115-125).  frame_pose = {tx, ty, tz, qw, qx, qy, qz}.
+ * The transform runs on the device while the points are read (bit-identical to the
+ * reference's double arithmetic), so the raw sensor buffer crosses PCIe once. */
+int ufo_b200_insert_pointcloud_frame(ufo_b200_map* m, const double origin[3], const void* points,
+                                     size_t n, int layout, const double frame_pose[7],
+                                     double max_range, uint32_t depth, int simple_ray_casting,
+                                     uint32_t early_stopping, int discrete, int async);
+
+/* Host helpers (no device needed).  ufo_b200_transform_points: Pose6::transform of n points of
+ * the given layout into out_xyz[n][3].  ufo_b200_pose_from_rpy: Pose6(x, y, z, roll, pitch,
+ * yaw) math/pose6.h:71-74 with Quaternion(roll, pitch, yaw) math/quaternion.h:69-93. */
+int ufo_b200_transform_points(const double frame_pose[7], const void* points, size_t n, int layout,
+                              double* out_xyz);
+int ufo_b200_pose_from_rpy(double x, double y, double z, double roll, double pitch, double yaw,
+                           double frame_pose[7]);
+
 int ufo_b200_wait(ufo_b200_map* m);           /* insertPointCloudWait */
 int ufo_b200_done(ufo_b200_map* m, int* done); /* insertPointCloudDone */
 

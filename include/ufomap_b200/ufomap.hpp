@@ -83,32 +83,37 @@ class Vector3
 	double v_[3];
 };
 
-// Unit quaternion (w, x, y, z) -- only what the cloud transform needs.
+// Unit quaternion (w, x, y, z) -- only what the cloud transform needs.  The arithmetic lives in
+// the library (ufo_b200_pose_from_rpy / ufo_b200_transform_points), which is compiled without
+// FMA contraction and reproduces math/quaternion.h:69-93,253-286 bit for bit whatever flags the
+// including translation unit is built with.
 class Quaternion
 {
  public:
 	Quaternion() : w_(1), x_(0), y_(0), z_(0) {}
 	Quaternion(double w, double x, double y, double z) : w_(w), x_(x), y_(y), z_(z) {}
-	// roll/pitch/yaw (ZYX) constructor
 	Quaternion(double roll, double pitch, double yaw)
 	{
-		double cr = std::cos(roll / 2), sr = std::sin(roll / 2), cp = std::cos(pitch / 2),
-		       sp = std::sin(pitch / 2), cy = std::cos(yaw / 2), sy = std::sin(yaw / 2);
-		w_ = cr * cp * cy + sr * sp * sy;
-		x_ = sr * cp * cy - cr * sp * sy;
-		y_ = cr * sp * cy + sr * cp * sy;
-		z_ = cr * cp * sy - sr * sp * cy;
+		double pose[7];
+		ufo_b200_pose_from_rpy(0, 0, 0, roll, pitch, yaw, pose);
+		w_ = pose[3];
+		x_ = pose[4];
+		y_ = pose[5];
+		z_ = pose[6];
 	}
 	double w() const { return w_; }
 	double x() const { return x_; }
 	double y() const { return y_; }
 	double z() const { return z_; }
+	Quaternion inversed() const { return Quaternion(w_, -x_, -y_, -z_); }
 	Vector3 rotate(Vector3 const& p) const
 	{
-		// p' = p + 2 w (q x p) + 2 q x (q x p)
-		Vector3 q(x_, y_, z_);
-		Vector3 t = q.cross(p) * 2.0;
-		return p + t * w_ + q.cross(t);
+		double pose[7] = {0, 0, 0, w_, x_, y_, z_};
+		double r[3];
+		ufo_b200_transform_points(pose, p.data(), 1, UFO_B200_XYZ_F64, r);
+		// (goes through the zero-translation transform: identical except that a -0.0 component
+		// comes back as +0.0, which no key computation can see)
+		return Vector3(r[0], r[1], r[2]);
 	}
 
  private:
@@ -124,9 +129,34 @@ class Pose6
 	    : t_(x, y, z), r_(roll, pitch, yaw)
 	{
 	}
+	Pose6(double t_x, double t_y, double t_z, double r_w, double r_x, double r_y, double r_z)
+	    : t_(t_x, t_y, t_z), r_(r_w, r_x, r_y, r_z)
+	{
+	}
 	Vector3 const& translation() const { return t_; }
+	Vector3& translation() { return t_; }
 	Quaternion const& rotation() const { return r_; }
-	Vector3 transform(Vector3 const& p) const { return r_.rotate(p) + t_; }
+	Quaternion& rotation() { return r_; }
+	// math/pose6.h:115-125
+	Vector3 transform(Vector3 const& p) const
+	{
+		double pose[7];
+		pack(pose);
+		double r[3];
+		ufo_b200_transform_points(pose, p.data(), 1, UFO_B200_XYZ_F64, r);
+		return Vector3(r[0], r[1], r[2]);
+	}
+	// tx ty tz qw qx qy qz, the C ABI's frame_pose
+	void pack(double pose[7]) const
+	{
+		pose[0] = t_.x();
+		pose[1] = t_.y();
+		pose[2] = t_.z();
+		pose[3] = r_.w();
+		pose[4] = r_.x();
+		pose[5] = r_.y();
+		pose[6] = r_.z();
+	}
 
  private:
 	Vector3 t_;
@@ -194,7 +224,7 @@ class PointCloudT
 	// point_cloud.h:150-166 (the `parallel` hint is accepted and ignored)
 	void transform(ufo::math::Pose6 const& pose, bool /*parallel*/ = false)
 	{
-		for (T& p : pts_) static_cast<Point3&>(p) = pose.transform(p);
+		for (T& p : pts_) static_cast<Point3&>(p) = pose.transform(p);  // exact, see Pose6
 	}
 
  private:
@@ -328,8 +358,9 @@ class MapFacade
 	                      double max_range = -1, DepthType depth = 0, bool simple_ray_casting = false,
 	                      unsigned int early_stopping = 0, bool async = false)
 	{
-		cloud.transform(frame_origin, async);
-		insert(sensor_origin, cloud, max_range, depth, simple_ray_casting, early_stopping, false, async);
+		// the transform is fused into the device-side point read (ufo_b200_insert_pointcloud_frame)
+		insert(sensor_origin, cloud, max_range, depth, simple_ray_casting, early_stopping, false, async,
+		       &frame_origin);
 	}
 
 	template <typename T>
@@ -346,8 +377,8 @@ class MapFacade
 	                              bool simple_ray_casting = false, unsigned int early_stopping = 0,
 	                              bool async = false)
 	{
-		cloud.transform(frame_origin, async);
-		insert(sensor_origin, cloud, max_range, depth, simple_ray_casting, early_stopping, true, async);
+		insert(sensor_origin, cloud, max_range, depth, simple_ray_casting, early_stopping, true, async,
+		       &frame_origin);
 	}
 
 	bool insertPointCloudDone() const
@@ -522,9 +553,12 @@ class MapFacade
 
 	template <typename T>
 	void insert(Point3 const& origin, T const& cloud, double max_range, DepthType depth, bool simple,
-	            unsigned int early_stopping, bool discrete, bool async)
+	            unsigned int early_stopping, bool discrete, bool async,
+	            ufo::math::Pose6 const* frame = nullptr)
 	{
 		using P = std::decay_t<decltype(cloud[0])>;
+		double pose[7];
+		if (frame) frame->pack(pose);
 		constexpr bool has_color = std::is_base_of_v<Point3Color, P>;
 		// repack into the C-ABI layout (the reference takes the cloud by value, i.e. copies it too)
 		std::size_t n = cloud.size();
@@ -539,8 +573,12 @@ class MapFacade
 				P const& p = cloud[i];
 				buf[i] = Rec{p.x(), p.y(), p.z(), p.getColor().r, p.getColor().g, p.getColor().b, {0, 0, 0, 0, 0}};
 			}
-			last_status_ = ufo_b200_insert_pointcloud(map_, origin.data(), buf.data(), n, UFO_B200_XYZRGB_F64,
-			                                          max_range, depth, simple, early_stopping, discrete, async);
+			last_status_ =
+			    frame ? ufo_b200_insert_pointcloud_frame(map_, origin.data(), buf.data(), n, UFO_B200_XYZRGB_F64,
+			                                             pose, max_range, depth, simple, early_stopping,
+			                                             discrete, async)
+			          : ufo_b200_insert_pointcloud(map_, origin.data(), buf.data(), n, UFO_B200_XYZRGB_F64,
+			                                       max_range, depth, simple, early_stopping, discrete, async);
 		} else {
 			std::vector<double> buf(3 * n);
 			for (std::size_t i = 0; i < n; ++i) {
@@ -548,8 +586,12 @@ class MapFacade
 				buf[3 * i + 1] = cloud[i].y();
 				buf[3 * i + 2] = cloud[i].z();
 			}
-			last_status_ = ufo_b200_insert_pointcloud(map_, origin.data(), buf.data(), n, UFO_B200_XYZ_F64,
-			                                          max_range, depth, simple, early_stopping, discrete, async);
+			last_status_ =
+			    frame ? ufo_b200_insert_pointcloud_frame(map_, origin.data(), buf.data(), n, UFO_B200_XYZ_F64,
+			                                             pose, max_range, depth, simple, early_stopping,
+			                                             discrete, async)
+			          : ufo_b200_insert_pointcloud(map_, origin.data(), buf.data(), n, UFO_B200_XYZ_F64,
+			                                       max_range, depth, simple, early_stopping, discrete, async);
 		}
 	}
 

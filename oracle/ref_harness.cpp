@@ -427,4 +427,34 @@ size_t ufo_ref_memory_usage(void* h)
 	return withMap(m, [&](auto& map) { return size_t(map.memoryUsage()); });
 }
 
+// The cloud transform of the insertPointCloud(..., frame_origin, ...) overloads, through the
+// reference's own PointCloud::transform (point_cloud.h:157-166).  pose7 = tx ty tz qw qx qy qz.
+void ufo_ref_transform(const double* pose7, const double* xyz, size_t n, double* out)
+{
+	ufo::math::Pose6 pose(pose7[0], pose7[1], pose7[2], pose7[3], pose7[4], pose7[5], pose7[6]);
+	PointCloud cloud;
+	cloud.reserve(n);
+	for (size_t i = 0; i < n; ++i) cloud.push_back(Point3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+	cloud.transform(pose);
+	for (size_t i = 0; i < n; ++i) {
+		out[3 * i + 0] = cloud[i][0];
+		out[3 * i + 1] = cloud[i][1];
+		out[3 * i + 2] = cloud[i][2];
+	}
+}
+
+// Pose6(x, y, z, roll, pitch, yaw) (math/pose6.h:71-74) as tx ty tz qw qx qy qz.
+void ufo_ref_pose_from_rpy(double x, double y, double z, double roll, double pitch, double yaw,
+                           double* pose7)
+{
+	ufo::math::Pose6 pose(x, y, z, roll, pitch, yaw);
+	pose7[0] = pose.translation()[0];
+	pose7[1] = pose.translation()[1];
+	pose7[2] = pose.translation()[2];
+	pose7[3] = pose.rotation().w();
+	pose7[4] = pose.rotation().x();
+	pose7[5] = pose.rotation().y();
+	pose7[6] = pose.rotation().z();
+}
+
 }  // extern "C"

@@ -1065,3 +1065,58 @@ void ufo_oracle_last_counters(void* h, uint64_t* out4)
 {
 	memcpy(out4, ((const omap*)h)->counters, 4 * sizeof(uint64_t));
 }
+
+/* ---- cloud frame (insertPointCloud(..., frame_origin, ...), OMB:313-327) -------------------
+ * Pose6::transform  ufomap/include/ufo/math/pose6.h:115-125
+ * Quaternion::rotate / operator*  ufomap/include/ufo/math/quaternion.h:253-286
+ * Quaternion(roll, pitch, yaw)    ufomap/include/ufo/math/quaternion.h:69-93 */
+typedef struct {
+	double w, x, y, z;
+} quat;
+
+static quat quat_product(quat a, quat b)
+{
+	quat r;
+	r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+	r.x = a.y * b.z - b.y * a.z + a.w * b.x + b.w * a.x;
+	r.y = a.z * b.x - b.z * a.x + a.w * b.y + b.w * a.y;
+	r.z = a.x * b.y - b.x * a.y + a.w * b.z + b.w * a.z;
+	return r;
+}
+
+void ufo_oracle_transform(const double* pose7, const double* xyz, size_t n, double* out)
+{
+	const quat q = {pose7[3], pose7[4], pose7[5], pose7[6]};
+	const quat qi = {q.w, -q.x, -q.y, -q.z};
+	for (size_t i = 0; i < n; ++i) {
+		const quat v = {0.0, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+		const quat r = quat_product(quat_product(q, v), qi);
+		out[3 * i + 0] = r.x + pose7[0];
+		out[3 * i + 1] = r.y + pose7[1];
+		out[3 * i + 2] = r.z + pose7[2];
+	}
+}
+
+/* std::max(0.0, v) */
+static double max0(double v) { return 0.0 < v ? v : 0.0; }
+
+void ufo_oracle_pose_from_rpy(double x, double y, double z, double roll, double pitch, double yaw,
+                              double* pose7)
+{
+	const double sr = sin(roll), sp = sin(pitch), sy = sin(yaw);
+	const double cr = cos(roll), cp = cos(pitch), cy = cos(yaw);
+	const double m[3][3] = {{cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr},
+	                        {sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr},
+	                        {-sp, cp * sr, cp * cr}};
+	const double w = sqrt(max0(1 + m[0][0] + m[1][1] + m[2][2])) / 2.0;
+	const double ax = sqrt(max0(1 + m[0][0] - m[1][1] - m[2][2])) / 2.0;
+	const double ay = sqrt(max0(1 - m[0][0] + m[1][1] - m[2][2])) / 2.0;
+	const double az = sqrt(max0(1 - m[0][0] - m[1][1] + m[2][2])) / 2.0;
+	pose7[0] = x;
+	pose7[1] = y;
+	pose7[2] = z;
+	pose7[3] = w;
+	pose7[4] = (m[2][1] - m[1][2]) >= 0 ? fabs(ax) : -fabs(ax);
+	pose7[5] = (m[0][2] - m[2][0]) >= 0 ? fabs(ay) : -fabs(ay);
+	pose7[6] = (m[1][0] - m[0][1]) >= 0 ? fabs(az) : -fabs(az);
+}

@@ -53,6 +53,11 @@ size_t ufo_oracle_memory_usage(void* h);
  * [2]=unique free codes U, [3]=unique hit codes U_h. */
 void ufo_oracle_last_counters(void* h, uint64_t* out4);
 
+/* cloud frame: pose7 = tx ty tz qw qx qy qz (Pose6::transform, Pose6(x,y,z,roll,pitch,yaw)) */
+void ufo_oracle_transform(const double* pose7, const double* xyz, size_t n, double* out);
+void ufo_oracle_pose_from_rpy(double x, double y, double z, double roll, double pitch, double yaw,
+                              double* pose7);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,12 @@ int main(int argc, char** argv)
 {
 	using namespace ufo::map;
 	bool compile_only = argc > 1 && 0 == std::strcmp(argv[1], "--no-device");
+	// Pose6 / PointCloud::transform are host code (math/pose6.h:115-125, point_cloud.h:157-166)
+	ufo::math::Pose6 pose(1.0, 2.0, 3.0, 0.0, 0.0, 1.5707963267948966);
+	PointCloud one;
+	one.push_back(Point3(1.0, 0.0, 0.0));
+	one.transform(pose);
+	if (std::fabs(one[0].x() - 1.0) > 1e-12 || std::fabs(one[0].y() - 3.0) > 1e-12 || one[0].z() != 3.0) return 10;
 	if (compile_only) {
 		// constructor arguments are validated before any device is touched (octree.h:931-935)
 		try {
@@ -47,10 +53,18 @@ int main(int argc, char** argv)
 	map.insertPointCloud(Point3(0, 0, 0), cloud, 5.0, 0, false, 3);
 	if (map.lastStatus() != UFO_B200_E_UNSUPPORTED) return 9;
 
-	ufo::math::Pose6 pose(1.0, 2.0, 3.0, 0.0, 0.0, 1.5707963267948966);
-	PointCloud moved = cloud;
-	moved.transform(pose);
-	if (std::fabs(moved[0].x() - 1.0) > 1e-12 || std::fabs(moved[0].y() - 3.0) > 1e-12) return 10;
+	// frame overload (device-side transform) == host transform + plain insert (occupancy_map_base.h:313-327)
+	ufo::math::Pose6 tilt(0.4, -0.2, 0.1, 0.03, -0.02, 0.9);
+	PointCloud local;
+	for (int i = 0; i < 50; ++i) local.push_back(Point3(2.0 + 0.07 * i, 0.031 * i, 0.011 * i - 0.2));
+	PointCloud world = local;
+	world.transform(tilt);
+	OccupancyMap fused(0.05), staged(0.05);
+	fused.insertPointCloud(tilt.translation(), local, tilt, 10.0);
+	staged.insertPointCloud(tilt.translation(), world, 10.0);
+	for (std::size_t i = 0; i < world.size(); ++i) {
+		if (fused.getOccupancy(world[i]) != staged.getOccupancy(world[i]) || !fused.isOccupied(world[i])) return 11;
+	}
 	std::puts("facade ok");
 	return 0;
 }

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from oracle_lib import RefMap, build_oracle  # noqa: E402
+from oracle_lib import REF_SO, RefMap, _load, build_oracle  # noqa: E402
 from ufomap_b200 import scans  # noqa: E402
 
 
@@ -79,8 +79,30 @@ def indexing_case():
     print("indexing", len(pts), "points")
 
 
+def frame_case():
+    """insertPointCloud(sensor_origin, cloud, frame_origin, ...): sensor-frame clouds + poses."""
+    api = _load(REF_SO, "ufo_ref_")
+    m = RefMap(0.1)
+    out = {"resolution": 0.1, "max_range": 20.0, "n_inserts": 3}
+    rpys = [(0.0, 0.0, 0.0), (0.02, -0.03, 0.7), (-0.4, 1.2, -2.9)]
+    for k, rpy in enumerate(rpys):
+        o, p = scans.velodyne64(k=k, rings=8, azimuths=96)
+        local = (p - o).astype(np.float32).astype(np.float64)   # what a sensor driver delivers
+        pose = np.empty(7)
+        api["pose_from_rpy"](*[float(v) for v in o], *rpy, pose.ctypes.data)
+        world = np.empty_like(local)
+        api["transform"](pose.ctypes.data, local.ctypes.data, len(local), world.ctypes.data)
+        m.insert(origin=pose[:3], xyz=world, max_range=20.0)
+        out["rpy%d" % k], out["pose%d" % k] = np.array(rpy), pose
+        out["local%d" % k], out["world%d" % k] = local, world
+    out["codes"], out["occ"], out["rgb"] = m.value_field()
+    np.savez_compressed(os.path.join(HERE, "frame_velodyne_10cm.npz"), **out)
+    print("frame_velodyne_10cm", len(out["codes"]), "voxels")
+
+
 def main():
     build_oracle()
+    frame_case()
     o, p = scans.random_shell(n=2000)
     scan_case("shell_16cm", dict(resolution=0.16), [dict(origin=o, xyz=p, max_range=5.0)])
     ins = []

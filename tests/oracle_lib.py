@@ -76,6 +76,8 @@ def _load(path, prefix):
         reset_change_bbox=sig("reset_change_bbox", None, [vp]),
         sensor_model=sig("sensor_model", None, [vp, vp]),
         memory_usage=sig("memory_usage", sz, [vp]),
+        transform=sig("transform", None, [vp, vp, sz, vp]),
+        pose_from_rpy=sig("pose_from_rpy", None, [dbl, dbl, dbl, dbl, dbl, dbl, vp]),
     )
     if prefix == "ufo_oracle_":
         api["last_counters"] = sig("last_counters", None, [vp, vp])

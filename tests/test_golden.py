@@ -14,7 +14,7 @@ from oracle_lib import OracleMap
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SCAN_CASES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "*.npz"))
-                    if not f.endswith("indexing.npz"))
+                    if not f.endswith("indexing.npz") and not os.path.basename(f).startswith("frame_"))
 
 
 def _load_case(name):
@@ -92,6 +92,55 @@ def test_cuda_library_host_geometry_matches_golden():
     from ufomap_b200.capi import Map
     m = Map(0.05, device=-2)
     _check_indexing(m)
+    m.close()
+
+
+def _frame_fixture():
+    return np.load(os.path.join(GOLD, "frame_velodyne_10cm.npz"))
+
+
+def test_oracle_frame_transform_matches_golden():
+    """Pose6(x,y,z,r,p,y) and PointCloud::transform outputs of the reference, bit for bit."""
+    from oracle_lib import ORACLE_SO, _load
+    api = _load(ORACLE_SO, "ufo_oracle_")
+    z = _frame_fixture()
+    m = OracleMap(float(z["resolution"]))
+    for k in range(int(z["n_inserts"])):
+        pose = np.empty(7)
+        api["pose_from_rpy"](*[float(v) for v in z["pose%d" % k][:3]], *[float(v) for v in z["rpy%d" % k]],
+                             pose.ctypes.data)
+        assert pose.tobytes() == z["pose%d" % k].tobytes()
+        local = np.ascontiguousarray(z["local%d" % k])
+        world = np.empty_like(local)
+        api["transform"](pose.ctypes.data, local.ctypes.data, len(local), world.ctypes.data)
+        assert world.tobytes() == z["world%d" % k].tobytes()
+        m.insert(origin=pose[:3], xyz=world, max_range=float(z["max_range"]))
+    assert_value_fields_equal(m.value_field(), (z["codes"], z["occ"], z["rgb"]), what="frame")
+
+
+def test_cuda_library_host_transform_matches_golden():
+    """ufo_b200_pose_from_rpy / ufo_b200_transform_points are host code: no GPU needed."""
+    from ufomap_b200 import capi
+    z = _frame_fixture()
+    for k in range(int(z["n_inserts"])):
+        pose = capi.pose_from_rpy(*z["pose%d" % k][:3], *z["rpy%d" % k])
+        assert pose.tobytes() == z["pose%d" % k].tobytes()
+        for dt in (np.float64, np.float32):
+            world = capi.transform_points(pose, z["local%d" % k], dtype=dt)
+            assert world.tobytes() == z["world%d" % k].tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_cuda_frame_insert_matches_golden(dtype):
+    """The fused device-side transform == the reference's host transform + insert."""
+    from ufomap_b200.capi import Map
+    z = _frame_fixture()
+    m = Map(float(z["resolution"]), initial_blocks=1 << 12)
+    for k in range(int(z["n_inserts"])):
+        pose = z["pose%d" % k]
+        m.insert_frame(pose[:3], z["local%d" % k], pose, max_range=float(z["max_range"]), dtype=dtype)
+    assert_value_fields_equal(m.value_field(), (z["codes"], z["occ"], z["rgb"]), what="frame")
     m.close()
 
 

@@ -257,3 +257,28 @@ def test_query_leaf_and_missing_nodes():
     occ, flags, _ = gpu.query([0], 16)
     assert occ.view(np.uint32)[0] == 0x3EE237E7 and flags[0] == 3
     gpu.close()
+
+
+@pytest.mark.parametrize("color,discrete,dtype", [(False, False, np.float64), (True, True, np.float32)])
+def test_frame_insert(color, discrete, dtype):
+    """insertPointCloud[Discrete](origin, cloud, frame_origin, ...) (occupancy_map_base.h:313-327,
+    403-417): the device-side transform == oracle transform + plain insert, voxel for voxel."""
+    from oracle_lib import ORACLE_SO, _load
+    from ufomap_b200 import capi
+    api = _load(ORACLE_SO, "ufo_oracle_")
+    gpu = Map(0.05, color=color, initial_blocks=1 << 14)
+    cpu = OracleMap(0.05, color=color)
+    for k, rpy in enumerate([(0.01, -0.02, 0.5), (-0.3, 0.9, 2.8), (0.0, 0.0, 0.0)]):
+        o, p, c = scans.rgbd(k=k, width=64, height=48)
+        local = (p - o).astype(np.float32).astype(np.float64)
+        pose = capi.pose_from_rpy(*o, *rpy)
+        world = np.empty_like(local)
+        api["transform"](pose.ctypes.data, local.ctypes.data, len(local), world.ctypes.data)
+        rgb = c if color else None
+        gpu.insert_frame(pose[:3], local, pose, rgb=rgb, max_range=4.0, discrete=discrete, dtype=dtype)
+        cpu.insert(origin=pose[:3], xyz=world, rgb=rgb, max_range=4.0, discrete=discrete)
+    assert_value_fields_equal(gpu.value_field(), cpu.value_field(), color_tol=1 if color else 0, what="frame")
+    mn, mx = gpu.change_bbox()
+    rmn, rmx = cpu.change_bbox()
+    assert np.array_equal(mn, rmn) and np.array_equal(mx, rmx)
+    gpu.close()

@@ -97,3 +97,28 @@ def test_indexing_and_rays():
     for d, simple in ((0, False), (1, False), (0, True)):
         assert np.array_equal(np.sort(r.free_set([0.01, 0.02, 0.03], ends, d, simple)),
                               np.sort(o.free_set([0.01, 0.02, 0.03], ends, d, simple)))
+
+
+def test_cloud_frame_transform():
+    """Pose6(x,y,z,r,p,y) and PointCloud::transform: oracle and the C ABI's host helpers against the
+    reference, bit for bit, over random poses (incl. identity, gimbal lock, large angles)."""
+    from oracle_lib import ORACLE_SO, REF_SO, _load
+    from ufomap_b200 import capi
+    ref, orc = _load(REF_SO, "ufo_ref_"), _load(ORACLE_SO, "ufo_oracle_")
+    rng = np.random.default_rng(5)
+    rpys = [np.zeros(3), np.array([0.0, np.pi / 2, 0.0]), np.array([np.pi, 0.0, -np.pi])]
+    rpys += list(rng.uniform(-3.3, 3.3, (60, 3)))
+    for rpy in rpys:
+        t = rng.uniform(-50, 50, 3)
+        pr, po = np.empty(7), np.empty(7)
+        ref["pose_from_rpy"](*t, *rpy, pr.ctypes.data)
+        orc["pose_from_rpy"](*t, *rpy, po.ctypes.data)
+        assert pr.tobytes() == po.tobytes() == capi.pose_from_rpy(*t, *rpy).tobytes()
+        pts = rng.uniform(-40, 40, (300, 3)).astype(np.float32).astype(np.float64)
+        pts[0] = 0.0
+        a, b = np.empty_like(pts), np.empty_like(pts)
+        ref["transform"](pr.ctypes.data, pts.ctypes.data, len(pts), a.ctypes.data)
+        orc["transform"](pr.ctypes.data, pts.ctypes.data, len(pts), b.ctypes.data)
+        assert a.tobytes() == b.tobytes()
+        assert a.tobytes() == capi.transform_points(pr, pts).tobytes()
+        assert a.tobytes() == capi.transform_points(pr, pts, dtype=np.float32).tobytes()

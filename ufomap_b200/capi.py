@@ -56,6 +56,7 @@ SYMBOLS = [
     "ufo_b200_export_leaves", "ufo_b200_set_sensor_model", "ufo_b200_sensor_model_logit",
     "ufo_b200_change_bbox", "ufo_b200_reset_change_bbox", "ufo_b200_last_scan_stats",
     "ufo_b200_set_profiling", "ufo_b200_clear", "ufo_b200_version", "ufo_b200_set_shard",
+    "ufo_b200_insert_pointcloud_frame", "ufo_b200_transform_points", "ufo_b200_pose_from_rpy",
 ]
 
 _lib = None
@@ -82,6 +83,10 @@ def load():
     lib.ufo_b200_set_stream.argtypes = [vp, vp]
     for f in (lib.ufo_b200_insert_pointcloud, lib.ufo_b200_insert_device):
         f.argtypes = [vp, vp, vp, sz, i32, dbl, u32, i32, u32, i32, i32]
+    lib.ufo_b200_insert_pointcloud_frame.argtypes = [vp, vp, vp, sz, i32, vp, dbl, u32, i32, u32, i32,
+                                                     i32]
+    lib.ufo_b200_transform_points.argtypes = [vp, vp, sz, i32, vp]
+    lib.ufo_b200_pose_from_rpy.argtypes = [dbl, dbl, dbl, dbl, dbl, dbl, vp]
     lib.ufo_b200_wait.argtypes = [vp]
     lib.ufo_b200_done.argtypes = [vp, C.POINTER(C.c_int)]
     lib.ufo_b200_compute_ray.argtypes = [vp, vp, vp, dbl, u32, u64p, sz, C.POINTER(sz)]
@@ -183,6 +188,19 @@ class Map:
         self._check(self.lib.ufo_b200_insert_pointcloud(
             self.h, o.ctypes.data, buf.ctypes.data, len(buf), layout, float(max_range), int(depth),
             int(simple), int(early_stopping), int(discrete), int(async_)))
+
+    def insert_frame(self, origin, xyz, frame_pose, rgb=None, max_range=-1.0, depth=0, simple=False,
+                     discrete=False, async_=False, dtype=np.float64):
+        """insertPointCloud(sensor_origin, cloud, frame_origin, ...): the cloud is moved into the
+        map frame on the device.  frame_pose = (tx, ty, tz, qw, qx, qy, qz)."""
+        buf, layout = pack_points(xyz, rgb, dtype)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        f = np.ascontiguousarray(frame_pose, dtype=np.float64)
+        assert f.shape == (7,)
+        self._keep = (buf, o, f)
+        self._check(self.lib.ufo_b200_insert_pointcloud_frame(
+            self.h, o.ctypes.data, buf.ctypes.data, len(buf), layout, f.ctypes.data,
+            float(max_range), int(depth), int(simple), 0, int(discrete), int(async_)))
 
     def insert_packed(self, origin, buf_ptr, n, layout, max_range=-1.0, depth=0, simple=False,
                       discrete=False, async_=False, on_device=False):
@@ -307,3 +325,25 @@ class Map:
         p = np.array([occupied_thres, free_thres, prob_hit, prob_miss, clamping_thres_min,
                       clamping_thres_max], dtype=np.float64)
         self._check(self.lib.ufo_b200_set_sensor_model(self.h, p.ctypes.data))
+
+
+def transform_points(frame_pose, xyz, dtype=np.float64):
+    """Pose6::transform on the host (bit-identical to the device path)."""
+    lib = load()
+    buf, layout = pack_points(xyz, None, dtype)
+    f = np.ascontiguousarray(frame_pose, dtype=np.float64)
+    out = np.empty((len(buf), 3), np.float64)
+    rc = lib.ufo_b200_transform_points(f.ctypes.data, buf.ctypes.data, len(buf), layout,
+                                       out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("ufo_b200_transform_points failed: %d" % rc)
+    return out
+
+
+def pose_from_rpy(x, y, z, roll, pitch, yaw):
+    """Pose6(x, y, z, roll, pitch, yaw) as (tx, ty, tz, qw, qx, qy, qz)."""
+    lib = load()
+    out = np.empty(7, np.float64)
+    lib.ufo_b200_pose_from_rpy(float(x), float(y), float(z), float(roll), float(pitch), float(yaw),
+                               out.ctypes.data)
+    return out

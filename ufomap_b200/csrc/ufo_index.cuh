@@ -91,6 +91,38 @@ UFO_HD double vsqnorm(Vec3 a)
 }
 UFO_HD double vnorm(Vec3 a) { return dop::sqrt(vsqnorm(a)); }
 
+// Rigid frame of a cloud: unit quaternion (w, x, y, z) + translation.
+struct Frame {
+	double qw, qx, qy, qz;
+	double tx, ty, tz;
+};
+
+// Hamilton product a*b with the term order of the reference's Quaternion::operator*
+// (math/quaternion.h:253-259); every sum is evaluated left to right.
+struct Quat {
+	double w, x, y, z;
+};
+UFO_HD Quat quat_mul(Quat a, Quat b)
+{
+	using namespace dop;
+	Quat r;
+	r.w = sub(sub(sub(mul(a.w, b.w), mul(a.x, b.x)), mul(a.y, b.y)), mul(a.z, b.z));
+	r.x = add(add(sub(mul(a.y, b.z), mul(b.y, a.z)), mul(a.w, b.x)), mul(b.w, a.x));
+	r.y = add(add(sub(mul(a.z, b.x), mul(b.z, a.x)), mul(a.w, b.y)), mul(b.w, a.y));
+	r.z = add(add(sub(mul(a.x, b.y), mul(b.x, a.y)), mul(a.w, b.z)), mul(b.w, a.z));
+	return r;
+}
+
+// Pose6::transform (math/pose6.h:115-125): the sandwich product q (0,v) conj(q) of
+// Quaternion::rotate (math/quaternion.h:277-286), then += translation.  Not simplified:
+// the zero-weight terms stay so that signed zeros and rounding match the reference.
+UFO_HD Vec3 frame_transform(const Frame& f, Vec3 v)
+{
+	Quat q{f.qw, f.qx, f.qy, f.qz};
+	Quat r = quat_mul(quat_mul(q, Quat{0.0, v.x, v.y, v.z}), Quat{f.qw, -f.qx, -f.qy, -f.qz});
+	return {dop::add(r.x, f.tx), dop::add(r.y, f.ty), dop::add(r.z, f.tz)};
+}
+
 struct Key3 {
 	uint32_t x, y, z;
 };

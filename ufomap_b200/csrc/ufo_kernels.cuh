@@ -44,6 +44,10 @@ struct ScanArgs {
 	uint32_t tab_mask;
 	uint32_t* hit_tab;  // [n] table position of the point's hit voxel or kNone
 	int count_visits;
+	// cloud frame applied while the points are read (insertPointCloud(..., frame_origin, ...),
+	// occupancy_map_base.h:313-327 -> PointCloudT::transform, point_cloud.h:157-166)
+	int has_frame;
+	Frame frame;
 	// ray-walk output: (block key, visited-voxel mask) records, one region per warp of 32 rays
 	struct QEntry* seg;
 	unsigned long long seg_cap;  // records
@@ -75,6 +79,7 @@ __device__ __forceinline__ void load_point(const ScanArgs& a, uint32_t i, Vec3& 
 			rgb = __float_as_uint(q.w) & 0xffffffu;
 		} break;
 	}
+	if (a.has_frame) p = frame_transform(a.frame, p);
 }
 
 __device__ __forceinline__ void bbox_accumulate(const DeviceMap& M, double lo[3], double hi[3],

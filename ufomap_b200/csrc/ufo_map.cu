@@ -461,6 +461,7 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 }
 
 int do_insert(Map* m, const double origin[3], const void* points, bool on_device, size_t n,
+              const double* frame_pose,
               int layout, double max_range, uint32_t depth, int simple, uint32_t early_stopping,
               int discrete, int async)
 {
@@ -504,6 +505,11 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	a.tab_mask = m->tab_size ? m->tab_size - 1 : 0;
 	a.hit_tab = use_color ? m->d_hit_tab : nullptr;
 	a.count_visits = m->profiling >= 2;
+	if (frame_pose) {
+		a.has_frame = 1;
+		a.frame = Frame{frame_pose[3], frame_pose[4], frame_pose[5], frame_pose[6],
+		                frame_pose[0], frame_pose[1], frame_pose[2]};
+	}
 	if (!simple) {
 		// first guess for the record buffer: 48 records per ray; grown on demand
 		ensure_seg(m, std::max<unsigned long long>(m->seg_cap, std::max<unsigned long long>(n, 1024) * 48ull));
@@ -830,8 +836,8 @@ int ufo_b200_insert_pointcloud(ufo_b200_map* m, const double origin[3], const vo
                                int async)
 {
 	return guarded(m, [&]() {
-		return do_insert(m, origin, points, false, n, layout, max_range, depth, simple_ray_casting,
-		                 early_stopping, discrete, async);
+		return do_insert(m, origin, points, false, n, nullptr, layout, max_range, depth,
+		                 simple_ray_casting, early_stopping, discrete, async);
 	});
 }
 
@@ -841,9 +847,72 @@ int ufo_b200_insert_device(ufo_b200_map* m, const double origin[3], const void* 
                            int async)
 {
 	return guarded(m, [&]() {
-		return do_insert(m, origin, d_points, true, n, layout, max_range, depth, simple_ray_casting,
-		                 early_stopping, discrete, async);
+		return do_insert(m, origin, d_points, true, n, nullptr, layout, max_range, depth,
+		                 simple_ray_casting, early_stopping, discrete, async);
 	});
+}
+
+int ufo_b200_insert_pointcloud_frame(ufo_b200_map* m, const double origin[3], const void* points,
+                                     size_t n, int layout, const double frame_pose[7],
+                                     double max_range, uint32_t depth, int simple_ray_casting,
+                                     uint32_t early_stopping, int discrete, int async)
+{
+	if (m && !frame_pose) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		return do_insert(m, origin, points, false, n, frame_pose, layout, max_range, depth,
+		                 simple_ray_casting, early_stopping, discrete, async);
+	});
+}
+
+int ufo_b200_transform_points(const double frame_pose[7], const void* points, size_t n, int layout,
+                              double* out_xyz)
+{
+	if (!frame_pose || (n && (!points || !out_xyz)) || layout < 0 || layout > 3)
+		return UFO_B200_E_INVALID;
+	const Frame f{frame_pose[3], frame_pose[4], frame_pose[5], frame_pose[6],
+	              frame_pose[0], frame_pose[1], frame_pose[2]};
+	const size_t stride = (layout == UFO_B200_XYZ_F64 || layout == UFO_B200_XYZ_F32) ? 3 : 4;
+	const bool f64 = layout == UFO_B200_XYZ_F64 || layout == UFO_B200_XYZRGB_F64;
+	for (size_t i = 0; i < n; ++i) {
+		Vec3 p;
+		if (f64) {
+			const double* q = static_cast<const double*>(points) + stride * i;
+			p = {q[0], q[1], q[2]};
+		} else {
+			const float* q = static_cast<const float*>(points) + stride * i;
+			p = {(double)q[0], (double)q[1], (double)q[2]};
+		}
+		Vec3 r = frame_transform(f, p);
+		out_xyz[3 * i + 0] = r.x;
+		out_xyz[3 * i + 1] = r.y;
+		out_xyz[3 * i + 2] = r.z;
+	}
+	return UFO_B200_OK;
+}
+
+int ufo_b200_pose_from_rpy(double x, double y, double z, double roll, double pitch, double yaw,
+                           double frame_pose[7])
+{
+	if (!frame_pose) return UFO_B200_E_INVALID;
+	// Quaternion(roll, pitch, yaw) of the reference goes through the ZYX rotation matrix and the
+	// trace formulas (math/quaternion.h:69-93); restated with the same expression order.
+	const double sr = sin(roll), sp = sin(pitch), sy = sin(yaw);
+	const double cr = cos(roll), cp = cos(pitch), cy = cos(yaw);
+	const double m00 = cy * cp, m01 = cy * sp * sr - sy * cr, m02 = cy * sp * cr + sy * sr;
+	const double m10 = sy * cp, m11 = sy * sp * sr + cy * cr, m12 = sy * sp * cr - cy * sr;
+	const double m20 = -sp, m21 = cp * sr, m22 = cp * cr;
+	const double qw = sqrt(std::max(0.0, 1 + m00 + m11 + m22)) / 2.0;
+	const double ax = sqrt(std::max(0.0, 1 + m00 - m11 - m22)) / 2.0;
+	const double ay = sqrt(std::max(0.0, 1 - m00 + m11 - m22)) / 2.0;
+	const double az = sqrt(std::max(0.0, 1 - m00 - m11 + m22)) / 2.0;
+	frame_pose[0] = x;
+	frame_pose[1] = y;
+	frame_pose[2] = z;
+	frame_pose[3] = qw;
+	frame_pose[4] = (m21 - m12) >= 0 ? fabs(ax) : -fabs(ax);
+	frame_pose[5] = (m02 - m20) >= 0 ? fabs(ay) : -fabs(ay);
+	frame_pose[6] = (m10 - m01) >= 0 ? fabs(az) : -fabs(az);
+	return UFO_B200_OK;
 }
 
 int ufo_b200_wait(ufo_b200_map* m)
