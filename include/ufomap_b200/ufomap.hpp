@@ -22,6 +22,7 @@
 // kept in lastError().
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -224,7 +225,23 @@ class PointCloudT
 	// point_cloud.h:150-166 (the `parallel` hint is accepted and ignored)
 	void transform(ufo::math::Pose6 const& pose, bool /*parallel*/ = false)
 	{
-		for (T& p : pts_) static_cast<Point3&>(p) = pose.transform(p);  // exact, see Pose6
+		// batched through the library (exact arithmetic, see Quaternion): one call per 1024 points
+		double f[7], in[3 * 1024], out[3 * 1024];
+		pose.pack(f);
+		for (std::size_t base = 0; base < pts_.size(); base += 1024) {
+			std::size_t m = std::min<std::size_t>(1024, pts_.size() - base);
+			for (std::size_t i = 0; i < m; ++i) {
+				in[3 * i] = pts_[base + i].x();
+				in[3 * i + 1] = pts_[base + i].y();
+				in[3 * i + 2] = pts_[base + i].z();
+			}
+			ufo_b200_transform_points(f, in, m, UFO_B200_XYZ_F64, out);
+			for (std::size_t i = 0; i < m; ++i) {
+				pts_[base + i].x() = out[3 * i];
+				pts_[base + i].y() = out[3 * i + 1];
+				pts_[base + i].z() = out[3 * i + 2];
+			}
+		}
 	}
 
  private:
