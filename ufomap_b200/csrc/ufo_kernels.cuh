@@ -929,6 +929,230 @@ __global__ void __launch_bounds__(kUpdThreads, UFO_UPD_MINBLOCKS) k_update(Devic
 	}
 }
 
+// K3, compacted variant (mono maps).  In the flat kernel above only ~23 % of the threads have a
+// leaf sector in flight (half of the blocks are unmarked, and a marked block has 3.7 of 8 octets
+// touched), so it is bound by latency x occupancy (Little's law: ~15 KB in flight per SM), not by
+// HBM bandwidth.  Here a CTA works on chunks of 128 consecutive blocks (two bricks): block threads
+// take the masks and build, by prefix sum, a dense list of the touched octets in shared memory;
+// then every thread takes one list entry, so nearly all threads hold a 32 B leaf sector in
+// flight; octet results go through shared memory to the block threads, which finish the
+// depth-1/2 aggregates exactly as k_update does.  CTAs are persistent and software-pipelined: the
+// masks of the CTA's next chunk are fetched while the current one is processed, and the block
+// header data (meta, depth-1 maxima) needed last is requested first, so a chunk exposes one DRAM
+// round trip (the leaf sectors) instead of three.  Same arrays, values and per-scan clearing.
+#ifndef UFO_UC_MINBLOCKS
+#define UFO_UC_MINBLOCKS 4
+#endif
+#ifndef UFO_UC_BLOCKS
+#define UFO_UC_BLOCKS 256
+#endif
+#ifndef UFO_UC_THREADS
+#define UFO_UC_THREADS 256
+#endif
+constexpr int kUcBlocks = UFO_UC_BLOCKS;  // blocks per chunk (<= kUcThreads, multiple of 32)
+constexpr int kUcThreads = UFO_UC_THREADS;
+static_assert(kUcBlocks <= kUcThreads && kUcBlocks % 32 == 0 && kUcBlocks * 8 <= 65536, "chunk shape");
+#ifndef UFO_UC_GRID_PER_SM
+#define UFO_UC_GRID_PER_SM UFO_UC_MINBLOCKS
+#endif
+
+__global__ void __launch_bounds__(kUcThreads, UFO_UC_MINBLOCKS) k_update_compact(DeviceMap M, float miss,
+                                                                               uint32_t first_brick,
+                                                                               uint32_t n_bricks,
+                                                                               uint32_t n_chunks)
+{
+	__shared__ unsigned long long s_mm[kUcBlocks], s_hm[kUcBlocks];
+	__shared__ uint16_t s_list[kUcBlocks * 8];
+	__shared__ float s_omax[8 * kUcBlocks];      // [octet][block]: conflict-free for the block threads
+	__shared__ unsigned char s_ofl[8 * kUcBlocks];
+	__shared__ uint32_t s_wtot[2][kUcBlocks / 32];
+	const uint32_t tid = threadIdx.x, lane = tid & 31;
+	const bool block_thread = tid < (uint32_t)kUcBlocks;
+	if (__ldg(&M.ctr->overflow)) return;  // see k_update
+	const size_t base0 = (size_t)first_brick * 64;
+	const size_t b_end = (size_t)n_bricks * 64;
+
+	unsigned int s_vox = 0, s_hit = 0, s_oct = 0, s_blk = 0, s_new = 0;
+	unsigned long long mm_next = 0ull, hm_next = 0ull;
+	if (block_thread) {
+		const size_t b = base0 + (size_t)blockIdx.x * kUcBlocks + tid;
+		if (b < b_end) {
+			mm_next = M.miss_mask[b];
+			hm_next = M.hit_mask[b];
+		}
+	}
+	uint32_t par = 0;
+	for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x, par ^= 1u) {
+		const size_t b0 = base0 + (size_t)c * kUcBlocks;
+		const size_t b = b0 + tid;
+		// ---- block threads: masks, touched-octet bitmap, list offsets ----
+		const unsigned long long mm = mm_next, hm = hm_next;
+		uint32_t mt = 0, t8 = 0, excl = 0;
+		float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+		const bool marked = (mm | hm) != 0ull;
+		if (block_thread) {
+			// masks of this CTA's next chunk: in flight while this chunk is processed
+			const size_t bn = b + (size_t)gridDim.x * kUcBlocks;
+			mm_next = 0ull;
+			hm_next = 0ull;
+			if (c + gridDim.x < n_chunks && bn < b_end) {
+				mm_next = M.miss_mask[bn];
+				hm_next = M.hit_mask[bn];
+			}
+			if (marked) {
+				const unsigned long long u = mm | hm;
+#pragma unroll
+				for (uint32_t o = 0; o < 8; ++o) {
+					const uint32_t base = ((o & 1u) << 1) | ((o & 2u) << 2) | ((o & 4u) << 3);
+					t8 |= (((u >> base) & 0x330033ull) ? 1u : 0u) << o;
+				}
+				// used last, requested first: block header and the depth-1 maxima of the octets
+				// that stay untouched (garbage for a never-written block; masked by meta below)
+				mt = M.meta[b];
+				if (t8 != 0xffu) {
+					const float4* sp = reinterpret_cast<const float4*>(M.sum1 + b * 8);
+					p0 = sp[0];
+					p1 = sp[1];
+				}
+				s_mm[tid] = mm;
+				s_hm[tid] = hm;
+			}
+			uint32_t incl = __popc(t8);
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= (uint32_t)o) incl += v;
+			}
+			excl = incl - __popc(t8);
+			if (lane == 31) s_wtot[par][tid >> 5] = incl;
+		}
+		__syncthreads();
+		uint32_t total = 0;
+#pragma unroll
+		for (int w = 0; w < kUcBlocks / 32; ++w) {
+			const uint32_t wt = s_wtot[par][w];
+			if (block_thread && (uint32_t)w < (tid >> 5)) excl += wt;
+			total += wt;
+		}
+		if (total == 0) continue;  // nothing marked in this chunk (uniform; s_wtot is double-buffered)
+		if (block_thread) {
+			uint32_t bits = t8, at = excl;
+			while (bits) {
+				const uint32_t o = __ffs(bits) - 1;
+				bits &= bits - 1;
+				s_list[at++] = (uint16_t)((tid << 3) | o);
+			}
+		}
+		__syncthreads();
+
+		// ---- all threads: one touched octet (= one 32 B sector) each ----
+#ifdef UFO_UC_ILP2
+		// two entries per trip, both sectors requested before either is processed
+		for (uint32_t i = tid; i < total; i += 2 * kUcThreads) {
+			const bool two = i + kUcThreads < total;
+			const uint32_t e = s_list[i], t = e >> 3, oct = e & 7u;
+			const uint32_t e2 = two ? s_list[i + kUcThreads] : e, t2 = e2 >> 3, oct2 = e2 & 7u;
+			float* lp = M.leaf + (b0 + t) * 64 + 8 * oct;
+			float* lp2 = M.leaf + (b0 + t2) * 64 + 8 * oct2;
+			const float4 a0 = reinterpret_cast<const float4*>(lp)[0], a1 = reinterpret_cast<const float4*>(lp)[1];
+			float4 c0 = a0, c1 = a1;
+			if (two) {
+				c0 = reinterpret_cast<const float4*>(lp2)[0];
+				c1 = reinterpret_cast<const float4*>(lp2)[1];
+			}
+			{
+				const uint32_t m8 = octet_bits8(s_mm[t], oct), h8 = octet_bits8(s_hm[t], oct);
+				float omax;
+				uint32_t ofl;
+				update_octet(M, miss, lp, m8, h8, a0, a1, omax, ofl);
+				s_omax[oct * kUcBlocks + t] = omax;
+				s_ofl[oct * kUcBlocks + t] = (unsigned char)ofl;
+				s_vox += __popc(m8 | h8);
+				s_hit += __popc(h8);
+				s_oct += 1;
+			}
+			if (two) {
+				const uint32_t m8 = octet_bits8(s_mm[t2], oct2), h8 = octet_bits8(s_hm[t2], oct2);
+				float omax;
+				uint32_t ofl;
+				update_octet(M, miss, lp2, m8, h8, c0, c1, omax, ofl);
+				s_omax[oct2 * kUcBlocks + t2] = omax;
+				s_ofl[oct2 * kUcBlocks + t2] = (unsigned char)ofl;
+				s_vox += __popc(m8 | h8);
+				s_hit += __popc(h8);
+				s_oct += 1;
+			}
+		}
+#else
+		for (uint32_t i = tid; i < total; i += kUcThreads) {
+			const uint32_t e = s_list[i], t = e >> 3, oct = e & 7u;
+			const uint32_t m8 = octet_bits8(s_mm[t], oct), h8 = octet_bits8(s_hm[t], oct);
+			float* lp = M.leaf + (b0 + t) * 64 + 8 * oct;
+			const float4 a0 = reinterpret_cast<const float4*>(lp)[0], a1 = reinterpret_cast<const float4*>(lp)[1];
+			float omax;
+			uint32_t ofl;
+			update_octet(M, miss, lp, m8, h8, a0, a1, omax, ofl);
+			s_omax[oct * kUcBlocks + t] = omax;
+			s_ofl[oct * kUcBlocks + t] = (unsigned char)ofl;
+			s_vox += __popc(m8 | h8);
+			s_hit += __popc(h8);
+			s_oct += 1;
+		}
+#endif
+		__syncthreads();
+
+		// ---- block threads: depth-1 sector, depth-2 aggregate, meta, mask clearing ----
+		if (block_thread && marked) {
+			const float old1[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+			float new1[8];
+			float bmax = -3.402823466e+38f;
+			uint32_t bfl = 0, newmeta = 0;
+#pragma unroll
+			for (uint32_t o = 0; o < 8; ++o) {
+				float om = 0.0f;
+				uint32_t fl = M.default_flags, touched = 0;
+				if ((t8 >> o) & 1u) {
+					om = s_omax[o * kUcBlocks + tid];
+					fl = s_ofl[o * kUcBlocks + tid];
+					touched = 1;
+				} else if ((mt >> (16 + o)) & 1u) {
+					om = old1[o];
+					fl = (mt >> (2 * o)) & 3u;
+				}
+				new1[o] = om;
+				bmax = fmaxf(bmax, om);
+				bfl |= fl;
+				newmeta |= (fl << (2 * o)) | (touched << (16 + o));
+			}
+			float4* sp = reinterpret_cast<float4*>(M.sum1 + b * 8);
+			sp[0] = make_float4(new1[0], new1[1], new1[2], new1[3]);
+			sp[1] = make_float4(new1[4], new1[5], new1[6], new1[7]);
+			M.agg2[b] = {bmax, bfl};
+			M.meta[b] = (newmeta & 0xffffffu) | (mt & 0xff0000u) | (M.scan_id << 24);
+			M.miss_mask[b] = 0ull;
+			if (hm) M.hit_mask[b] = 0ull;
+			s_blk += 1;
+			s_new += (mt & 0xff0000u) ? 0u : 1u;
+		}
+	}
+	// counters: per-thread sums over the CTA's chunks, one warp reduction and one set of atomics
+	for (int o = 16; o > 0; o >>= 1) {
+		s_vox += __shfl_xor_sync(0xffffffffu, s_vox, o);
+		s_hit += __shfl_xor_sync(0xffffffffu, s_hit, o);
+		s_oct += __shfl_xor_sync(0xffffffffu, s_oct, o);
+		s_blk += __shfl_xor_sync(0xffffffffu, s_blk, o);
+		s_new += __shfl_xor_sync(0xffffffffu, s_new, o);
+	}
+	if (lane == 0) {
+		unsigned long long* slot = M.ctr->stat[(blockIdx.x * (kUcThreads / 32) + (tid >> 5)) % kStatSlots];
+		if (s_vox) atomicAdd(&slot[0], (unsigned long long)s_vox);
+		if (s_hit) atomicAdd(&slot[1], (unsigned long long)s_hit);
+		if (s_oct) atomicAdd(&slot[2], (unsigned long long)s_oct);
+		if (s_blk) atomicAdd(&slot[3], (unsigned long long)s_blk);
+		if (s_new) atomicAdd(&slot[4], (unsigned long long)s_new);
+	}
+}
+
 __device__ __forceinline__ bool alias_source(const DeviceMap& M, uint32_t brick, uint32_t& tx, uint32_t& ty,
                                              uint32_t& tz);
 

@@ -422,7 +422,16 @@ void launch_update(Map* m, float miss, uint32_t first, uint32_t last)
 	const uint32_t groups = (last - first) * 64u;  // one eight-lane group per (brick, child)
 	const uint32_t grid = (groups + kUpdThreads / 8 - 1) / (kUpdThreads / 8);
 	if (m->M.color) k_update<true><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
+#ifndef UFO_UPD_FLAT
+	else {
+		// persistent CTAs (all resident), each looping over chunks of kUcBlocks blocks
+		const uint32_t n_chunks = (groups + kUcBlocks - 1) / kUcBlocks;
+		const uint32_t ugrid = std::min<uint32_t>(n_chunks, (uint32_t)m->sm_count * UFO_UC_GRID_PER_SM);
+		k_update_compact<<<ugrid, kUcThreads, 0, m->stream>>>(m->M, miss, first, last, n_chunks);
+	}
+#else
 	else k_update<false><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
+#endif
 	++m->launches;
 }
 
