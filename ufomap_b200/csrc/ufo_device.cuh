@@ -178,6 +178,16 @@ __device__ __forceinline__ ulonglong2 ld_volatile_entry(const ulonglong2* p)
 	return v;
 }
 
+// L1-cached read of an entry, for optimistic first probes: a stale line can only show an entry
+// as still empty / pending or with an old stamp (keys never change inside a kernel), and every
+// caller falls back to the volatile / atomic path in those cases.
+__device__ __forceinline__ ulonglong2 ld_cached_entry(const ulonglong2* p)
+{
+	ulonglong2 v;
+	asm volatile("ld.global.ca.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+	return v;
+}
+
 // value field of an entry: low 32 bits = brick slot / kPending / kFailed
 __device__ __forceinline__ uint32_t brick_find(const DeviceMap& M, uint64_t key)
 {

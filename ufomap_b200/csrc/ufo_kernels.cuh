@@ -666,56 +666,112 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 #define UFO_SCATTER_MINBLOCKS 8
 #endif
 // GENERIC = false is the common case (insert depth <= 2, unsharded map): the extra tests are
-// compiled out so that the hot path keeps to 32 registers without spills.
+// compiled out so that the hot path stays small.
+template <bool GENERIC>
+__device__ __forceinline__ void scatter_record(const DeviceMap& M, const ScanArgs& a, const ulonglong2 v)
+{
+	uint32_t x, y, z;
+	unpack_key(v.y, x, y, z);
+	if ((GENERIC && a.depth >= 3) || ((x | y | z) & ~M.g.key_mask)) {
+		// rare: free-space nodes larger than a block, or a key outside the tree.  The lean
+		// variant has no slow path: it asks the host for the alias arrays (bit 5), and the
+		// re-run -- like every later scan of this map -- uses the generic variant.
+		if (GENERIC) scatter_slow(M, x, y, z, v.x, a.depth);
+		else atomicOr(&M.ctr->overflow, 32u);
+		return;
+	}
+	x >>= 2;  // block coordinates
+	y >>= 2;
+	z >>= 2;
+	const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
+	if (GENERIC && M.shard_world > 1 && brick_owner(bkey, M.shard_world) != M.shard_rank) return;  // another GPU's brick
+	const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
+	// (thousands of records near the sensor resolve to the same few bricks at the same time:
+	// served from L1 instead of all queueing at one L2 slice)
+#ifdef UFO_SCATTER_VOLATILE_PROBE
+	const ulonglong2 e0 = ld_volatile_entry(&M.bh_tab[hidx]);
+	const ulonglong2 e1 = ld_volatile_entry(&M.bh_tab[hidx + 1]);
+#else
+	const ulonglong2 e0 = ld_cached_entry(&M.bh_tab[hidx]);
+	const ulonglong2 e1 = ld_cached_entry(&M.bh_tab[hidx + 1]);
+#endif
+	const bool hit0 = e0.x == bkey, hit1 = e1.x == bkey;
+	const ulonglong2 ent = hit0 ? e0 : e1;
+	const uint32_t hpos = hit0 ? hidx : hidx + 1;
+	uint32_t brick = (uint32_t)ent.y;
+	if ((hit0 || hit1) && brick != kPending && brick != kFailed) {
+		if ((uint32_t)(ent.y >> 32) != M.scan_id) {
+			M.brick_stamp[brick] = M.scan_id;
+			reinterpret_cast<uint32_t*>(&M.bh_tab[hpos].y)[1] = M.scan_id;
+		}
+	} else {
+		brick = brick_find_or_create_from(M, bkey, hidx);
+		if (brick == kNone) return;
+		M.brick_stamp[brick] = M.scan_id;
+	}
+	atomicOr(&M.miss_mask[(size_t)brick * 64 + morton2(x, y, z)], v.x);
+}
+
+// The loop is software-pipelined over the CTA's items: while the record of item k is resolved
+// (hash probe -> atomic), the record of item k+1 and the region length/base of item k+2 are
+// already in flight, so an item exposes one dependent round trip instead of four.
 template <bool GENERIC>
 __global__ void __launch_bounds__(kChunk, UFO_SCATTER_MINBLOCKS) k_scatter(DeviceMap M, ScanArgs a)
 {
 	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;
 	const uint32_t n_regions = (a.n + 31) / 32;
-	const unsigned long long n_items = (unsigned long long)ld_volatile_u32(&M.ctr->n_chunks) * n_regions;
-	// (keeping the region lengths in shared memory to skip empty items without a load was
-	// measured slightly slower than this plain loop: 0.537 vs 0.513 ms)
-	for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x) {
-		const uint32_t j = (uint32_t)(it / n_regions), r = (uint32_t)(it % n_regions);
-		const uint32_t cnt = a.seg_count[r];
-		if ((unsigned long long)j * kChunk >= cnt) continue;
-		const uint32_t hi = cnt - j * kChunk;  // one past the slice's last record
-		const uint32_t lo = hi > kChunk ? hi - kChunk : 0u;
-		if (lo + threadIdx.x >= hi) continue;
-		const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&a.seg[a.seg_base[r] + lo + threadIdx.x]);
-		uint32_t x, y, z;
-		unpack_key(v.y, x, y, z);
-		if ((GENERIC && a.depth >= 3) || ((x | y | z) & ~M.g.key_mask)) {
-			// rare: free-space nodes larger than a block, or a key outside the tree.  The lean
-			// variant has no slow path: it asks the host for the alias arrays (bit 5), and the
-			// re-run -- like every later scan of this map -- uses the generic variant.
-			if (GENERIC) scatter_slow(M, x, y, z, v.x, a.depth);
-			else atomicOr(&M.ctr->overflow, 32u);
-			continue;
+	const uint32_t n_chunks = ld_volatile_u32(&M.ctr->n_chunks);
+	// item (j, r), visited j-major; the iterator advances by gridDim.x items without dividing
+	const uint32_t dj = gridDim.x / n_regions, dr = gridDim.x % n_regions;
+	uint32_t jA = blockIdx.x / n_regions, rA = blockIdx.x % n_regions;
+	// stage 1 (item k+1): region length and base known, record not yet requested
+	uint32_t cnt1 = 0, base1 = 0, j1 = jA;
+	bool v1 = jA < n_chunks;
+	if (v1) {
+		cnt1 = a.seg_count[rA];
+		base1 = a.seg_base[rA];
+	}
+	rA += dr;
+	jA += dj;
+	if (rA >= n_regions) {
+		rA -= n_regions;
+		++jA;
+	}
+	// stage 0 (item k): record in registers
+	ulonglong2 rec0 = make_ulonglong2(0ull, 0ull);
+	bool ok0 = false;
+	while (v1 || ok0) {
+		// item k+2: region length and base
+		const bool v2 = jA < n_chunks;
+		const uint32_t j2 = jA;
+		uint32_t cnt2 = 0, base2 = 0;
+		if (v2) {
+			cnt2 = a.seg_count[rA];
+			base2 = a.seg_base[rA];
 		}
-		x >>= 2;  // block coordinates
-		y >>= 2;
-		z >>= 2;
-		const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
-		if (GENERIC && M.shard_world > 1 && brick_owner(bkey, M.shard_world) != M.shard_rank) continue;  // another GPU's brick
-		const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
-		const ulonglong2 e0 = ld_volatile_entry(&M.bh_tab[hidx]);
-		const ulonglong2 e1 = ld_volatile_entry(&M.bh_tab[hidx + 1]);
-		const bool hit0 = e0.x == bkey, hit1 = e1.x == bkey;
-		const ulonglong2 ent = hit0 ? e0 : e1;
-		const uint32_t hpos = hit0 ? hidx : hidx + 1;
-		uint32_t brick = (uint32_t)ent.y;
-		if ((hit0 || hit1) && brick != kPending && brick != kFailed) {
-			if ((uint32_t)(ent.y >> 32) != M.scan_id) {
-				M.brick_stamp[brick] = M.scan_id;
-				reinterpret_cast<uint32_t*>(&M.bh_tab[hpos].y)[1] = M.scan_id;
-			}
-		} else {
-			brick = brick_find_or_create_from(M, bkey, hidx);
-			if (brick == kNone) continue;
-			M.brick_stamp[brick] = M.scan_id;
+		rA += dr;
+		jA += dj;
+		if (rA >= n_regions) {
+			rA -= n_regions;
+			++jA;
 		}
-		atomicOr(&M.miss_mask[(size_t)brick * 64 + morton2(x, y, z)], v.x);
+		// item k+1: its record (slice j1 counted from the end of the region)
+		ulonglong2 rec1 = make_ulonglong2(0ull, 0ull);
+		bool ok1 = false;
+		if (v1 && (unsigned long long)j1 * kChunk < cnt1) {
+			const uint32_t hi = cnt1 - j1 * kChunk;  // one past the slice's last record
+			const uint32_t lo = hi > kChunk ? hi - kChunk : 0u;
+			ok1 = lo + threadIdx.x < hi;
+			if (ok1) rec1 = *reinterpret_cast<const ulonglong2*>(&a.seg[(size_t)base1 + lo + threadIdx.x]);
+		}
+		// item k
+		if (ok0) scatter_record<GENERIC>(M, a, rec0);
+		rec0 = rec1;
+		ok0 = ok1;
+		cnt1 = cnt2;
+		base1 = base2;
+		j1 = j2;
+		v1 = v2;
 	}
 }
 

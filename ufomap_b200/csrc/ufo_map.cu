@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <numeric>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -462,7 +463,13 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 		m->ev7_valid = true;
 	}
 	{
-		uint32_t sgrid = (uint32_t)m->sm_count * 8;  // all CTAs resident, looping over the work items
+		// all CTAs resident, looping over the work items (j, region) with stride = grid size.
+		// The grid size is made coprime with the number of regions so that every CTA walks
+		// through ALL regions: region length correlates with the region index (ring order of
+		// the sensor), and a stride sharing a factor with it gives some CTAs only long regions.
+		uint32_t sgrid = (uint32_t)m->sm_count * 8;
+		const uint32_t n_regions = (a.n + 31) / 32;
+		while (sgrid > 1 && std::gcd(sgrid, n_regions) != 1) --sgrid;
 		if (a.depth >= 3 || m->M.shard_world > 1 || m->M.alias_miss) k_scatter<true><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
 		else k_scatter<false><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
 	}
