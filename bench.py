@@ -49,7 +49,7 @@ def measured_peak():
 
 def algorithmic_bytes(st, color=False, p_in=12, part="scan"):
     """N*P_in + U*S_leaf + D1*8*S_leaf + sum_{l>=1} D_l*S_inner + sum_{l>=2} D_l*8*S_inner.
-    part="update" keeps the terms the leaf-update kernels (k_update + k_brick_agg) are responsible
+    part="update" keeps the terms the leaf-update kernels (k_update_compact / k_update + k_brick_agg) are responsible
     for: everything except the point input and the levels above the brick (depth >= 5)."""
     s_leaf, s_inner = (8, 12) if color else (4, 8)
     n, u = st["points"], st["touched_voxels"]
@@ -342,7 +342,7 @@ def main():
     t_scan_ms = float(np.mean([s["ms_total"] for s in per_scan]))
     kern = {k: float(np.mean([s[k] for s in per_scan])) for k in
             ("ms_h2d", "ms_points", "ms_rays", "ms_scatter", "ms_update", "ms_propagate")}
-    # dominant kernel: the leaf update (k_update + k_brick_agg between two CUDA events)
+    # dominant kernel: the leaf update (k_update_compact + k_brick_agg between two CUDA events)
     achieved = alg_upd / (kern["ms_update"] * 1e-3) / 1e9
     pipeline = alg / (t_scan_ms * 1e-3) / 1e9
     traffic, traffic_src = measured_traffic()
@@ -364,7 +364,7 @@ def main():
                     "h2d_bytes_per_step": int(n_pts * 12), "d2h_bytes_per_step": int(last["result_bytes"])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_update (+k_brick_agg): hit/miss log-odds update of the marked voxels and "
+                         "kernel": "k_update_compact (+k_brick_agg): hit/miss log-odds update of the marked voxels and "
                                    "depth 1-4 aggregates; CUDA events on the map's stream around every launch "
                                    "of the timed region",
                          "algorithmic_bytes_per_launch": alg_upd, "ms_per_launch": kern["ms_update"],
