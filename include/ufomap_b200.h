@@ -105,6 +105,25 @@ int ufo_b200_insert_pointcloud_frame(ufo_b200_map* m, const double origin[3], co
                                      double max_range, uint32_t depth, int simple_ray_casting,
                                      uint32_t early_stopping, int discrete, int async);
 
+/* A sensor_msgs/PointCloud2 buffer exactly as ROS delivers it: n = width*height records of
+ * point_step bytes, x/y/z FLOAT32 fields at the given byte offsets, colour bytes at off_r/g/b
+ * (for the usual packed "rgb" field at offset o: r = o+2, g = o+1, b = o; -1 = no colour).
+ * Replaces rosToUfo (ufomap_ros/ufomap_ros/src/conversions.cpp:77-138): records with a NaN
+ * coordinate are skipped, float32 is widened to double, on the device -- the raw buffer is the
+ * only thing that crosses PCIe.  frame_pose may be NULL (cloud already in the map frame);
+ * otherwise it is the transform the server applies next (server.cpp:116). */
+typedef struct ufo_b200_cloud2 {
+	const void* data;
+	size_t n;
+	uint32_t point_step;
+	uint32_t off_x, off_y, off_z;
+	int32_t off_r, off_g, off_b;
+	int32_t on_device; /* != 0: data is device memory on the map's device */
+} ufo_b200_cloud2;
+int ufo_b200_insert_pointcloud2(ufo_b200_map* m, const double origin[3], const ufo_b200_cloud2* cloud,
+                                const double* frame_pose, double max_range, uint32_t depth,
+                                int simple_ray_casting, uint32_t early_stopping, int discrete, int async);
+
 /* Host helpers (no device needed).  ufo_b200_transform_points: Pose6::transform of n points of
  * the given layout into out_xyz[n][3].  ufo_b200_pose_from_rpy: Pose6(x, y, z, roll, pitch,
  * yaw) math/pose6.h:71-74 with Quaternion(roll, pitch, yaw) math/quaternion.h:69-93. */

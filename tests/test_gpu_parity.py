@@ -282,3 +282,46 @@ def test_frame_insert(color, discrete, dtype):
     rmn, rmx = cpu.change_bbox()
     assert np.array_equal(mn, rmn) and np.array_equal(mx, rmx)
     gpu.close()
+
+
+@pytest.mark.parametrize("color,discrete", [(False, False), (True, True)])
+def test_pointcloud2_ingestion(color, discrete):
+    """Raw sensor_msgs/PointCloud2 records (x,y,z FLOAT32 + packed rgb, NaN rows) + frame pose ==
+    rosToUfo (NaN rows dropped, ufomap_ros/src/conversions.cpp:88-95,115-137) + cloud.transform +
+    insertPointCloud[Discrete] (server.cpp:113-120)."""
+    from oracle_lib import ORACLE_SO, _load
+    from ufomap_b200 import capi
+    api = _load(ORACLE_SO, "ufo_oracle_")
+    gpu = Map(0.05, color=color, initial_blocks=1 << 14)
+    cpu = OracleMap(0.05, color=color)
+    rng = np.random.default_rng(9)
+    step = 32
+    for k, rpy in enumerate([(0.02, 0.01, -0.4), (0.0, -0.05, 1.9)]):
+        o, p, c = scans.rgbd(k=k, width=64, height=48)
+        local = (p - o).astype(np.float32)
+        n = len(local)
+        rec = np.zeros((n, step), np.uint8)
+        rec[:, 0:12] = local.view(np.uint8).reshape(n, 12)
+        rec[:, 16] = c[:, 2]   # packed "rgb" field at offset 16: b, g, r, 0
+        rec[:, 17] = c[:, 1]
+        rec[:, 18] = c[:, 0]
+        rec[:, 20:24] = rng.integers(0, 255, (n, 4), dtype=np.uint8)   # some other field
+        bad = rng.random(n) < 0.05
+        nan_col = rng.integers(0, 3, n)
+        xyz = rec[:, 0:12].view(np.float32)      # view into rec
+        xyz[bad, nan_col[bad]] = np.nan
+        pose = capi.pose_from_rpy(*o, *rpy)
+        keep = ~bad
+        kept = np.ascontiguousarray(local[keep].astype(np.float64))
+        world = np.empty_like(kept)
+        api["transform"](pose.ctypes.data, kept.ctypes.data, len(kept), world.ctypes.data)
+        gpu.insert_pointcloud2(pose[:3], rec, step, off_xyz=(0, 4, 8), off_rgb=16 if color else None,
+                               frame_pose=pose, max_range=4.0, discrete=discrete)
+        cpu.insert(origin=pose[:3], xyz=world, rgb=c[keep] if color else None, max_range=4.0,
+                   discrete=discrete)
+        assert gpu.stats()["points"] == n
+    assert_value_fields_equal(gpu.value_field(), cpu.value_field(), color_tol=1 if color else 0, what="pc2")
+    mn, mx = gpu.change_bbox()
+    rmn, rmx = cpu.change_bbox()
+    assert np.array_equal(mn, rmn) and np.array_equal(mx, rmx)
+    gpu.close()

@@ -57,7 +57,16 @@ SYMBOLS = [
     "ufo_b200_change_bbox", "ufo_b200_reset_change_bbox", "ufo_b200_last_scan_stats",
     "ufo_b200_set_profiling", "ufo_b200_clear", "ufo_b200_version", "ufo_b200_set_shard",
     "ufo_b200_insert_pointcloud_frame", "ufo_b200_transform_points", "ufo_b200_pose_from_rpy",
+    "ufo_b200_insert_pointcloud2",
 ]
+
+class Cloud2(C.Structure):
+    """ufo_b200_cloud2: a sensor_msgs/PointCloud2 data buffer + field offsets."""
+    _fields_ = [("data", C.c_void_p), ("n", C.c_size_t), ("point_step", C.c_uint32),
+                ("off_x", C.c_uint32), ("off_y", C.c_uint32), ("off_z", C.c_uint32),
+                ("off_r", C.c_int32), ("off_g", C.c_int32), ("off_b", C.c_int32),
+                ("on_device", C.c_int32)]
+
 
 _lib = None
 
@@ -85,6 +94,7 @@ def load():
         f.argtypes = [vp, vp, vp, sz, i32, dbl, u32, i32, u32, i32, i32]
     lib.ufo_b200_insert_pointcloud_frame.argtypes = [vp, vp, vp, sz, i32, vp, dbl, u32, i32, u32, i32,
                                                      i32]
+    lib.ufo_b200_insert_pointcloud2.argtypes = [vp, vp, C.POINTER(Cloud2), vp, dbl, u32, i32, u32, i32, i32]
     lib.ufo_b200_transform_points.argtypes = [vp, vp, sz, i32, vp]
     lib.ufo_b200_pose_from_rpy.argtypes = [dbl, dbl, dbl, dbl, dbl, dbl, vp]
     lib.ufo_b200_wait.argtypes = [vp]
@@ -201,6 +211,23 @@ class Map:
         self._check(self.lib.ufo_b200_insert_pointcloud_frame(
             self.h, o.ctypes.data, buf.ctypes.data, len(buf), layout, f.ctypes.data,
             float(max_range), int(depth), int(simple), 0, int(discrete), int(async_)))
+
+    def insert_pointcloud2(self, origin, data, point_step, off_xyz=(0, 4, 8), off_rgb=None,
+                           frame_pose=None, max_range=-1.0, depth=0, simple=False, discrete=False,
+                           async_=False):
+        """Insert a raw sensor_msgs/PointCloud2 data buffer (numpy uint8 array); NaN points are
+        skipped on the device like rosToUfo does."""
+        buf = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        assert len(buf) % point_step == 0
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        f = None if frame_pose is None else np.ascontiguousarray(frame_pose, dtype=np.float64)
+        r, g, b = (-1, -1, -1) if off_rgb is None else (off_rgb + 2, off_rgb + 1, off_rgb)
+        c = Cloud2(buf.ctypes.data, len(buf) // point_step, point_step, off_xyz[0], off_xyz[1], off_xyz[2],
+                   r, g, b, 0)
+        self._keep = (buf, o, f, c)
+        self._check(self.lib.ufo_b200_insert_pointcloud2(
+            self.h, o.ctypes.data, C.byref(c), None if f is None else f.ctypes.data, float(max_range),
+            int(depth), int(simple), 0, int(discrete), int(async_)))
 
     def insert_packed(self, origin, buf_ptr, n, layout, max_range=-1.0, depth=0, simple=False,
                       discrete=False, async_=False, on_device=False):

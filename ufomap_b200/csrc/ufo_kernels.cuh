@@ -48,6 +48,10 @@ struct ScanArgs {
 	// occupancy_map_base.h:313-327 -> PointCloudT::transform, point_cloud.h:157-166)
 	int has_frame;
 	Frame frame;
+	// layout 4 (sensor_msgs/PointCloud2 records): byte stride and field offsets; NaN points are
+	// skipped like rosToUfo does (ufomap_ros/ufomap_ros/src/conversions.cpp:88-95, :115-137)
+	uint32_t pc2_step, pc2_x, pc2_y, pc2_z;
+	int pc2_r, pc2_g, pc2_b;
 	// ray-walk output: (block key, visited-voxel mask) records, one region per warp of 32 rays
 	struct QEntry* seg;
 	unsigned long long seg_cap;  // records
@@ -56,10 +60,20 @@ struct ScanArgs {
 	uint32_t* order;             // [ceil(n/32)] ray batches sorted by estimated work, longest first
 };
 
-__device__ __forceinline__ void load_point(const ScanArgs& a, uint32_t i, Vec3& p, uint32_t& rgb)
+// returns false for a point the ingestion drops (PointCloud2 records with a NaN coordinate)
+__device__ __forceinline__ bool load_point(const ScanArgs& a, uint32_t i, Vec3& p, uint32_t& rgb)
 {
 	rgb = 0;
 	switch (a.layout) {
+		case 4: {
+			const unsigned char* rec = reinterpret_cast<const unsigned char*>(a.points) + (size_t)a.pc2_step * i;
+			const float x = *reinterpret_cast<const float*>(rec + a.pc2_x);
+			const float y = *reinterpret_cast<const float*>(rec + a.pc2_y);
+			const float z = *reinterpret_cast<const float*>(rec + a.pc2_z);
+			p = {(double)x, (double)y, (double)z};
+			if (x != x || y != y || z != z) return false;
+			if (a.pc2_r >= 0) rgb = (uint32_t)rec[a.pc2_r] | ((uint32_t)rec[a.pc2_g] << 8) | ((uint32_t)rec[a.pc2_b] << 16);
+		} break;
 		case 0: {
 			const double* q = reinterpret_cast<const double*>(a.points) + 3 * (size_t)i;
 			p = {q[0], q[1], q[2]};
@@ -80,6 +94,7 @@ __device__ __forceinline__ void load_point(const ScanArgs& a, uint32_t i, Vec3& 
 		} break;
 	}
 	if (a.has_frame) p = frame_transform(a.frame, p);
+	return true;
 }
 
 __device__ __forceinline__ void bbox_accumulate(const DeviceMap& M, double lo[3], double hi[3],
@@ -212,10 +227,15 @@ __global__ void __launch_bounds__(256) k_points(DeviceMap M, ScanArgs a)
 	double lo[3], hi[3];
 	bool contributes = false, cast = false;
 	uint32_t bound = 0;
-	if (i < a.n) {
-		Vec3 end;
-		uint32_t rgb;
-		load_point(a, i, end, rgb);
+	Vec3 end = {0.0, 0.0, 0.0};
+	uint32_t rgb = 0;
+	const bool valid = i < a.n && load_point(a, i, end, rgb);
+	if (i < a.n && !valid) {
+		// dropped by the ingestion: casts no ray, marks no hit
+		a.ray_end[3 * (size_t)i] = __longlong_as_double(0x7ff8000000000000ll);
+		if (a.hit_tab) a.hit_tab[i] = kNone;
+	}
+	if (valid) {
 		const Geometry& g = M.g;
 		const double bhi = node_half(g, g.depth_levels), blo = -bhi;
 		uint32_t hit_slot = kNone;

@@ -479,13 +479,27 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 int do_insert(Map* m, const double origin[3], const void* points, bool on_device, size_t n,
               const double* frame_pose,
               int layout, double max_range, uint32_t depth, int simple, uint32_t early_stopping,
-              int discrete, int async)
+              int discrete, int async, const ufo_b200_cloud2* pc2 = nullptr)
 {
 	if (!m || !origin || (!points && n)) return UFO_B200_E_INVALID;
-	size_t stride = layout_stride(layout);
+	size_t stride = pc2 ? pc2->point_step : layout_stride(layout);
 	if (!stride || n > 0x7fffffffull) {
 		m->set_error("invalid layout %d or point count %zu", layout, n);
 		return UFO_B200_E_INVALID;
+	}
+	bool pc2_rgb = false;
+	if (pc2) {
+		layout = 4;
+		pc2_rgb = pc2->off_r >= 0 && pc2->off_g >= 0 && pc2->off_b >= 0;
+		const uint32_t fx[3] = {pc2->off_x, pc2->off_y, pc2->off_z};
+		bool ok = pc2->point_step % 4 == 0;
+		for (uint32_t f : fx) ok = ok && f % 4 == 0 && (size_t)f + 4 <= pc2->point_step;
+		const int32_t fc[3] = {pc2->off_r, pc2->off_g, pc2->off_b};
+		for (int32_t c : fc) ok = ok && (c < 0 || (size_t)c < pc2->point_step);
+		if (!ok) {
+			m->set_error("PointCloud2 descriptor: x/y/z must be 4-byte aligned FLOAT32 fields inside point_step");
+			return UFO_B200_E_INVALID;
+		}
 	}
 	if (early_stopping != 0) {
 		m->set_error("early_stopping is order-dependent in the reference (occupancy_map_base.h:1289-1298) and is not supported");
@@ -501,7 +515,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 
 	DeviceMap& M = m->M;
 	cudaStream_t s = m->stream;
-	const bool has_rgb = layout == UFO_B200_XYZRGB_F64 || layout == UFO_B200_XYZRGB_F32;
+	const bool has_rgb = layout == UFO_B200_XYZRGB_F64 || layout == UFO_B200_XYZRGB_F32 || pc2_rgb;
 	const bool use_color = M.color && has_rgb;
 	const bool need_table = discrete || use_color;
 	ensure_scan_buffers(m, n, need_table);
@@ -521,6 +535,15 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	a.tab_mask = m->tab_size ? m->tab_size - 1 : 0;
 	a.hit_tab = use_color ? m->d_hit_tab : nullptr;
 	a.count_visits = m->profiling >= 2;
+	if (pc2) {
+		a.pc2_step = pc2->point_step;
+		a.pc2_x = pc2->off_x;
+		a.pc2_y = pc2->off_y;
+		a.pc2_z = pc2->off_z;
+		a.pc2_r = pc2_rgb ? pc2->off_r : -1;
+		a.pc2_g = pc2_rgb ? pc2->off_g : -1;
+		a.pc2_b = pc2_rgb ? pc2->off_b : -1;
+	}
 	if (frame_pose) {
 		a.has_frame = 1;
 		a.frame = Frame{frame_pose[3], frame_pose[4], frame_pose[5], frame_pose[6],
@@ -877,6 +900,17 @@ int ufo_b200_insert_pointcloud_frame(ufo_b200_map* m, const double origin[3], co
 	return guarded(m, [&]() {
 		return do_insert(m, origin, points, false, n, frame_pose, layout, max_range, depth,
 		                 simple_ray_casting, early_stopping, discrete, async);
+	});
+}
+
+int ufo_b200_insert_pointcloud2(ufo_b200_map* m, const double origin[3], const ufo_b200_cloud2* cloud,
+                                const double* frame_pose, double max_range, uint32_t depth,
+                                int simple_ray_casting, uint32_t early_stopping, int discrete, int async)
+{
+	if (m && !cloud) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		return do_insert(m, origin, cloud->data, cloud->on_device != 0, cloud->n, frame_pose, 4, max_range,
+		                 depth, simple_ray_casting, early_stopping, discrete, async, cloud);
 	});
 }
 
