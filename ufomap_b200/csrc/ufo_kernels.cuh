@@ -685,9 +685,10 @@ __global__ void __launch_bounds__(kRayThreads, UFO_RAY_MINBLOCKS) k_rays(DeviceM
 #ifndef UFO_SCATTER_MINBLOCKS
 #define UFO_SCATTER_MINBLOCKS 8
 #endif
-// GENERIC = false is the common case (insert depth <= 2, unsharded map): the extra tests are
-// compiled out so that the hot path stays small.
-template <bool GENERIC>
+// GENERIC = false is the common case (insert depth <= 2, no out-of-tree keys seen yet): the slow
+// paths are compiled out so that the hot path stays small.  SHARD adds the ownership filter of a
+// spatially sharded map (records of bricks another GPU owns are dropped before any memory access).
+template <bool GENERIC, bool SHARD>
 __device__ __forceinline__ void scatter_record(const DeviceMap& M, const ScanArgs& a, const ulonglong2 v)
 {
 	uint32_t x, y, z;
@@ -704,7 +705,7 @@ __device__ __forceinline__ void scatter_record(const DeviceMap& M, const ScanArg
 	y >>= 2;
 	z >>= 2;
 	const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
-	if (GENERIC && M.shard_world > 1 && brick_owner(bkey, M.shard_world) != M.shard_rank) return;  // another GPU's brick
+	if (SHARD && brick_owner(bkey, M.shard_world) != M.shard_rank) return;  // another GPU's brick
 	const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
 	// (thousands of records near the sensor resolve to the same few bricks at the same time:
 	// served from L1 instead of all queueing at one L2 slice)
@@ -735,7 +736,7 @@ __device__ __forceinline__ void scatter_record(const DeviceMap& M, const ScanArg
 // The loop is software-pipelined over the CTA's items: while the record of item k is resolved
 // (hash probe -> atomic), the record of item k+1 and the region length/base of item k+2 are
 // already in flight, so an item exposes one dependent round trip instead of four.
-template <bool GENERIC>
+template <bool GENERIC, bool SHARD>
 __global__ void __launch_bounds__(kChunk, UFO_SCATTER_MINBLOCKS) k_scatter(DeviceMap M, ScanArgs a)
 {
 	if (ld_volatile_u32(&M.ctr->overflow) & 8u) return;
@@ -785,7 +786,7 @@ __global__ void __launch_bounds__(kChunk, UFO_SCATTER_MINBLOCKS) k_scatter(Devic
 			if (ok1) rec1 = *reinterpret_cast<const ulonglong2*>(&a.seg[(size_t)base1 + lo + threadIdx.x]);
 		}
 		// item k
-		if (ok0) scatter_record<GENERIC>(M, a, rec0);
+		if (ok0) scatter_record<GENERIC, SHARD>(M, a, rec0);
 		rec0 = rec1;
 		ok0 = ok1;
 		cnt1 = cnt2;
@@ -907,6 +908,8 @@ __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, flo
 	}
 	// contains_free = any voxel below the free threshold, contains_unknown = any in between
 	oflags = (omin < M.free_ceil ? 1u : 0u) | (unk ? 2u : 0u);
+	// (streaming/evict-first hints on these stores and on the record traffic of K2/K2b were
+	// measured: no effect beyond run-to-run noise)
 	reinterpret_cast<float4*>(lp)[0] = make_float4(v[0], v[1], v[2], v[3]);
 	reinterpret_cast<float4*>(lp)[1] = make_float4(v[4], v[5], v[6], v[7]);
 }

@@ -470,8 +470,11 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 		uint32_t sgrid = (uint32_t)m->sm_count * 8;
 		const uint32_t n_regions = (a.n + 31) / 32;
 		while (sgrid > 1 && std::gcd(sgrid, n_regions) != 1) --sgrid;
-		if (a.depth >= 3 || m->M.shard_world > 1 || m->M.alias_miss) k_scatter<true><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
-		else k_scatter<false><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
+		const bool generic = a.depth >= 3 || m->M.alias_miss, shard = m->M.shard_world > 1;
+		if (generic && shard) k_scatter<true, true><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
+		else if (generic) k_scatter<true, false><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
+		else if (shard) k_scatter<false, true><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
+		else k_scatter<false, false><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
 	}
 	++m->launches;
 }
