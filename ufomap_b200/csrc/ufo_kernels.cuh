@@ -5,15 +5,20 @@
 //                  front end :354-399 / occupancy_map_color.h:195-246)
 //   k_hits     K1b colour maps: first point per voxel blends its colour into the leaf
 //                  (updateNodeColor, occupancy_map_color.cpp:142-171) and marks the hit
-//   k_rays     K2  one thread per ray: exact FP64 backward voxel walk
+//   k_order_batches   sorts the batches of 32 rays by estimated walk length (load balance of K2)
+//   k_rays     K2  one thread per ray, warp in lock-step: exact FP64 backward voxel walk
 //                  (freeSpaceNormal, occupancy_map_base.h:1261-1301); visited voxels are
-//                  OR-accumulated per 4^3 block in a register and flushed with one atomicOr
-//                  when the ray leaves the block (set semantics of CodeMap::try_emplace)
+//                  OR-accumulated per 4^3 block in a register; leaving the block appends a
+//                  16-byte (mask, voxel key) record to the warp's region of the record buffer
+//   k_scatter  K2b one thread per record: brick hash probe -> atomicOr into the block's miss
+//                  mask (set semantics of CodeMap::try_emplace, code.h:675-694)
 //   k_rays_simple  fixed-step variant (freeSpaceSimple, occupancy_map_base.h:1303-1339)
-//   k_update   K3  one warp per touched brick: hit-then-miss float log-odds update of the
-//                  marked voxels (updateOccupancy :1139-1145), depth-1/2 aggregates per block,
-//                  depth-3/4 aggregates per brick (updateNode :1179-1224)
-//   k_upper_*  K4  aggregates of the dirty nodes of depth >= 5, one launch per level
+//   k_update_compact / k_update<COLOR>
+//              K3  hit-then-miss float log-odds update of the marked voxels
+//                  (updateOccupancy :1139-1145) and depth-1/2 aggregates per block;
+//   k_brick_agg    depth-3/4 aggregates per brick (updateNode :1179-1224)
+//   k_alias_*      marks of keys outside the tree (octree.h:321), launched only when present
+//   k_upper_*  K4  aggregates of the dirty nodes of depth >= 5 (seed, levels 5-6, one-CTA tail)
 #pragma once
 
 #include "ufo_device.cuh"

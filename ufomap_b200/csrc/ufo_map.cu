@@ -2,8 +2,9 @@
 // and the C ABI declared in include/ufomap_b200.h.
 //
 // One map = one CUDA device + one stream.  An insert enqueues
-//   H2D(points) -> K1 k_points [-> K1b k_hits] -> K2 k_rays -> (counter read-back,
-//   grow pools and re-run K1/K2 if an allocation overflowed) -> K3 k_update -> K4 k_upper_*
+//   H2D(points) -> K1 k_points [-> K1b k_hits] -> K2 k_rays -> K2b k_scatter -> speculative K3
+//   (k_update_compact / k_update<COLOR>) while the counters are read back on a second stream ->
+//   (grow pools and re-run K1/K2/K2b if an allocation overflowed) -> K3 remainder -> K4 k_upper_*
 // which mirrors insertPointCloud + insertPointCloudHelper
 // (/root/reference/ufomap/include/ufo/map/occupancy_map_base.h:270-327, :1345-1373).
 // There is no CPU fallback anywhere in this file.
