@@ -712,18 +712,27 @@ __device__ __forceinline__ void scatter_record(const DeviceMap& M, const ScanArg
 	const unsigned long long bkey = pack_key(x >> 2, y >> 2, z >> 2);
 	if (SHARD && brick_owner(bkey, M.shard_world) != M.shard_rank) return;  // another GPU's brick
 	const uint32_t hidx = hash_u64(bkey) & M.bh_mask & ~1u;
-	// (thousands of records near the sensor resolve to the same few bricks at the same time:
-	// served from L1 instead of all queueing at one L2 slice)
-#ifdef UFO_SCATTER_VOLATILE_PROBE
-	const ulonglong2 e0 = ld_volatile_entry(&M.bh_tab[hidx]);
-	const ulonglong2 e1 = ld_volatile_entry(&M.bh_tab[hidx + 1]);
-#else
+	// First entry of the two-entry bucket first (it holds the key three times out of four), the
+	// second only on a mismatch: K2b is bound by L1 wavefronts of its scattered accesses as much
+	// as by latency, and this drops a quarter of them.  L1-cached loads: thousands of records
+	// near the sensor resolve to the same few bricks at the same time.
+#ifdef UFO_SCATTER_BOTH_ENTRIES
 	const ulonglong2 e0 = ld_cached_entry(&M.bh_tab[hidx]);
 	const ulonglong2 e1 = ld_cached_entry(&M.bh_tab[hidx + 1]);
-#endif
 	const bool hit0 = e0.x == bkey, hit1 = e1.x == bkey;
 	const ulonglong2 ent = hit0 ? e0 : e1;
 	const uint32_t hpos = hit0 ? hidx : hidx + 1;
+#else
+	ulonglong2 ent = ld_cached_entry(&M.bh_tab[hidx]);
+	const bool hit0 = ent.x == bkey;
+	bool hit1 = false;
+	uint32_t hpos = hidx;
+	if (!hit0) {
+		ent = ld_cached_entry(&M.bh_tab[hidx + 1]);
+		hit1 = ent.x == bkey;
+		hpos = hidx + 1;
+	}
+#endif
 	uint32_t brick = (uint32_t)ent.y;
 	if ((hit0 || hit1) && brick != kPending && brick != kFailed) {
 		if ((uint32_t)(ent.y >> 32) != M.scan_id) {
