@@ -1036,6 +1036,9 @@ __global__ void __launch_bounds__(kUpdThreads, UFO_UPD_MINBLOCKS) k_update(Devic
 #ifndef UFO_UC_MINBLOCKS
 #define UFO_UC_MINBLOCKS 4
 #endif
+#ifndef UFO_UC_MINBLOCKS_COLOR
+#define UFO_UC_MINBLOCKS_COLOR 4
+#endif
 #ifndef UFO_UC_BLOCKS
 #define UFO_UC_BLOCKS 256
 #endif
@@ -1049,7 +1052,8 @@ static_assert(kUcBlocks <= kUcThreads && kUcBlocks % 32 == 0 && kUcBlocks * 8 <=
 #define UFO_UC_GRID_PER_SM UFO_UC_MINBLOCKS
 #endif
 
-__global__ void __launch_bounds__(kUcThreads, UFO_UC_MINBLOCKS) k_update_compact(DeviceMap M, float miss,
+template <bool COLOR>
+__global__ void __launch_bounds__(kUcThreads, COLOR ? UFO_UC_MINBLOCKS_COLOR : UFO_UC_MINBLOCKS) k_update_compact(DeviceMap M, float miss,
                                                                                uint32_t first_brick,
                                                                                uint32_t n_bricks,
                                                                                uint32_t n_chunks)
@@ -1058,6 +1062,7 @@ __global__ void __launch_bounds__(kUcThreads, UFO_UC_MINBLOCKS) k_update_compact
 	__shared__ uint16_t s_list[kUcBlocks * 8];
 	__shared__ float s_omax[8 * kUcBlocks];      // [octet][block]: conflict-free for the block threads
 	__shared__ unsigned char s_ofl[8 * kUcBlocks];
+	__shared__ uint32_t s_orgb[COLOR ? 8 * kUcBlocks : 1];  // depth-1 colours of the touched octets
 	__shared__ uint32_t s_wtot[2][kUcBlocks / 32];
 	const uint32_t tid = threadIdx.x, lane = tid & 31;
 	const bool block_thread = tid < (uint32_t)kUcBlocks;
@@ -1082,6 +1087,7 @@ __global__ void __launch_bounds__(kUcThreads, UFO_UC_MINBLOCKS) k_update_compact
 		const unsigned long long mm = mm_next, hm = hm_next;
 		uint32_t mt = 0, t8 = 0, excl = 0;
 		float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+		uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0;
 		const bool marked = (mm | hm) != 0ull;
 		if (block_thread) {
 			// masks of this CTA's next chunk: in flight while this chunk is processed
@@ -1106,6 +1112,11 @@ __global__ void __launch_bounds__(kUcThreads, UFO_UC_MINBLOCKS) k_update_compact
 					const float4* sp = reinterpret_cast<const float4*>(M.sum1 + b * 8);
 					p0 = sp[0];
 					p1 = sp[1];
+					if (COLOR) {
+						const uint4* cp = reinterpret_cast<const uint4*>(M.sum1_rgb + b * 8);
+						q0 = cp[0];
+						q1 = cp[1];
+					}
 				}
 				s_mm[tid] = mm;
 				s_hm[tid] = hm;
@@ -1139,44 +1150,6 @@ __global__ void __launch_bounds__(kUcThreads, UFO_UC_MINBLOCKS) k_update_compact
 		__syncthreads();
 
 		// ---- all threads: one touched octet (= one 32 B sector) each ----
-#ifdef UFO_UC_ILP2
-		// two entries per trip, both sectors requested before either is processed
-		for (uint32_t i = tid; i < total; i += 2 * kUcThreads) {
-			const bool two = i + kUcThreads < total;
-			const uint32_t e = s_list[i], t = e >> 3, oct = e & 7u;
-			const uint32_t e2 = two ? s_list[i + kUcThreads] : e, t2 = e2 >> 3, oct2 = e2 & 7u;
-			float* lp = M.leaf + (b0 + t) * 64 + 8 * oct;
-			float* lp2 = M.leaf + (b0 + t2) * 64 + 8 * oct2;
-			const float4 a0 = reinterpret_cast<const float4*>(lp)[0], a1 = reinterpret_cast<const float4*>(lp)[1];
-			float4 c0 = a0, c1 = a1;
-			if (two) {
-				c0 = reinterpret_cast<const float4*>(lp2)[0];
-				c1 = reinterpret_cast<const float4*>(lp2)[1];
-			}
-			{
-				const uint32_t m8 = octet_bits8(s_mm[t], oct), h8 = octet_bits8(s_hm[t], oct);
-				float omax;
-				uint32_t ofl;
-				update_octet(M, miss, lp, m8, h8, a0, a1, omax, ofl);
-				s_omax[oct * kUcBlocks + t] = omax;
-				s_ofl[oct * kUcBlocks + t] = (unsigned char)ofl;
-				s_vox += __popc(m8 | h8);
-				s_hit += __popc(h8);
-				s_oct += 1;
-			}
-			if (two) {
-				const uint32_t m8 = octet_bits8(s_mm[t2], oct2), h8 = octet_bits8(s_hm[t2], oct2);
-				float omax;
-				uint32_t ofl;
-				update_octet(M, miss, lp2, m8, h8, c0, c1, omax, ofl);
-				s_omax[oct2 * kUcBlocks + t2] = omax;
-				s_ofl[oct2 * kUcBlocks + t2] = (unsigned char)ofl;
-				s_vox += __popc(m8 | h8);
-				s_hit += __popc(h8);
-				s_oct += 1;
-			}
-		}
-#else
 		for (uint32_t i = tid; i < total; i += kUcThreads) {
 			const uint32_t e = s_list[i], t = e >> 3, oct = e & 7u;
 			const uint32_t m8 = octet_bits8(s_mm[t], oct), h8 = octet_bits8(s_hm[t], oct);
@@ -1187,32 +1160,43 @@ __global__ void __launch_bounds__(kUcThreads, UFO_UC_MINBLOCKS) k_update_compact
 			update_octet(M, miss, lp, m8, h8, a0, a1, omax, ofl);
 			s_omax[oct * kUcBlocks + t] = omax;
 			s_ofl[oct * kUcBlocks + t] = (unsigned char)ofl;
+			if (COLOR) {
+				// depth-1 colour of the octet (getAverageChildColor, occupancy_map_color.cpp:177-194)
+				const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + (b0 + t) * 64 + 8 * oct);
+				const uint4 c0 = cp[0], c1 = cp[1];
+				const uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+				s_orgb[oct * kUcBlocks + t] = rms_rgb(cc, 8);
+			}
 			s_vox += __popc(m8 | h8);
 			s_hit += __popc(h8);
 			s_oct += 1;
 		}
-#endif
 		__syncthreads();
 
 		// ---- block threads: depth-1 sector, depth-2 aggregate, meta, mask clearing ----
 		if (block_thread && marked) {
 			const float old1[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+			const uint32_t oldc[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 			float new1[8];
+			uint32_t newc[8];
 			float bmax = -3.402823466e+38f;
 			uint32_t bfl = 0, newmeta = 0;
 #pragma unroll
 			for (uint32_t o = 0; o < 8; ++o) {
 				float om = 0.0f;
-				uint32_t fl = M.default_flags, touched = 0;
+				uint32_t fl = M.default_flags, touched = 0, oc = 0;
 				if ((t8 >> o) & 1u) {
 					om = s_omax[o * kUcBlocks + tid];
 					fl = s_ofl[o * kUcBlocks + tid];
+					if (COLOR) oc = s_orgb[o * kUcBlocks + tid];
 					touched = 1;
 				} else if ((mt >> (16 + o)) & 1u) {
 					om = old1[o];
 					fl = (mt >> (2 * o)) & 3u;
+					if (COLOR) oc = oldc[o];
 				}
 				new1[o] = om;
+				newc[o] = oc;
 				bmax = fmaxf(bmax, om);
 				bfl |= fl;
 				newmeta |= (fl << (2 * o)) | (touched << (16 + o));
@@ -1221,6 +1205,12 @@ __global__ void __launch_bounds__(kUcThreads, UFO_UC_MINBLOCKS) k_update_compact
 			sp[0] = make_float4(new1[0], new1[1], new1[2], new1[3]);
 			sp[1] = make_float4(new1[4], new1[5], new1[6], new1[7]);
 			M.agg2[b] = {bmax, bfl};
+			if (COLOR) {
+				uint4* cp = reinterpret_cast<uint4*>(M.sum1_rgb + b * 8);
+				cp[0] = make_uint4(newc[0], newc[1], newc[2], newc[3]);
+				cp[1] = make_uint4(newc[4], newc[5], newc[6], newc[7]);
+				M.rgb2[b] = rms_rgb(newc, 8);
+			}
 			M.meta[b] = (newmeta & 0xffffffu) | (mt & 0xff0000u) | (M.scan_id << 24);
 			M.miss_mask[b] = 0ull;
 			if (hm) M.hit_mask[b] = 0ull;

@@ -423,16 +423,25 @@ void launch_update(Map* m, float miss, uint32_t first, uint32_t last)
 {
 	const uint32_t groups = (last - first) * 64u;  // one eight-lane group per (brick, child)
 	const uint32_t grid = (groups + kUpdThreads / 8 - 1) / (kUpdThreads / 8);
+#ifdef UFO_UPD_FLAT
 	if (m->M.color) k_update<true><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
-#ifndef UFO_UPD_FLAT
-	else {
+	else k_update<false><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
+#else
+	{
 		// persistent CTAs (all resident), each looping over chunks of kUcBlocks blocks
 		const uint32_t n_chunks = (groups + kUcBlocks - 1) / kUcBlocks;
-		const uint32_t ugrid = std::min<uint32_t>(n_chunks, (uint32_t)m->sm_count * UFO_UC_GRID_PER_SM);
-		k_update_compact<<<ugrid, kUcThreads, 0, m->stream>>>(m->M, miss, first, last, n_chunks);
-	}
+		if (m->M.color) {
+#ifdef UFO_UPD_FLAT_COLOR
+			k_update<true><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
 #else
-	else k_update<false><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
+			const uint32_t ugrid = std::min<uint32_t>(n_chunks, (uint32_t)m->sm_count * UFO_UC_MINBLOCKS_COLOR);
+			k_update_compact<true><<<ugrid, kUcThreads, 0, m->stream>>>(m->M, miss, first, last, n_chunks);
+#endif
+		} else {
+			const uint32_t ugrid = std::min<uint32_t>(n_chunks, (uint32_t)m->sm_count * UFO_UC_GRID_PER_SM);
+			k_update_compact<false><<<ugrid, kUcThreads, 0, m->stream>>>(m->M, miss, first, last, n_chunks);
+		}
+	}
 #endif
 	++m->launches;
 }
