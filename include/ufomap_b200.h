@@ -163,6 +163,22 @@ int ufo_b200_query(ufo_b200_map* m, const uint64_t* codes, const uint32_t* depth
 int ufo_b200_export_leaves(ufo_b200_map* m, uint64_t* codes, float* logodds, uint8_t* rgb,
                            size_t cap, size_t* n);
 
+/* Octree::write(std::ostream&) / write(filename) with compress = false (octree.h:784-864,
+ * writeNodes occupancy_map_base.h:1457-1533): the map as a UFOMap file image -- text header, then
+ * the pre-order node stream -- which the reference's Octree::read / the RViz plugin / ufoToMsg
+ * consumers parse.  expanded = 0: the canonical tree of the map's value field (a node whose eight
+ * children are leaves with equal payload is a leaf).  The reference collapses such nodes itself
+ * (updateNode, occupancy_map_base.h:1210-1212 -- logically even with automatic pruning off,
+ * octree.h:1060-1066), so this is byte-identical to its own file unless its update order left a
+ * collapsible node behind (updateParents stops at the first unchanged aggregate, :1126-1133);
+ * then the two files differ in shape only and read back to the same map.  expanded != 0: every
+ * octet that was ever touched is written as eight voxels (value-equivalent, larger).
+ * ufo_b200_write: *size receives the image size; the image is copied when it fits into cap
+ * (call with buf = NULL to size the buffer).  Whole map only (no bounding-volume / min_depth
+ * filter, no LZ4). */
+int ufo_b200_write(ufo_b200_map* m, void* buf, size_t cap, size_t* size, int expanded);
+int ufo_b200_write_file(ufo_b200_map* m, const char* filename, int expanded);
+
 /* Sensor model  occupancy_map_base.h:734-773.  out6/in: occupied_thres,
  * free_thres, prob_hit, prob_miss, clamping_thres_min, clamping_thres_max as
  * probabilities (setters) or as stored double log-odds (ufo_b200_sensor_model_logit). */

@@ -19,6 +19,8 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <sstream>
+#include <string>
 #include <vector>
 
 // ---- LZ4 stubs (compressed file I/O is never used by the oracle) -------------
@@ -425,6 +427,27 @@ size_t ufo_ref_memory_usage(void* h)
 {
 	RefMap* m = static_cast<RefMap*>(h);
 	return withMap(m, [&](auto& map) { return size_t(map.memoryUsage()); });
+}
+
+// Octree::write(std::ostream&) with compress = false (octree.h:833-864): the complete file image.
+// Returns its size; copies it when it fits into cap.
+size_t ufo_ref_write(void* h, uint8_t* buf, size_t cap)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	std::stringstream ss(std::ios_base::in | std::ios_base::out | std::ios_base::binary);
+	withMap(m, [&](auto& map) { return map.write(ss, false); });
+	const std::string str = ss.str();
+	if (buf && str.size() <= cap) std::memcpy(buf, str.data(), str.size());
+	return str.size();
+}
+
+// Octree::read(std::istream&) (octree.h:699-733): replaces the map's content.  1 = ok.
+int ufo_ref_read(void* h, const uint8_t* buf, size_t size)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	std::stringstream ss(std::string(reinterpret_cast<const char*>(buf), size),
+	                     std::ios_base::in | std::ios_base::out | std::ios_base::binary);
+	return withMap(m, [&](auto& map) { return map.read(ss); }) ? 1 : 0;
 }
 
 // The cloud transform of the insertPointCloud(..., frame_origin, ...) overloads, through the

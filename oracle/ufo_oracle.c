@@ -25,6 +25,7 @@
 
 #include <float.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -1119,4 +1120,95 @@ void ufo_oracle_pose_from_rpy(double x, double y, double z, double roll, double 
 	pose7[4] = (m[2][1] - m[1][2]) >= 0 ? fabs(ax) : -fabs(ax);
 	pose7[5] = (m[0][2] - m[2][0]) >= 0 ? fabs(ay) : -fabs(ay);
 	pose7[6] = (m[1][0] - m[0][1]) >= 0 ? fabs(az) : -fabs(az);
+}
+
+/* ---- file image (Octree::write with compress = false, OCT:833-864; writeNodes /
+ * writeNodesRecurs OMB:1457-1533; node payloads occupancy_map_node.h:71-75, :106-110, :150-153)
+ * header text, then a pre-order walk: one byte per inner node with children (bit i = child i
+ * has children), leaf payloads (float occupancy [+ 3 colour bytes]) in child order; the
+ * children of depth-1 nodes are written as 8 payloads without a mask byte. */
+typedef struct {
+	uint8_t* buf;
+	size_t cap, n;
+} wbuf;
+
+static void wb_put(wbuf* w, const void* p, size_t len)
+{
+	if (w->buf && w->n + len <= w->cap) memcpy(w->buf + w->n, p, len);
+	w->n += len;
+}
+
+static void wb_payload(const omap* m, wbuf* w, const node* n)
+{
+	wb_put(w, &n->occ, 4);
+	if (m->color) wb_put(w, n->rgb, 3);
+}
+
+static void write_rec(const omap* m, wbuf* w, const node* n, unsigned depth)
+{
+	const unsigned cd = depth - 1;
+	uint8_t children = 0;
+	for (unsigned i = 0; i < 8; ++i)
+		if (cd > 0 && !n->ch[i].is_leaf) children |= (uint8_t)(1u << i);
+	wb_put(w, &children, 1);
+	for (unsigned i = 0; i < 8; ++i) {
+		const node* c = &n->ch[i];
+		if ((children >> i) & 1u) {
+			if (1 == cd) {
+				for (unsigned j = 0; j < 8; ++j) wb_payload(m, w, &c->ch[j]);
+			} else {
+				write_rec(m, w, c, cd);
+			}
+		} else {
+			wb_payload(m, w, c);
+		}
+	}
+}
+
+size_t ufo_oracle_write(void* h, uint8_t* buf, size_t cap)
+{
+	const omap* m = (const omap*)h;
+	/* data first (its size goes into the header) */
+	wbuf d = {NULL, 0, 0};
+	uint8_t children = m->root.is_leaf ? 0 : 0xff;
+	for (int pass = 0; pass < 2; ++pass) {
+		char head[512];
+		int hl = 0;
+		if (pass) {
+			hl = snprintf(head, sizeof head,
+			              "# UFOMap file\n# (feel free to add / change comments, but leave the first line as it "
+			              "is!)\n#\nversion 1.0.0\nid %s\nresolution %g\ndepth_levels %u\ncompressed 0\n"
+			              "uncompressed_data_size %d\ndata\n",
+			              m->color ? "occupancy_map_color" : "occupancy_map", m->res, m->levels, (int)d.n);
+		}
+		wbuf w = {pass ? buf : NULL, pass ? cap : 0, 0};
+		if (pass) wb_put(&w, head, (size_t)hl);
+		wb_put(&w, &children, 1);
+		if (children) write_rec(m, &w, &m->root, m->levels);
+		else wb_payload(m, &w, &m->root);
+		if (!pass) d = w;
+		else return w.n;
+	}
+	return 0;
+}
+
+/* Test helper: collapse every collapsible node bottom-up (the canonical minimal tree of the map's
+ * value field).  The reference's own tree is not always canonical: updateParents stops as soon as
+ * an updateNode reports "unchanged" (OMB:1126-1133), so a collapse further up can be missed. */
+static void canon_rec(omap* m, node* n, unsigned depth)
+{
+	if (n->is_leaf) return;
+	if (depth > 1)
+		for (int i = 0; i < 8; ++i) canon_rec(m, &n->ch[i], depth - 1);
+	if (collapsible(m, n, depth)) {
+		n->occ = n->ch[0].occ;
+		memcpy(n->rgb, n->ch[0].rgb, 3);
+		delete_children(m, n, depth);
+	}
+}
+
+void ufo_oracle_canonicalize(void* h)
+{
+	omap* m = (omap*)h;
+	canon_rec(m, &m->root, m->levels);
 }

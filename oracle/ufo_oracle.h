@@ -58,6 +58,13 @@ void ufo_oracle_transform(const double* pose7, const double* xyz, size_t n, doub
 void ufo_oracle_pose_from_rpy(double x, double y, double z, double roll, double pitch, double yaw,
                               double* pose7);
 
+/* Octree::write(ostream, compress = false): complete file image; returns its size, copies it
+ * when it fits into cap */
+size_t ufo_oracle_write(void* h, uint8_t* buf, size_t cap);
+
+/* test helper: collapse every collapsible node (canonical minimal tree of the value field) */
+void ufo_oracle_canonicalize(void* h);
+
 #ifdef __cplusplus
 }
 #endif

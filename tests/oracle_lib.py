@@ -76,11 +76,15 @@ def _load(path, prefix):
         reset_change_bbox=sig("reset_change_bbox", None, [vp]),
         sensor_model=sig("sensor_model", None, [vp, vp]),
         memory_usage=sig("memory_usage", sz, [vp]),
+        write=sig("write", sz, [vp, vp, sz]),
         transform=sig("transform", None, [vp, vp, sz, vp]),
         pose_from_rpy=sig("pose_from_rpy", None, [dbl, dbl, dbl, dbl, dbl, dbl, vp]),
     )
+    if prefix == "ufo_ref_":
+        api["read"] = sig("read", i32, [vp, vp, sz])
     if prefix == "ufo_oracle_":
         api["last_counters"] = sig("last_counters", None, [vp, vp])
+        api["canonicalize"] = sig("canonicalize", None, [vp])
     _libs[key] = api
     return api
 
@@ -234,15 +238,31 @@ class _CpuMap:
     def memory_usage(self):
         return int(self.api["memory_usage"](self.h))
 
+    def write(self):
+        """Octree::write(ostream, compress=False): the complete file image as bytes."""
+        n = self.api["write"](self.h, None, 0)
+        buf = np.empty(n, np.uint8)
+        assert self.api["write"](self.h, buf.ctypes.data, n) == n
+        return buf.tobytes()
+
 
 class RefMap(_CpuMap):
     _path = REF_SO
     _prefix = "ufo_ref_"
 
+    def read(self, image):
+        """Octree::read(istream): replace the map's content by a file image."""
+        buf = np.frombuffer(image, np.uint8)
+        return bool(self.api["read"](self.h, buf.ctypes.data, len(buf)))
+
 
 class OracleMap(_CpuMap):
     _path = ORACLE_SO
     _prefix = "ufo_oracle_"
+
+    def canonicalize(self):
+        """Collapse every collapsible node: the canonical minimal tree of the value field."""
+        self.api["canonicalize"](self.h)
 
     def last_counters(self):
         out = np.empty(4, np.uint64)

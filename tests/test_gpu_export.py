@@ -1,0 +1,85 @@
+"""The map in the reference's file format: ufo_b200_write against
+Octree::write of the reference / the oracle's restatement of it: byte for byte (the canonical
+tree is the reference's tree on these histories), and by reading the image back through the
+reference's own Octree::read."""
+import numpy as np
+import pytest
+
+from oracle_lib import OracleMap, RefMap, have_ref
+from ufomap_b200 import scans
+from ufomap_b200.capi import Map
+
+pytestmark = pytest.mark.gpu
+
+
+def _cpu_maps(color, **kw):
+    maps = [OracleMap(color=color, **kw)]
+    if have_ref():
+        maps.append(RefMap(color=color, **kw))
+    return maps
+
+
+def _scenario(name):
+    if name == "velodyne":
+        ins = []
+        for k in range(3):
+            o, p = scans.velodyne64(k=k, rings=8, azimuths=128)
+            ins.append(dict(origin=o, xyz=p, max_range=25.0))
+        return dict(resolution=0.2), ins, False
+    if name == "rgbd_color_discrete":
+        ins = []
+        for k in range(2):
+            o, p, c = scans.rgbd(k=k, width=48, height=36)
+            ins.append(dict(origin=o, xyz=p, rgb=c, max_range=3.0, discrete=True))
+        return dict(resolution=0.04), ins, True
+    o, p = scans.random_shell(n=1500)
+    return dict(resolution=0.16, depth_levels=12), [dict(origin=o, xyz=p, max_range=5.0)], False
+
+
+@pytest.mark.parametrize("name", ["velodyne", "rgbd_color_discrete", "shell_small_tree"])
+@pytest.mark.parametrize("pruning", [False, True])
+def test_image_is_byte_identical(name, pruning, tmp_path):
+    """Canonical export == the reference's own file (and the oracle's restatement of it) on
+    histories where the reference's tree is canonical (all of these; checked on the CPU side by
+    tests/test_oracle_vs_reference.py::test_reference_tree_is_canonical_here)."""
+    kw, inserts, color = _scenario(name)
+    gpu = Map(color=color, automatic_pruning=pruning, initial_blocks=1 << 12, **kw)
+    cpus = _cpu_maps(color, automatic_pruning=pruning, **kw)
+    for c in cpus:
+        assert gpu.write() == c.write(), "empty map"
+    for ins in inserts:
+        gpu.insert(**ins)
+        for c in cpus:
+            c.insert(**ins)
+    image = gpu.write()
+    for c in cpus:
+        assert image == c.write(), type(c).__name__
+    path = tmp_path / "map.ufo"
+    gpu.write_file(str(path))
+    assert path.read_bytes() == image
+    gpu.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="reference harness not built")
+@pytest.mark.parametrize("name,depth", [("velodyne", 0), ("rgbd_color_discrete", 0), ("velodyne", 2)])
+@pytest.mark.parametrize("expanded", [False, True])
+def test_image_reads_back_in_the_reference(name, depth, expanded):
+    """Octree::read of the reference parses the image and ends up with the same value field; the
+    canonical image is never larger than the reference's own."""
+    kw, inserts, color = _scenario(name)
+    gpu = Map(color=color, initial_blocks=1 << 12, **kw)
+    ref = RefMap(color=color, **kw)
+    for ins in inserts:
+        gpu.insert(depth=depth, **ins)
+        ref.insert(depth=depth, **ins)
+    image = gpu.write(expanded=expanded)
+    back = RefMap(color=color, **kw)
+    assert back.read(image)
+    a, b = back.value_field(), ref.value_field()
+    assert np.array_equal(a[0], b[0])
+    assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    if color:
+        assert np.abs(a[2].astype(int) - b[2].astype(int)).max() <= 1
+    if not expanded:
+        assert len(image) <= len(ref.write())
+    gpu.close()

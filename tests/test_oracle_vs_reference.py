@@ -122,3 +122,55 @@ def test_cloud_frame_transform():
         assert a.tobytes() == b.tobytes()
         assert a.tobytes() == capi.transform_points(pr, pts).tobytes()
         assert a.tobytes() == capi.transform_points(pr, pts, dtype=np.float32).tobytes()
+
+
+@pytest.mark.parametrize("color", [False, True])
+@pytest.mark.parametrize("pruning", [True, False])
+def test_file_image(color, pruning):
+    """Octree::write (header + pre-order node stream): the oracle's restatement is byte-identical to
+    the reference's file, and the reference reads it back to the same map."""
+    kw = dict(resolution=0.1, automatic_pruning=pruning)
+    ref, orc = RefMap(color=color, **kw), OracleMap(color=color, **kw)
+    assert ref.write() == orc.write()          # empty map
+    for k in range(3):
+        o, p, c = scans.rgbd(k=k, width=40, height=30)
+        for m in (ref, orc):
+            m.insert(origin=o, xyz=p, rgb=c if color else None, max_range=3.0,
+                     discrete=bool(k & 1) or color, depth=1 if k == 2 else 0)
+    image = ref.write()
+    assert image == orc.write()
+    back = RefMap(color=color, **kw)
+    assert back.read(image)
+    a, b = back.value_field(), ref.value_field()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert np.array_equal(a[2], b[2])
+
+
+def test_reference_tree_is_canonical_here():
+    """The reference's file equals the canonical minimal tree of its value field on the histories
+    the GPU export tests use (automatic pruning on or off) -- which is why ufo_b200_write can be
+    compared byte for byte there."""
+    cases = []
+    ins = []
+    for k in range(3):
+        o, p = scans.velodyne64(k=k, rings=8, azimuths=128)
+        ins.append(dict(origin=o, xyz=p, max_range=25.0))
+    cases.append((dict(resolution=0.2), ins, False))
+    ins = []
+    for k in range(2):
+        o, p, c = scans.rgbd(k=k, width=48, height=36)
+        ins.append(dict(origin=o, xyz=p, rgb=c, max_range=3.0, discrete=True))
+    cases.append((dict(resolution=0.04), ins, True))
+    o, p = scans.random_shell(n=1500)
+    cases.append((dict(resolution=0.16, depth_levels=12), [dict(origin=o, xyz=p, max_range=5.0)], False))
+    for kw, inserts, color in cases:
+        for pruning in (True, False):
+            ref = RefMap(color=color, automatic_pruning=pruning, **kw)
+            orc = OracleMap(color=color, automatic_pruning=pruning, **kw)
+            for i in inserts:
+                ref.insert(**i)
+                orc.insert(**i)
+            image = ref.write()
+            assert image == orc.write()
+            orc.canonicalize()
+            assert image == orc.write()

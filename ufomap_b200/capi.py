@@ -57,7 +57,7 @@ SYMBOLS = [
     "ufo_b200_change_bbox", "ufo_b200_reset_change_bbox", "ufo_b200_last_scan_stats",
     "ufo_b200_set_profiling", "ufo_b200_clear", "ufo_b200_version", "ufo_b200_set_shard",
     "ufo_b200_insert_pointcloud_frame", "ufo_b200_transform_points", "ufo_b200_pose_from_rpy",
-    "ufo_b200_insert_pointcloud2",
+    "ufo_b200_insert_pointcloud2", "ufo_b200_write", "ufo_b200_write_file",
 ]
 
 class Cloud2(C.Structure):
@@ -95,6 +95,8 @@ def load():
     lib.ufo_b200_insert_pointcloud_frame.argtypes = [vp, vp, vp, sz, i32, vp, dbl, u32, i32, u32, i32,
                                                      i32]
     lib.ufo_b200_insert_pointcloud2.argtypes = [vp, vp, C.POINTER(Cloud2), vp, dbl, u32, i32, u32, i32, i32]
+    lib.ufo_b200_write.argtypes = [vp, vp, sz, C.POINTER(sz), i32]
+    lib.ufo_b200_write_file.argtypes = [vp, C.c_char_p, i32]
     lib.ufo_b200_transform_points.argtypes = [vp, vp, sz, i32, vp]
     lib.ufo_b200_pose_from_rpy.argtypes = [dbl, dbl, dbl, dbl, dbl, dbl, vp]
     lib.ufo_b200_wait.argtypes = [vp]
@@ -263,6 +265,19 @@ class Map:
     def set_shard(self, rank, world):
         """Keep only the bricks this rank owns (spatial sharding over several GPUs)."""
         self._check(self.lib.ufo_b200_set_shard(self.h, int(rank), int(world)))
+
+    # -- file / wire format -------------------------------------------------
+    def write(self, expanded=False):
+        """The map as a UFOMap file image (bytes), Octree::write with compress=False."""
+        n = C.c_size_t()
+        self._check(self.lib.ufo_b200_write(self.h, None, 0, C.byref(n), int(expanded)))
+        buf = np.empty(n.value, np.uint8)
+        self._check(self.lib.ufo_b200_write(self.h, buf.ctypes.data, n.value, C.byref(n), int(expanded)))
+        assert n.value == len(buf)
+        return buf.tobytes()
+
+    def write_file(self, filename, expanded=False):
+        self._check(self.lib.ufo_b200_write_file(self.h, os.fsencode(filename), int(expanded)))
 
     # -- state ----------------------------------------------------------------
     def value_field(self):

@@ -24,6 +24,7 @@
 
 #include "../../include/ufomap_b200.h"
 #include "ufo_kernels.cuh"
+#include "ufo_export.cuh"
 
 using namespace ufo_b200;
 
@@ -422,7 +423,9 @@ void ensure_seg(Map* m, unsigned long long want)
 void launch_update(Map* m, float miss, uint32_t first, uint32_t last)
 {
 	const uint32_t groups = (last - first) * 64u;  // one eight-lane group per (brick, child)
+#if defined(UFO_UPD_FLAT) || defined(UFO_UPD_FLAT_COLOR)
 	const uint32_t grid = (groups + kUpdThreads / 8 - 1) / (kUpdThreads / 8);
+#endif
 #ifdef UFO_UPD_FLAT
 	if (m->M.color) k_update<true><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
 	else k_update<false><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
@@ -1160,6 +1163,282 @@ int ufo_b200_export_leaves(ufo_b200_map* m, uint64_t* codes, float* logodds, uin
 		}
 		cudaFree(d_count);
 		return (int)UFO_B200_OK;
+	});
+}
+
+}  // extern "C"
+
+namespace
+{
+// ---- file image (ufo_export.cuh): the levels above the bricks, on the host ----
+struct UpNode {
+	int32_t child[8];  // -1: absent; >= 0: index into nodes (depth > 5) or into the sorted brick list (depth 5)
+	uint8_t mask;      // children that have children
+	bool has;          // false: collapsed to a leaf (pruned export only)
+	float occ;
+	uint32_t rgb;
+	unsigned long long size;  // bytes of the node's record (payload size if it is a leaf)
+};
+
+struct ExportPlan {
+	std::vector<uint32_t> order;  // bricks of the map in Morton (= stream) order
+	std::vector<BrickInfo> info;  // indexed by brick slot
+	std::vector<UpNode> nodes;    // nodes[0] = root (if any brick exists)
+	std::vector<unsigned long long> codes;
+	uint32_t P = 4;
+	uint32_t levels = 16;
+	bool pruned = false;
+};
+
+unsigned long long spread3_host(unsigned long long v)
+{
+	unsigned long long r = 0;
+	for (int i = 0; i < 21; ++i) r |= ((v >> i) & 1ull) << (3 * i);
+	return r;
+}
+
+// builds the node of depth d that covers order[lo, hi); returns its index in plan.nodes
+int32_t build_upper(ExportPlan& plan, uint32_t d, size_t lo, size_t hi)
+{
+	const int32_t self = (int32_t)plan.nodes.size();
+	plan.nodes.push_back(UpNode{});
+	UpNode n{};
+	n.mask = 0;
+	n.has = true;
+	n.size = 1;
+	const uint32_t shift = 3 * (d - 5);  // child index of a depth-d node inside the brick code
+	float occ[8];
+	uint32_t rgb[8];
+	bool leaf[8];
+	size_t pos = lo;
+	for (uint32_t i = 0; i < 8; ++i) {
+		size_t end = pos;
+		while (end < hi && ((plan.codes[end] >> shift) & 7ull) == i) ++end;
+		n.child[i] = -1;
+		occ[i] = 0.0f;
+		rgb[i] = 0;
+		leaf[i] = true;
+		if (end > pos) {
+			if (d == 5) {
+				const BrickInfo& bi = plan.info[plan.order[pos]];
+				n.child[i] = (int32_t)pos;
+				leaf[i] = !(bi.flags & 1u);
+				occ[i] = bi.occ;
+				rgb[i] = bi.rgb;
+				n.size += bi.size;
+			} else {
+				const int32_t c = build_upper(plan, d - 1, pos, end);
+				n.child[i] = c;
+				leaf[i] = !plan.nodes[c].has;
+				occ[i] = plan.nodes[c].occ;
+				rgb[i] = plan.nodes[c].rgb;
+				n.size += plan.nodes[c].size;
+			}
+			if (!leaf[i]) n.mask |= (uint8_t)(1u << i);
+		} else {
+			n.size += plan.P;
+		}
+		pos = end;
+	}
+	if (plan.pruned && n.mask == 0) {
+		bool same = true;
+		for (int i = 1; i < 8; ++i) same = same && occ[i] == occ[0] && rgb[i] == rgb[0];
+		if (same) {
+			n.has = false;
+			n.size = plan.P;
+		}
+	}
+	n.occ = occ[0];
+	n.rgb = rgb[0];
+	plan.nodes[self] = n;
+	return self;
+}
+
+template <class Sink>
+void put_payload_host(Sink& sink, uint32_t P, float occ, uint32_t rgb)
+{
+	uint8_t b[7];
+	std::memcpy(b, &occ, 4);
+	b[4] = (uint8_t)rgb;
+	b[5] = (uint8_t)(rgb >> 8);
+	b[6] = (uint8_t)(rgb >> 16);
+	sink(b, P);
+}
+
+template <class Sink>
+void emit_upper(const ExportPlan& plan, const std::vector<unsigned long long>& offs, const uint8_t* packed,
+                int32_t idx, uint32_t d, Sink& sink)
+{
+	const UpNode& n = plan.nodes[idx];
+	sink(&n.mask, 1);
+	for (uint32_t i = 0; i < 8; ++i) {
+		const int32_t c = n.child[i];
+		if (c < 0) {
+			put_payload_host(sink, plan.P, 0.0f, 0u);
+		} else if (d == 5) {
+			const uint32_t slot = plan.order[c];
+			const BrickInfo& bi = plan.info[slot];
+			if (bi.flags & 1u) sink(packed + offs[slot], bi.size);
+			else put_payload_host(sink, plan.P, bi.occ, bi.rgb);
+		} else if (plan.nodes[c].has) {
+			emit_upper(plan, offs, packed, c, d - 1, sink);
+		} else {
+			put_payload_host(sink, plan.P, plan.nodes[c].occ, plan.nodes[c].rgb);
+		}
+	}
+}
+
+// Produces the file image through sink(ptr, len) calls, in order.  *total = bytes produced.
+template <class Sink>
+int export_image(Map* m, int pruned, Sink&& sink, unsigned long long* total)
+{
+	if (m->device == -2) return UFO_B200_E_CUDA;
+	if (m->M.g.depth_levels < 5) {
+		m->set_error("file export needs depth_levels >= 5");
+		return UFO_B200_E_UNSUPPORTED;
+	}
+	CK(cudaSetDevice(m->device));
+	sync_map(m);
+	cudaStream_t s = m->stream;
+	const uint32_t nb = m->n_bricks;
+	const bool color = m->M.color != 0;
+	ExportPlan plan;
+	plan.P = color ? 7 : 4;
+	plan.levels = m->M.g.depth_levels;
+	plan.pruned = pruned != 0;
+	plan.info.resize(nb);
+	std::vector<unsigned long long> keys(nb);
+	BrickInfo* d_info = nullptr;
+	unsigned long long* d_offs = nullptr;
+	uint8_t* d_out = nullptr;
+	auto cleanup = [&]() {
+		if (d_info) cudaFree(d_info);
+		if (d_offs) cudaFree(d_offs);
+		if (d_out) cudaFree(d_out);
+	};
+	try {
+		if (nb) {
+			CK(cudaMalloc(&d_info, sizeof(BrickInfo) * nb));
+			if (color) k_brick_stream<true><<<nb, 64, 0, s>>>(m->M, nb, pruned, d_info, nullptr, nullptr);
+			else k_brick_stream<false><<<nb, 64, 0, s>>>(m->M, nb, pruned, d_info, nullptr, nullptr);
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync(plan.info.data(), d_info, sizeof(BrickInfo) * nb, cudaMemcpyDeviceToHost, s));
+			CK(cudaMemcpyAsync(keys.data(), m->M.brick_key, 8ull * nb, cudaMemcpyDeviceToHost, s));
+			CK(cudaStreamSynchronize(s));
+		}
+		// bricks that are part of the tree, in Morton order; a leaf brick with the default payload is
+		// indistinguishable from untouched space
+		std::vector<std::pair<unsigned long long, uint32_t>> sorted;
+		sorted.reserve(nb);
+		for (uint32_t b = 0; b < nb; ++b) {
+			const BrickInfo& bi = plan.info[b];
+			if (bi.flags & 2u) continue;
+			if (!(bi.flags & 1u) && bi.occ == 0.0f && bi.rgb == 0u) continue;
+			uint32_t x, y, z;
+			unpack_key(keys[b], x, y, z);
+			sorted.emplace_back(spread3_host(x) | (spread3_host(y) << 1) | (spread3_host(z) << 2), b);
+		}
+		std::sort(sorted.begin(), sorted.end());
+		plan.order.resize(sorted.size());
+		plan.codes.resize(sorted.size());
+		std::vector<unsigned long long> offs(nb, ~0ull);
+		unsigned long long packed_bytes = 0;
+		for (size_t i = 0; i < sorted.size(); ++i) {
+			plan.codes[i] = sorted[i].first;
+			plan.order[i] = sorted[i].second;
+			const BrickInfo& bi = plan.info[sorted[i].second];
+			if (bi.flags & 1u) {
+				offs[sorted[i].second] = packed_bytes;
+				packed_bytes += bi.size;
+			}
+		}
+		bool root_has = false;
+		unsigned long long data_size = 1 + plan.P;  // children byte + root payload
+		if (!sorted.empty()) {
+			build_upper(plan, plan.levels, 0, sorted.size());
+			root_has = plan.nodes[0].has;
+			data_size = 1 + plan.nodes[0].size;
+		}
+		std::vector<uint8_t> packed(packed_bytes);
+		if (packed_bytes) {
+			CK(cudaMalloc(&d_offs, 8ull * nb));
+			CK(cudaMalloc(&d_out, packed_bytes));
+			CK(cudaMemcpyAsync(d_offs, offs.data(), 8ull * nb, cudaMemcpyHostToDevice, s));
+			if (color) k_brick_stream<true><<<nb, 64, kBrickStreamMax, s>>>(m->M, nb, pruned, d_info, d_offs, d_out);
+			else k_brick_stream<false><<<nb, 64, kBrickStreamMax, s>>>(m->M, nb, pruned, d_info, d_offs, d_out);
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync(packed.data(), d_out, packed_bytes, cudaMemcpyDeviceToHost, s));
+			CK(cudaStreamSynchronize(s));
+		}
+		// header (octree.h:850-860; doubles print with the default ostream precision = %g)
+		char head[512];
+		const int hl = snprintf(head, sizeof head,
+		                        "# UFOMap file\n# (feel free to add / change comments, but leave the first line as it "
+		                        "is!)\n#\nversion 1.0.0\nid %s\nresolution %g\ndepth_levels %u\ncompressed 0\n"
+		                        "uncompressed_data_size %d\ndata\n",
+		                        color ? "occupancy_map_color" : "occupancy_map", m->M.g.resolution, plan.levels,
+		                        (int)data_size);
+		unsigned long long produced = 0;
+		auto counted = [&](const void* p, size_t len) {
+			sink(p, len);
+			produced += len;
+		};
+		counted(head, (size_t)hl);
+		const uint8_t children = root_has ? 0xff : 0x00;
+		counted(&children, 1);
+		if (root_has) {
+			emit_upper(plan, offs, packed.data(), 0, plan.levels, counted);
+		} else {
+			const float occ = sorted.empty() ? 0.0f : plan.nodes[0].occ;
+			const uint32_t rgb = sorted.empty() ? 0u : plan.nodes[0].rgb;
+			put_payload_host(counted, plan.P, occ, rgb);
+		}
+		*total = produced;
+	} catch (...) {
+		cleanup();
+		throw;
+	}
+	cleanup();
+	return UFO_B200_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ufo_b200_write(ufo_b200_map* m, void* buf, size_t cap, size_t* size, int expanded)
+{
+	if (!m || !size) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		uint8_t* out = static_cast<uint8_t*>(buf);
+		size_t at = 0;
+		unsigned long long total = 0;
+		int rc = export_image(m, expanded ? 0 : 1, [&](const void* p, size_t len) {
+			if (out && at + len <= cap) std::memcpy(out + at, p, len);
+			at += len;
+		}, &total);
+		*size = (size_t)total;
+		return rc;
+	});
+}
+
+int ufo_b200_write_file(ufo_b200_map* m, const char* filename, int expanded)
+{
+	if (!m || !filename) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		FILE* f = fopen(filename, "wb");
+		if (!f) {
+			m->set_error("cannot open %s", filename);
+			return (int)UFO_B200_E_INVALID;
+		}
+		unsigned long long total = 0;
+		bool ok = true;
+		int rc = export_image(m, expanded ? 0 : 1, [&](const void* p, size_t len) { ok = ok && fwrite(p, 1, len, f) == len; }, &total);
+		ok = fclose(f) == 0 && ok;
+		if (rc == UFO_B200_OK && !ok) {
+			m->set_error("short write to %s", filename);
+			return (int)UFO_B200_E_INVALID;
+		}
+		return rc;
 	});
 }
 
