@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdint>
 #include <stdexcept>
+#include <ostream>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -358,6 +359,28 @@ class MapFacade
 	virtual ~MapFacade() { ufo_b200_destroy(map_); }
 
 	virtual std::string getTreeType() const noexcept { return COLOR ? "occupancy_map_color" : "occupancy_map"; }
+
+	//
+	// File / wire format (octree.h:776-864): whole map, uncompressed.  compress = true, a
+	// min_depth > 0 or a bounding volume are not supported and return false.
+	//
+	bool write(std::string const& filename, bool compress = false, DepthType min_depth = 0,
+	           int /*compression_acceleration_level*/ = 1, int /*compression_level*/ = 0) const
+	{
+		if (compress || min_depth != 0) return false;
+		return UFO_B200_OK == ufo_b200_write_file(map_, filename.c_str(), 0);
+	}
+	bool write(std::ostream& s, bool compress = false, DepthType min_depth = 0,
+	           int /*compression_acceleration_level*/ = 1, int /*compression_level*/ = 0) const
+	{
+		if (compress || min_depth != 0) return false;
+		std::size_t n = 0;
+		if (UFO_B200_OK != ufo_b200_write(map_, nullptr, 0, &n, 0)) return false;
+		std::vector<char> image(n);
+		if (UFO_B200_OK != ufo_b200_write(map_, image.data(), n, &n, 0)) return false;
+		s.write(image.data(), (std::streamsize)n);
+		return s.good();
+	}
 
 	//
 	// Integration (occupancy_map_base.h:270-443, occupancy_map_color.h:87-267)

@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <sstream>
 
 int main(int argc, char** argv)
 {
@@ -65,6 +66,11 @@ int main(int argc, char** argv)
 	for (std::size_t i = 0; i < world.size(); ++i) {
 		if (fused.getOccupancy(world[i]) != staged.getOccupancy(world[i]) || !fused.isOccupied(world[i])) return 11;
 	}
+	// Octree::write(std::ostream&) (octree.h:812-864)
+	std::ostringstream os;
+	if (!fused.write(os) || os.str().compare(0, 13, "# UFOMap file") != 0) return 12;
+	if (os.str().find("id occupancy_map\nresolution 0.05\ndepth_levels 16\ncompressed 0\n") == std::string::npos) return 13;
+	if (fused.write(os, /*compress*/ true)) return 14;
 	std::puts("facade ok");
 	return 0;
 }

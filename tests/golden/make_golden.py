@@ -100,9 +100,24 @@ def frame_case():
     print("frame_velodyne_10cm", len(out["codes"]), "voxels")
 
 
+def file_image_case():
+    """Octree::write (uncompressed) of a small colour map: the reference's own file image."""
+    m = RefMap(0.08, color=True, automatic_pruning=False)
+    out = {"resolution": 0.08, "n_inserts": 2, "max_range": 3.0}
+    for k in range(2):
+        o, p, c = scans.rgbd(k=k, width=24, height=18)
+        m.insert(origin=o, xyz=p, rgb=c, max_range=3.0, discrete=True)
+        out["origin%d" % k], out["xyz%d" % k], out["rgb%d" % k] = o, p, c
+    image = m.write()
+    out["image"] = np.frombuffer(image, np.uint8)
+    np.savez_compressed(os.path.join(HERE, "fileimage_rgbd_8cm.npz"), **out)
+    print("fileimage_rgbd_8cm", len(image), "bytes")
+
+
 def main():
     build_oracle()
     frame_case()
+    file_image_case()
     o, p = scans.random_shell(n=2000)
     scan_case("shell_16cm", dict(resolution=0.16), [dict(origin=o, xyz=p, max_range=5.0)])
     ins = []

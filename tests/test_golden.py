@@ -14,7 +14,8 @@ from oracle_lib import OracleMap
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SCAN_CASES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "*.npz"))
-                    if not f.endswith("indexing.npz") and not os.path.basename(f).startswith("frame_"))
+                    if not f.endswith("indexing.npz")
+                    and not os.path.basename(f).startswith(("frame_", "fileimage_")))
 
 
 def _load_case(name):
@@ -128,6 +129,29 @@ def test_cuda_library_host_transform_matches_golden():
         for dt in (np.float64, np.float32):
             world = capi.transform_points(pose, z["local%d" % k], dtype=dt)
             assert world.tobytes() == z["world%d" % k].tobytes()
+
+
+def _replay_file_image(cls, **extra):
+    z = np.load(os.path.join(GOLD, "fileimage_rgbd_8cm.npz"))
+    m = cls(float(z["resolution"]), color=True, automatic_pruning=False, **extra)
+    for k in range(int(z["n_inserts"])):
+        m.insert(origin=z["origin%d" % k], xyz=z["xyz%d" % k], rgb=z["rgb%d" % k],
+                 max_range=float(z["max_range"]), discrete=True)
+    return z["image"].tobytes(), m
+
+
+def test_oracle_file_image_matches_golden():
+    """The reference's own Octree::write output, byte for byte."""
+    image, m = _replay_file_image(OracleMap)
+    assert m.write() == image
+
+
+@pytest.mark.gpu
+def test_cuda_file_image_matches_golden():
+    from ufomap_b200.capi import Map
+    image, m = _replay_file_image(Map, initial_blocks=1 << 12)
+    assert m.write() == image
+    m.close()
 
 
 @pytest.mark.gpu
