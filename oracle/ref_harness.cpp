@@ -441,6 +441,24 @@ size_t ufo_ref_write(void* h, uint8_t* buf, size_t cap)
 	return str.size();
 }
 
+// Octree::writeData(stream, bounding_volume, compress = false, min_depth) (octree.h:885-917) -- the
+// payload ufoToMsg puts into a UFOMap message (ufomap_msgs/conversions.h:161-185).  box6 = AABB
+// min xyz, max xyz (the server's change box, server.cpp:184) or NULL for the whole map.
+size_t ufo_ref_write_data(void* h, const double* box6, unsigned min_depth, uint8_t* buf, size_t cap)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	std::stringstream ss(std::ios_base::in | std::ios_base::out | std::ios_base::binary);
+	ufo::geometry::BoundingVolume bv;
+	if (box6) {
+		bv.add(ufo::geometry::AABB(ufo::geometry::Point(box6[0], box6[1], box6[2]),
+		                           ufo::geometry::Point(box6[3], box6[4], box6[5])));
+	}
+	withMap(m, [&](auto& map) { return map.writeData(ss, bv, false, min_depth); });
+	const std::string str = ss.str();
+	if (buf && str.size() <= cap) std::memcpy(buf, str.data(), str.size());
+	return str.size();
+}
+
 // Octree::read(std::istream&) (octree.h:699-733): replaces the map's content.  1 = ok.
 int ufo_ref_read(void* h, const uint8_t* buf, size_t size)
 {

@@ -1212,3 +1212,88 @@ void ufo_oracle_canonicalize(void* h)
 	omap* m = (omap*)h;
 	canon_rec(m, &m->root, m->levels);
 }
+
+/* ---- partial / truncated node stream: Octree::writeData(stream, bounding_volume, false,
+ * min_depth) (OCT:885-917) with writeNodes / writeNodesRecurs OMB:1457-1533.  Children at
+ * min_depth are written as leaves (their aggregate payload); children whose cube misses the
+ * bounding box are skipped.  Box test: geometry::intersects(AABB, AABB)
+ * (ufomap/src/geometry/collision_checks.cpp:256-264) on getMin()/getMax() of AABB(min, max)
+ * (ufomap/include/ufo/geometry/aabb.h:62-69); child centres by getChildCenter (OCT:625-633). */
+typedef struct {
+	int on;
+	double lo[3], hi[3];
+} wbox;
+
+static int box_hits(const wbox* bx, const double c[3], double hs)
+{
+	if (!bx->on) return 1;
+	for (int k = 0; k < 3; ++k) {
+		const double mn = c[k] - hs, mx = c[k] + hs;
+		if (!(mn <= bx->hi[k])) return 0;
+		if (!(bx->lo[k] <= mx)) return 0;
+	}
+	return 1;
+}
+
+static void child_center(const double c[3], double hs, unsigned i, double out[3])
+{
+	out[0] = c[0] + ((i & 1u) ? hs : -hs);
+	out[1] = c[1] + ((i & 2u) ? hs : -hs);
+	out[2] = c[2] + ((i & 4u) ? hs : -hs);
+}
+
+static void write_data_rec(const omap* m, wbuf* w, const node* n, unsigned depth, const double c[3],
+                           unsigned min_depth, const wbox* bx)
+{
+	const unsigned cd = depth - 1;
+	const double chs = m->half[cd];
+	uint8_t children = 0;
+	double cc[8][3];
+	int hit[8];
+	for (unsigned i = 0; i < 8; ++i) {
+		if (cd > min_depth && !n->ch[i].is_leaf) children |= (uint8_t)(1u << i);
+		child_center(c, chs, i, cc[i]);
+		hit[i] = box_hits(bx, cc[i], chs);
+	}
+	wb_put(w, &children, 1);
+	for (unsigned i = 0; i < 8; ++i) {
+		if (!hit[i]) continue;
+		const node* ch = &n->ch[i];
+		if ((children >> i) & 1u) {
+			if (1 == cd) {
+				const double ghs = m->half[0];
+				for (unsigned j = 0; j < 8; ++j) {
+					double gc[3];
+					child_center(cc[i], ghs, j, gc);
+					if (box_hits(bx, gc, ghs)) wb_payload(m, w, &ch->ch[j]);
+				}
+			} else {
+				write_data_rec(m, w, ch, cd, cc[i], min_depth, bx);
+			}
+		} else {
+			wb_payload(m, w, ch);
+		}
+	}
+}
+
+size_t ufo_oracle_write_data(void* h, const double* box6, unsigned min_depth, uint8_t* buf, size_t cap)
+{
+	const omap* m = (const omap*)h;
+	wbox bx = {0, {0, 0, 0}, {0, 0, 0}};
+	if (box6) {
+		bx.on = 1;
+		for (int k = 0; k < 3; ++k) {
+			const double hs = (box6[3 + k] - box6[k]) / 2.0, ct = box6[k] + hs;
+			bx.lo[k] = ct - hs;
+			bx.hi[k] = ct + hs;
+		}
+	}
+	wbuf w = {buf, cap, 0};
+	const double c0[3] = {0.0, 0.0, 0.0};
+	if (!box_hits(&bx, c0, m->half[m->levels])) return 0; /* "No node intersects" */
+	uint8_t children = (!m->root.is_leaf && m->levels > min_depth) ? 0xff : 0;
+	wb_put(&w, &children, 1);
+	if (children) write_data_rec(m, &w, &m->root, m->levels, c0, min_depth, &bx);
+	else wb_payload(m, &w, &m->root);
+	return w.n;
+}

@@ -65,6 +65,9 @@ size_t ufo_oracle_write(void* h, uint8_t* buf, size_t cap);
 /* test helper: collapse every collapsible node (canonical minimal tree of the value field) */
 void ufo_oracle_canonicalize(void* h);
 
+/* Octree::writeData(stream, AABB or none, compress = false, min_depth): the node stream only */
+size_t ufo_oracle_write_data(void* h, const double* box6, unsigned min_depth, uint8_t* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

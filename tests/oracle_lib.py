@@ -77,6 +77,7 @@ def _load(path, prefix):
         sensor_model=sig("sensor_model", None, [vp, vp]),
         memory_usage=sig("memory_usage", sz, [vp]),
         write=sig("write", sz, [vp, vp, sz]),
+        write_data=sig("write_data", sz, [vp, vp, u32, vp, sz]),
         transform=sig("transform", None, [vp, vp, sz, vp]),
         pose_from_rpy=sig("pose_from_rpy", None, [dbl, dbl, dbl, dbl, dbl, dbl, vp]),
     )
@@ -237,6 +238,15 @@ class _CpuMap:
 
     def memory_usage(self):
         return int(self.api["memory_usage"](self.h))
+
+    def write_data(self, box=None, min_depth=0):
+        """Octree::writeData(stream, AABB(min, max) or the whole map, False, min_depth): node stream."""
+        b = None if box is None else np.ascontiguousarray(np.concatenate([box[0], box[1]]), np.float64)
+        bp = None if b is None else b.ctypes.data
+        n = self.api["write_data"](self.h, bp, int(min_depth), None, 0)
+        buf = np.empty(max(n, 1), np.uint8)
+        assert self.api["write_data"](self.h, bp, int(min_depth), buf.ctypes.data, n) == n
+        return buf[:n].tobytes()
 
     def write(self):
         """Octree::write(ostream, compress=False): the complete file image as bytes."""

@@ -83,3 +83,32 @@ def test_image_reads_back_in_the_reference(name, depth, expanded):
     if not expanded:
         assert len(image) <= len(ref.write())
     gpu.close()
+
+
+@pytest.mark.parametrize("name", ["velodyne", "rgbd_color_discrete"])
+def test_partial_and_truncated_stream(name):
+    """Octree::writeData with a bounding box and/or min_depth -- what ufoToMsg publishes
+    (change box of the last scans at depths 0..publish_depth, server.cpp:184-199)."""
+    kw, inserts, color = _scenario(name)
+    gpu = Map(color=color, initial_blocks=1 << 12, **kw)
+    cpus = _cpu_maps(color, **kw)
+    for ins in inserts:
+        gpu.insert(**ins)
+        for c in cpus:
+            c.insert(**ins)
+    rng = np.random.default_rng(17)
+    mn, mx = cpus[0].change_bbox()
+    span = mx - mn
+    boxes = [None, (mn, mx), (mn + 0.4 * span, mn + 0.6 * span), (mn - 5.0, mn - 4.0),
+             (np.array([1e4, 1e4, 1e4]), np.array([2e4, 2e4, 2e4]))]
+    for _ in range(6):
+        lo = mn + rng.uniform(-0.1, 0.9, 3) * span
+        boxes.append((lo, lo + rng.uniform(0.01, 0.6, 3) * span))
+    res = kw["resolution"]
+    boxes.append((np.array([3 * res, 0.0, 0.0]), np.array([3 * res, 4 * res, res])))   # faces on voxel borders
+    for box in boxes:
+        for md in range(5):
+            got = gpu.write_data(box, md)
+            for c in cpus:
+                assert got == c.write_data(box, md), (type(c).__name__, box, md, len(got))
+    gpu.close()

@@ -174,3 +174,26 @@ def test_reference_tree_is_canonical_here():
             assert image == orc.write()
             orc.canonicalize()
             assert image == orc.write()
+
+
+@pytest.mark.parametrize("color", [False, True])
+def test_partial_and_truncated_stream(color):
+    """Octree::writeData(stream, AABB, false, min_depth): oracle restatement == reference bytes."""
+    kw = dict(resolution=0.05)
+    ref, orc = RefMap(color=color, **kw), OracleMap(color=color, **kw)
+    for k in range(2):
+        o, p, c = scans.rgbd(k=k, width=48, height=36)
+        for m in (ref, orc):
+            m.insert(origin=o, xyz=p, rgb=c if color else None, max_range=3.0, discrete=True)
+    image = ref.write()
+    assert ref.write_data(None, 0) == image[image.index(b"data\n") + 5:]
+    rng = np.random.default_rng(1)
+    mn, mx = ref.change_bbox()
+    boxes = [None, (mn, mx), (np.array([100.0, 100, 100]), np.array([101.0, 101, 101])),
+             (np.array([1e4, 1e4, 1e4]), np.array([2e4, 2e4, 2e4]))]
+    for _ in range(8):
+        lo = rng.uniform(-1, 2, 3)
+        boxes.append((lo, lo + rng.uniform(0.05, 2.0, 3)))
+    for box in boxes:
+        for md in (0, 1, 2, 3, 4, 5, 7, 16):
+            assert ref.write_data(box, md) == orc.write_data(box, md), (box, md)

@@ -58,6 +58,7 @@ SYMBOLS = [
     "ufo_b200_set_profiling", "ufo_b200_clear", "ufo_b200_version", "ufo_b200_set_shard",
     "ufo_b200_insert_pointcloud_frame", "ufo_b200_transform_points", "ufo_b200_pose_from_rpy",
     "ufo_b200_insert_pointcloud2", "ufo_b200_write", "ufo_b200_write_file",
+    "ufo_b200_write_data",
 ]
 
 class Cloud2(C.Structure):
@@ -97,6 +98,7 @@ def load():
     lib.ufo_b200_insert_pointcloud2.argtypes = [vp, vp, C.POINTER(Cloud2), vp, dbl, u32, i32, u32, i32, i32]
     lib.ufo_b200_write.argtypes = [vp, vp, sz, C.POINTER(sz), i32]
     lib.ufo_b200_write_file.argtypes = [vp, C.c_char_p, i32]
+    lib.ufo_b200_write_data.argtypes = [vp, vp, u32, vp, sz, C.POINTER(sz)]
     lib.ufo_b200_transform_points.argtypes = [vp, vp, sz, i32, vp]
     lib.ufo_b200_pose_from_rpy.argtypes = [dbl, dbl, dbl, dbl, dbl, dbl, vp]
     lib.ufo_b200_wait.argtypes = [vp]
@@ -275,6 +277,17 @@ class Map:
         self._check(self.lib.ufo_b200_write(self.h, buf.ctypes.data, n.value, C.byref(n), int(expanded)))
         assert n.value == len(buf)
         return buf.tobytes()
+
+    def write_data(self, box=None, min_depth=0):
+        """Octree::writeData(stream, AABB(min, max) or whole map, False, min_depth): node stream."""
+        b = None if box is None else np.ascontiguousarray(np.concatenate([box[0], box[1]]), np.float64)
+        bp = None if b is None else b.ctypes.data
+        n = C.c_size_t()
+        self._check(self.lib.ufo_b200_write_data(self.h, bp, int(min_depth), None, 0, C.byref(n)))
+        buf = np.empty(max(n.value, 1), np.uint8)
+        self._check(self.lib.ufo_b200_write_data(self.h, bp, int(min_depth), buf.ctypes.data, n.value,
+                                                 C.byref(n)))
+        return buf[:n.value].tobytes()
 
     def write_file(self, filename, expanded=False):
         self._check(self.lib.ufo_b200_write_file(self.h, os.fsencode(filename), int(expanded)))

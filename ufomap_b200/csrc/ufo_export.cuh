@@ -28,10 +28,40 @@ namespace ufo_b200
 {
 constexpr int kBrickStreamMax = 1 + 8 * (1 + 8 * (1 + 64 * 7));  // colour payloads: 28 745 bytes
 
+// Partial / truncated export (Octree::writeData(stream, bounding_volume, false, min_depth),
+// octree.h:885-917): children at min_depth are written as leaves carrying their aggregate
+// payload; a child whose cube misses the box is skipped.  lo/hi are getMin()/getMax() of the
+// reference's AABB(min, max) (geometry/aabb.h:62-69); the test is intersects(AABB, AABB) of
+// collision_checks.cpp:256-264; node centres are accumulated top-down like getChildCenter
+// (octree.h:625-633) so that the comparisons see the same doubles.
+struct ExportBox {
+	int on;
+	double lo[3], hi[3];
+};
+
+UFO_HD bool box_hits(const ExportBox& bx, const double c[3], double hs)
+{
+	if (!bx.on) return true;
+	for (int k = 0; k < 3; ++k) {
+		const double mn = dop::sub(c[k], hs), mx = dop::add(c[k], hs);
+		if (!(mn <= bx.hi[k])) return false;
+		if (!(bx.lo[k] <= mx)) return false;
+	}
+	return true;
+}
+
+UFO_HD void child_center(const double c[3], double hs, uint32_t i, double out[3])
+{
+	out[0] = dop::add(c[0], (i & 1u) ? hs : -hs);
+	out[1] = dop::add(c[1], (i & 2u) ? hs : -hs);
+	out[2] = dop::add(c[2], (i & 4u) ? hs : -hs);
+}
+
 struct BrickInfo {
-	uint32_t size;   // bytes of the brick's stream (payload size when the brick is a leaf)
-	uint32_t flags;  // bit 0: has children; bit 1: not part of the map (alias collector)
-	float occ;       // leaf payload when bit 0 is clear
+	uint32_t size;   // bytes the brick contributes to the stream (0: skipped by the box)
+	uint32_t flags;  // bit 0: has children (in the map); bit 1: not part of the map (alias collector);
+	                 // bit 2: written as a record (size bytes at its offset), else as a payload
+	float occ;       // payload when bit 2 is clear: the leaf value, or the depth-4 aggregate
 	uint32_t rgb;
 };
 
@@ -50,31 +80,85 @@ __device__ __forceinline__ void put_payload(uint8_t* p, float occ, uint32_t rgb)
 	}
 }
 
-// offsets == nullptr: size pass (fills info); otherwise the stream of every brick that has
-// children is written to out + offsets[brick].
+// One octet of block b: returns its bytes in the stream and writes them when dst != nullptr.
 template <bool COLOR>
-__global__ void __launch_bounds__(64) k_brick_stream(DeviceMap M, uint32_t n_bricks, int pruned, BrickInfo* info,
+__device__ __forceinline__ uint32_t octet_record(const DeviceMap& M, size_t b, uint32_t o, bool has,
+                                                 float leaf_occ, uint32_t leaf_rgb, uint32_t min_depth,
+                                                 const ExportBox& bx, const double oc[3], uint8_t* dst)
+{
+	constexpr uint32_t P = COLOR ? 7u : 4u;
+	if (!box_hits(bx, oc, M.g.half_size[1])) return 0;
+	if (has && min_depth == 0) {
+		uint32_t n = 0;
+		for (uint32_t j = 0; j < 8; ++j) {
+			double vc[3];
+			child_center(oc, M.g.half_size[0], j, vc);
+			if (!box_hits(bx, vc, M.g.half_size[0])) continue;
+			if (dst) put_payload<COLOR>(dst + n, M.leaf[b * 64 + 8 * o + j], COLOR ? M.leaf_rgb[b * 64 + 8 * o + j] : 0u);
+			n += P;
+		}
+		return n;
+	}
+	if (dst) {
+		if (has) put_payload<COLOR>(dst, M.sum1[b * 8 + o], COLOR ? M.sum1_rgb[b * 8 + o] : 0u);
+		else put_payload<COLOR>(dst, leaf_occ, leaf_rgb);
+	}
+	return P;
+}
+
+// offsets == nullptr: size pass (fills info); otherwise the record of every brick whose info has
+// bit 2 set is written to out + offsets[brick].
+template <bool COLOR>
+__global__ void __launch_bounds__(64) k_brick_stream(DeviceMap M, uint32_t n_bricks, int pruned, uint32_t min_depth,
+                                                     ExportBox bx, BrickInfo* info,
                                                      const unsigned long long* offsets, uint8_t* out)
 {
 	extern __shared__ uint8_t s_buf[];
 	__shared__ uint32_t s_blk_size[64], s_blk_rgb[64], s_d3_size[8], s_d3_rgb[8], s_d3_off[8];
 	__shared__ float s_blk_occ[64], s_d3_occ[8];
-	__shared__ uint8_t s_blk_has[64], s_d3_has[8], s_d3_mask[8];
-	__shared__ uint32_t s_brick_size, s_brick_has;
+	__shared__ uint8_t s_blk_has[64], s_d3_has[8], s_d3_mask[8], s_d3_hit[8];
+	__shared__ uint32_t s_brick_size, s_brick_record;
+	__shared__ double s_center[3];
 	constexpr uint32_t P = COLOR ? 7u : 4u;
 	const uint32_t brick = blockIdx.x, t = threadIdx.x;
 	if (brick >= n_bricks) return;
-	{
-		uint32_t x, y, z;
-		unpack_key(M.brick_key[brick], x, y, z);
-		if ((x | y | z) & ~(M.g.key_mask >> 4)) {  // collects out-of-tree marks, owns no voxels
-			if (!offsets && t == 0) info[brick] = {0u, 2u, 0.0f, 0u};
-			return;
-		}
+	uint32_t kx, ky, kz;
+	unpack_key(M.brick_key[brick], kx, ky, kz);
+	if ((kx | ky | kz) & ~(M.g.key_mask >> 4)) {  // collects out-of-tree marks, owns no voxels
+		if (!offsets && t == 0) info[brick] = {0u, 2u, 0.0f, 0u};
+		return;
 	}
+	if (t == 0) {
+		// centre of the brick, accumulated from the root like the reference's recursion
+		double c[3] = {0.0, 0.0, 0.0};
+		for (uint32_t d = M.g.depth_levels; d > 4; --d) {
+			const uint32_t bit = d - 5;  // brick-key bit that selects the child of the depth-d node
+			const uint32_t i = ((kx >> bit) & 1u) | (((ky >> bit) & 1u) << 1) | (((kz >> bit) & 1u) << 2);
+			double n[3];
+			child_center(c, M.g.half_size[d - 1], i, n);
+			c[0] = n[0];
+			c[1] = n[1];
+			c[2] = n[2];
+		}
+		s_center[0] = c[0];
+		s_center[1] = c[1];
+		s_center[2] = c[2];
+	}
+	__syncthreads();
+	const uint32_t j3 = t >> 3, k3 = t & 7u;
+	double bc[3], d3c[3], blkc[3];
+	bc[0] = s_center[0];
+	bc[1] = s_center[1];
+	bc[2] = s_center[2];
+	child_center(bc, M.g.half_size[3], j3, d3c);
+	child_center(d3c, M.g.half_size[2], k3, blkc);
+	const bool brick_hit = box_hits(bx, bc, M.g.half_size[4]);
+	const bool d3_hit = box_hits(bx, d3c, M.g.half_size[3]);
+	const bool blk_hit = box_hits(bx, blkc, M.g.half_size[2]);
+
 	const size_t b = (size_t)brick * 64 + t;
 	const uint32_t init8 = (M.meta[b] >> 16) & 0xffu;
-	// octets: has children (8 voxel payloads follow) or leaf with one payload
+	// octets in the map: has children, or a leaf with one payload
 	uint32_t oct_has = 0;
 	float oocc[8];
 	uint32_t orgb[8];
@@ -102,29 +186,52 @@ __global__ void __launch_bounds__(64) k_brick_stream(DeviceMap M, uint32_t n_bri
 	}
 	bool blk_has = oct_has != 0;
 	if (pruned && !blk_has) {
+#pragma unroll
 		for (int o = 1; o < 8; ++o) blk_has = blk_has || oocc[o] != oocc[0] || orgb[o] != orgb[0];
 	}
-	const uint32_t n_oct = __popc(oct_has);
+	// the block's contribution to the stream
+	uint32_t blk_size = 0;
+	if (blk_hit && d3_hit && brick_hit) {
+		if (blk_has && min_depth < 2) {
+			blk_size = 1;
+#pragma unroll
+			for (uint32_t o = 0; o < 8; ++o) {
+				double oc[3];
+				child_center(blkc, M.g.half_size[1], o, oc);
+				blk_size += octet_record<COLOR>(M, b, o, (oct_has >> o) & 1u, oocc[o], orgb[o], min_depth, bx, oc, nullptr);
+			}
+		} else {
+			blk_size = P;
+		}
+	}
 	s_blk_has[t] = blk_has ? 1 : 0;
-	s_blk_size[t] = blk_has ? 1u + n_oct * 8u * P + (8u - n_oct) * P : P;
-	s_blk_occ[t] = oocc[0];  // the block's payload when it is a leaf (default payload if unpruned)
-	s_blk_rgb[t] = orgb[0];
+	s_blk_size[t] = blk_size;
+	// payload when the block is written as a leaf: its value, or its depth-2 aggregate
+	s_blk_occ[t] = blk_has ? M.agg2[b].occ : oocc[0];
+	s_blk_rgb[t] = blk_has ? (COLOR ? M.rgb2[b] : 0u) : orgb[0];
 	__syncthreads();
 	if (t < 8) {
+		double c3[3];
+		child_center(bc, M.g.half_size[3], t, c3);
+		const bool hit = brick_hit && box_hits(bx, c3, M.g.half_size[3]);
 		bool has = false;
 		uint32_t size = 1, mask = 0;
 		for (int k = 0; k < 8; ++k) {
 			const int c = 8 * t + k;
 			has = has || s_blk_has[c];
-			mask |= (uint32_t)s_blk_has[c] << k;
+			if (min_depth < 2) mask |= (uint32_t)s_blk_has[c] << k;
 			size += s_blk_size[c];
-			if (pruned && (s_blk_occ[c] != s_blk_occ[8 * t] || s_blk_rgb[c] != s_blk_rgb[8 * t])) has = true;
+		}
+		if (pruned && !has) {
+			// leaf blocks only: s_blk_occ / s_blk_rgb hold their leaf payloads
+			for (int k = 1; k < 8; ++k) has = has || s_blk_occ[8 * t + k] != s_blk_occ[8 * t] || s_blk_rgb[8 * t + k] != s_blk_rgb[8 * t];
 		}
 		s_d3_has[t] = has ? 1 : 0;
+		s_d3_hit[t] = hit ? 1 : 0;
 		s_d3_mask[t] = (uint8_t)mask;
-		s_d3_size[t] = has ? size : P;
-		s_d3_occ[t] = s_blk_occ[8 * t];
-		s_d3_rgb[t] = s_blk_rgb[8 * t];
+		s_d3_size[t] = !hit ? 0u : ((has && min_depth < 3) ? size : P);
+		s_d3_occ[t] = has ? M.brick_sum3[(size_t)brick * 8 + t].occ : s_blk_occ[8 * t];
+		s_d3_rgb[t] = has ? (COLOR ? M.brick_rgb3[(size_t)brick * 8 + t] : 0u) : s_blk_rgb[8 * t];
 	}
 	__syncthreads();
 	if (t == 0) {
@@ -134,47 +241,51 @@ __global__ void __launch_bounds__(64) k_brick_stream(DeviceMap M, uint32_t n_bri
 			has = has || s_d3_has[j];
 			s_d3_off[j] = size;
 			size += s_d3_size[j];
-			if (pruned && (s_d3_occ[j] != s_d3_occ[0] || s_d3_rgb[j] != s_d3_rgb[0])) has = true;
 		}
-		s_brick_has = has ? 1u : 0u;
-		s_brick_size = has ? size : P;
-		if (!offsets) info[brick] = {s_brick_size, s_brick_has, s_d3_occ[0], s_d3_rgb[0]};
+		if (pruned && !has) {
+			for (int j = 1; j < 8; ++j) has = has || s_d3_occ[j] != s_d3_occ[0] || s_d3_rgb[j] != s_d3_rgb[0];
+		}
+		const bool record = has && min_depth < 4 && brick_hit;
+		s_brick_record = record ? 1u : 0u;
+		s_brick_size = !brick_hit ? 0u : (record ? size : P);
+		if (!offsets) {
+			const float occ = has ? M.brick_sum4[brick].occ : s_d3_occ[0];
+			const uint32_t rgb = has ? (COLOR ? M.brick_rgb4[brick] : 0u) : s_d3_rgb[0];
+			info[brick] = {s_brick_size, (has ? 1u : 0u) | (record ? 4u : 0u), occ, rgb};
+		}
 	}
 	__syncthreads();
-	if (!offsets || !s_brick_has) return;
+	if (!offsets || !s_brick_record) return;
 
-	// ---- build the stream in shared memory ----
-	const uint32_t j = t >> 3, k = t & 7u;
+	// ---- build the record in shared memory ----
 	if (t == 0) {
 		uint32_t mask4 = 0;
-		for (int q = 0; q < 8; ++q) mask4 |= (uint32_t)s_d3_has[q] << q;
+		if (min_depth < 3)
+			for (int q = 0; q < 8; ++q) mask4 |= (uint32_t)s_d3_has[q] << q;
 		s_buf[0] = (uint8_t)mask4;
 	}
-	if (s_d3_has[j]) {
-		uint32_t at = s_d3_off[j];
-		if (k == 0) s_buf[at] = s_d3_mask[j];
-		at += 1;
-		for (uint32_t q = 0; q < k; ++q) at += s_blk_size[8 * j + q];
-		if (blk_has) {
-			s_buf[at++] = (uint8_t)oct_has;
-			for (uint32_t o = 0; o < 8; ++o) {
-				if ((oct_has >> o) & 1u) {
-					const float* lp = M.leaf + b * 64 + 8 * o;
-					const uint32_t* cp = COLOR ? M.leaf_rgb + b * 64 + 8 * o : nullptr;
-					for (int v = 0; v < 8; ++v) {
-						put_payload<COLOR>(s_buf + at, lp[v], COLOR ? cp[v] : 0u);
-						at += P;
+	if (s_d3_hit[j3]) {
+		if (s_d3_has[j3] && min_depth < 3) {
+			uint32_t at = s_d3_off[j3];
+			if (k3 == 0) s_buf[at] = s_d3_mask[j3];
+			at += 1;
+			for (uint32_t q = 0; q < k3; ++q) at += s_blk_size[8 * j3 + q];
+			if (blk_size) {
+				if (blk_has && min_depth < 2) {
+					s_buf[at++] = (uint8_t)(min_depth < 1 ? oct_has : 0u);
+#pragma unroll
+					for (uint32_t o = 0; o < 8; ++o) {
+						double oc[3];
+						child_center(blkc, M.g.half_size[1], o, oc);
+						at += octet_record<COLOR>(M, b, o, (oct_has >> o) & 1u, oocc[o], orgb[o], min_depth, bx, oc, s_buf + at);
 					}
 				} else {
-					put_payload<COLOR>(s_buf + at, oocc[o], orgb[o]);
-					at += P;
+					put_payload<COLOR>(s_buf + at, s_blk_occ[t], s_blk_rgb[t]);
 				}
 			}
-		} else {
-			put_payload<COLOR>(s_buf + at, s_blk_occ[t], s_blk_rgb[t]);
+		} else if (k3 == 0) {
+			put_payload<COLOR>(s_buf + s_d3_off[j3], s_d3_occ[j3], s_d3_rgb[j3]);
 		}
-	} else if (k == 0) {
-		put_payload<COLOR>(s_buf + s_d3_off[j], s_d3_occ[j], s_d3_rgb[j]);
 	}
 	__syncthreads();
 	uint8_t* dst = out + offsets[brick];

@@ -1173,11 +1173,12 @@ namespace
 // ---- file image (ufo_export.cuh): the levels above the bricks, on the host ----
 struct UpNode {
 	int32_t child[8];  // -1: absent; >= 0: index into nodes (depth > 5) or into the sorted brick list (depth 5)
-	uint8_t mask;      // children that have children
-	bool has;          // false: collapsed to a leaf (pruned export only)
+	uint8_t mask;      // children written as records (they have children and lie above min_depth)
+	uint8_t hit;       // children whose cube intersects the export box
+	bool has;          // false: collapsed to a leaf (canonical export only)
 	float occ;
 	uint32_t rgb;
-	unsigned long long size;  // bytes of the node's record (payload size if it is a leaf)
+	unsigned long long size;  // bytes of the node's record
 };
 
 struct ExportPlan {
@@ -1187,7 +1188,10 @@ struct ExportPlan {
 	std::vector<unsigned long long> codes;
 	uint32_t P = 4;
 	uint32_t levels = 16;
+	uint32_t min_depth = 0;
 	bool pruned = false;
+	ExportBox box{};
+	const Geometry* g = nullptr;
 };
 
 unsigned long long spread3_host(unsigned long long v)
@@ -1197,58 +1201,64 @@ unsigned long long spread3_host(unsigned long long v)
 	return r;
 }
 
-// builds the node of depth d that covers order[lo, hi); returns its index in plan.nodes
-int32_t build_upper(ExportPlan& plan, uint32_t d, size_t lo, size_t hi)
+// builds the node of depth d (centre c) that covers order[lo, hi); returns its index in plan.nodes
+int32_t build_upper(ExportPlan& plan, uint32_t d, size_t lo, size_t hi, const double c[3])
 {
 	const int32_t self = (int32_t)plan.nodes.size();
 	plan.nodes.push_back(UpNode{});
 	UpNode n{};
-	n.mask = 0;
 	n.has = true;
 	n.size = 1;
 	const uint32_t shift = 3 * (d - 5);  // child index of a depth-d node inside the brick code
+	const double chs = plan.g->half_size[d - 1];
 	float occ[8];
 	uint32_t rgb[8];
-	bool leaf[8];
+	bool any_children = false;
 	size_t pos = lo;
 	for (uint32_t i = 0; i < 8; ++i) {
 		size_t end = pos;
 		while (end < hi && ((plan.codes[end] >> shift) & 7ull) == i) ++end;
+		double cc[3];
+		child_center(c, chs, i, cc);
+		const bool hit = box_hits(plan.box, cc, chs);
+		if (hit) n.hit |= (uint8_t)(1u << i);
 		n.child[i] = -1;
 		occ[i] = 0.0f;
 		rgb[i] = 0;
-		leaf[i] = true;
+		unsigned long long bytes = plan.P;  // absent child: one default payload
 		if (end > pos) {
 			if (d == 5) {
 				const BrickInfo& bi = plan.info[plan.order[pos]];
 				n.child[i] = (int32_t)pos;
-				leaf[i] = !(bi.flags & 1u);
 				occ[i] = bi.occ;
 				rgb[i] = bi.rgb;
-				n.size += bi.size;
+				if (bi.flags & 1u) {
+					any_children = true;
+					if (plan.min_depth < 4) n.mask |= (uint8_t)(1u << i);
+				}
+				bytes = bi.size;  // 0 when the brick's cube misses the box (same test on the device)
 			} else {
-				const int32_t c = build_upper(plan, d - 1, pos, end);
-				n.child[i] = c;
-				leaf[i] = !plan.nodes[c].has;
-				occ[i] = plan.nodes[c].occ;
-				rgb[i] = plan.nodes[c].rgb;
-				n.size += plan.nodes[c].size;
+				const int32_t ci = build_upper(plan, d - 1, pos, end, cc);
+				const UpNode& ch = plan.nodes[ci];
+				n.child[i] = ci;
+				occ[i] = ch.occ;
+				rgb[i] = ch.rgb;
+				if (ch.has) {
+					any_children = true;
+					n.mask |= (uint8_t)(1u << i);  // d - 1 >= 5 > min_depth
+					bytes = ch.size;
+				}
 			}
-			if (!leaf[i]) n.mask |= (uint8_t)(1u << i);
-		} else {
-			n.size += plan.P;
 		}
+		if (hit) n.size += bytes;
 		pos = end;
 	}
-	if (plan.pruned && n.mask == 0) {
+	if (plan.pruned && !any_children) {
 		bool same = true;
 		for (int i = 1; i < 8; ++i) same = same && occ[i] == occ[0] && rgb[i] == rgb[0];
-		if (same) {
-			n.has = false;
-			n.size = plan.P;
-		}
+		if (same) n.has = false;
 	}
-	n.occ = occ[0];
+	n.occ = occ[0];  // payload if collapsed
 	n.rgb = rgb[0];
 	plan.nodes[self] = n;
 	return self;
@@ -1272,13 +1282,15 @@ void emit_upper(const ExportPlan& plan, const std::vector<unsigned long long>& o
 	const UpNode& n = plan.nodes[idx];
 	sink(&n.mask, 1);
 	for (uint32_t i = 0; i < 8; ++i) {
+		if (!((n.hit >> i) & 1u)) continue;
 		const int32_t c = n.child[i];
 		if (c < 0) {
 			put_payload_host(sink, plan.P, 0.0f, 0u);
 		} else if (d == 5) {
 			const uint32_t slot = plan.order[c];
 			const BrickInfo& bi = plan.info[slot];
-			if (bi.flags & 1u) sink(packed + offs[slot], bi.size);
+			if (bi.size == 0) continue;
+			if (bi.flags & 4u) sink(packed + offs[slot], bi.size);
 			else put_payload_host(sink, plan.P, bi.occ, bi.rgb);
 		} else if (plan.nodes[c].has) {
 			emit_upper(plan, offs, packed, c, d - 1, sink);
@@ -1288,13 +1300,19 @@ void emit_upper(const ExportPlan& plan, const std::vector<unsigned long long>& o
 	}
 }
 
-// Produces the file image through sink(ptr, len) calls, in order.  *total = bytes produced.
+// Produces the node stream (optionally behind the file header) through sink(ptr, len) calls, in
+// order.  *total = bytes produced.
 template <class Sink>
-int export_image(Map* m, int pruned, Sink&& sink, unsigned long long* total)
+int export_image(Map* m, int pruned, uint32_t min_depth, const double* box6, bool with_header, Sink&& sink,
+                 unsigned long long* total)
 {
 	if (m->device == -2) return UFO_B200_E_CUDA;
 	if (m->M.g.depth_levels < 5) {
-		m->set_error("file export needs depth_levels >= 5");
+		m->set_error("export needs depth_levels >= 5");
+		return UFO_B200_E_UNSUPPORTED;
+	}
+	if (min_depth > 4) {
+		m->set_error("export with min_depth %u > 4 is not supported", min_depth);
 		return UFO_B200_E_UNSUPPORTED;
 	}
 	CK(cudaSetDevice(m->device));
@@ -1305,7 +1323,27 @@ int export_image(Map* m, int pruned, Sink&& sink, unsigned long long* total)
 	ExportPlan plan;
 	plan.P = color ? 7 : 4;
 	plan.levels = m->M.g.depth_levels;
+	plan.min_depth = min_depth;
 	plan.pruned = pruned != 0;
+	plan.g = &m->M.g;
+	if (box6) {
+		// AABB(min, max) of the reference keeps centre and half size (geometry/aabb.h:62-69)
+		plan.box.on = 1;
+		for (int k = 0; k < 3; ++k) {
+			const double hs = (box6[3 + k] - box6[k]) / 2.0, ct = box6[k] + hs;
+			plan.box.lo[k] = ct - hs;
+			plan.box.hi[k] = ct + hs;
+		}
+	}
+	*total = 0;
+	const double c0[3] = {0.0, 0.0, 0.0};
+	if (!box_hits(plan.box, c0, plan.g->half_size[plan.levels])) {
+		if (with_header) {
+			m->set_error("the export box misses the map");
+			return UFO_B200_E_INVALID;
+		}
+		return UFO_B200_OK;  // "No node intersects": the reference writes nothing
+	}
 	plan.info.resize(nb);
 	std::vector<unsigned long long> keys(nb);
 	BrickInfo* d_info = nullptr;
@@ -1319,8 +1357,8 @@ int export_image(Map* m, int pruned, Sink&& sink, unsigned long long* total)
 	try {
 		if (nb) {
 			CK(cudaMalloc(&d_info, sizeof(BrickInfo) * nb));
-			if (color) k_brick_stream<true><<<nb, 64, 0, s>>>(m->M, nb, pruned, d_info, nullptr, nullptr);
-			else k_brick_stream<false><<<nb, 64, 0, s>>>(m->M, nb, pruned, d_info, nullptr, nullptr);
+			if (color) k_brick_stream<true><<<nb, 64, 0, s>>>(m->M, nb, pruned, min_depth, plan.box, d_info, nullptr, nullptr);
+			else k_brick_stream<false><<<nb, 64, 0, s>>>(m->M, nb, pruned, min_depth, plan.box, d_info, nullptr, nullptr);
 			CK(cudaGetLastError());
 			CK(cudaMemcpyAsync(plan.info.data(), d_info, sizeof(BrickInfo) * nb, cudaMemcpyDeviceToHost, s));
 			CK(cudaMemcpyAsync(keys.data(), m->M.brick_key, 8ull * nb, cudaMemcpyDeviceToHost, s));
@@ -1347,7 +1385,7 @@ int export_image(Map* m, int pruned, Sink&& sink, unsigned long long* total)
 			plan.codes[i] = sorted[i].first;
 			plan.order[i] = sorted[i].second;
 			const BrickInfo& bi = plan.info[sorted[i].second];
-			if (bi.flags & 1u) {
+			if (bi.flags & 4u) {
 				offs[sorted[i].second] = packed_bytes;
 				packed_bytes += bi.size;
 			}
@@ -1355,35 +1393,37 @@ int export_image(Map* m, int pruned, Sink&& sink, unsigned long long* total)
 		bool root_has = false;
 		unsigned long long data_size = 1 + plan.P;  // children byte + root payload
 		if (!sorted.empty()) {
-			build_upper(plan, plan.levels, 0, sorted.size());
+			build_upper(plan, plan.levels, 0, sorted.size(), c0);
 			root_has = plan.nodes[0].has;
-			data_size = 1 + plan.nodes[0].size;
+			if (root_has) data_size = 1 + plan.nodes[0].size;
 		}
 		std::vector<uint8_t> packed(packed_bytes);
 		if (packed_bytes) {
 			CK(cudaMalloc(&d_offs, 8ull * nb));
 			CK(cudaMalloc(&d_out, packed_bytes));
 			CK(cudaMemcpyAsync(d_offs, offs.data(), 8ull * nb, cudaMemcpyHostToDevice, s));
-			if (color) k_brick_stream<true><<<nb, 64, kBrickStreamMax, s>>>(m->M, nb, pruned, d_info, d_offs, d_out);
-			else k_brick_stream<false><<<nb, 64, kBrickStreamMax, s>>>(m->M, nb, pruned, d_info, d_offs, d_out);
+			if (color) k_brick_stream<true><<<nb, 64, kBrickStreamMax, s>>>(m->M, nb, pruned, min_depth, plan.box, d_info, d_offs, d_out);
+			else k_brick_stream<false><<<nb, 64, kBrickStreamMax, s>>>(m->M, nb, pruned, min_depth, plan.box, d_info, d_offs, d_out);
 			CK(cudaGetLastError());
 			CK(cudaMemcpyAsync(packed.data(), d_out, packed_bytes, cudaMemcpyDeviceToHost, s));
 			CK(cudaStreamSynchronize(s));
 		}
-		// header (octree.h:850-860; doubles print with the default ostream precision = %g)
-		char head[512];
-		const int hl = snprintf(head, sizeof head,
-		                        "# UFOMap file\n# (feel free to add / change comments, but leave the first line as it "
-		                        "is!)\n#\nversion 1.0.0\nid %s\nresolution %g\ndepth_levels %u\ncompressed 0\n"
-		                        "uncompressed_data_size %d\ndata\n",
-		                        color ? "occupancy_map_color" : "occupancy_map", m->M.g.resolution, plan.levels,
-		                        (int)data_size);
 		unsigned long long produced = 0;
 		auto counted = [&](const void* p, size_t len) {
 			sink(p, len);
 			produced += len;
 		};
-		counted(head, (size_t)hl);
+		if (with_header) {
+			// octree.h:850-860; doubles print with the default ostream precision = %g
+			char head[512];
+			const int hl = snprintf(head, sizeof head,
+			                        "# UFOMap file\n# (feel free to add / change comments, but leave the first line as it "
+			                        "is!)\n#\nversion 1.0.0\nid %s\nresolution %g\ndepth_levels %u\ncompressed 0\n"
+			                        "uncompressed_data_size %d\ndata\n",
+			                        color ? "occupancy_map_color" : "occupancy_map", m->M.g.resolution, plan.levels,
+			                        (int)data_size);
+			counted(head, (size_t)hl);
+		}
 		const uint8_t children = root_has ? 0xff : 0x00;
 		counted(&children, 1);
 		if (root_has) {
@@ -1412,7 +1452,24 @@ int ufo_b200_write(ufo_b200_map* m, void* buf, size_t cap, size_t* size, int exp
 		uint8_t* out = static_cast<uint8_t*>(buf);
 		size_t at = 0;
 		unsigned long long total = 0;
-		int rc = export_image(m, expanded ? 0 : 1, [&](const void* p, size_t len) {
+		int rc = export_image(m, expanded ? 0 : 1, 0, nullptr, true, [&](const void* p, size_t len) {
+			if (out && at + len <= cap) std::memcpy(out + at, p, len);
+			at += len;
+		}, &total);
+		*size = (size_t)total;
+		return rc;
+	});
+}
+
+int ufo_b200_write_data(ufo_b200_map* m, const double* box6, uint32_t min_depth, void* buf, size_t cap,
+                        size_t* size)
+{
+	if (!m || !size) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		uint8_t* out = static_cast<uint8_t*>(buf);
+		size_t at = 0;
+		unsigned long long total = 0;
+		int rc = export_image(m, 1, min_depth, box6, false, [&](const void* p, size_t len) {
 			if (out && at + len <= cap) std::memcpy(out + at, p, len);
 			at += len;
 		}, &total);
@@ -1432,7 +1489,8 @@ int ufo_b200_write_file(ufo_b200_map* m, const char* filename, int expanded)
 		}
 		unsigned long long total = 0;
 		bool ok = true;
-		int rc = export_image(m, expanded ? 0 : 1, [&](const void* p, size_t len) { ok = ok && fwrite(p, 1, len, f) == len; }, &total);
+		int rc = export_image(m, expanded ? 0 : 1, 0, nullptr, true,
+		                      [&](const void* p, size_t len) { ok = ok && fwrite(p, 1, len, f) == len; }, &total);
 		ok = fclose(f) == 0 && ok;
 		if (rc == UFO_B200_OK && !ok) {
 			m->set_error("short write to %s", filename);
