@@ -182,10 +182,11 @@ int ufo_b200_write_file(ufo_b200_map* m, const char* filename, int expanded);
 /* Octree::writeData(stream, bounding_volume, compress = false, min_depth) (octree.h:885-917): the
  * node stream alone, as ufoToMsg puts it into a UFOMap message
  * (ufomap_ros/ufomap_msgs/include/ufomap_msgs/conversions.h:161-185; the mapping server publishes
- * the changed region at depths 0..publish_depth this way, server.cpp:184-199).  box6 = AABB min
- * xyz, max xyz (NULL: whole map): children whose cube misses the box are skipped
- * (intersects(AABB, AABB), collision_checks.cpp:256-264, on the reference's own centre/half-size
- * form of the box).  Children at min_depth are written as leaves carrying their aggregate
+ * the changed region at depths 0..publish_depth this way, server.cpp:184-199).  box6 = the
+ * fields of a ufo::geometry::AABB: centre xyz, half_size xyz (geometry/aabb.h:49-70; for
+ * AABB(min, max) that is half = (max - min) / 2, centre = min + half) or NULL for the whole map:
+ * children whose cube misses the box are skipped (intersects(AABB, AABB),
+ * collision_checks.cpp:256-264).  Children at min_depth are written as leaves carrying their aggregate
  * (max occupancy, mean colour); min_depth 0..4 is supported.  Canonical tree, see above.
  * *size = 0 when the box misses the map (the reference writes nothing then). */
 int ufo_b200_write_data(ufo_b200_map* m, const double* box6, uint32_t min_depth, void* buf, size_t cap,

@@ -166,6 +166,21 @@ class Pose6
 };
 }  // namespace ufo::math
 
+namespace ufo::geometry
+{
+using Point = ufo::math::Vector3;
+// geometry/aabb.h:49-70 -- the one bounding volume the mapping server exports with
+struct AABB {
+	Point center;
+	Point half_size;
+	AABB() {}
+	AABB(Point const& c, double hs) : center(c), half_size(hs, hs, hs) {}
+	AABB(Point const& min, Point const& max) : half_size((max - min) / 2.0) { center = min + half_size; }
+	Point getMin() const { return center - half_size; }
+	Point getMax() const { return center + half_size; }
+};
+}  // namespace ufo::geometry
+
 namespace ufo::map
 {
 using CodeType = std::uint64_t;
@@ -369,6 +384,23 @@ class MapFacade
 	{
 		if (compress || min_depth != 0) return false;
 		return UFO_B200_OK == ufo_b200_write_file(map_, filename.c_str(), 0);
+	}
+	// Octree::writeData (octree.h:866-917): the node stream of a UFOMap message, whole map or the
+	// part inside an AABB, truncated at min_depth (0..4).  Returns the number of bytes written, -1
+	// on error (as the reference does).
+	int writeData(std::ostream& s, bool compress = false, DepthType min_depth = 0,
+	              int /*compression_acceleration_level*/ = 1, int /*compression_level*/ = 0) const
+	{
+		return writeDataImpl(s, nullptr, compress, min_depth);
+	}
+	int writeData(std::ostream& s, ufo::geometry::AABB const& bounding_volume, bool compress = false,
+	              DepthType min_depth = 0, int /*compression_acceleration_level*/ = 1,
+	              int /*compression_level*/ = 0) const
+	{
+		double box[6] = {bounding_volume.center.x(),    bounding_volume.center.y(),
+		                 bounding_volume.center.z(),    bounding_volume.half_size.x(),
+		                 bounding_volume.half_size.y(), bounding_volume.half_size.z()};
+		return writeDataImpl(s, box, compress, min_depth);
 	}
 	bool write(std::ostream& s, bool compress = false, DepthType min_depth = 0,
 	           int /*compression_acceleration_level*/ = 1, int /*compression_level*/ = 0) const
@@ -633,6 +665,17 @@ class MapFacade
 			          : ufo_b200_insert_pointcloud(map_, origin.data(), buf.data(), n, UFO_B200_XYZ_F64,
 			                                       max_range, depth, simple, early_stopping, discrete, async);
 		}
+	}
+
+	int writeDataImpl(std::ostream& s, double const* box, bool compress, DepthType min_depth) const
+	{
+		if (compress) return -1;
+		std::size_t n = 0;
+		if (UFO_B200_OK != ufo_b200_write_data(map_, box, min_depth, nullptr, 0, &n)) return -1;
+		std::vector<char> data(n ? n : 1);
+		if (UFO_B200_OK != ufo_b200_write_data(map_, box, min_depth, data.data(), n, &n)) return -1;
+		s.write(data.data(), (std::streamsize)n);
+		return s.good() ? (int)n : -1;
 	}
 
 	ufo_b200_map* map_ = nullptr;

@@ -71,6 +71,11 @@ int main(int argc, char** argv)
 	if (!fused.write(os) || os.str().compare(0, 13, "# UFOMap file") != 0) return 12;
 	if (os.str().find("id occupancy_map\nresolution 0.05\ndepth_levels 16\ncompressed 0\n") == std::string::npos) return 13;
 	if (fused.write(os, /*compress*/ true)) return 14;
+	// Octree::writeData with the change box, as ufoToMsg calls it (ufomap_msgs/conversions.h:176-178)
+	std::ostringstream part, whole;
+	ufo::geometry::AABB aabb(world[10] - Point3(0.3, 0.3, 0.3), world[10] + Point3(0.3, 0.3, 0.3));
+	int n_part = fused.writeData(part, aabb, false, 2), n_whole = fused.writeData(whole, false, 0);
+	if (n_part <= 0 || n_whole <= n_part || (std::size_t)n_whole != whole.str().size()) return 15;
 	std::puts("facade ok");
 	return 0;
 }

@@ -279,8 +279,13 @@ class Map:
         return buf.tobytes()
 
     def write_data(self, box=None, min_depth=0):
-        """Octree::writeData(stream, AABB(min, max) or whole map, False, min_depth): node stream."""
-        b = None if box is None else np.ascontiguousarray(np.concatenate([box[0], box[1]]), np.float64)
+        """Octree::writeData(stream, AABB(min, max) or whole map, False, min_depth): node stream.
+        box = (min xyz, max xyz); converted to the AABB's centre / half size like its constructor."""
+        b = None
+        if box is not None:
+            mn, mx = np.asarray(box[0], np.float64), np.asarray(box[1], np.float64)
+            half = (mx - mn) / 2.0
+            b = np.ascontiguousarray(np.concatenate([mn + half, half]), np.float64)
         bp = None if b is None else b.ctypes.data
         n = C.c_size_t()
         self._check(self.lib.ufo_b200_write_data(self.h, bp, int(min_depth), None, 0, C.byref(n)))

@@ -1327,12 +1327,11 @@ int export_image(Map* m, int pruned, uint32_t min_depth, const double* box6, boo
 	plan.pruned = pruned != 0;
 	plan.g = &m->M.g;
 	if (box6) {
-		// AABB(min, max) of the reference keeps centre and half size (geometry/aabb.h:62-69)
+		// the reference's AABB stores centre and half size (geometry/aabb.h:49-70); getMin/getMax
 		plan.box.on = 1;
 		for (int k = 0; k < 3; ++k) {
-			const double hs = (box6[3 + k] - box6[k]) / 2.0, ct = box6[k] + hs;
-			plan.box.lo[k] = ct - hs;
-			plan.box.hi[k] = ct + hs;
+			plan.box.lo[k] = box6[k] - box6[3 + k];
+			plan.box.hi[k] = box6[k] + box6[3 + k];
 		}
 	}
 	*total = 0;
