@@ -163,6 +163,15 @@ int ufo_b200_query(ufo_b200_map* m, const uint64_t* codes, const uint32_t* depth
 int ufo_b200_export_leaves(ufo_b200_map* m, uint64_t* codes, float* logodds, uint8_t* rgb,
                            size_t cap, size_t* n);
 
+/* setValueVolume(AABB, occupancy probability, min_depth)  occupancy_map_base.h:492-518 -- the
+ * other map writer the mapping server uses (robot clearing server.cpp:152-154, clear_volume
+ * service :354).  box6 = the AABB's centre xyz and half_size xyz (geometry/aabb.h:49-70).  Every
+ * node of depth min_depth whose cube -- and every ancestor cube -- intersects the box is set to
+ * clamp(float(logit(occupancy))) (setOccupancy, :1151-1157), i.e. all voxels below it.
+ * min_depth 0..4; colour maps at min_depth 0 only (deeper, the reference also replaces the
+ * voxels' colours by the node's mean colour). */
+int ufo_b200_set_value_volume(ufo_b200_map* m, const double box6[6], double occupancy, uint32_t min_depth);
+
 /* Octree::write(std::ostream&) / write(filename) with compress = false (octree.h:784-864,
  * writeNodes occupancy_map_base.h:1457-1533): the map as a UFOMap file image -- text header, then
  * the pre-order node stream -- which the reference's Octree::read / the RViz plugin / ufoToMsg

@@ -385,6 +385,18 @@ class MapFacade
 		if (compress || min_depth != 0) return false;
 		return UFO_B200_OK == ufo_b200_write_file(map_, filename.c_str(), 0);
 	}
+	// setValueVolume (occupancy_map_base.h:492-518) for the bounding volume the mapping server uses
+	// (robot clearing server.cpp:152-154, clear_volume service :354): AABB, min_depth 0..4; colour
+	// maps at min_depth 0.  Other cases set lastStatus() to UFO_B200_E_UNSUPPORTED.
+	void setValueVolume(ufo::geometry::AABB const& bounding_volume, double occupancy_value,
+	                    DepthType min_depth = 0)
+	{
+		double box[6] = {bounding_volume.center.x(),    bounding_volume.center.y(),
+		                 bounding_volume.center.z(),    bounding_volume.half_size.x(),
+		                 bounding_volume.half_size.y(), bounding_volume.half_size.z()};
+		last_status_ = ufo_b200_set_value_volume(map_, box, occupancy_value, min_depth);
+	}
+
 	// Octree::writeData (octree.h:866-917): the node stream of a UFOMap message, whole map or the
 	// part inside an AABB, truncated at min_depth (0..4).  Returns the number of bytes written, -1
 	// on error (as the reference does).
@@ -608,7 +620,9 @@ class MapFacade
 		ufo_b200_query(map_, &c, &d, 1, &v.logodds, &v.flags, COLOR ? v.rgb : nullptr);
 		return v;
 	}
-	static double toProb(double logit) { return 1.0 / (1.0 + std::exp(-logit)); }
+	// occupancy_map_base.h:911 -- LogitType is float there: the argument narrows to float and the
+	// exponential is the float one, for the sensor-model getters as well as for getOccupancy
+	static double toProb(float logit) { return 1.0 / (1.0 + std::exp(-logit)); }
 	double const* model() const
 	{
 		ufo_b200_sensor_model_logit(map_, model_);

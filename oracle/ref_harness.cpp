@@ -441,6 +441,16 @@ size_t ufo_ref_write(void* h, uint8_t* buf, size_t cap)
 	return str.size();
 }
 
+// setValueVolume(AABB(min, max), occupancy probability, min_depth) (occupancy_map_base.h:492-518),
+// the call behind the server's robot clearing and clear_volume service (server.cpp:152-154, :354).
+void ufo_ref_set_value_volume(void* h, const double* box6, double occupancy, unsigned min_depth)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	ufo::geometry::AABB aabb(ufo::geometry::Point(box6[0], box6[1], box6[2]),
+	                         ufo::geometry::Point(box6[3], box6[4], box6[5]));
+	withMap(m, [&](auto& map) { map.setValueVolume(aabb, occupancy, min_depth); });
+}
+
 // Octree::writeData(stream, bounding_volume, compress = false, min_depth) (octree.h:885-917) -- the
 // payload ufoToMsg puts into a UFOMap message (ufomap_msgs/conversions.h:161-185).  box6 = AABB
 // min xyz, max xyz (the server's change box, server.cpp:184) or NULL for the whole map.

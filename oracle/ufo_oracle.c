@@ -1297,3 +1297,60 @@ size_t ufo_oracle_write_data(void* h, const double* box6, unsigned min_depth, ui
 	else wb_payload(m, &w, &m->root);
 	return w.n;
 }
+
+/* ---- setValueVolume(AABB, occupancy, min_depth)  OMB:492-518, setValueVolumeRecurs OMB:986-1031,
+ * setOccupancy(LogitType&, LogitType const&) OMB:1151-1157 (float clamp of the float logit). */
+static int set_occ(const omap* m, float* cur, float v)
+{
+	const float old = *cur, lo = (float)m->cmin, hi = (float)m->cmax;
+	*cur = v < lo ? lo : (hi < v ? hi : v); /* std::clamp<float> */
+	return old != *cur;
+}
+
+static int set_volume_rec(omap* m, const wbox* bx, float value, node* n, const double c[3], unsigned depth,
+                          unsigned min_depth)
+{
+	const unsigned cd = depth - 1;
+	const double chs = m->half[cd];
+	create_children(m, n);
+	int changed = 0;
+	for (unsigned i = 0; i < 8; ++i) {
+		double cc[3];
+		child_center(c, chs, i, cc);
+		if (!box_hits(bx, cc, chs)) continue;
+		node* ch = &n->ch[i];
+		if (0 == cd) {
+			if (set_occ(m, &ch->occ, value)) changed = 1;
+		} else if (min_depth < cd) {
+			if (set_volume_rec(m, bx, value, ch, cc, cd, min_depth)) changed = 1;
+		} else {
+			delete_children(m, ch, cd);
+			if (set_occ(m, &ch->occ, value)) changed = 1;
+			if (update_node(m, ch, cd)) changed = 1;
+		}
+	}
+	return !changed || update_node(m, n, depth);
+}
+
+void ufo_oracle_set_value_volume(void* h, const double* box6, double occupancy, unsigned min_depth)
+{
+	omap* m = (omap*)h;
+	if (m->levels < min_depth) return;
+	wbox bx = {1, {0, 0, 0}, {0, 0, 0}};
+	for (int k = 0; k < 3; ++k) {
+		const double hs = (box6[3 + k] - box6[k]) / 2.0, ct = box6[k] + hs;
+		bx.lo[k] = ct - hs;
+		bx.hi[k] = ct + hs;
+	}
+	const double c0[3] = {0.0, 0.0, 0.0};
+	if (!box_hits(&bx, c0, m->half[m->levels])) return;
+	/* the double logit narrows to float at the LogitType parameter of setOccupancy */
+	const float value = (float)to_logit(occupancy);
+	if (m->levels == min_depth) {
+		delete_children(m, &m->root, m->levels);
+		set_occ(m, &m->root.occ, value);
+		update_node(m, &m->root, m->levels);
+		return;
+	}
+	if (set_volume_rec(m, &bx, value, &m->root, c0, m->levels, min_depth)) update_node(m, &m->root, m->levels);
+}

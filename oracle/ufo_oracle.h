@@ -68,6 +68,9 @@ void ufo_oracle_canonicalize(void* h);
 /* Octree::writeData(stream, AABB or none, compress = false, min_depth): the node stream only */
 size_t ufo_oracle_write_data(void* h, const double* box6, unsigned min_depth, uint8_t* buf, size_t cap);
 
+/* setValueVolume(AABB(min, max), occupancy probability, min_depth) */
+void ufo_oracle_set_value_volume(void* h, const double* box6, double occupancy, unsigned min_depth);
+
 #ifdef __cplusplus
 }
 #endif

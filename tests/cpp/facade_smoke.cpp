@@ -76,6 +76,10 @@ int main(int argc, char** argv)
 	ufo::geometry::AABB aabb(world[10] - Point3(0.3, 0.3, 0.3), world[10] + Point3(0.3, 0.3, 0.3));
 	int n_part = fused.writeData(part, aabb, false, 2), n_whole = fused.writeData(whole, false, 0);
 	if (n_part <= 0 || n_whole <= n_part || (std::size_t)n_whole != whole.str().size()) return 15;
+	// clear the robot's volume like the server does (server.cpp:150-154)
+	Point3 r(0.2, 0.2, 0.1);
+	fused.setValueVolume(ufo::geometry::AABB(world[20] - r, world[20] + r), fused.getClampingThresMin(), 0);
+	if (fused.lastStatus() != UFO_B200_OK || !fused.isFree(world[20])) return 16;
 	std::puts("facade ok");
 	return 0;
 }

@@ -76,6 +76,7 @@ def _load(path, prefix):
         reset_change_bbox=sig("reset_change_bbox", None, [vp]),
         sensor_model=sig("sensor_model", None, [vp, vp]),
         memory_usage=sig("memory_usage", sz, [vp]),
+        set_value_volume=sig("set_value_volume", None, [vp, vp, dbl, u32]),
         write=sig("write", sz, [vp, vp, sz]),
         write_data=sig("write_data", sz, [vp, vp, u32, vp, sz]),
         transform=sig("transform", None, [vp, vp, sz, vp]),
@@ -238,6 +239,11 @@ class _CpuMap:
 
     def memory_usage(self):
         return int(self.api["memory_usage"](self.h))
+
+    def set_value_volume(self, box, occupancy, min_depth=0):
+        """setValueVolume(AABB(min, max), occupancy probability, min_depth)."""
+        b = np.ascontiguousarray(np.concatenate([box[0], box[1]]), np.float64)
+        self.api["set_value_volume"](self.h, b.ctypes.data, float(occupancy), int(min_depth))
 
     def write_data(self, box=None, min_depth=0):
         """Octree::writeData(stream, AABB(min, max) or the whole map, False, min_depth): node stream."""

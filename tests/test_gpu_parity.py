@@ -325,3 +325,45 @@ def test_pointcloud2_ingestion(color, discrete):
     rmn, rmx = cpu.change_bbox()
     assert np.array_equal(mn, rmn) and np.array_equal(mx, rmx)
     gpu.close()
+
+
+@pytest.mark.parametrize("color", [False, True])
+def test_set_value_volume(color):
+    """setValueVolume(AABB, p, min_depth) (occupancy_map_base.h:492-518) -- robot clearing /
+    clear_volume of the mapping server -- interleaved with scans; value field, aggregates and the
+    next scans on top must match the reference."""
+    kw = dict(resolution=0.05)
+    gpu = Map(color=color, initial_blocks=1 << 12, **kw)
+    cpus = [OracleMap(color=color, **kw)] + ([RefMap(color=color, **kw)] if have_ref() else [])
+    rng = np.random.default_rng(23)
+    res = kw["resolution"]
+    depths = [0, 0, 0, 0] if color else [0, 1, 2, 3, 4, 0]
+    values = [0.1192, 0.7, 0.5, 0.1192, 0.99, 0.3]
+    for k in range(3):
+        o, p, c = scans.rgbd(k=k, width=56, height=42)
+        ins = dict(origin=o, xyz=p, rgb=c if color else None, max_range=3.0, discrete=True)
+        gpu.insert(**ins)
+        for m in cpus:
+            m.insert(**ins)
+        for t in range(2):
+            i = 2 * k + t
+            md, val = depths[i % len(depths)], values[i % len(values)]
+            lo = np.array([0.5, -0.6, -0.5]) + rng.uniform(-0.4, 0.8, 3)
+            hi = lo + rng.uniform(0.03, 0.7, 3)
+            if i == 1:   # faces exactly on voxel borders; partly outside anything touched so far
+                lo = np.array([4 * res, -6 * res, 30 * res])
+                hi = lo + np.array([8 * res, 5 * res, 3 * res])
+            gpu.set_value_volume((lo, hi), val, md)
+            for m in cpus:
+                m.set_value_volume((lo, hi), val, md)
+            field = gpu.value_field()
+            for m in cpus:
+                assert_value_fields_equal(field, m.value_field(), color_tol=1 if color else 0,
+                                          what="%s after volume %d (depth %d)" % (type(m).__name__, i, md))
+    check_inner_against_field(gpu, cpus[0].value_field(), cpus[0].sensor_model(), levels=(1, 2, 3, 4, 5, 6, 9, 16))
+    # outside the map / unsupported depth
+    gpu.set_value_volume((np.array([1e5, 1e5, 1e5]), np.array([2e5, 2e5, 2e5])), 0.2, 0)
+    with pytest.raises(UfoError) as e:
+        gpu.set_value_volume((np.zeros(3), np.ones(3)), 0.2, 5)
+    assert e.value.status == E_UNSUPPORTED
+    gpu.close()

@@ -58,7 +58,7 @@ SYMBOLS = [
     "ufo_b200_set_profiling", "ufo_b200_clear", "ufo_b200_version", "ufo_b200_set_shard",
     "ufo_b200_insert_pointcloud_frame", "ufo_b200_transform_points", "ufo_b200_pose_from_rpy",
     "ufo_b200_insert_pointcloud2", "ufo_b200_write", "ufo_b200_write_file",
-    "ufo_b200_write_data",
+    "ufo_b200_write_data", "ufo_b200_set_value_volume",
 ]
 
 class Cloud2(C.Structure):
@@ -98,6 +98,7 @@ def load():
     lib.ufo_b200_insert_pointcloud2.argtypes = [vp, vp, C.POINTER(Cloud2), vp, dbl, u32, i32, u32, i32, i32]
     lib.ufo_b200_write.argtypes = [vp, vp, sz, C.POINTER(sz), i32]
     lib.ufo_b200_write_file.argtypes = [vp, C.c_char_p, i32]
+    lib.ufo_b200_set_value_volume.argtypes = [vp, vp, dbl, u32]
     lib.ufo_b200_write_data.argtypes = [vp, vp, u32, vp, sz, C.POINTER(sz)]
     lib.ufo_b200_transform_points.argtypes = [vp, vp, sz, i32, vp]
     lib.ufo_b200_pose_from_rpy.argtypes = [dbl, dbl, dbl, dbl, dbl, dbl, vp]
@@ -277,6 +278,13 @@ class Map:
         self._check(self.lib.ufo_b200_write(self.h, buf.ctypes.data, n.value, C.byref(n), int(expanded)))
         assert n.value == len(buf)
         return buf.tobytes()
+
+    def set_value_volume(self, box, occupancy, min_depth=0):
+        """setValueVolume(AABB(min, max), occupancy probability, min_depth); box = (min xyz, max xyz)."""
+        mn, mx = np.asarray(box[0], np.float64), np.asarray(box[1], np.float64)
+        half = (mx - mn) / 2.0
+        b = np.ascontiguousarray(np.concatenate([mn + half, half]), np.float64)
+        self._check(self.lib.ufo_b200_set_value_volume(self.h, b.ctypes.data, float(occupancy), int(min_depth)))
 
     def write_data(self, box=None, min_depth=0):
         """Octree::writeData(stream, AABB(min, max) or whole map, False, min_depth): node stream.

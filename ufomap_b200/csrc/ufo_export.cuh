@@ -291,4 +291,92 @@ __global__ void __launch_bounds__(64) k_brick_stream(DeviceMap M, uint32_t n_bri
 	uint8_t* dst = out + offsets[brick];
 	for (uint32_t i = t; i < s_brick_size; i += 64) dst[i] = s_buf[i];
 }
+
+// ---------------------------------------------------------------------------
+// setValueVolume(AABB, value, min_depth)   occupancy_map_base.h:492-518, :986-1031
+// ---------------------------------------------------------------------------
+// The reference descends from the root and, at every level down to min_depth, keeps the children
+// whose cube intersects the box; the nodes reached at min_depth are collapsed and set.  On the
+// value field: a voxel is set iff every ancestor cube from depth L-1 down to min_depth (itself at
+// min_depth 0) intersects the box.  k_volume_mark evaluates exactly that chain -- centres
+// accumulated top-down like getChildCenter -- for one candidate brick per CTA, one 4^3 block per
+// thread, and leaves the result as a bit mask in the block's miss mask; the set itself is the K3
+// update kernel in SET mode, followed by the usual aggregate passes.
+struct VolumeArgs {
+	ExportBox box;
+	uint32_t min_depth;       // 0..4
+	uint32_t bx0, by0, bz0;   // first candidate brick (brick coordinates)
+	uint32_t nx, ny, nz;      // candidate bricks per axis
+};
+
+__global__ void __launch_bounds__(64) k_volume_mark(DeviceMap M, VolumeArgs v)
+{
+	__shared__ double s_center[3];
+	__shared__ uint32_t s_slot;
+	const uint32_t t = threadIdx.x;
+	const uint32_t ix = blockIdx.x % v.nx, iy = (blockIdx.x / v.nx) % v.ny, iz = blockIdx.x / (v.nx * v.ny);
+	const uint32_t kx = v.bx0 + ix, ky = v.by0 + iy, kz = v.bz0 + iz;
+	if (t == 0) {
+		double c[3] = {0.0, 0.0, 0.0};
+		bool ok = true;
+		for (uint32_t d = M.g.depth_levels; d > 4; --d) {
+			const uint32_t bit = d - 5;
+			const uint32_t i = ((kx >> bit) & 1u) | (((ky >> bit) & 1u) << 1) | (((kz >> bit) & 1u) << 2);
+			double n[3];
+			child_center(c, M.g.half_size[d - 1], i, n);
+			c[0] = n[0];
+			c[1] = n[1];
+			c[2] = n[2];
+			ok = ok && box_hits(v.box, c, M.g.half_size[d - 1]);  // cube of the depth d-1 ancestor
+		}
+		uint32_t slot = kNone;
+		if (ok) {
+			slot = brick_find_or_create(M, pack_key(kx, ky, kz));
+			if (slot != kNone) M.brick_stamp[slot] = M.scan_id;
+		}
+		s_slot = slot;
+		s_center[0] = c[0];
+		s_center[1] = c[1];
+		s_center[2] = c[2];
+	}
+	__syncthreads();
+	const uint32_t slot = s_slot;
+	if (slot == kNone) return;
+	unsigned long long mask = 0ull;
+	if (v.min_depth >= 4) {
+		mask = ~0ull;
+	} else {
+		double bc[3] = {s_center[0], s_center[1], s_center[2]}, d3c[3], blkc[3];
+		child_center(bc, M.g.half_size[3], t >> 3, d3c);
+		child_center(d3c, M.g.half_size[2], t & 7u, blkc);
+		if (box_hits(v.box, d3c, M.g.half_size[3])) {
+			if (v.min_depth == 3) {
+				mask = ~0ull;
+			} else if (box_hits(v.box, blkc, M.g.half_size[2])) {
+				if (v.min_depth == 2) {
+					mask = ~0ull;
+				} else {
+					for (uint32_t o = 0; o < 8; ++o) {
+						double oc[3];
+						child_center(blkc, M.g.half_size[1], o, oc);
+						if (!box_hits(v.box, oc, M.g.half_size[1])) continue;
+						const uint32_t x0 = (o & 1u) << 1, y0 = o & 2u, z0 = (o & 4u) >> 1;
+						if (v.min_depth == 1) {
+							mask |= octet_mask_of(x0, y0, z0);
+							continue;
+						}
+						for (uint32_t j = 0; j < 8; ++j) {
+							double vc[3];
+							child_center(oc, M.g.half_size[0], j, vc);
+							if (box_hits(v.box, vc, M.g.half_size[0]))
+								mask |= 1ull << linear2(x0 + (j & 1u), y0 + ((j >> 1) & 1u), z0 + (j >> 2));
+						}
+					}
+				}
+			}
+		}
+	}
+	// the masks of a block belong to one thread here, and no scan is in flight
+	if (mask) M.miss_mask[(size_t)slot * 64 + t] |= mask;
+}
 }  // namespace ufo_b200

@@ -895,6 +895,9 @@ __device__ __forceinline__ uint32_t rms_rgb(const uint32_t* c, int n)
 #endif
 constexpr int kUpdThreads = 256;
 
+// SET = true: the marked voxels are set to `miss` (already clamped) instead of updated --
+// setValueVolume, occupancy_map_base.h:492-518, :1151-1157.
+template <bool SET = false>
 __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, float* lp, uint32_t m8,
                                              uint32_t h8, float4 a0, float4 a1, float& omax,
                                              uint32_t& oflags)
@@ -905,7 +908,7 @@ __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, flo
 	bool unk = false;
 	// all hits of a scan are applied before its misses (occupancy_map_base.h:1351-1365);
 	// hits are rare (one voxel per ray), so their arithmetic is skipped for octets without one
-	if (h8) {
+	if (!SET && h8) {
 #pragma unroll
 		for (int j = 0; j < 8; ++j) {
 			float hv = apply_update(M, v[j], M.hit);
@@ -914,7 +917,7 @@ __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, flo
 	}
 #pragma unroll
 	for (int j = 0; j < 8; ++j) {
-		float mv = apply_update(M, v[j], miss);
+		float mv = SET ? miss : apply_update(M, v[j], miss);
 		v[j] = ((m8 >> j) & 1u) ? mv : v[j];
 		omax = fmaxf(omax, v[j]);
 		omin = fminf(omin, v[j]);
@@ -930,7 +933,7 @@ __device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, flo
 
 constexpr int kStatSlots = 64;  // per-scan counters are spread over slots to avoid same-address atomics
 
-template <bool COLOR>
+template <bool COLOR, bool SET = false>
 __global__ void __launch_bounds__(kUpdThreads, UFO_UPD_MINBLOCKS) k_update(DeviceMap M, float miss, uint32_t first_brick,
                                                            uint32_t n_bricks)
 {
@@ -960,7 +963,7 @@ __global__ void __launch_bounds__(kUpdThreads, UFO_UPD_MINBLOCKS) k_update(Devic
 		if (m8 | h8) {
 			float* lp = M.leaf + b * 64 + 8 * oct;
 			const float4 a0 = reinterpret_cast<const float4*>(lp)[0], a1 = reinterpret_cast<const float4*>(lp)[1];
-			update_octet(M, miss, lp, m8, h8, a0, a1, omax, ofl);
+			update_octet<SET>(M, miss, lp, m8, h8, a0, a1, omax, ofl);
 			touched = 1;
 			s_vox = __popc(m8 | h8);
 			s_hit = __popc(h8);
@@ -1052,7 +1055,7 @@ static_assert(kUcBlocks <= kUcThreads && kUcBlocks % 32 == 0 && kUcBlocks * 8 <=
 #define UFO_UC_GRID_PER_SM UFO_UC_MINBLOCKS
 #endif
 
-template <bool COLOR>
+template <bool COLOR, bool SET = false>
 __global__ void __launch_bounds__(kUcThreads, COLOR ? UFO_UC_MINBLOCKS_COLOR : UFO_UC_MINBLOCKS) k_update_compact(DeviceMap M, float miss,
                                                                                uint32_t first_brick,
                                                                                uint32_t n_bricks,
@@ -1157,7 +1160,7 @@ __global__ void __launch_bounds__(kUcThreads, COLOR ? UFO_UC_MINBLOCKS_COLOR : U
 			const float4 a0 = reinterpret_cast<const float4*>(lp)[0], a1 = reinterpret_cast<const float4*>(lp)[1];
 			float omax;
 			uint32_t ofl;
-			update_octet(M, miss, lp, m8, h8, a0, a1, omax, ofl);
+			update_octet<SET>(M, miss, lp, m8, h8, a0, a1, omax, ofl);
 			s_omax[oct * kUcBlocks + t] = omax;
 			s_ofl[oct * kUcBlocks + t] = (unsigned char)ofl;
 			if (COLOR) {

@@ -420,12 +420,20 @@ void ensure_seg(Map* m, unsigned long long want)
 }
 
 // k_update over the bricks [first, last)
-void launch_update(Map* m, float miss, uint32_t first, uint32_t last)
+void launch_update(Map* m, float miss, uint32_t first, uint32_t last, bool set_mode = false)
 {
 	const uint32_t groups = (last - first) * 64u;  // one eight-lane group per (brick, child)
 #if defined(UFO_UPD_FLAT) || defined(UFO_UPD_FLAT_COLOR)
 	const uint32_t grid = (groups + kUpdThreads / 8 - 1) / (kUpdThreads / 8);
 #endif
+	if (set_mode) {
+		// setValueVolume: the flat kernel in SET mode (not a hot path)
+		const uint32_t sgrid = (groups + kUpdThreads / 8 - 1) / (kUpdThreads / 8);
+		if (m->M.color) k_update<true, true><<<sgrid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
+		else k_update<false, true><<<sgrid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
+		++m->launches;
+		return;
+	}
 #ifdef UFO_UPD_FLAT
 	if (m->M.color) k_update<true><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
 	else k_update<false><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
@@ -495,7 +503,8 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 int do_insert(Map* m, const double origin[3], const void* points, bool on_device, size_t n,
               const double* frame_pose,
               int layout, double max_range, uint32_t depth, int simple, uint32_t early_stopping,
-              int discrete, int async, const ufo_b200_cloud2* pc2 = nullptr)
+              int discrete, int async, const ufo_b200_cloud2* pc2 = nullptr, const VolumeArgs* vol = nullptr,
+              float set_value = 0.0f)
 {
 	if (!m || !origin || (!points && n)) return UFO_B200_E_INVALID;
 	size_t stride = pc2 ? pc2->point_step : layout_stride(layout);
@@ -610,7 +619,12 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 			CK(cudaMemsetAsync(m->d_tab_keys, 0xff, (size_t)m->tab_size * sizeof(unsigned long long), s));
 			CK(cudaMemsetAsync(m->d_tab_min, 0xff, (size_t)m->tab_size * sizeof(uint32_t), s));
 		}
-		if (n) {
+		if (vol) {
+			// setValueVolume: the marks come from the box instead of a scan
+			k_volume_mark<<<vol->nx * vol->ny * vol->nz, 64, 0, s>>>(M, *vol);
+			++m->launches;
+			if (m->profiling) CK(cudaEventRecord(m->ev[2], s));
+		} else if (n) {
 			uint32_t grid = (uint32_t)((n + 255) / 256);
 			k_points<<<grid, 256, 0, s>>>(M, a);
 			++m->launches;
@@ -631,7 +645,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		// pool overflowed); bricks created by this scan follow once their number is known.
 		CK(cudaEventRecord(m->ev_marked, s));
 		const bool aliases_possible = M.alias_miss != nullptr;
-		const bool speculate = !aliases_possible && bricks_before > 0;
+		const bool speculate = !aliases_possible && bricks_before > 0 && !vol;
 		if (speculate) {
 			if (m->profiling) CK(cudaEventRecord(m->ev[4], s));
 			launch_update(m, a.miss, 0, bricks_before);
@@ -691,7 +705,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	// K3 (the part not launched speculatively above)
 	if (m->n_bricks) {
 		const uint32_t first = speculated ? bricks_before : 0u;
-		if (first < m->n_bricks) launch_update(m, a.miss, first, m->n_bricks);
+		if (first < m->n_bricks) launch_update(m, vol ? set_value : a.miss, first, m->n_bricks, vol != nullptr);
 		const uint32_t agrid = (m->n_bricks + 7) / 8;
 		if (aliases) {
 			k_alias_apply<<<alias_grid, 256, 0, s>>>(M, m->n_bricks, a.miss, 0);
@@ -1443,6 +1457,67 @@ int export_image(Map* m, int pruned, uint32_t min_depth, const double* box6, boo
 }  // namespace
 
 extern "C" {
+
+int ufo_b200_set_value_volume(ufo_b200_map* m, const double box6[6], double occupancy, uint32_t min_depth)
+{
+	if (!m || !box6) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		if (min_depth > 4 || m->M.g.depth_levels < 5) {
+			m->set_error("setValueVolume: min_depth %u > 4 (or depth_levels < 5) is not supported", min_depth);
+			return (int)UFO_B200_E_UNSUPPORTED;
+		}
+		if (m->M.color && min_depth > 0) {
+			m->set_error("setValueVolume on a colour map is supported at min_depth 0 only");
+			return (int)UFO_B200_E_UNSUPPORTED;
+		}
+		if (m->M.shard_world > 1) {
+			m->set_error("setValueVolume on a sharded map is not supported");
+			return (int)UFO_B200_E_UNSUPPORTED;
+		}
+		const Geometry& g = m->M.g;
+		VolumeArgs v{};
+		v.min_depth = min_depth;
+		v.box.on = 1;
+		for (int k = 0; k < 3; ++k) {
+			v.box.lo[k] = box6[k] - box6[3 + k];
+			v.box.hi[k] = box6[k] + box6[3 + k];
+		}
+		const double c0[3] = {0.0, 0.0, 0.0};
+		if (!box_hits(v.box, c0, g.half_size[g.depth_levels])) return (int)UFO_B200_OK;  // no node intersects
+		// candidate bricks: the key range of the box, one brick of slack on every side (the kernel
+		// decides with the reference's own cube tests)
+		const double ext = g.half_size[g.depth_levels];
+		const long long top = (1ll << (g.depth_levels - 4)) - 1;
+		uint32_t first[3], count[3];
+		unsigned long long total = 1;
+		for (int k = 0; k < 3; ++k) {
+			const double lo = std::max(v.box.lo[k], -ext), hi = std::min(v.box.hi[k], ext);
+			long long a = ((long long)std::floor(lo * g.resolution_factor) + (long long)g.max_value) >> 4;
+			long long b = ((long long)std::floor(hi * g.resolution_factor) + (long long)g.max_value) >> 4;
+			a = std::min(std::max(a - 1, 0ll), top);
+			b = std::min(std::max(b + 1, 0ll), top);
+			first[k] = (uint32_t)a;
+			count[k] = (uint32_t)(b - a + 1);
+			total *= count[k];
+		}
+		if (total > (1ull << 22)) {
+			m->set_error("setValueVolume: the box covers %llu bricks (limit 4194304)", total);
+			return (int)UFO_B200_E_UNSUPPORTED;
+		}
+		v.bx0 = first[0];
+		v.by0 = first[1];
+		v.bz0 = first[2];
+		v.nx = count[0];
+		v.ny = count[1];
+		v.nz = count[2];
+		// setOccupancy(LogitType&, LogitType const&): float clamp of the float logit (OMB:1151-1157)
+		const float lo = (float)m->cmin_log, hi = (float)m->cmax_log;
+		float value = (float)to_logit(occupancy);
+		value = value < lo ? lo : (hi < value ? hi : value);
+		const double origin[3] = {0.0, 0.0, 0.0};
+		return do_insert(m, origin, nullptr, false, 0, nullptr, UFO_B200_XYZ_F64, -1.0, 0, 0, 0, 0, 0, nullptr, &v, value);
+	});
+}
 
 int ufo_b200_write(ufo_b200_map* m, void* buf, size_t cap, size_t* size, int expanded)
 {
