@@ -172,21 +172,24 @@ int ufo_b200_export_leaves(ufo_b200_map* m, uint64_t* codes, float* logodds, uin
  * voxels' colours by the node's mean colour). */
 int ufo_b200_set_value_volume(ufo_b200_map* m, const double box6[6], double occupancy, uint32_t min_depth);
 
-/* Octree::write(std::ostream&) / write(filename) with compress = false (octree.h:784-864,
- * writeNodes occupancy_map_base.h:1457-1533): the map as a UFOMap file image -- text header, then
- * the pre-order node stream -- which the reference's Octree::read / the RViz plugin / ufoToMsg
- * consumers parse.  expanded = 0: the canonical tree of the map's value field (a node whose eight
- * children are leaves with equal payload is a leaf).  The reference collapses such nodes itself
- * (updateNode, occupancy_map_base.h:1210-1212 -- logically even with automatic pruning off,
+/* Octree::write(std::ostream& / filename, bounding_volume, compress = false, min_depth)
+ * (octree.h:776-864, writeNodes occupancy_map_base.h:1457-1533): the map as a UFOMap file image
+ * -- text header, then the pre-order node stream -- which the reference's Octree::read / the RViz
+ * plugin parse; the save_map service of the mapping server (server.cpp:381-392).  box6 (NULL =
+ * whole map) and min_depth as for ufo_b200_write_data below.
+ * expanded = 0: the canonical tree of the map's value field (a node whose eight children are
+ * leaves with equal payload is a leaf).  The reference collapses such nodes itself (updateNode,
+ * occupancy_map_base.h:1210-1212 -- logically even with automatic pruning off,
  * octree.h:1060-1066), so this is byte-identical to its own file unless its update order left a
  * collapsible node behind (updateParents stops at the first unchanged aggregate, :1126-1133);
  * then the two files differ in shape only and read back to the same map.  expanded != 0: every
  * octet that was ever touched is written as eight voxels (value-equivalent, larger).
  * ufo_b200_write: *size receives the image size; the image is copied when it fits into cap
- * (call with buf = NULL to size the buffer).  Whole map only (no bounding-volume / min_depth
- * filter, no LZ4). */
-int ufo_b200_write(ufo_b200_map* m, void* buf, size_t cap, size_t* size, int expanded);
-int ufo_b200_write_file(ufo_b200_map* m, const char* filename, int expanded);
+ * (call with buf = NULL to size the buffer).  No LZ4. */
+int ufo_b200_write(ufo_b200_map* m, const double* box6, uint32_t min_depth, int expanded, void* buf, size_t cap,
+                   size_t* size);
+int ufo_b200_write_file(ufo_b200_map* m, const char* filename, const double* box6, uint32_t min_depth,
+                        int expanded);
 
 /* Octree::writeData(stream, bounding_volume, compress = false, min_depth) (octree.h:885-917): the
  * node stream alone, as ufoToMsg puts it into a UFOMap message
@@ -239,6 +242,10 @@ typedef struct {
 } ufo_b200_scan_stats;
 
 int ufo_b200_last_scan_stats(ufo_b200_map* m, ufo_b200_scan_stats* out);
+/* Octree::clear(resolution, depth_levels)  octree.h:541-560 -- the server's reset service
+ * (server.cpp:364-378): empties the map and changes its geometry. */
+int ufo_b200_clear_resize(ufo_b200_map* m, double resolution, uint32_t depth_levels);
+
 /* 0: off; 1: per-kernel CUDA-event timing; 2: additionally count ray-walk visits
  * (one extra atomic per ray). */
 int ufo_b200_set_profiling(ufo_b200_map* m, int enable);

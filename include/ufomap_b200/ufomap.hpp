@@ -376,24 +376,44 @@ class MapFacade
 	virtual std::string getTreeType() const noexcept { return COLOR ? "occupancy_map_color" : "occupancy_map"; }
 
 	//
-	// File / wire format (octree.h:776-864): whole map, uncompressed.  compress = true, a
-	// min_depth > 0 or a bounding volume are not supported and return false.
+	// File / wire format (octree.h:776-864), uncompressed: whole map or the part inside an AABB,
+	// truncated at min_depth (0..4).  compress = true is not supported and returns false.
 	//
 	bool write(std::string const& filename, bool compress = false, DepthType min_depth = 0,
 	           int /*compression_acceleration_level*/ = 1, int /*compression_level*/ = 0) const
 	{
-		if (compress || min_depth != 0) return false;
-		return UFO_B200_OK == ufo_b200_write_file(map_, filename.c_str(), 0);
+		if (compress) return false;
+		return UFO_B200_OK == ufo_b200_write_file(map_, filename.c_str(), nullptr, min_depth, 0);
 	}
+	bool write(std::string const& filename, ufo::geometry::AABB const& bounding_volume, bool compress = false,
+	           DepthType min_depth = 0, int /*compression_acceleration_level*/ = 1,
+	           int /*compression_level*/ = 0) const
+	{
+		if (compress) return false;
+		double box[6];
+		packBox(bounding_volume, box);
+		return UFO_B200_OK == ufo_b200_write_file(map_, filename.c_str(), box, min_depth, 0);
+	}
+	bool write(std::ostream& s, bool compress = false, DepthType min_depth = 0,
+	           int /*compression_acceleration_level*/ = 1, int /*compression_level*/ = 0) const
+	{
+		if (compress) return false;
+		std::size_t n = 0;
+		if (UFO_B200_OK != ufo_b200_write(map_, nullptr, min_depth, 0, nullptr, 0, &n)) return false;
+		std::vector<char> image(n);
+		if (UFO_B200_OK != ufo_b200_write(map_, nullptr, min_depth, 0, image.data(), n, &n)) return false;
+		s.write(image.data(), (std::streamsize)n);
+		return s.good();
+	}
+
 	// setValueVolume (occupancy_map_base.h:492-518) for the bounding volume the mapping server uses
 	// (robot clearing server.cpp:152-154, clear_volume service :354): AABB, min_depth 0..4; colour
 	// maps at min_depth 0.  Other cases set lastStatus() to UFO_B200_E_UNSUPPORTED.
 	void setValueVolume(ufo::geometry::AABB const& bounding_volume, double occupancy_value,
 	                    DepthType min_depth = 0)
 	{
-		double box[6] = {bounding_volume.center.x(),    bounding_volume.center.y(),
-		                 bounding_volume.center.z(),    bounding_volume.half_size.x(),
-		                 bounding_volume.half_size.y(), bounding_volume.half_size.z()};
+		double box[6];
+		packBox(bounding_volume, box);
 		last_status_ = ufo_b200_set_value_volume(map_, box, occupancy_value, min_depth);
 	}
 
@@ -409,21 +429,9 @@ class MapFacade
 	              DepthType min_depth = 0, int /*compression_acceleration_level*/ = 1,
 	              int /*compression_level*/ = 0) const
 	{
-		double box[6] = {bounding_volume.center.x(),    bounding_volume.center.y(),
-		                 bounding_volume.center.z(),    bounding_volume.half_size.x(),
-		                 bounding_volume.half_size.y(), bounding_volume.half_size.z()};
+		double box[6];
+		packBox(bounding_volume, box);
 		return writeDataImpl(s, box, compress, min_depth);
-	}
-	bool write(std::ostream& s, bool compress = false, DepthType min_depth = 0,
-	           int /*compression_acceleration_level*/ = 1, int /*compression_level*/ = 0) const
-	{
-		if (compress || min_depth != 0) return false;
-		std::size_t n = 0;
-		if (UFO_B200_OK != ufo_b200_write(map_, nullptr, 0, &n, 0)) return false;
-		std::vector<char> image(n);
-		if (UFO_B200_OK != ufo_b200_write(map_, image.data(), n, &n, 0)) return false;
-		s.write(image.data(), (std::streamsize)n);
-		return s.good();
 	}
 
 	//
@@ -600,6 +608,12 @@ class MapFacade
 	}
 
 	void clear() { ufo_b200_clear(map_); }
+	// Octree::clear(resolution, depth_levels) octree.h:541-560 (the server's reset service)
+	void clear(double new_resolution, DepthType new_depth_levels)
+	{
+		if (UFO_B200_E_INVALID == ufo_b200_clear_resize(map_, new_resolution, new_depth_levels))
+			throw std::invalid_argument("depth_levels has to be [2, 21]");
+	}
 
 	// status of the last insert (the reference's insert functions are void and never throw)
 	int lastStatus() const noexcept { return last_status_; }
@@ -681,6 +695,15 @@ class MapFacade
 		}
 	}
 
+	static void packBox(ufo::geometry::AABB const& b, double box[6])
+	{
+		box[0] = b.center.x();
+		box[1] = b.center.y();
+		box[2] = b.center.z();
+		box[3] = b.half_size.x();
+		box[4] = b.half_size.y();
+		box[5] = b.half_size.z();
+	}
 	int writeDataImpl(std::ostream& s, double const* box, bool compress, DepthType min_depth) const
 	{
 		if (compress) return -1;

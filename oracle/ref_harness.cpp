@@ -469,6 +469,30 @@ size_t ufo_ref_write_data(void* h, const double* box6, unsigned min_depth, uint8
 	return str.size();
 }
 
+// Octree::write(std::ostream&, bounding_volume, compress = false, min_depth) (octree.h:826-864):
+// file image of a region -- the server's save_map service (server.cpp:381-392).
+size_t ufo_ref_write_region(void* h, const double* box6, unsigned min_depth, uint8_t* buf, size_t cap)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	std::stringstream ss(std::ios_base::in | std::ios_base::out | std::ios_base::binary);
+	ufo::geometry::BoundingVolume bv;
+	if (box6) {
+		bv.add(ufo::geometry::AABB(ufo::geometry::Point(box6[0], box6[1], box6[2]),
+		                           ufo::geometry::Point(box6[3], box6[4], box6[5])));
+	}
+	withMap(m, [&](auto& map) { return map.write(ss, bv, false, min_depth); });
+	const std::string str = ss.str();
+	if (buf && str.size() <= cap) std::memcpy(buf, str.data(), str.size());
+	return str.size();
+}
+
+// Octree::clear(resolution, depth_levels) (octree.h:541-560)
+void ufo_ref_clear(void* h, double resolution, unsigned depth_levels)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	withMap(m, [&](auto& map) { map.clear(resolution, depth_levels); });
+}
+
 // Octree::read(std::istream&) (octree.h:699-733): replaces the map's content.  1 = ok.
 int ufo_ref_read(void* h, const uint8_t* buf, size_t size)
 {

@@ -84,6 +84,8 @@ def _load(path, prefix):
     )
     if prefix == "ufo_ref_":
         api["read"] = sig("read", i32, [vp, vp, sz])
+        api["write_region"] = sig("write_region", sz, [vp, vp, u32, vp, sz])
+        api["clear"] = sig("clear", None, [vp, dbl, u32])
     if prefix == "ufo_oracle_":
         api["last_counters"] = sig("last_counters", None, [vp, vp])
         api["canonicalize"] = sig("canonicalize", None, [vp])
@@ -265,6 +267,19 @@ class _CpuMap:
 class RefMap(_CpuMap):
     _path = REF_SO
     _prefix = "ufo_ref_"
+
+    def write_region(self, box=None, min_depth=0):
+        """Octree::write(stream, AABB(min, max) or whole map, False, min_depth): file image."""
+        b = None if box is None else np.ascontiguousarray(np.concatenate([box[0], box[1]]), np.float64)
+        bp = None if b is None else b.ctypes.data
+        n = self.api["write_region"](self.h, bp, int(min_depth), None, 0)
+        buf = np.empty(n, np.uint8)
+        assert self.api["write_region"](self.h, bp, int(min_depth), buf.ctypes.data, n) == n
+        return buf.tobytes()
+
+    def clear(self, resolution, depth_levels):
+        """Octree::clear(resolution, depth_levels)."""
+        self.api["clear"](self.h, float(resolution), int(depth_levels))
 
     def read(self, image):
         """Octree::read(istream): replace the map's content by a file image."""

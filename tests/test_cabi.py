@@ -60,3 +60,30 @@ def test_no_oracle_in_product_path():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                     text = open(os.path.join(dirpath, f)).read()
                     assert "ufo_oracle" not in text and "libufo_ref" not in text and "oracle_lib" not in text, f
+
+
+def test_device_entry_points_bind_and_fail_loudly_without_a_device(tmp_path):
+    """Every wrapper that needs device state reaches the library with a well-formed call (no
+    ctypes TypeError) and, on a geometry-only handle, fails with UFO_B200_E_CUDA instead of
+    falling back to anything."""
+    import numpy as np
+    from ufomap_b200 import capi
+    m = capi.Map(0.1, device=-2)
+    box = (np.zeros(3), np.ones(3))
+    pts = np.ones((4, 3))
+    rec = np.zeros((4, 16), np.uint8)
+    calls = [
+        lambda: m.insert([0, 0, 0], pts),
+        lambda: m.insert_frame([0, 0, 0], pts, capi.pose_from_rpy(0, 0, 0, 0, 0, 0)),
+        lambda: m.insert_pointcloud2([0, 0, 0], rec, 16),
+        lambda: m.write(), lambda: m.write(box=box, min_depth=2, expanded=True),
+        lambda: m.write_file(str(tmp_path / "x.ufo")), lambda: m.write_file(str(tmp_path / "y.ufo"), box=box),
+        lambda: m.write_data(box, 1), lambda: m.set_value_volume(box, 0.2, 0),
+        lambda: m.clear_resize(0.2, 12), lambda: m.clear(), lambda: m.value_field(),
+        lambda: m.query(np.zeros(1, np.uint64), 0), lambda: m.stats(), lambda: m.wait(),
+    ]
+    for i, call in enumerate(calls):
+        with pytest.raises(capi.UfoError) as e:
+            call()
+        assert e.value.status == capi.E_CUDA, i
+    m.close()

@@ -112,3 +112,35 @@ def test_partial_and_truncated_stream(name):
             for c in cpus:
                 assert got == c.write_data(box, md), (type(c).__name__, box, md, len(got))
     gpu.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="reference harness not built")
+def test_region_file_and_reset(tmp_path):
+    """save_map (Octree::write(filename, bounding volume, compress, depth), server.cpp:381-392) and
+    reset (Octree::clear(resolution, depth_levels), server.cpp:364-378)."""
+    kw, inserts, color = _scenario("velodyne")
+    gpu = Map(color=color, initial_blocks=1 << 12, **kw)
+    ref = RefMap(color=color, **kw)
+    for ins in inserts:
+        gpu.insert(**ins)
+        ref.insert(**ins)
+    mn, mx = ref.change_bbox()
+    mid = (mn + mx) / 2
+    for box, md in [((mn, mid), 0), ((mid - 1.0, mid + 2.0), 3), (None, 2),
+                    ((np.array([1e4, 1e4, 1e4]), np.array([2e4, 2e4, 2e4])), 0)]:
+        expect = ref.write_region(box, md)
+        assert gpu.write(box=box, min_depth=md) == expect, (box, md)
+        path = tmp_path / "region.ufo"
+        gpu.write_file(str(path), box=box, min_depth=md)
+        assert path.read_bytes() == expect
+    # reset to another geometry, then map again
+    gpu.clear_resize(0.1, 14)
+    ref.clear(0.1, 14)
+    assert gpu.write() == ref.write()
+    for ins in inserts[:2]:
+        gpu.insert(**ins)
+        ref.insert(**ins)
+    assert gpu.write() == ref.write()
+    a, b = gpu.value_field(), ref.value_field()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    gpu.close()

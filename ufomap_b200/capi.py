@@ -58,7 +58,7 @@ SYMBOLS = [
     "ufo_b200_set_profiling", "ufo_b200_clear", "ufo_b200_version", "ufo_b200_set_shard",
     "ufo_b200_insert_pointcloud_frame", "ufo_b200_transform_points", "ufo_b200_pose_from_rpy",
     "ufo_b200_insert_pointcloud2", "ufo_b200_write", "ufo_b200_write_file",
-    "ufo_b200_write_data", "ufo_b200_set_value_volume",
+    "ufo_b200_write_data", "ufo_b200_set_value_volume", "ufo_b200_clear_resize",
 ]
 
 class Cloud2(C.Structure):
@@ -96,8 +96,9 @@ def load():
     lib.ufo_b200_insert_pointcloud_frame.argtypes = [vp, vp, vp, sz, i32, vp, dbl, u32, i32, u32, i32,
                                                      i32]
     lib.ufo_b200_insert_pointcloud2.argtypes = [vp, vp, C.POINTER(Cloud2), vp, dbl, u32, i32, u32, i32, i32]
-    lib.ufo_b200_write.argtypes = [vp, vp, sz, C.POINTER(sz), i32]
-    lib.ufo_b200_write_file.argtypes = [vp, C.c_char_p, i32]
+    lib.ufo_b200_write.argtypes = [vp, vp, u32, i32, vp, sz, C.POINTER(sz)]
+    lib.ufo_b200_write_file.argtypes = [vp, C.c_char_p, vp, u32, i32]
+    lib.ufo_b200_clear_resize.argtypes = [vp, dbl, u32]
     lib.ufo_b200_set_value_volume.argtypes = [vp, vp, dbl, u32]
     lib.ufo_b200_write_data.argtypes = [vp, vp, u32, vp, sz, C.POINTER(sz)]
     lib.ufo_b200_transform_points.argtypes = [vp, vp, sz, i32, vp]
@@ -270,30 +271,47 @@ class Map:
         self._check(self.lib.ufo_b200_set_shard(self.h, int(rank), int(world)))
 
     # -- file / wire format -------------------------------------------------
-    def write(self, expanded=False):
+    @staticmethod
+    def _box6(box):
+        """(min xyz, max xyz) -> the AABB's centre / half size, like its (min, max) constructor."""
+        if box is None:
+            return None
+        mn, mx = np.asarray(box[0], np.float64), np.asarray(box[1], np.float64)
+        half = (mx - mn) / 2.0
+        return np.ascontiguousarray(np.concatenate([mn + half, half]), np.float64)
+
+    def write(self, expanded=False, box=None, min_depth=0):
         """The map as a UFOMap file image (bytes), Octree::write with compress=False."""
+        b = self._box6(box)
+        bp = None if b is None else b.ctypes.data
         n = C.c_size_t()
-        self._check(self.lib.ufo_b200_write(self.h, None, 0, C.byref(n), int(expanded)))
+        self._check(self.lib.ufo_b200_write(self.h, bp, int(min_depth), int(expanded), None, 0, C.byref(n)))
         buf = np.empty(n.value, np.uint8)
-        self._check(self.lib.ufo_b200_write(self.h, buf.ctypes.data, n.value, C.byref(n), int(expanded)))
+        self._check(self.lib.ufo_b200_write(self.h, bp, int(min_depth), int(expanded), buf.ctypes.data, n.value,
+                                            C.byref(n)))
         assert n.value == len(buf)
         return buf.tobytes()
 
+    def write_file(self, filename, expanded=False, box=None, min_depth=0):
+        b = self._box6(box)
+        self._check(self.lib.ufo_b200_write_file(self.h, os.fsencode(filename),
+                                                 None if b is None else b.ctypes.data, int(min_depth),
+                                                 int(expanded)))
+
+    def clear_resize(self, resolution, depth_levels):
+        """Octree::clear(resolution, depth_levels)."""
+        self._check(self.lib.ufo_b200_clear_resize(self.h, float(resolution), int(depth_levels)))
+        self.resolution, self.depth_levels = resolution, depth_levels
+
     def set_value_volume(self, box, occupancy, min_depth=0):
         """setValueVolume(AABB(min, max), occupancy probability, min_depth); box = (min xyz, max xyz)."""
-        mn, mx = np.asarray(box[0], np.float64), np.asarray(box[1], np.float64)
-        half = (mx - mn) / 2.0
-        b = np.ascontiguousarray(np.concatenate([mn + half, half]), np.float64)
+        b = self._box6(box)
         self._check(self.lib.ufo_b200_set_value_volume(self.h, b.ctypes.data, float(occupancy), int(min_depth)))
 
     def write_data(self, box=None, min_depth=0):
         """Octree::writeData(stream, AABB(min, max) or whole map, False, min_depth): node stream.
         box = (min xyz, max xyz); converted to the AABB's centre / half size like its constructor."""
-        b = None
-        if box is not None:
-            mn, mx = np.asarray(box[0], np.float64), np.asarray(box[1], np.float64)
-            half = (mx - mn) / 2.0
-            b = np.ascontiguousarray(np.concatenate([mn + half, half]), np.float64)
+        b = self._box6(box)
         bp = None if b is None else b.ctypes.data
         n = C.c_size_t()
         self._check(self.lib.ufo_b200_write_data(self.h, bp, int(min_depth), None, 0, C.byref(n)))
@@ -301,9 +319,6 @@ class Map:
         self._check(self.lib.ufo_b200_write_data(self.h, bp, int(min_depth), buf.ctypes.data, n.value,
                                                  C.byref(n)))
         return buf[:n.value].tobytes()
-
-    def write_file(self, filename, expanded=False):
-        self._check(self.lib.ufo_b200_write_file(self.h, os.fsencode(filename), int(expanded)))
 
     # -- state ----------------------------------------------------------------
     def value_field(self):

@@ -1350,12 +1350,23 @@ int export_image(Map* m, int pruned, uint32_t min_depth, const double* box6, boo
 	}
 	*total = 0;
 	const double c0[3] = {0.0, 0.0, 0.0};
+	auto header = [&](char* head, size_t cap, unsigned long long data_size) {
+		// octree.h:850-860; doubles print with the default ostream precision = %g
+		return snprintf(head, cap,
+		                "# UFOMap file\n# (feel free to add / change comments, but leave the first line as it "
+		                "is!)\n#\nversion 1.0.0\nid %s\nresolution %g\ndepth_levels %u\ncompressed 0\n"
+		                "uncompressed_data_size %d\ndata\n",
+		                color ? "occupancy_map_color" : "occupancy_map", m->M.g.resolution, plan.levels, (int)data_size);
+	};
 	if (!box_hits(plan.box, c0, plan.g->half_size[plan.levels])) {
+		// "No node intersects": the reference writes no node data at all (OMB:1462-1468)
 		if (with_header) {
-			m->set_error("the export box misses the map");
-			return UFO_B200_E_INVALID;
+			char head[512];
+			const int hl = header(head, sizeof head, 0);
+			sink(head, (size_t)hl);
+			*total = (unsigned long long)hl;
 		}
-		return UFO_B200_OK;  // "No node intersects": the reference writes nothing
+		return UFO_B200_OK;
 	}
 	plan.info.resize(nb);
 	std::vector<unsigned long long> keys(nb);
@@ -1427,14 +1438,8 @@ int export_image(Map* m, int pruned, uint32_t min_depth, const double* box6, boo
 			produced += len;
 		};
 		if (with_header) {
-			// octree.h:850-860; doubles print with the default ostream precision = %g
 			char head[512];
-			const int hl = snprintf(head, sizeof head,
-			                        "# UFOMap file\n# (feel free to add / change comments, but leave the first line as it "
-			                        "is!)\n#\nversion 1.0.0\nid %s\nresolution %g\ndepth_levels %u\ncompressed 0\n"
-			                        "uncompressed_data_size %d\ndata\n",
-			                        color ? "occupancy_map_color" : "occupancy_map", m->M.g.resolution, plan.levels,
-			                        (int)data_size);
+			const int hl = header(head, sizeof head, data_size);
 			counted(head, (size_t)hl);
 		}
 		const uint8_t children = root_has ? 0xff : 0x00;
@@ -1519,14 +1524,15 @@ int ufo_b200_set_value_volume(ufo_b200_map* m, const double box6[6], double occu
 	});
 }
 
-int ufo_b200_write(ufo_b200_map* m, void* buf, size_t cap, size_t* size, int expanded)
+int ufo_b200_write(ufo_b200_map* m, const double* box6, uint32_t min_depth, int expanded, void* buf, size_t cap,
+                   size_t* size)
 {
 	if (!m || !size) return UFO_B200_E_INVALID;
 	return guarded(m, [&]() {
 		uint8_t* out = static_cast<uint8_t*>(buf);
 		size_t at = 0;
 		unsigned long long total = 0;
-		int rc = export_image(m, expanded ? 0 : 1, 0, nullptr, true, [&](const void* p, size_t len) {
+		int rc = export_image(m, expanded ? 0 : 1, min_depth, box6, true, [&](const void* p, size_t len) {
 			if (out && at + len <= cap) std::memcpy(out + at, p, len);
 			at += len;
 		}, &total);
@@ -1552,7 +1558,8 @@ int ufo_b200_write_data(ufo_b200_map* m, const double* box6, uint32_t min_depth,
 	});
 }
 
-int ufo_b200_write_file(ufo_b200_map* m, const char* filename, int expanded)
+int ufo_b200_write_file(ufo_b200_map* m, const char* filename, const double* box6, uint32_t min_depth,
+                        int expanded)
 {
 	if (!m || !filename) return UFO_B200_E_INVALID;
 	return guarded(m, [&]() {
@@ -1563,7 +1570,7 @@ int ufo_b200_write_file(ufo_b200_map* m, const char* filename, int expanded)
 		}
 		unsigned long long total = 0;
 		bool ok = true;
-		int rc = export_image(m, expanded ? 0 : 1, 0, nullptr, true,
+		int rc = export_image(m, expanded ? 0 : 1, min_depth, box6, true,
 		                      [&](const void* p, size_t len) { ok = ok && fwrite(p, 1, len, f) == len; }, &total);
 		ok = fclose(f) == 0 && ok;
 		if (rc == UFO_B200_OK && !ok) {
@@ -1685,6 +1692,22 @@ int ufo_b200_clear(ufo_b200_map* m)
 		M.scan_id = 0;
 		reset_bbox(m);
 		CK(cudaStreamSynchronize(s));
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_clear_resize(ufo_b200_map* m, double resolution, uint32_t depth_levels)
+{
+	if (!m) return UFO_B200_E_INVALID;
+	if (depth_levels < 2 || depth_levels > 21 || !(resolution > 0)) return UFO_B200_E_INVALID;  // octree.h:931-935
+	int rc = ufo_b200_clear(m);
+	if (rc != UFO_B200_OK) return rc;
+	return guarded(m, [&]() {
+		m->params.resolution = resolution;
+		m->params.depth_levels = depth_levels;
+		m->M.g = make_geometry(resolution, depth_levels);
+		refresh_model(m);
+		reset_bbox(m);
 		return (int)UFO_B200_OK;
 	});
 }
