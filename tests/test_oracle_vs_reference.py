@@ -197,3 +197,28 @@ def test_partial_and_truncated_stream(color):
     for box in boxes:
         for md in (0, 1, 2, 3, 4, 5, 7, 16):
             assert ref.write_data(box, md) == orc.write_data(box, md), (box, md)
+
+
+@pytest.mark.parametrize("color", [False, True])
+@pytest.mark.parametrize("pruning", [True, False])
+def test_set_value_volume(color, pruning):
+    """setValueVolume(AABB, p, min_depth) interleaved with scans: the oracle's tree stays
+    node-for-node equal to the reference's (compared through the file image)."""
+    kw = dict(resolution=0.05, automatic_pruning=pruning)
+    ref, orc = RefMap(color=color, **kw), OracleMap(color=color, **kw)
+    rng = np.random.default_rng(2)
+    for k in range(2):
+        o, p, c = scans.rgbd(k=k, width=48, height=36)
+        for m in (ref, orc):
+            m.insert(origin=o, xyz=p, rgb=c if color else None, max_range=3.0, discrete=True)
+        for t in range(3):
+            lo = rng.uniform(-0.5, 2, 3)
+            hi = lo + rng.uniform(0.05, 0.8, 3)
+            md, val = [0, 1, 2, 3, 4, 0][3 * k + t], [0.1192, 0.7, 0.5, 0.1192, 0.99, 0.3][3 * k + t]
+            for m in (ref, orc):
+                m.set_value_volume((lo, hi), val, md)
+            assert ref.write() == orc.write(), (k, t, md)
+    o, p, c = scans.rgbd(k=3, width=48, height=36)
+    for m in (ref, orc):
+        m.insert(origin=o, xyz=p, rgb=c if color else None, max_range=3.0, discrete=True)
+    assert ref.write() == orc.write()
