@@ -493,6 +493,23 @@ void ufo_ref_clear(void* h, double resolution, unsigned depth_levels)
 	withMap(m, [&](auto& map) { map.clear(resolution, depth_levels); });
 }
 
+// Octree::readData(stream, bounding_volume, resolution, depth_levels) (octree.h:735-774): merge a
+// node stream (a UFOMap message, msgToUfo ufomap_msgs/conversions.h:122-134) into the map.
+int ufo_ref_read_data(void* h, const double* box6, const uint8_t* buf, size_t size)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	std::stringstream ss(std::string(reinterpret_cast<const char*>(buf), size),
+	                     std::ios_base::in | std::ios_base::out | std::ios_base::binary);
+	ufo::geometry::BoundingVolume bv;
+	if (box6) {
+		bv.add(ufo::geometry::AABB(ufo::geometry::Point(box6[0], box6[1], box6[2]),
+		                           ufo::geometry::Point(box6[3], box6[4], box6[5])));
+	}
+	return withMap(m, [&](auto& map) {
+		return map.readData(ss, bv, map.getResolution(), map.getTreeDepthLevels());
+	}) ? 1 : 0;
+}
+
 // Octree::read(std::istream&) (octree.h:699-733): replaces the map's content.  1 = ok.
 int ufo_ref_read(void* h, const uint8_t* buf, size_t size)
 {

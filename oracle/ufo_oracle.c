@@ -1354,3 +1354,88 @@ void ufo_oracle_set_value_volume(void* h, const double* box6, double occupancy, 
 	}
 	if (set_volume_rec(m, &bx, value, &m->root, c0, m->levels, min_depth)) update_node(m, &m->root, m->levels);
 }
+
+/* ---- readData(stream, bounding volume): readNodes / readNodesRecurs OMB:1379-1455 -- merges a
+ * node stream (whole map or the part inside the box it was written with) into the tree. */
+typedef struct {
+	const uint8_t* p;
+	size_t n, at;
+} rbuf;
+
+static void rb_get(rbuf* r, void* dst, size_t len)
+{
+	if (r->at + len <= r->n) memcpy(dst, r->p + r->at, len);
+	else memset(dst, 0, len);
+	r->at += len;
+}
+
+static void rb_payload(const omap* m, rbuf* r, node* n)
+{
+	rb_get(r, &n->occ, 4);
+	if (m->color) rb_get(r, n->rgb, 3);
+}
+
+static void read_rec(omap* m, rbuf* r, node* n, unsigned depth, const double c[3], const wbox* bx)
+{
+	const unsigned cd = depth - 1;
+	const double chs = m->half[cd];
+	uint8_t children = 0;
+	rb_get(r, &children, 1);
+	double cc[8][3];
+	int hit[8];
+	for (unsigned i = 0; i < 8; ++i) {
+		child_center(c, chs, i, cc[i]);
+		hit[i] = box_hits(bx, cc[i], chs);
+	}
+	create_children(m, n);
+	for (unsigned i = 0; i < 8; ++i) {
+		if (!hit[i]) continue;
+		node* ch = &n->ch[i];
+		if ((children >> i) & 1u) {
+			if (1 == cd) {
+				const double ghs = m->half[0];
+				create_children(m, ch);
+				for (unsigned j = 0; j < 8; ++j) {
+					double gc[3];
+					child_center(cc[i], ghs, j, gc);
+					if (box_hits(bx, gc, ghs)) rb_payload(m, r, &ch->ch[j]);
+				}
+				update_node(m, ch, cd);
+			} else {
+				read_rec(m, r, ch, cd, cc[i], bx);
+			}
+		} else {
+			delete_children(m, ch, cd);
+			rb_payload(m, r, ch);
+			update_node(m, ch, cd);
+		}
+	}
+	update_node(m, n, depth);
+}
+
+int ufo_oracle_read_data(void* h, const double* box6, const uint8_t* buf, size_t size)
+{
+	omap* m = (omap*)h;
+	wbox bx = {0, {0, 0, 0}, {0, 0, 0}};
+	if (box6) {
+		bx.on = 1;
+		for (int k = 0; k < 3; ++k) {
+			const double hs = (box6[3 + k] - box6[k]) / 2.0, ct = box6[k] + hs;
+			bx.lo[k] = ct - hs;
+			bx.hi[k] = ct + hs;
+		}
+	}
+	const double c0[3] = {0.0, 0.0, 0.0};
+	if (!box_hits(&bx, c0, m->half[m->levels])) return 1;
+	rbuf r = {buf, size, 0};
+	uint8_t children = 0;
+	rb_get(&r, &children, 1);
+	if (0 == children) {
+		delete_children(m, &m->root, m->levels);
+		rb_payload(m, &r, &m->root);
+		update_node(m, &m->root, m->levels);
+		return 1;
+	}
+	read_rec(m, &r, &m->root, m->levels, c0, &bx);
+	return r.at <= r.n;
+}

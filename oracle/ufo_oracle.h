@@ -71,6 +71,9 @@ size_t ufo_oracle_write_data(void* h, const double* box6, unsigned min_depth, ui
 /* setValueVolume(AABB(min, max), occupancy probability, min_depth) */
 void ufo_oracle_set_value_volume(void* h, const double* box6, double occupancy, unsigned min_depth);
 
+/* Octree::readData(stream, AABB or none): merge a node stream into the map; 1 = ok */
+int ufo_oracle_read_data(void* h, const double* box6, const uint8_t* buf, size_t size);
+
 #ifdef __cplusplus
 }
 #endif

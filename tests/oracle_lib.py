@@ -77,6 +77,7 @@ def _load(path, prefix):
         sensor_model=sig("sensor_model", None, [vp, vp]),
         memory_usage=sig("memory_usage", sz, [vp]),
         set_value_volume=sig("set_value_volume", None, [vp, vp, dbl, u32]),
+        read_data=sig("read_data", i32, [vp, vp, vp, sz]),
         write=sig("write", sz, [vp, vp, sz]),
         write_data=sig("write_data", sz, [vp, vp, u32, vp, sz]),
         transform=sig("transform", None, [vp, vp, sz, vp]),
@@ -241,6 +242,13 @@ class _CpuMap:
 
     def memory_usage(self):
         return int(self.api["memory_usage"](self.h))
+
+    def read_data(self, data, box=None):
+        """Octree::readData(stream, AABB(min, max) or none): merge a node stream into the map."""
+        b = None if box is None else np.ascontiguousarray(np.concatenate([box[0], box[1]]), np.float64)
+        buf = np.frombuffer(data, np.uint8)
+        return bool(self.api["read_data"](self.h, None if b is None else b.ctypes.data,
+                                          buf.ctypes.data if len(buf) else None, len(buf)))
 
     def set_value_volume(self, box, occupancy, min_depth=0):
         """setValueVolume(AABB(min, max), occupancy probability, min_depth)."""

@@ -222,3 +222,25 @@ def test_set_value_volume(color, pruning):
     for m in (ref, orc):
         m.insert(origin=o, xyz=p, rgb=c if color else None, max_range=3.0, discrete=True)
     assert ref.write() == orc.write()
+
+
+@pytest.mark.parametrize("color", [False, True])
+def test_read_data_merges_streams(color):
+    """Octree::readData (msgToUfo): whole-map and change-box streams written by one map are merged
+    into another, differently filled map; oracle restatement == reference, byte for byte."""
+    kw = dict(resolution=0.05)
+    src = RefMap(color=color, **kw)
+    dst_r, dst_o = RefMap(color=color, **kw), OracleMap(color=color, **kw)
+    for k in range(2):
+        o, p, c = scans.rgbd(k=k, width=48, height=36)
+        src.insert(origin=o, xyz=p, rgb=c if color else None, max_range=3.0, discrete=True)
+    o, p, c = scans.rgbd(k=5, width=32, height=24)
+    for m in (dst_r, dst_o):
+        m.insert(origin=o, xyz=p, rgb=c if color else None, max_range=2.0, discrete=True)
+    mn, mx = src.change_bbox()
+    mid = (mn + mx) / 2
+    for box in [(mid - 0.4, mid + 0.3), (mn, mid), None]:
+        data = src.write_data(box, 0)
+        assert dst_r.read_data(data, box) and dst_o.read_data(data, box)
+        assert dst_r.write() == dst_o.write(), box
+    assert dst_r.write() == src.write()     # after the whole-map stream the copy is complete
