@@ -244,3 +244,44 @@ def test_read_data_merges_streams(color):
         assert dst_r.read_data(data, box) and dst_o.read_data(data, box)
         assert dst_r.write() == dst_o.write(), box
     assert dst_r.write() == src.write()     # after the whole-map stream the copy is complete
+
+
+def test_randomised_differential():
+    """Seeded random configurations -- resolution, tree depth, sensor model, map type, insert mode,
+    depth, ray casting, early stopping, max range, pruning -- each a short sequence of scans (and a
+    volume set); after every step the oracle's tree must equal the reference's byte for byte."""
+    rng = np.random.default_rng(20260923)
+    for case in range(64):
+        res = float(rng.choice([0.05, 0.08, 0.1, 0.2, 0.25]))
+        levels = int(rng.choice([10, 12, 16]))
+        color = bool(rng.integers(0, 2))
+        model = dict(prob_hit=float(rng.choice([0.7, 0.85, 0.6])), prob_miss=float(rng.choice([0.4, 0.3, 0.45])),
+                     clamping_thres_min=float(rng.choice([0.1192, 0.05])),
+                     clamping_thres_max=float(rng.choice([0.971, 0.9])),
+                     occupied_thres=float(rng.choice([0.5, 0.6])), free_thres=float(rng.choice([0.5, 0.4])))
+        kw = dict(resolution=res, depth_levels=levels, automatic_pruning=bool(rng.integers(0, 2)), **model)
+        ref, orc = RefMap(color=color, **kw), OracleMap(color=color, **kw)
+        for step in range(3):
+            n = int(rng.integers(1, 400))
+            o = rng.uniform(-1, 1, 3)
+            d = rng.normal(size=(n, 3))
+            d /= np.linalg.norm(d, axis=1, keepdims=True)
+            p = (o + d * rng.uniform(0.3, 40 * res, (n, 1))).astype(np.float32).astype(np.float64)
+            c = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+            discrete = bool(rng.integers(0, 2)) or color     # colour + non-discrete is uninstantiable (G5)
+            ins = dict(origin=o, xyz=p, rgb=c if color else None, discrete=discrete,
+                       max_range=float(rng.choice([-1.0, 12 * res, 25 * res])),
+                       depth=int(rng.choice([0, 0, 1, 2, 3])), simple=bool(rng.integers(0, 4) == 0),
+                       early_stopping=int(rng.choice([0, 0, 2])))
+            ref.insert(**ins)
+            orc.insert(**ins)
+            assert ref.write() == orc.write(), (case, step, ins["depth"], ins["simple"], discrete)
+            if step == 1:
+                lo = o + rng.uniform(-1, 1, 3)
+                box = (lo, lo + rng.uniform(res, 20 * res, 3))
+                md = int(rng.choice([0, 1, 2]))
+                ref.set_value_volume(box, 0.2, md)
+                orc.set_value_volume(box, 0.2, md)
+                assert ref.write() == orc.write(), (case, "volume", md)
+        assert np.array_equal(ref.change_bbox()[0], orc.change_bbox()[0])
+        assert np.array_equal(ref.change_bbox()[1], orc.change_bbox()[1])
