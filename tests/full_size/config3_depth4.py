@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""BASELINE config #3 (OccupancyMapColor 2 mm, 640x480 RGB-D, 5 m, insertPointCloudDiscrete) at
+"""Full-size parity + timing script (test infrastructure: it loads the reference harness under oracle/).
+BASELINE config #3 (OccupancyMapColor 2 mm, 640x480 RGB-D, 5 m, insertPointCloudDiscrete) at
 insert_depth 4 -- the setting at which the reference's CPU path can run this config at all
 (depth 0 exceeds 62 GB of host RAM).  Times the CUDA path and the unmodified
 reference on the same full-size scans and compares the occupancy of sampled voxels bit for bit.
-usage (on the GPU box): python tools/config3_depth4.py [--scans 3] [--samples 200000]"""
+usage (on the GPU box): python tests/full_size/config3_depth4.py [--scans 3] [--samples 200000]"""
 import argparse
 import os
 import sys
@@ -11,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle_lib import RefMap, have_ref  # noqa: E402
