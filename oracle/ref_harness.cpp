@@ -76,6 +76,16 @@ class Probe : public MAP
 		walkRec(this->getRoot(), this->getTreeDepthLevels(), 0, out, leaves);
 	}
 
+	// Value field in code order: every depth-0 voxel whose payload is not the default
+	// (0.0, black), collapsed / never-split nodes expanded.  Pre-order over the children in
+	// index order is ascending Morton order, so the output is sorted.  Pass null arrays to count.
+	size_t field(uint64_t* codes, float* occ, uint8_t* rgb, size_t cap) const
+	{
+		size_t n = 0;
+		fieldRec(this->getRoot(), this->getTreeDepthLevels(), 0, codes, occ, rgb, cap, n);
+		return n;
+	}
+
 	// getNodePath semantics (octree.h:957-972): deepest existing node on the
 	// path to `code`.
 	bool nodeAt(uint64_t code, unsigned depth, NodeRec& rec)
@@ -124,6 +134,45 @@ class Probe : public MAP
 	}
 
  private:
+	static void emit(uint64_t code, unsigned depth, float o, uint8_t const* c, uint64_t* codes, float* occ,
+	                 uint8_t* rgb, size_t cap, size_t& n)
+	{
+		if (o == 0.0f && !(c[0] | c[1] | c[2])) return;
+		const uint64_t count = uint64_t(1) << (3 * depth);
+		if (codes && n + count <= cap) {
+			for (uint64_t i = 0; i < count; ++i) {
+				codes[n + i] = code + i;
+				occ[n + i] = o;
+				if (rgb) std::memcpy(rgb + 3 * (n + i), c, 3);
+			}
+		}
+		n += count;
+	}
+
+	template <class NODE>
+	void fieldRec(NODE const& node, unsigned depth, uint64_t code, uint64_t* codes, float* occ, uint8_t* rgb,
+	              size_t cap, size_t& n) const
+	{
+		if (node.is_leaf) {
+			uint8_t c[3];
+			colorOf(node.value, c);
+			emit(code, depth, node.value.occupancy, c, codes, occ, rgb, cap, n);
+			return;
+		}
+		unsigned cd = depth - 1;
+		for (unsigned i = 0; i < 8; ++i) {
+			uint64_t ccode = code + (uint64_t(i) << (3 * cd));
+			if (0 == cd) {
+				auto const& leaf = MAP::getLeafChild(node, i);
+				uint8_t c[3];
+				colorOf(leaf.value, c);
+				emit(ccode, 0, leaf.value.occupancy, c, codes, occ, rgb, cap, n);
+			} else {
+				fieldRec(MAP::getInnerChild(node, i), cd, ccode, codes, occ, rgb, cap, n);
+			}
+		}
+	}
+
 	template <class NODE>
 	void walkRec(NODE const& node, unsigned depth, uint64_t code, std::vector<NodeRec>& out,
 	             bool leaves) const
@@ -295,6 +344,30 @@ void ufo_ref_walk_fetch(void* h, uint64_t* codes, uint32_t* depths, float* occ, 
 	}
 	m->scratch.clear();
 	m->scratch.shrink_to_fit();
+}
+
+// Sorted, expanded value field (see Probe::field); null arrays: count only.
+size_t ufo_ref_field(void* h, uint64_t* codes, float* occ, uint8_t* rgb, size_t cap)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	return withMap(m, [&](auto& map) { return map.field(codes, occ, rgb, cap); });
+}
+
+// Batched ufo_ref_node: deepest existing node on the path to every (code, depth).
+void ufo_ref_node_batch(void* h, const uint64_t* codes, const uint32_t* depths, size_t n, float* occ,
+                        uint8_t* rgb, uint8_t* flags, uint32_t* found_depth)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	withMap(m, [&](auto& map) {
+		for (size_t i = 0; i < n; ++i) {
+			NodeRec r;
+			map.nodeAt(codes[i], depths[i], r);
+			occ[i] = r.occ;
+			if (rgb) std::memcpy(rgb + 3 * i, r.rgb, 3);
+			if (flags) flags[i] = r.flags;
+			if (found_depth) found_depth[i] = r.depth;
+		}
+	});
 }
 
 // Returns 1 if a node exists at exactly (code, depth); out describes the deepest

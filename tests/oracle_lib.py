@@ -87,6 +87,8 @@ def _load(path, prefix):
         api["read"] = sig("read", i32, [vp, vp, sz])
         api["write_region"] = sig("write_region", sz, [vp, vp, u32, vp, sz])
         api["clear"] = sig("clear", None, [vp, dbl, u32])
+        api["field"] = sig("field", sz, [vp, vp, vp, vp, sz])
+        api["node_batch"] = sig("node_batch", None, [vp, vp, vp, sz, vp, vp, vp, vp])
     if prefix == "ufo_oracle_":
         api["last_counters"] = sig("last_counters", None, [vp, vp])
         api["canonicalize"] = sig("canonicalize", None, [vp])
@@ -284,6 +286,36 @@ class RefMap(_CpuMap):
         buf = np.empty(n, np.uint8)
         assert self.api["write_region"](self.h, bp, int(min_depth), buf.ctypes.data, n) == n
         return buf.tobytes()
+
+    def value_field(self):
+        """Same result as _CpuMap.value_field, produced by the harness in one ordered tree walk
+        (no numpy expansion / sort: full-size maps hold ~10^8 voxels)."""
+        n = self.api["field"](self.h, None, None, None, 0)
+        codes = np.empty(n, np.uint64)
+        occ = np.empty(n, np.float32)
+        rgb = np.zeros((n, 3), np.uint8)
+        if n:
+            got = self.api["field"](self.h, codes.ctypes.data, occ.ctypes.data,
+                                    rgb.ctypes.data if self.color else None, n)
+            assert got == n
+        return codes, occ, rgb
+
+    def field_count(self):
+        """Number of non-default depth-0 voxels (collapsed nodes counted as 8^depth)."""
+        return int(self.api["field"](self.h, None, None, None, 0))
+
+    def node_batch(self, codes, depths=0):
+        """Deepest existing node on the path to each code: (occ f32, rgb u8[n,3], flags, depth found)."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        depths = np.ascontiguousarray(np.broadcast_to(depths, codes.shape), dtype=np.uint32)
+        n = len(codes)
+        occ = np.empty(n, np.float32)
+        rgb = np.zeros((n, 3), np.uint8)
+        flags = np.empty(n, np.uint8)
+        fd = np.empty(n, np.uint32)
+        self.api["node_batch"](self.h, codes.ctypes.data, depths.ctypes.data, n, occ.ctypes.data,
+                               rgb.ctypes.data, flags.ctypes.data, fd.ctypes.data)
+        return occ, rgb, flags, fd
 
     def clear(self, resolution, depth_levels):
         """Octree::clear(resolution, depth_levels)."""

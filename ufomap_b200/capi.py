@@ -321,8 +321,9 @@ class Map:
         return buf[:n.value].tobytes()
 
     # -- state ----------------------------------------------------------------
-    def value_field(self):
-        """(codes sorted, occ f32, rgb u8[n,3]): every voxel with a non-default payload."""
+    def value_field(self, sort=True):
+        """(codes sorted, occ f32, rgb u8[n,3]): every voxel with a non-default payload.
+        sort=False returns them in the device's emission order."""
         n = C.c_size_t()
         self._check(self.lib.ufo_b200_export_leaves(self.h, None, None, None, 0, C.byref(n)))
         cnt = n.value
@@ -334,8 +335,16 @@ class Map:
                 self.h, codes.ctypes.data, occ.ctypes.data, rgb.ctypes.data if self.color else None,
                 cnt, C.byref(n)))
             assert n.value == cnt
+        if not sort:
+            return codes, occ, rgb
         order = np.argsort(codes, kind="stable")
         return codes[order], occ[order], rgb[order]
+
+    def value_field_count(self):
+        """Number of voxels value_field() would return."""
+        n = C.c_size_t()
+        self._check(self.lib.ufo_b200_export_leaves(self.h, None, None, None, 0, C.byref(n)))
+        return int(n.value)
 
     def query(self, codes, depths):
         codes = np.ascontiguousarray(codes, dtype=np.uint64)
