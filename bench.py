@@ -1,22 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- points integrated per second on BASELINE.json configs[1]:
-OccupancyMap 2 cm, 131 072-point Velodyne-64-shaped synthetic scan stream,
-max_range 30 m (one "step" = insertPointCloud of one scan).
+"""bench.py -- points integrated per second on the BASELINE.json workloads (one "step" =
+insertPointCloud of one synthetic scan of the named shape).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4] [--impl reference]
 
-* value  : whole-job points/s with the scans already resident in HBM
-           (ufo_b200_insert_device), CUDA events on the map's stream, max over ranks.
-* e2e    : the same metric through the reference-facing C-ABI call with HOST (pinned)
-           buffers: H2D of the scan and D2H of the scan's result counters are inside
-           the timed region (ufo_b200_insert_pointcloud).
-* roofline: algorithmic bytes (SURVEY.md 8(d) formula on the live counters) over the
-           CUDA-event time of the device work of one insert, against the measured HBM peak.
-* cpu_baseline / --impl reference: the unmodified reference (oracle/_ref/libufo_ref.so)
-           on a bounded sample of the same workload on the host cores.
+Default = BASELINE configs[1] ("config 2": OccupancyMap 2 cm, 131 072-point Velodyne-64-shaped
+scan stream, max_range 30 m), the configuration the metric is quoted on; --config 3 (colour map,
+2 mm, 640x480 RGB-D, discrete insert) and --config 4 (5 cm, 100 m) time the other single-GPU
+configurations the same way.
 
-Multi-GPU (torchrun, one rank per GPU): weak scaling, one sensor stream + map per GPU
-(BASELINE configs[4] shape without the boundary merge); no data-path collective.
+* value  : whole-job points/s with the scans already resident in HBM (ufo_b200_insert_device,
+           async = 1), CUDA events on the map's stream, max over ranks.
+* e2e    : the same metric through the reference-facing C-ABI call with HOST (pinned) buffers,
+           the way the ROS server drives it (async = 1): every step copies its scan H2D and
+           reads back the result counters of a scan D2H inside the timed region; the copy of
+           scan k+1 overlaps the kernels of scan k.  e2e.sync is the fully serialised variant
+           (wait + read the scan's own counters after every insert).
+* sustained: the e2e loop kept running for >= 2 s over the same scans (clock record included).
+* roofline: algorithmic bytes (SURVEY.md 8(d) formula on the live device counters) over CUDA-event
+           time, against the measured HBM peak: for the dominant kernel and for the whole scan.
+* raycast: voxel visits/s and mark atomics/s of the fused walk against the measured L2 atomic
+           ceiling (tools/atomic_ceiling.cu -> profiles/r02_atomic_ceiling.jsonl).
+* cpu_baseline / --impl reference: the unmodified reference (oracle/_ref/libufo_ref.so) on a bounded
+           sample of the same workload on the host cores.
+
+Multi-GPU (torchrun, one rank per GPU): --mode sensors = one sensor stream + map per GPU (weak
+scaling, replicas); --mode shard = ONE scan stream, map sharded by brick ownership.
 """
 import argparse
 import json
@@ -31,10 +40,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-RESOLUTION = 0.02
-MAX_RANGE = 30.0
-RINGS, AZIMUTHS = 64, 2048
-WORKLOAD = "OccupancyMap 2 cm depth 16, 131072-pt Velodyne-64-shaped synthetic scan stream, max_range 30 m"
+CONFIGS = {
+    2: dict(resolution=0.02, max_range=30.0, color=False, discrete=False, kind="velodyne", bricks=1 << 19,
+            workload="OccupancyMap 2 cm depth 16, 131072-pt Velodyne-64-shaped synthetic scan stream, max_range 30 m"),
+    3: dict(resolution=0.002, max_range=5.0, color=True, discrete=True, kind="rgbd", bricks=1 << 20,
+            workload="OccupancyMapColor 2 mm depth 16, 307200-pt RGB-D-shaped synthetic scan stream, max_range 5 m, "
+                     "insertPointCloudDiscrete depth 0"),
+    4: dict(resolution=0.05, max_range=100.0, color=False, discrete=False, kind="velodyne", bricks=1 << 18,
+            workload="OccupancyMap 5 cm depth 16, 131072-pt Velodyne-64-shaped synthetic scan stream, max_range 100 m"),
+}
 
 
 def measured_peak():
@@ -47,10 +61,24 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def atomic_ceiling():
+    """L2-resident 64-bit reduction throughput measured by tools/atomic_ceiling.cu (G ops/s)."""
+    path = os.path.join(ROOT, "profiles", "r02_atomic_ceiling.jsonl")
+    best = {}
+    try:
+        for line in open(path):
+            d = json.loads(line)
+            if d["pattern"] == "red64_uniform":
+                best[d["footprint_mb"]] = d["gops_per_s"]
+        return {"l2_resident_gops": best.get(32.0), "at_128mb_gops": best.get(128.0), "source": "profiles/r02_atomic_ceiling.jsonl"}
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(st, color=False, p_in=12, part="scan"):
     """N*P_in + U*S_leaf + D1*8*S_leaf + sum_{l>=1} D_l*S_inner + sum_{l>=2} D_l*8*S_inner.
-    part="update" keeps the terms the leaf-update kernels (k_update_compact / k_update + k_brick_agg) are responsible
-    for: everything except the point input and the levels above the brick (depth >= 5)."""
+    part="update" keeps the terms the leaf-update kernel (k_update_compact) is responsible for:
+    everything except the point input and the levels above the brick (depth >= 5)."""
     s_leaf, s_inner = (8, 12) if color else (4, 8)
     n, u = st["points"], st["touched_voxels"]
     d1, d2, d3, d4, up = (st["touched_octets"], st["touched_blocks"], st["touched_d3"],
@@ -64,12 +92,13 @@ def algorithmic_bytes(st, color=False, p_in=12, part="scan"):
 
 def measured_traffic():
     """dram read+write bytes per launch of the dominant kernel from the committed ncu capture."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        d = json.load(open(path))
-        return float(d["traffic_bytes_per_launch"]), d["source"]
-    except Exception:
-        return None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return float(d["traffic_bytes_per_launch"]), d["source"]
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -77,16 +106,17 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_ms=100):
         self.path = "/tmp/ufo_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
         self.proc = None
         self.gpu = gpu_index
+        self.period = period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", str(self.period)],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -125,21 +155,30 @@ class ClockSampler:
         return out
 
 
-def make_scans(count, rank):
-    """Scans of this rank's sensor: float32 xyz, float64 origins."""
-    from ufomap_b200 import scans
+def make_scans(cfg, count, rank):
+    """Scans of this rank's sensor: (origins float64, packed clouds, layout, xyz float64 list, rgb list)."""
+    from ufomap_b200 import capi, scans
+    origins, packed, xyzs, rgbs = [], [], [], []
+    layout = capi.XYZ_F32
     base = scans.sensor_ring(rank, 8) if rank else None
-    origins, clouds = [], []
     for k in range(count):
-        if rank == 0:
-            o, p = scans.velodyne64(k=k, rings=RINGS, azimuths=AZIMUTHS)
+        rgb = None
+        if cfg["kind"] == "rgbd":
+            if rank == 0:
+                o, p, rgb = scans.rgbd(k=k)
+            else:
+                o, p, rgb = scans.rgbd(k=k, origin=np.array([0.0013 + 0.02 * k, 0.0021 + 0.01 * k + 0.5 * rank, 0.0007]))
+        elif rank == 0:
+            o, p = scans.velodyne64(k=k)
         else:
             o = base + np.array([0.25 * k, 0.10 * k, 0.0])
-            o, p = scans.velodyne64(k=k, rings=RINGS, azimuths=AZIMUTHS, origin=o,
-                                    seed=88172645463325252 + 7919 * rank)
+            o, p = scans.velodyne64(k=k, origin=o, seed=88172645463325252 + 7919 * rank)
+        buf, layout = capi.pack_points(p, rgb, np.float32)
         origins.append(o)
-        clouds.append(np.ascontiguousarray(p, dtype=np.float32))
-    return origins, clouds
+        packed.append(np.ascontiguousarray(buf))
+        xyzs.append(p)
+        rgbs.append(rgb)
+    return origins, packed, layout, xyzs, rgbs
 
 
 def max_over_ranks(value, world, device=None):
@@ -153,58 +192,69 @@ def max_over_ranks(value, world, device=None):
     return float(t.item())
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU insertPointCloud on the host cores,
-    each step a bounded sample (every `stride`-th point of scan k) of the same workload."""
-    if rank != 0:
-        return
+def _ref_class():
     import oracle_lib
     kind = "reference" if oracle_lib.have_ref() else "port"
-    cls = oracle_lib.RefMap if kind == "reference" else oracle_lib.OracleMap
     if kind == "port":
         oracle_lib.build_oracle()
-    stride = 64
+    return kind, (oracle_lib.RefMap if kind == "reference" else oracle_lib.OracleMap)
+
+
+def run_reference(args, cfg, rank, world):
+    """--impl reference: the reference's own CPU insertPointCloud on the host cores, each step a
+    bounded sample (every `stride`-th point of scan k) of the same workload.  The stride starts at
+    4 (config 3: 64, the reference cannot hold denser 2 mm scans in memory) and is doubled if the
+    projected run would exceed --ref-budget seconds."""
+    if rank != 0:
+        return
+    kind, cls = _ref_class()
+    stride = 64 if args.config == 3 else 4
     total = args.steps + args.warmup
-    origins, clouds = make_scans(total, 0)
-    m = cls(RESOLUTION)
-    times = []
+    origins, _, _, xyzs, rgbs = make_scans(cfg, total, 0)
+    m = cls(cfg["resolution"], color=cfg["color"])
+    times, strides, npts = [], [], []
+    t_start = time.time()
     for k in range(total):
-        pts = clouds[k][::stride].astype(np.float64)
-        secs = m.insert(origins[k], pts, max_range=MAX_RANGE)
+        elapsed = time.time() - t_start
+        if k >= 1 and elapsed / k * total > args.ref_budget and stride < 64:
+            stride *= 2
+        pts = xyzs[k][::stride]
+        rgb = rgbs[k][::stride] if rgbs[k] is not None else None
+        secs = m.insert(origins[k], pts, rgb=rgb, max_range=cfg["max_range"], discrete=cfg["discrete"])
         if k >= args.warmup:
             times.append(secs)
-    npts = len(clouds[0][::stride])
+            strides.append(stride)
+            npts.append(len(pts))
     t = float(np.sum(times))
-    value = npts * len(times) / t
+    value = float(np.sum(npts)) / t
+    sample = "every %s-th point of each scan (%d..%d pts/step)" % (
+        "/".join(str(s) for s in sorted(set(strides))), min(npts), max(npts))
     line = {
         "impl": "reference", "metric": "points_integrated_per_s", "value": value, "unit": "points/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 geometry + f32 log-odds", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": "every %d-th point of each scan (%d pts/step)" % (stride, npts)},
+        "config": {"workload": cfg["workload"], "sample": sample},
+        "same_config": False, "sample_stride": sorted(set(strides)),
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": 2, "kind": kind,
-                         "sample": "insertPointCloud of every %d-th point (%d pts) of scans %d..%d, one map, "
-                                   "async=false; the reference uses 1 caller + 1 hit thread of %d host cores"
-                                   % (stride, npts, args.warmup, total - 1, os.cpu_count() or 0)},
+                         "sample": "insertPointCloud of %s of scans %d..%d, one map, async=false; the reference uses "
+                                   "1 caller + 1 hit thread of %d host cores" % (sample, args.warmup, total - 1, os.cpu_count() or 0)},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample(origins, clouds):
+def cpu_baseline_sample(cfg, origins, xyzs, rgbs):
     """Bounded CPU sample for the main line: ~10-30 s of the reference on scan 0 and 1."""
-    import oracle_lib
-    kind = "reference" if oracle_lib.have_ref() else "port"
-    if kind == "port":
-        oracle_lib.build_oracle()
-    cls = oracle_lib.RefMap if kind == "reference" else oracle_lib.OracleMap
-    stride = 16
-    m = cls(RESOLUTION)
+    kind, cls = _ref_class()
+    stride = 64 if cfg["kind"] == "rgbd" else 16
+    m = cls(cfg["resolution"], color=cfg["color"])
     secs, npts = 0.0, 0
     for k in range(2):
-        pts = clouds[k][::stride].astype(np.float64)
-        t = m.insert(origins[k], pts, max_range=MAX_RANGE)
+        pts = xyzs[k][::stride]
+        rgb = rgbs[k][::stride] if rgbs[k] is not None else None
+        t = m.insert(origins[k], pts, rgb=rgb, max_range=cfg["max_range"], discrete=cfg["discrete"])
         if k >= 1:  # scan 0 warms allocator and hash tables (BASELINE.md section 4)
             secs += t
             npts += len(pts)
@@ -220,20 +270,24 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained e2e loop (0: skip)")
+    ap.add_argument("--ref-budget", type=float, default=1200.0, help="--impl reference: wall-clock budget in seconds")
     ap.add_argument("--mode", default="sensors", choices=["sensors", "shard"],
                     help="N>1: 'sensors' = one sensor stream + map per GPU (weak scaling, default); "
                          "'shard' = ONE scan stream, broadcast over NCCL, map sharded by brick ownership "
                          "(strong scaling, SURVEY.md 8(e) variant 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    cfg = CONFIGS[args.config]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, cfg, rank, world)
         return
 
     import torch
@@ -248,9 +302,11 @@ def main():
 
     total = args.steps + args.warmup
     shard = args.mode == "shard" and world > 1
-    origins, clouds = make_scans(total, 0 if shard else rank)
-    n_pts = clouds[0].shape[0]
+    origins, packed, layout, xyzs, rgbs = make_scans(cfg, total, 0 if shard else rank)
+    n_pts = packed[0].shape[0]
+    p_in = packed[0].nbytes // n_pts
     stream = torch.cuda.current_stream(dev)
+    ins_kw = dict(max_range=cfg["max_range"], discrete=cfg["discrete"])
 
     def barrier():
         if world > 1:
@@ -258,15 +314,14 @@ def main():
         torch.cuda.synchronize(dev)
 
     def fresh_map():
-        m = capi.Map(RESOLUTION, device=local_rank, initial_bricks=1 << 19)
+        m = capi.Map(cfg["resolution"], color=cfg["color"], device=local_rank, initial_bricks=cfg["bricks"])
         m.set_stream(stream.cuda_stream)
         if shard:
             m.set_shard(rank, world)
         return m
 
-    def timed_loop(m, feed):
-        for k in range(args.warmup):
-            feed(m, k)
+    def timed_loop(m, feed, first, count, sync_each=False):
+        """`count` steps starting at scan index `first`; returns (ms, per-scan stats, launches, clocks)."""
         m.wait()
         barrier()
         sampler = ClockSampler(local_rank)
@@ -274,79 +329,113 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         per_scan, launches = [], 0
         e0.record(stream)
-        for k in range(args.warmup, total):
-            feed(m, k)
-            st = m.stats()  # D2H of the scan's counters (the step's result)
-            per_scan.append(st)
-            launches += st["launches"]
+        for k in range(first, first + count):
+            feed(m, k % total)
+            # D2H of a scan's counters (the step's result): of this scan (sync_each) or, pipelined,
+            # of the previous one while this one runs
+            st = m.stats() if sync_each else m.completed_stats()
+            if st["points"]:
+                per_scan.append(st)
+                launches += st["launches"]
+        m.wait()
         e1.record(stream)
         barrier()
         clocks = sampler.stop()
         ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+        if not sync_each:
+            per_scan.append(m.stats())
+            per_scan = per_scan[-count:]
+        launches = sum(s["launches"] for s in per_scan)
         return ms, per_scan, launches, clocks
 
     # ---- device-resident inputs: `value` ---------------------------------
-    d_clouds = [torch.from_numpy(c).to(dev) for c in clouds]
+    d_clouds = [torch.from_numpy(c).to(dev) for c in packed]
     torch.cuda.synchronize(dev)
     m = fresh_map()
     m.set_profiling(1)
-
     bcast = torch.empty_like(d_clouds[0]) if shard else None
 
     def feed_device(mm, k):
         src = d_clouds[k]
         if shard:
-            # the one collective of the sharded mode: rank 0's scan goes to every GPU (1.5 MB)
+            # the one collective of the sharded mode: rank 0's scan goes to every GPU
             if rank == 0:
                 bcast.copy_(src)
             dist.broadcast(bcast, src=0)
             src = bcast
-        mm.insert_packed(origins[k], src.data_ptr(), n_pts, capi.XYZ_F32, max_range=MAX_RANGE,
-                         on_device=True, async_=True)
+        mm.insert_packed(origins[k], src.data_ptr(), n_pts, layout, on_device=True, async_=True, **ins_kw)
 
-    ms_dev, per_scan, launches, clocks = timed_loop(m, feed_device)
+    for k in range(args.warmup):
+        feed_device(m, k)
+    ms_dev, per_scan, launches, clocks = timed_loop(m, feed_device, args.warmup, args.steps)
     dev_bytes = per_scan[-1]["device_bytes"]
+    # one more scan with visit / mark counting switched on (not timed): raycast counters
+    m.set_profiling(2)
+    feed_device(m, total - 1)
+    counted = m.stats()
     m.close()
     del d_clouds
     torch.cuda.empty_cache()
 
     # ---- host buffers through the C ABI: `e2e` -----------------------------
-    h_clouds = [torch.from_numpy(c).pin_memory() for c in clouds]
+    h_clouds = [torch.from_numpy(c).pin_memory() for c in packed]
     m = fresh_map()
-
-    stage = torch.empty(n_pts, 3, dtype=torch.float32, device=dev) if shard else None
+    stage = torch.empty_like(torch.from_numpy(packed[0]), device=dev) if shard else None
 
     def feed_host(mm, k):
         if shard:
             if rank == 0:
                 stage.copy_(h_clouds[k], non_blocking=True)  # H2D once, on rank 0
             dist.broadcast(stage, src=0)
-            mm.insert_packed(origins[k], stage.data_ptr(), n_pts, capi.XYZ_F32, max_range=MAX_RANGE,
-                             on_device=True, async_=True)
+            mm.insert_packed(origins[k], stage.data_ptr(), n_pts, layout, on_device=True, async_=True, **ins_kw)
             return
-        mm.insert_packed(origins[k], h_clouds[k].data_ptr(), n_pts, capi.XYZ_F32, max_range=MAX_RANGE,
-                         on_device=False, async_=True)
+        mm.insert_packed(origins[k], h_clouds[k].data_ptr(), n_pts, layout, on_device=False, async_=True, **ins_kw)
 
-    ms_e2e, _, _, clocks_e2e = timed_loop(m, feed_host)
+    for k in range(args.warmup):
+        feed_host(m, k)
+    ms_e2e, e2e_scans, _, clocks_e2e = timed_loop(m, feed_host, args.warmup, args.steps)
+    d2h = int(e2e_scans[-1]["result_bytes"])
+    # fully serialised variant on a fresh map (same scans)
+    m.close()
+    m = fresh_map()
+    for k in range(args.warmup):
+        feed_host(m, k)
+    ms_sync, _, _, _ = timed_loop(m, feed_host, args.warmup, args.steps, sync_each=True)
+    # sustained: keep the pipelined e2e loop running for >= args.sustain seconds over the same scans
+    sustained = None
+    if args.sustain > 0:
+        est = max(ms_e2e / args.steps, 1e-3)
+        count = int(args.sustain * 1e3 / est) + 1
+        ms_sus, _, _, clocks_sus = timed_loop(m, feed_host, 0, count)
+        streams_ = 1 if shard else world
+        sustained = {"seconds": ms_sus * 1e-3, "steps": count, "value": streams_ * count * n_pts / (ms_sus * 1e-3),
+                     "unit": "points/s", "ms_per_step": ms_sus / count, "clocks": clocks_sus,
+                     "note": "scans cycle through the same %d poses (the map stops growing; work per scan unchanged)" % total}
     m.close()
 
     steps = args.steps
     streams = 1 if shard else world  # sharded mode integrates ONE stream with all GPUs
     value = streams * steps * n_pts / (ms_dev * 1e-3)
     e2e = streams * steps * n_pts / (ms_e2e * 1e-3)
+    e2e_sync = streams * steps * n_pts / (ms_sync * 1e-3)
 
     # roofline of the device work of one insert (K1..K4), averaged over the timed scans
     peak, peak_src = measured_peak()
-    alg = float(np.mean([algorithmic_bytes(s) for s in per_scan]))
-    alg_upd = float(np.mean([algorithmic_bytes(s, part="update") for s in per_scan]))
+    color = cfg["color"]
+    alg = float(np.mean([algorithmic_bytes(s, color, p_in) for s in per_scan]))
+    alg_upd = float(np.mean([algorithmic_bytes(s, color, p_in, part="update") for s in per_scan]))
     t_scan_ms = float(np.mean([s["ms_total"] for s in per_scan]))
     kern = {k: float(np.mean([s[k] for s in per_scan])) for k in
             ("ms_h2d", "ms_points", "ms_rays", "ms_scatter", "ms_update", "ms_propagate")}
-    # dominant kernel: the leaf update (k_update_compact + k_brick_agg between two CUDA events)
     achieved = alg_upd / (kern["ms_update"] * 1e-3) / 1e9
     pipeline = alg / (t_scan_ms * 1e-3) / 1e9
     traffic, traffic_src = measured_traffic()
     last = per_scan[-1]
+    ceil = atomic_ceiling()
+    t_walk = (kern["ms_rays"] + kern["ms_scatter"]) * 1e-3
+    raycast = {"kernel": "k_split + k_walk_mark (fused exact FP64 walk + mask reductions)", "ms": t_walk * 1e3,
+               "visits": int(counted["visits"]), "visits_per_s": counted["visits"] / t_walk if t_walk else None,
+               "l2_atomic_ceiling": ceil}
 
     if rank == 0:
         line = {
@@ -354,25 +443,31 @@ def main():
             "scans_per_s": value / n_pts, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "strong" if shard else "weak",
             "vs_baseline": None, "dtype": "f64 geometry + f32 log-odds", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points_per_scan": n_pts, "input": "float32 xyz",
+            "config": {"workload": cfg["workload"], "points_per_scan": n_pts,
+                       "input": "float32 xyz" + (" + rgb" if color else ""),
                        "parallelism": ("1 map per GPU" if world == 1 else
                                        ("one scan stream broadcast over NCCL, map sharded by brick ownership"
-                                        if shard else "one sensor stream + map per GPU, no merge")),
+                                        if shard else "one sensor stream + map per GPU, no merge (replicas)")),
                        "l2": "per-scan working set (%.1f GB leaf data touched, map %.1f GB) exceeds the 126 MB L2; no flush"
-                             % (last["touched_blocks"] * 256 / 1e9, dev_bytes / 1e9)},
+                             % (last["touched_blocks"] * (512 if color else 256) / 1e9, dev_bytes / 1e9)},
             "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e / steps,
-                    "h2d_bytes_per_step": int(n_pts * 12), "d2h_bytes_per_step": int(last["result_bytes"])},
+                    "h2d_bytes_per_step": int(n_pts * p_in), "d2h_bytes_per_step": d2h,
+                    "mode": "async=1 (server default): H2D of scan k+1 overlaps the kernels of scan k",
+                    "sync": {"value": e2e_sync, "ms_per_step": ms_sync / steps,
+                             "mode": "wait + read the scan's own counters after every insert"}},
+            "sustained": sustained,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_update_compact (+k_brick_agg): hit/miss log-odds update of the marked voxels and "
-                                   "depth 1-4 aggregates; CUDA events on the map's stream around every launch "
-                                   "of the timed region",
+                         "kernel": "k_update_compact: hit/miss log-odds update of the marked voxels and depth 1-4 "
+                                   "aggregates over the scan's touched bricks; CUDA events on the map's stream "
+                                   "around every launch of the timed region",
                          "algorithmic_bytes_per_launch": alg_upd, "ms_per_launch": kern["ms_update"],
                          "traffic_source": traffic_src,
                          # SURVEY.md 8(d)'s whole-pipeline figure: all algorithmic bytes of a scan over the
                          # device time of the whole insert (K1..K4)
                          "pipeline": {"algorithmic_bytes_per_scan": alg, "device_ms_per_scan": t_scan_ms,
                                       "achieved": pipeline, "frac": pipeline / peak}},
+            "raycast": raycast,
             "kernels_ms": kern,
             "counters": {k: int(last[k]) for k in ("rays", "touched_voxels", "hit_voxels", "touched_octets",
                                                     "touched_blocks", "touched_d3", "touched_bricks",
@@ -382,7 +477,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             try:
-                line["cpu_baseline"] = cpu_baseline_sample(origins, clouds)
+                line["cpu_baseline"] = cpu_baseline_sample(cfg, origins, xyzs, rgbs)
             except Exception as e:  # the checker is optional for the GPU number
                 line["cpu_baseline"] = {"value": None, "error": str(e)}
         print(json.dumps(line), flush=True)

@@ -208,6 +208,13 @@ int ufo_b200_write_data(ufo_b200_map* m, const double* box6, uint32_t min_depth,
  * free_thres, prob_hit, prob_miss, clamping_thres_min, clamping_thres_max as
  * probabilities (setters) or as stored double log-odds (ufo_b200_sensor_model_logit). */
 int ufo_b200_set_sensor_model(ufo_b200_map* m, const double prob6[6]);
+/* One sensor-model parameter, the way the reference's setters work (occupancy_map_base.h:748-773:
+ * setProbHit / setProbMiss / setClampingThresMin / setClampingThresMax / setOccupiedFreeThres each
+ * store toLogit(p) into ONE member and leave the others' stored log-odds untouched).
+ * index: 0 occupied_thres, 1 free_thres, 2 prob_hit, 3 prob_miss, 4 clamping_thres_min,
+ * 5 clamping_thres_max.  Changing a threshold (0, 1) re-derives the contains_free /
+ * contains_unknown flags of every inner node, like the reference's write + read round trip. */
+int ufo_b200_set_sensor_model_field(ufo_b200_map* m, int index, double probability);
 int ufo_b200_sensor_model_logit(const ufo_b200_map* m, double logit6[6]);
 
 /* min/max change detection  occupancy_map_base.h:792-822 (always enabled). */
@@ -242,6 +249,11 @@ typedef struct {
 } ufo_b200_scan_stats;
 
 int ufo_b200_last_scan_stats(ufo_b200_map* m, ufo_b200_scan_stats* out);
+/* Statistics of the most recent scan whose integration is COMPLETE, without waiting for the scan
+ * in flight: after an async insert of scan k this returns scan k-1 (its counters were read back
+ * when scan k was enqueued).  For callers that stream scans with async = 1 and still want each
+ * scan's result.  points == 0 in *out: no scan has completed yet. */
+int ufo_b200_completed_scan_stats(ufo_b200_map* m, ufo_b200_scan_stats* out);
 /* Octree::clear(resolution, depth_levels)  octree.h:541-560 -- the server's reset service
  * (server.cpp:364-378): empties the map and changes its geometry. */
 int ufo_b200_clear_resize(ufo_b200_map* m, double resolution, uint32_t depth_levels);

@@ -573,11 +573,17 @@ class MapFacade
 	double getProbMiss() const { return toProb(model()[3]); }
 	double getClampingThresMin() const { return toProb(model()[4]); }
 	double getClampingThresMax() const { return toProb(model()[5]); }
-	void setOccupiedFreeThres(double occupied, double free) { setModel(0, occupied, 1, free); }
-	void setProbHit(double p) { setModel(2, p); }
-	void setProbMiss(double p) { setModel(3, p); }
-	void setClampingThresMin(double p) { setModel(4, p); }
-	void setClampingThresMax(double p) { setModel(5, p); }
+	// each setter stores toLogit(p) into ONE parameter; the other stored log-odds stay bit for bit
+	// (occupancy_map_base.h:748-773) -- no probability round trip
+	void setOccupiedFreeThres(double occupied, double free)
+	{
+		ufo_b200_set_sensor_model_field(map_, 0, occupied);
+		ufo_b200_set_sensor_model_field(map_, 1, free);
+	}
+	void setProbHit(double p) { ufo_b200_set_sensor_model_field(map_, 2, p); }
+	void setProbMiss(double p) { ufo_b200_set_sensor_model_field(map_, 3, p); }
+	void setClampingThresMin(double p) { ufo_b200_set_sensor_model_field(map_, 4, p); }
+	void setClampingThresMax(double p) { ufo_b200_set_sensor_model_field(map_, 5, p); }
 
 	//
 	// Min/max change detection (occupancy_map_base.h:792-822); always recorded on the device
@@ -613,6 +619,9 @@ class MapFacade
 	{
 		if (UFO_B200_E_INVALID == ufo_b200_clear_resize(map_, new_resolution, new_depth_levels))
 			throw std::invalid_argument("depth_levels has to be [2, 21]");
+		// the geometry getters (getResolution, getTreeDepthLevels, getMin/getMax, isInside ...) read params_
+		params_.resolution = new_resolution;
+		params_.depth_levels = new_depth_levels;
 	}
 
 	// status of the last insert (the reference's insert functions are void and never throw)
@@ -641,14 +650,6 @@ class MapFacade
 	{
 		ufo_b200_sensor_model_logit(map_, model_);
 		return model_;
-	}
-	void setModel(int i, double p, int j = -1, double q = 0)
-	{
-		double prob[6];
-		for (int k = 0; k < 6; ++k) prob[k] = toProb(model()[k]);
-		prob[i] = p;
-		if (j >= 0) prob[j] = q;
-		ufo_b200_set_sensor_model(map_, prob);
 	}
 
 	template <typename T>

@@ -80,6 +80,33 @@ int main(int argc, char** argv)
 	Point3 r(0.2, 0.2, 0.1);
 	fused.setValueVolume(ufo::geometry::AABB(world[20] - r, world[20] + r), fused.getClampingThresMin(), 0);
 	if (fused.lastStatus() != UFO_B200_OK || !fused.isFree(world[20])) return 16;
+	// a setter changes ONE stored log-odds; the others stay bit for bit (occupancy_map_base.h:748-773)
+	{
+		OccupancyMap a(0.05), b(0.05);
+		double before[6], after[6];
+		ufo_b200_sensor_model_logit(a.handle(), before);
+		a.setProbMiss(0.4);  // same value again: nothing may move
+		ufo_b200_sensor_model_logit(a.handle(), after);
+		for (int i = 0; i < 6; ++i)
+			if (std::memcmp(&before[i], &after[i], sizeof(double)) != 0) return 17;
+		a.setProbMiss(0.35);
+		ufo_b200_sensor_model_logit(a.handle(), after);
+		for (int i = 0; i < 6; ++i)
+			if ((i == 3) == (std::memcmp(&before[i], &after[i], sizeof(double)) == 0)) return 18;
+		// hits are still applied with the untouched hit increment: same value as on a fresh map
+		a.insertPointCloud(tilt.translation(), world, 10.0);
+		b.insertPointCloud(tilt.translation(), world, 10.0);
+		a.insertPointCloud(tilt.translation(), world, 10.0);
+		b.insertPointCloud(tilt.translation(), world, 10.0);
+		if (a.getOccupancy(world[7]) == b.getOccupancy(world[7])) return 19;  // different miss, end voxel gets both
+	}
+	// Octree::clear(resolution, depth_levels): the geometry getters follow (server.cpp:364-378)
+	fused.clear(0.1, 14);
+	if (fused.getResolution() != 0.1 || fused.getTreeDepthLevels() != 14) return 20;
+	if (fused.getMax().x() != 0.1 * 8192 || fused.getMin().x() != -0.1 * 8192) return 21;
+	if (!fused.isInside(Point3(800.0, 0, 0)) || fused.isInside(Point3(900.0, 0, 0))) return 22;
+	fused.insertPointCloud(tilt.translation(), world, 10.0);
+	if (!fused.isOccupied(world[3])) return 23;
 	std::puts("facade ok");
 	return 0;
 }

@@ -12,8 +12,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libufomap_b200.so")
+import glob
+
 SOURCES = [os.path.join(CSRC, "ufo_map.cu")]
-HEADERS = [os.path.join(CSRC, f) for f in ("ufo_index.cuh", "ufo_device.cuh", "ufo_kernels.cuh")] + [
+# every header the translation unit can include (ufo_export.cuh was missing here)
+HEADERS = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [
     os.path.join(os.path.dirname(HERE), "include", "ufomap_b200.h")]
 
 NVCC_FLAGS = [

@@ -59,6 +59,7 @@ SYMBOLS = [
     "ufo_b200_insert_pointcloud_frame", "ufo_b200_transform_points", "ufo_b200_pose_from_rpy",
     "ufo_b200_insert_pointcloud2", "ufo_b200_write", "ufo_b200_write_file",
     "ufo_b200_write_data", "ufo_b200_set_value_volume", "ufo_b200_clear_resize",
+    "ufo_b200_completed_scan_stats", "ufo_b200_set_sensor_model_field",
 ]
 
 class Cloud2(C.Structure):
@@ -120,6 +121,8 @@ def load():
     lib.ufo_b200_change_bbox.argtypes = [vp, vp, vp]
     lib.ufo_b200_reset_change_bbox.argtypes = [vp]
     lib.ufo_b200_last_scan_stats.argtypes = [vp, C.POINTER(ScanStats)]
+    lib.ufo_b200_completed_scan_stats.argtypes = [vp, C.POINTER(ScanStats)]
+    lib.ufo_b200_set_sensor_model_field.argtypes = [vp, i32, dbl]
     lib.ufo_b200_set_profiling.argtypes = [vp, i32]
     lib.ufo_b200_clear.argtypes = [vp]
     lib.ufo_b200_set_shard.argtypes = [vp, u32, u32]
@@ -262,6 +265,16 @@ class Map:
         st = ScanStats()
         self._check(self.lib.ufo_b200_last_scan_stats(self.h, C.byref(st)))
         return st.as_dict()
+
+    def completed_stats(self):
+        """Statistics of the last COMPLETED scan (no wait for the scan in flight)."""
+        st = ScanStats()
+        self._check(self.lib.ufo_b200_completed_scan_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def set_sensor_model_field(self, index, probability):
+        """One parameter, like the reference's setProbHit/... (the other stored log-odds stay)."""
+        self._check(self.lib.ufo_b200_set_sensor_model_field(self.h, int(index), float(probability)))
 
     def clear(self):
         self._check(self.lib.ufo_b200_clear(self.h))

@@ -42,6 +42,10 @@ struct Counters {
 	uint32_t n_bricks;   // next free brick slot
 	uint32_t n_upper;    // next free upper-node slot
 	uint32_t overflow;   // bit1 bricks/brick hash, bit2 upper nodes, bit3 ray-record buffer, bit4 ray bound violated (bug), bit5 alias arrays needed
+	uint32_t n_touched;    // bricks stamped by this scan = length of DeviceMap::touched
+	uint32_t item_cursor;  // next work unit of the fused walk (k_walk_mark)
+	uint32_t max_span;     // longest ray of the scan in dominant-axis steps (sets the shell thickness)
+	uint32_t pad0;
 	uint32_t list_count[3];  // dirty-list lengths of the upper-level pass (rotating by depth % 3)
 	uint32_t n_rays;
 	uint32_t ray_batch;  // next batch of 32 rays for the persistent ray-walk warps
@@ -83,6 +87,7 @@ struct DeviceMap {
 	// brick pool
 	unsigned long long* brick_key;
 	uint32_t* brick_stamp;  // scan id of the last scan that touched the brick
+	uint32_t* touched;      // [brick_cap] bricks stamped by the current scan, in stamping order (touch_brick)
 	Agg* brick_sum3;        // [brick][8]
 	Agg* brick_sum4;        // [brick]
 	uint32_t* brick_rgb3;   // colour maps: [brick][8] packed rgb of depth-3 nodes
@@ -114,6 +119,7 @@ struct DeviceMap {
 	uint32_t* up_rgb;
 	uint32_t* up_stamp;
 	uint32_t up_cap;
+	uint32_t up_epoch;  // id of the current upper-level pass (a pass repeated after a pool growth gets a new one)
 
 	Counters* ctr;
 };
@@ -202,6 +208,14 @@ __device__ __forceinline__ uint32_t brick_find(const DeviceMap& M, uint64_t key)
 		i = (i + 1) & M.bh_mask;
 	}
 	return kNone;
+}
+
+// First mark of a brick in a scan: stamp it and append it to the scan's touched list, which is
+// what the update and propagation kernels iterate over (cost of a scan = O(touched), not O(map)).
+__device__ __forceinline__ void touch_brick(const DeviceMap& M, uint32_t slot)
+{
+	if (ld_volatile_u32(&M.brick_stamp[slot]) == M.scan_id) return;
+	if (atomicExch(&M.brick_stamp[slot], M.scan_id) != M.scan_id) M.touched[atomicAdd(&M.ctr->n_touched, 1u)] = slot;
 }
 
 // continues a probe sequence at table index i (entry e already loaded or not)

@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(64) k_volume_mark(DeviceMap M, VolumeArgs v)
 		uint32_t slot = kNone;
 		if (ok) {
 			slot = brick_find_or_create(M, pack_key(kx, ky, kz));
-			if (slot != kNone) M.brick_stamp[slot] = M.scan_id;
+			if (slot != kNone) touch_brick(M, slot);
 		}
 		s_slot = slot;
 		s_center[0] = c[0];

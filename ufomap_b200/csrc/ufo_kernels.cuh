@@ -22,6 +22,7 @@
 #pragma once
 
 #include "ufo_device.cuh"
+#include "ufo_update.cuh"
 
 namespace ufo_b200
 {
@@ -31,6 +32,21 @@ struct QEntry {
 	unsigned long long acc;  // visited-voxel bits of one 4^3 block (linear order)
 	unsigned long long key;  // packed masked block coordinates (key >> 2)
 };
+
+// fused walk (ufo_walk.cuh): start state of one ray segment, and the per-ray constants
+struct __align__(16) Item {
+	double tx, ty, tz;        // t_max at the segment's first voxel
+	uint32_t cx, cy, cz;      // first voxel (raw key, may lie outside the tree like the walk's own keys)
+	uint32_t ex, ey, ez;      // end key: first voxel of the next segment, or the walk's end key
+	uint32_t sgn;             // step signs, 2 bits per axis (1: +, 2: -, 0: none); 0xffffffff: no segment
+	uint32_t pad[3];
+};
+static_assert(sizeof(Item) == 64, "Item is read as four 16-byte words");
+struct __align__(16) RayConst {
+	double dx, dy, dz;  // t_delta
+	double dist;        // length of the (clipped) ray: the walk continues while min t_max <= dist
+};
+constexpr uint32_t kShells = 16;  // segments per ray at most
 
 struct ScanArgs {
 	Vec3 origin;       // sensor origin
@@ -63,6 +79,11 @@ struct ScanArgs {
 	uint32_t* seg_base;          // [ceil(n/32)] first record of the warp's region
 	uint32_t* seg_count;         // [ceil(n/32)] K1: capacity of the region, K2: records written
 	uint32_t* order;             // [ceil(n/32)] ray batches sorted by estimated work, longest first
+	// fused walk: segments by shell, [kShells][item_stride]; validity masks [kShells][ceil(n/32)]
+	Item* items;
+	size_t item_stride;
+	uint32_t* vmask;
+	RayConst* rc;                // [n]
 };
 
 // returns false for a point the ingestion drops (PointCloud2 records with a NaN coordinate)
@@ -165,8 +186,8 @@ __device__ __noinline__ void mark_alias(const DeviceMap M, uint32_t bx, uint32_t
 	const uint32_t src = brick_find_or_create(M, pack_key(bx >> 2, by >> 2, bz >> 2));
 	const uint32_t dst = brick_find_or_create(M, pack_key((bx & km) >> 2, (by & km) >> 2, (bz & km) >> 2));
 	if (src == kNone || dst == kNone) return;
-	M.brick_stamp[src] = M.scan_id;
-	M.brick_stamp[dst] = M.scan_id;
+	touch_brick(M, src);
+	touch_brick(M, dst);
 	atomicOr(&(is_hit ? M.alias_hit : M.alias_miss)[(size_t)src * 64 + morton2(bx, by, bz)], bits);
 	atomicAdd(&M.ctr->alias_marks, 1u);
 }
@@ -190,7 +211,7 @@ __device__ __noinline__ void mark_node_miss(const DeviceMap M, uint32_t x, uint3
 	if (M.shard_world > 1 && brick_owner(pack_key(bx0 >> 2, by0 >> 2, bz0 >> 2), M.shard_world) != M.shard_rank) return;
 	const uint32_t brick = brick_find_or_create(M, pack_key(bx0 >> 2, by0 >> 2, bz0 >> 2));
 	if (brick == kNone) return;
-	M.brick_stamp[brick] = M.scan_id;
+	touch_brick(M, brick);
 	// the blocks of a depth-3 node are 8 consecutive Morton children, a depth-4 node is all 64
 	const uint32_t first = depth == 3 ? (morton2(bx0, by0, bz0) & ~7u) : 0u;
 	const uint32_t count = depth == 3 ? 8u : 64u;
@@ -218,7 +239,7 @@ __device__ __forceinline__ void mark_hit(const DeviceMap& M, Key3 k)
 	if (M.shard_world > 1 && brick_owner(bkey, M.shard_world) != M.shard_rank) return;
 	uint32_t brick = brick_find_or_create(M, bkey);
 	if (brick == kNone) return;
-	M.brick_stamp[brick] = M.scan_id;
+	touch_brick(M, brick);
 	const size_t b = (size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2);
 	atomicOr(&M.hit_mask[b], 1ull << linear2(k.x, k.y, k.z));
 }
@@ -231,7 +252,7 @@ __global__ void __launch_bounds__(256) k_points(DeviceMap M, ScanArgs a)
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	double lo[3], hi[3];
 	bool contributes = false, cast = false;
-	uint32_t bound = 0;
+	uint32_t bound = 0, span = 0;
 	Vec3 end = {0.0, 0.0, 0.0};
 	uint32_t rgb = 0;
 	const bool valid = i < a.n && load_point(a, i, end, rgb);
@@ -348,10 +369,16 @@ __global__ void __launch_bounds__(256) k_points(DeviceMap M, ScanArgs a)
 				uint32_t dy = (uint32_t)abs((int)(kf.y - kt.y));
 				uint32_t dz = (uint32_t)abs((int)(kf.z - kt.z));
 				bound = (dx >> 2) + (dy >> 2) + (dz >> 2) + 8u;
+				span = max(dx, max(dy, dz)) >> a.depth;
 			}
 		}
 	}
 	bbox_accumulate(M, lo, hi, contributes, cast);
+	if (a.items) {
+		// longest ray in dominant-axis steps: sets the shell thickness of the fused walk
+		for (int o = 16; o > 0; o >>= 1) span = max(span, __shfl_xor_sync(0xffffffffu, span, o));
+		if ((threadIdx.x & 31) == 0 && span) atomicMax(&M.ctr->max_span, span);
+	}
 	if (a.seg_base) {
 		for (int o = 16; o > 0; o >>= 1) bound += __shfl_xor_sync(0xffffffffu, bound, o);
 		if ((threadIdx.x & 31) == 0 && i < a.n) {
@@ -396,7 +423,7 @@ __global__ void __launch_bounds__(256) k_hits(DeviceMap M, ScanArgs a)
 	if (M.shard_world > 1 && brick_owner(pack_key(k.x >> 4, k.y >> 4, k.z >> 4), M.shard_world) != M.shard_rank) return;
 	uint32_t brick = brick_find_or_create(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
 	if (brick == kNone) return;
-	M.brick_stamp[brick] = M.scan_id;
+	touch_brick(M, brick);
 	const size_t slot = (size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2);
 	uint32_t v = morton2(k.x, k.y, k.z);
 	const unsigned long long hbit = 1ull << linear2(k.x, k.y, k.z);
@@ -458,7 +485,7 @@ __device__ __forceinline__ void flush_block(const DeviceMap& M, BrickCache& bc, 
 		bc.by = by;
 		bc.bz = bz;
 		bc.slot = brick_find_or_create(M, pack_key(bx, by, bz));
-		if (bc.slot != kNone) M.brick_stamp[bc.slot] = M.scan_id;
+		if (bc.slot != kNone) touch_brick(M, bc.slot);
 	}
 	if (bc.slot == kNone) return;
 	atomicOr(&M.miss_mask[(size_t)bc.slot * 64 + morton2(kx >> 2, ky >> 2, kz >> 2)], bits);
@@ -736,13 +763,13 @@ __device__ __forceinline__ void scatter_record(const DeviceMap& M, const ScanArg
 	uint32_t brick = (uint32_t)ent.y;
 	if ((hit0 || hit1) && brick != kPending && brick != kFailed) {
 		if ((uint32_t)(ent.y >> 32) != M.scan_id) {
-			M.brick_stamp[brick] = M.scan_id;
+			touch_brick(M, brick);
 			reinterpret_cast<uint32_t*>(&M.bh_tab[hpos].y)[1] = M.scan_id;
 		}
 	} else {
 		brick = brick_find_or_create_from(M, bkey, hidx);
 		if (brick == kNone) return;
-		M.brick_stamp[brick] = M.scan_id;
+		touch_brick(M, brick);
 	}
 	atomicOr(&M.miss_mask[(size_t)brick * 64 + morton2(x, y, z)], v.x);
 }
@@ -860,453 +887,6 @@ __global__ void __launch_bounds__(128) k_rays_simple(DeviceMap M, ScanArgs a)
 }
 
 // ---------------------------------------------------------------------------
-// K3
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t rms_rgb(const uint32_t* c, int n)
-{
-	// getAverageColor (occupancy_map_color.cpp:200-222) over the set colours
-	double s[3] = {0, 0, 0};
-	int cnt = 0;
-	for (int i = 0; i < n; ++i) {
-		if (!c[i]) continue;
-		for (int k = 0; k < 3; ++k) {
-			double v = (double)((c[i] >> (8 * k)) & 0xffu);
-			s[k] = dop::add(s[k], dop::mul(v, v));
-		}
-		++cnt;
-	}
-	if (!cnt) return 0;
-	uint32_t out = 0;
-	for (int k = 0; k < 3; ++k)
-		out |= ((uint32_t)(int)dop::sqrt(dop::div(s[k], (double)cnt)) & 0xffu) << (8 * k);
-	return out;
-}
-
-// K3 is flat: one eight-lane group per (brick, child block) pair, lane%8 owns one octet
-// (8 voxels = one 32 B sector).  A group reads its block's two masks, and if the block was
-// marked, only the touched leaf sectors; it writes them back, the block's depth-1 maxima
-// (a full sector) and its depth-2 aggregate.  There is no cross-group dependency, so
-// millions of independent groups hide the DRAM latency; groups of unmarked blocks retire
-// after one coalesced mask read.  The brick-level aggregates follow in k_brick_agg.
-//   hit-then-miss float log-odds update   updateOccupancy, occupancy_map_base.h:1139-1145
-//   depth-1/2 aggregates per block, depth-3/4 per brick   updateNode, :1179-1224
-#ifndef UFO_UPD_MINBLOCKS
-#define UFO_UPD_MINBLOCKS 8
-#endif
-constexpr int kUpdThreads = 256;
-
-// SET = true: the marked voxels are set to `miss` (already clamped) instead of updated --
-// setValueVolume, occupancy_map_base.h:492-518, :1151-1157.
-template <bool SET = false>
-__device__ __forceinline__ void update_octet(const DeviceMap& M, float miss, float* lp, uint32_t m8,
-                                             uint32_t h8, float4 a0, float4 a1, float& omax,
-                                             uint32_t& oflags)
-{
-	float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-	omax = -3.402823466e+38f;
-	float omin = 3.402823466e+38f;
-	bool unk = false;
-	// all hits of a scan are applied before its misses (occupancy_map_base.h:1351-1365);
-	// hits are rare (one voxel per ray), so their arithmetic is skipped for octets without one
-	if (!SET && h8) {
-#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			float hv = apply_update(M, v[j], M.hit);
-			v[j] = ((h8 >> j) & 1u) ? hv : v[j];
-		}
-	}
-#pragma unroll
-	for (int j = 0; j < 8; ++j) {
-		float mv = SET ? miss : apply_update(M, v[j], miss);
-		v[j] = ((m8 >> j) & 1u) ? mv : v[j];
-		omax = fmaxf(omax, v[j]);
-		omin = fminf(omin, v[j]);
-		unk = unk || (v[j] >= M.free_ceil && v[j] <= M.occ_floor);
-	}
-	// contains_free = any voxel below the free threshold, contains_unknown = any in between
-	oflags = (omin < M.free_ceil ? 1u : 0u) | (unk ? 2u : 0u);
-	// (streaming/evict-first hints on these stores and on the record traffic of K2/K2b were
-	// measured: no effect beyond run-to-run noise)
-	reinterpret_cast<float4*>(lp)[0] = make_float4(v[0], v[1], v[2], v[3]);
-	reinterpret_cast<float4*>(lp)[1] = make_float4(v[4], v[5], v[6], v[7]);
-}
-
-constexpr int kStatSlots = 64;  // per-scan counters are spread over slots to avoid same-address atomics
-
-template <bool COLOR, bool SET = false>
-__global__ void __launch_bounds__(kUpdThreads, UFO_UPD_MINBLOCKS) k_update(DeviceMap M, float miss, uint32_t first_brick,
-                                                           uint32_t n_bricks)
-{
-	const uint32_t lane = threadIdx.x & 31, oct = threadIdx.x & 7;
-	// = brick * 64 + child
-	const size_t b = (size_t)first_brick * 64 + (size_t)blockIdx.x * (kUpdThreads / 8) + (threadIdx.x >> 3);
-	const uint32_t brick = (uint32_t)(b >> 6);
-	if (brick >= n_bricks) return;
-	// launched before the host has seen this scan's allocation counters: if a pool overflowed,
-	// the marking kernels are re-run and nothing may be consumed yet
-	// (plain cached load: the flag is final before this kernel starts, and a volatile load from
-	// every thread would hammer one L2 slice)
-	if (__ldg(&M.ctr->overflow)) return;
-	// No brick_stamp check: the masks of a brick nothing marked this scan are all zero
-	// (every scan clears what it consumed), so the mask read itself is the filter.
-	// The four groups of a warp belong to the same brick: `brick` is warp-uniform.
-	const unsigned long long mm = M.miss_mask[b], hm = M.hit_mask[b];
-	const bool marked = (mm | hm) != 0ull;
-	if (!__any_sync(0xffffffffu, marked)) return;
-	const uint32_t gmask = 0xffu << (lane & 24);
-	unsigned int s_vox = 0, s_hit = 0, s_oct = 0, s_blk = 0, s_new = 0;
-	if (marked) {
-		const uint32_t mt = M.meta[b];
-		const uint32_t m8 = octet_bits8(mm, oct), h8 = octet_bits8(hm, oct);
-		float omax = 0.0f;
-		uint32_t ofl = M.default_flags, touched = 0, orgb = 0;
-		if (m8 | h8) {
-			float* lp = M.leaf + b * 64 + 8 * oct;
-			const float4 a0 = reinterpret_cast<const float4*>(lp)[0], a1 = reinterpret_cast<const float4*>(lp)[1];
-			update_octet<SET>(M, miss, lp, m8, h8, a0, a1, omax, ofl);
-			touched = 1;
-			s_vox = __popc(m8 | h8);
-			s_hit = __popc(h8);
-			s_oct = 1;
-			if (COLOR) {
-				// depth-1 colour of the octet (getAverageChildColor, occupancy_map_color.cpp:177-194)
-				const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + b * 64 + 8 * oct);
-				uint4 c0 = cp[0], c1 = cp[1];
-				uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-				orgb = rms_rgb(cc, 8);
-			}
-		} else if ((mt >> (16 + oct)) & 1u) {
-			omax = M.sum1[b * 8 + oct];
-			ofl = (mt >> (2 * oct)) & 3u;
-			if (COLOR) orgb = M.sum1_rgb[b * 8 + oct];
-		}
-		// the group rewrites the whole 32 B sector of depth-1 maxima (no partial-sector write)
-		M.sum1[b * 8 + oct] = omax;
-		if (COLOR) M.sum1_rgb[b * 8 + oct] = orgb;
-		// depth-2 aggregate over the 8 octets of the block
-		float bmax = omax;
-		uint32_t bfl = ofl;
-		uint32_t newmeta = (ofl << (2 * oct)) | (touched << (16 + oct));
-#pragma unroll
-		for (int o = 1; o < 8; o <<= 1) {
-			bmax = fmaxf(bmax, __shfl_xor_sync(gmask, bmax, o));
-			bfl |= __shfl_xor_sync(gmask, bfl, o);
-			newmeta |= __shfl_xor_sync(gmask, newmeta, o);
-		}
-		uint32_t brgb = 0;
-		if (COLOR) {
-			uint32_t oc[8];
-#pragma unroll
-			for (int j = 0; j < 8; ++j) oc[j] = __shfl_sync(gmask, orgb, (lane & 24) + j);
-			brgb = rms_rgb(oc, 8);
-		}
-		if (oct == 0) {
-			M.agg2[b] = {bmax, bfl};
-			// bits 24..31: low byte of the scan that last updated the block (read by k_brick_agg)
-			M.meta[b] = (newmeta & 0xffffffu) | (mt & 0xff0000u) | (M.scan_id << 24);
-			if (COLOR) M.rgb2[b] = brgb;
-			M.miss_mask[b] = 0ull;  // masks cleared for the next scan
-			if (hm) M.hit_mask[b] = 0ull;
-			s_blk = 1;
-			s_new = (mt & 0xff0000u) ? 0u : 1u;
-		}
-	}
-	// counters: packed into one word (per warp: voxels <= 256, hits <= 256, octets <= 32,
-	// blocks <= 4, new blocks <= 4), one shuffle reduction and one set of atomics per warp
-	uint32_t packed = s_vox | (s_hit << 10) | (s_oct << 20) | (s_blk << 26) | (s_new << 29);
-	for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
-	if (lane == 0) {
-		unsigned long long* slot = M.ctr->stat[(blockIdx.x * 8 + (threadIdx.x >> 5)) % kStatSlots];
-		atomicAdd(&slot[0], (unsigned long long)(packed & 0x3ffu));
-		if ((packed >> 10) & 0x3ffu) atomicAdd(&slot[1], (unsigned long long)((packed >> 10) & 0x3ffu));
-		atomicAdd(&slot[2], (unsigned long long)((packed >> 20) & 0x3fu));
-		atomicAdd(&slot[3], (unsigned long long)((packed >> 26) & 0x7u));
-		if (packed >> 29) atomicAdd(&slot[4], (unsigned long long)(packed >> 29));
-	}
-}
-
-// K3, compacted variant (mono maps).  In the flat kernel above only ~23 % of the threads have a
-// leaf sector in flight (half of the blocks are unmarked, and a marked block has 3.7 of 8 octets
-// touched), so it is bound by latency x occupancy (Little's law: ~15 KB in flight per SM), not by
-// HBM bandwidth.  Here a CTA works on chunks of 128 consecutive blocks (two bricks): block threads
-// take the masks and build, by prefix sum, a dense list of the touched octets in shared memory;
-// then every thread takes one list entry, so nearly all threads hold a 32 B leaf sector in
-// flight; octet results go through shared memory to the block threads, which finish the
-// depth-1/2 aggregates exactly as k_update does.  CTAs are persistent and software-pipelined: the
-// masks of the CTA's next chunk are fetched while the current one is processed, and the block
-// header data (meta, depth-1 maxima) needed last is requested first, so a chunk exposes one DRAM
-// round trip (the leaf sectors) instead of three.  Same arrays, values and per-scan clearing.
-#ifndef UFO_UC_MINBLOCKS
-#define UFO_UC_MINBLOCKS 4
-#endif
-#ifndef UFO_UC_MINBLOCKS_COLOR
-#define UFO_UC_MINBLOCKS_COLOR 4
-#endif
-#ifndef UFO_UC_BLOCKS
-#define UFO_UC_BLOCKS 256
-#endif
-#ifndef UFO_UC_THREADS
-#define UFO_UC_THREADS 256
-#endif
-constexpr int kUcBlocks = UFO_UC_BLOCKS;  // blocks per chunk (<= kUcThreads, multiple of 32)
-constexpr int kUcThreads = UFO_UC_THREADS;
-static_assert(kUcBlocks <= kUcThreads && kUcBlocks % 32 == 0 && kUcBlocks * 8 <= 65536, "chunk shape");
-#ifndef UFO_UC_GRID_PER_SM
-#define UFO_UC_GRID_PER_SM UFO_UC_MINBLOCKS
-#endif
-
-template <bool COLOR, bool SET = false>
-__global__ void __launch_bounds__(kUcThreads, COLOR ? UFO_UC_MINBLOCKS_COLOR : UFO_UC_MINBLOCKS) k_update_compact(DeviceMap M, float miss,
-                                                                               uint32_t first_brick,
-                                                                               uint32_t n_bricks,
-                                                                               uint32_t n_chunks)
-{
-	__shared__ unsigned long long s_mm[kUcBlocks], s_hm[kUcBlocks];
-	__shared__ uint16_t s_list[kUcBlocks * 8];
-	__shared__ float s_omax[8 * kUcBlocks];      // [octet][block]: conflict-free for the block threads
-	__shared__ unsigned char s_ofl[8 * kUcBlocks];
-	__shared__ uint32_t s_orgb[COLOR ? 8 * kUcBlocks : 1];  // depth-1 colours of the touched octets
-	__shared__ uint32_t s_wtot[2][kUcBlocks / 32];
-	const uint32_t tid = threadIdx.x, lane = tid & 31;
-	const bool block_thread = tid < (uint32_t)kUcBlocks;
-	if (__ldg(&M.ctr->overflow)) return;  // see k_update
-	const size_t base0 = (size_t)first_brick * 64;
-	const size_t b_end = (size_t)n_bricks * 64;
-
-	unsigned int s_vox = 0, s_hit = 0, s_oct = 0, s_blk = 0, s_new = 0;
-	unsigned long long mm_next = 0ull, hm_next = 0ull;
-	if (block_thread) {
-		const size_t b = base0 + (size_t)blockIdx.x * kUcBlocks + tid;
-		if (b < b_end) {
-			mm_next = M.miss_mask[b];
-			hm_next = M.hit_mask[b];
-		}
-	}
-	uint32_t par = 0;
-	for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x, par ^= 1u) {
-		const size_t b0 = base0 + (size_t)c * kUcBlocks;
-		const size_t b = b0 + tid;
-		// ---- block threads: masks, touched-octet bitmap, list offsets ----
-		const unsigned long long mm = mm_next, hm = hm_next;
-		uint32_t mt = 0, t8 = 0, excl = 0;
-		float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-		uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0;
-		const bool marked = (mm | hm) != 0ull;
-		if (block_thread) {
-			// masks of this CTA's next chunk: in flight while this chunk is processed
-			const size_t bn = b + (size_t)gridDim.x * kUcBlocks;
-			mm_next = 0ull;
-			hm_next = 0ull;
-			if (c + gridDim.x < n_chunks && bn < b_end) {
-				mm_next = M.miss_mask[bn];
-				hm_next = M.hit_mask[bn];
-			}
-			if (marked) {
-				const unsigned long long u = mm | hm;
-#pragma unroll
-				for (uint32_t o = 0; o < 8; ++o) {
-					const uint32_t base = ((o & 1u) << 1) | ((o & 2u) << 2) | ((o & 4u) << 3);
-					t8 |= (((u >> base) & 0x330033ull) ? 1u : 0u) << o;
-				}
-				// used last, requested first: block header and the depth-1 maxima of the octets
-				// that stay untouched (garbage for a never-written block; masked by meta below)
-				mt = M.meta[b];
-				if (t8 != 0xffu) {
-					const float4* sp = reinterpret_cast<const float4*>(M.sum1 + b * 8);
-					p0 = sp[0];
-					p1 = sp[1];
-					if (COLOR) {
-						const uint4* cp = reinterpret_cast<const uint4*>(M.sum1_rgb + b * 8);
-						q0 = cp[0];
-						q1 = cp[1];
-					}
-				}
-				s_mm[tid] = mm;
-				s_hm[tid] = hm;
-			}
-			uint32_t incl = __popc(t8);
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-				if (lane >= (uint32_t)o) incl += v;
-			}
-			excl = incl - __popc(t8);
-			if (lane == 31) s_wtot[par][tid >> 5] = incl;
-		}
-		__syncthreads();
-		uint32_t total = 0;
-#pragma unroll
-		for (int w = 0; w < kUcBlocks / 32; ++w) {
-			const uint32_t wt = s_wtot[par][w];
-			if (block_thread && (uint32_t)w < (tid >> 5)) excl += wt;
-			total += wt;
-		}
-		if (total == 0) continue;  // nothing marked in this chunk (uniform; s_wtot is double-buffered)
-		if (block_thread) {
-			uint32_t bits = t8, at = excl;
-			while (bits) {
-				const uint32_t o = __ffs(bits) - 1;
-				bits &= bits - 1;
-				s_list[at++] = (uint16_t)((tid << 3) | o);
-			}
-		}
-		__syncthreads();
-
-		// ---- all threads: one touched octet (= one 32 B sector) each ----
-		for (uint32_t i = tid; i < total; i += kUcThreads) {
-			const uint32_t e = s_list[i], t = e >> 3, oct = e & 7u;
-			const uint32_t m8 = octet_bits8(s_mm[t], oct), h8 = octet_bits8(s_hm[t], oct);
-			float* lp = M.leaf + (b0 + t) * 64 + 8 * oct;
-			const float4 a0 = reinterpret_cast<const float4*>(lp)[0], a1 = reinterpret_cast<const float4*>(lp)[1];
-			float omax;
-			uint32_t ofl;
-			update_octet<SET>(M, miss, lp, m8, h8, a0, a1, omax, ofl);
-			s_omax[oct * kUcBlocks + t] = omax;
-			s_ofl[oct * kUcBlocks + t] = (unsigned char)ofl;
-			if (COLOR) {
-				// depth-1 colour of the octet (getAverageChildColor, occupancy_map_color.cpp:177-194)
-				const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + (b0 + t) * 64 + 8 * oct);
-				const uint4 c0 = cp[0], c1 = cp[1];
-				const uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-				s_orgb[oct * kUcBlocks + t] = rms_rgb(cc, 8);
-			}
-			s_vox += __popc(m8 | h8);
-			s_hit += __popc(h8);
-			s_oct += 1;
-		}
-		__syncthreads();
-
-		// ---- block threads: depth-1 sector, depth-2 aggregate, meta, mask clearing ----
-		if (block_thread && marked) {
-			const float old1[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-			const uint32_t oldc[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-			float new1[8];
-			uint32_t newc[8];
-			float bmax = -3.402823466e+38f;
-			uint32_t bfl = 0, newmeta = 0;
-#pragma unroll
-			for (uint32_t o = 0; o < 8; ++o) {
-				float om = 0.0f;
-				uint32_t fl = M.default_flags, touched = 0, oc = 0;
-				if ((t8 >> o) & 1u) {
-					om = s_omax[o * kUcBlocks + tid];
-					fl = s_ofl[o * kUcBlocks + tid];
-					if (COLOR) oc = s_orgb[o * kUcBlocks + tid];
-					touched = 1;
-				} else if ((mt >> (16 + o)) & 1u) {
-					om = old1[o];
-					fl = (mt >> (2 * o)) & 3u;
-					if (COLOR) oc = oldc[o];
-				}
-				new1[o] = om;
-				newc[o] = oc;
-				bmax = fmaxf(bmax, om);
-				bfl |= fl;
-				newmeta |= (fl << (2 * o)) | (touched << (16 + o));
-			}
-			float4* sp = reinterpret_cast<float4*>(M.sum1 + b * 8);
-			sp[0] = make_float4(new1[0], new1[1], new1[2], new1[3]);
-			sp[1] = make_float4(new1[4], new1[5], new1[6], new1[7]);
-			M.agg2[b] = {bmax, bfl};
-			if (COLOR) {
-				uint4* cp = reinterpret_cast<uint4*>(M.sum1_rgb + b * 8);
-				cp[0] = make_uint4(newc[0], newc[1], newc[2], newc[3]);
-				cp[1] = make_uint4(newc[4], newc[5], newc[6], newc[7]);
-				M.rgb2[b] = rms_rgb(newc, 8);
-			}
-			M.meta[b] = (newmeta & 0xffffffu) | (mt & 0xff0000u) | (M.scan_id << 24);
-			M.miss_mask[b] = 0ull;
-			if (hm) M.hit_mask[b] = 0ull;
-			s_blk += 1;
-			s_new += (mt & 0xff0000u) ? 0u : 1u;
-		}
-	}
-	// counters: per-thread sums over the CTA's chunks, one warp reduction and one set of atomics
-	for (int o = 16; o > 0; o >>= 1) {
-		s_vox += __shfl_xor_sync(0xffffffffu, s_vox, o);
-		s_hit += __shfl_xor_sync(0xffffffffu, s_hit, o);
-		s_oct += __shfl_xor_sync(0xffffffffu, s_oct, o);
-		s_blk += __shfl_xor_sync(0xffffffffu, s_blk, o);
-		s_new += __shfl_xor_sync(0xffffffffu, s_new, o);
-	}
-	if (lane == 0) {
-		unsigned long long* slot = M.ctr->stat[(blockIdx.x * (kUcThreads / 32) + (tid >> 5)) % kStatSlots];
-		if (s_vox) atomicAdd(&slot[0], (unsigned long long)s_vox);
-		if (s_hit) atomicAdd(&slot[1], (unsigned long long)s_hit);
-		if (s_oct) atomicAdd(&slot[2], (unsigned long long)s_oct);
-		if (s_blk) atomicAdd(&slot[3], (unsigned long long)s_blk);
-		if (s_new) atomicAdd(&slot[4], (unsigned long long)s_new);
-	}
-}
-
-__device__ __forceinline__ bool alias_source(const DeviceMap& M, uint32_t brick, uint32_t& tx, uint32_t& ty,
-                                             uint32_t& tz);
-
-// depth-3 / depth-4 aggregates of every touched brick from its 64 depth-2 aggregates:
-// one warp per brick, lane owns children 2*lane and 2*lane+1 (both under depth-3 node lane/4)
-template <bool COLOR>
-__global__ void __launch_bounds__(256) k_brick_agg(DeviceMap M, uint32_t n_bricks)
-{
-	const uint32_t lane = threadIdx.x & 31;
-	const uint32_t brick = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (brick >= n_bricks || M.brick_stamp[brick] != M.scan_id) return;
-	constexpr uint32_t FULL = 0xffffffffu;
-	if (M.alias_miss) {  // bricks that only collect out-of-tree marks own no voxels
-		uint32_t ax, ay, az;
-		if (alias_source(M, brick, ax, ay, az)) return;
-	}
-	const size_t b = (size_t)brick * 64 + 2 * lane;
-	const uint2 mt = *reinterpret_cast<const uint2*>(&M.meta[b]);
-	const uint4 ag = *reinterpret_cast<const uint4*>(&M.agg2[b]);
-	Agg c0 = {__uint_as_float(ag.x), ag.y}, c1 = {__uint_as_float(ag.z), ag.w};
-	if (!(mt.x & 0xff0000u)) c0 = {0.0f, M.default_flags};  // never written: unknown space
-	if (!(mt.y & 0xff0000u)) c1 = {0.0f, M.default_flags};
-	const uint32_t tag = M.scan_id & 0xffu;
-	const bool upd = ((mt.x & 0xff0000u) && (mt.x >> 24) == tag) || ((mt.y & 0xff0000u) && (mt.y >> 24) == tag);
-	float m3 = fmaxf(c0.occ, c1.occ);
-	uint32_t f3 = c0.flags | c1.flags;
-#pragma unroll
-	for (int o = 1; o < 4; o <<= 1) {
-		m3 = fmaxf(m3, __shfl_xor_sync(FULL, m3, o));
-		f3 |= __shfl_xor_sync(FULL, f3, o);
-	}
-	float m4 = m3;
-	uint32_t f4 = f3;
-#pragma unroll
-	for (int o = 4; o < 32; o <<= 1) {
-		m4 = fmaxf(m4, __shfl_xor_sync(FULL, m4, o));
-		f4 |= __shfl_xor_sync(FULL, f4, o);
-	}
-	if ((lane & 3) == 0) M.brick_sum3[(size_t)brick * 8 + (lane >> 2)] = {m3, f3};
-	if (lane == 0) M.brick_sum4[brick] = {m4, f4};
-	if (COLOR) {
-		const uint2 cr = *reinterpret_cast<const uint2*>(&M.rgb2[b]);
-		const uint32_t r0 = (mt.x & 0xff0000u) ? cr.x : 0u, r1 = (mt.y & 0xff0000u) ? cr.y : 0u;
-		uint32_t cc[8];
-#pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			cc[2 * j] = __shfl_sync(FULL, r0, (lane & 28) + j);
-			cc[2 * j + 1] = __shfl_sync(FULL, r1, (lane & 28) + j);
-		}
-		const uint32_t rgb3 = rms_rgb(cc, 8);
-#pragma unroll
-		for (int j = 0; j < 8; ++j) cc[j] = __shfl_sync(FULL, rgb3, 4 * j);
-		const uint32_t rgb4 = rms_rgb(cc, 8);
-		if ((lane & 3) == 0) M.brick_rgb3[(size_t)brick * 8 + (lane >> 2)] = rgb3;
-		if (lane == 0) M.brick_rgb4[brick] = rgb4;
-	}
-	// D_3 / D_4 counters: depth-3 node touched <=> any of its 8 children updated this scan
-	const uint32_t ub = __ballot_sync(FULL, upd);
-	if (lane == 0) {
-		uint32_t d3 = 0;
-		for (int k = 0; k < 8; ++k) d3 += ((ub >> (4 * k)) & 0xfu) ? 1u : 0u;
-		unsigned long long* slot = M.ctr->stat[brick % kStatSlots];
-		atomicAdd(&slot[5], 1ull);
-		atomicAdd(&slot[6], (unsigned long long)d3);
-	}
-}
-
-// ---------------------------------------------------------------------------
 // Out-of-tree keys (rare; launched only when a scan produced any)
 // ---------------------------------------------------------------------------
 // The reference applies to a voxel every hit of the scan first and every miss afterwards
@@ -1327,93 +907,89 @@ __device__ __forceinline__ void atomic_apply(const DeviceMap& M, float* addr, fl
 	}
 }
 
-__device__ __forceinline__ bool alias_source(const DeviceMap& M, uint32_t brick, uint32_t& tx, uint32_t& ty,
-                                             uint32_t& tz)
+// one thread per (touched alias brick, child block), grid-stride over the scan's touched list
+__global__ void __launch_bounds__(256) k_alias_apply(DeviceMap M, float upd, int hits)
 {
-	uint32_t x, y, z;
-	unpack_key(M.brick_key[brick], x, y, z);
-	const uint32_t km = M.g.key_mask >> 4;
-	tx = x & km;
-	ty = y & km;
-	tz = z & km;
-	return ((x | y | z) & ~km) != 0;
-}
-
-// one thread per (alias brick, child block)
-__global__ void __launch_bounds__(256) k_alias_apply(DeviceMap M, uint32_t n_bricks, float upd, int hits)
-{
-	const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t brick = (uint32_t)(b >> 6);
-	if (brick >= n_bricks || M.brick_stamp[brick] != M.scan_id) return;
-	uint32_t tx, ty, tz;
-	if (!alias_source(M, brick, tx, ty, tz)) return;
-	unsigned long long m = (hits ? M.alias_hit : M.alias_miss)[b];
-	if (!m) return;
-	const uint32_t dst = brick_find(M, pack_key(tx, ty, tz));
-	if (dst == kNone) return;
-	float* leaf = M.leaf + ((size_t)dst * 64 + (b & 63)) * 64;
-	while (m) {
-		const uint32_t bit = __ffsll((long long)m) - 1;
-		m &= m - 1;
-		// mask bit order is linear (x + 4y + 16z), leaves are in Morton order
-		atomic_apply(M, leaf + morton2(bit & 3u, (bit >> 2) & 3u, bit >> 4), upd);
-	}
-}
-
-// one thread per (alias brick, child block): recompute the wrapped block's aggregates
-__global__ void __launch_bounds__(256) k_alias_refresh(DeviceMap M, uint32_t n_bricks)
-{
-	const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t brick = (uint32_t)(b >> 6);
-	if (brick >= n_bricks || M.brick_stamp[brick] != M.scan_id) return;
-	uint32_t tx, ty, tz;
-	if (!alias_source(M, brick, tx, ty, tz)) return;
-	if (!(M.alias_hit[b] | M.alias_miss[b])) return;
-	M.alias_hit[b] = 0ull;
-	M.alias_miss[b] = 0ull;
-	const uint32_t dst = brick_find(M, pack_key(tx, ty, tz));
-	if (dst == kNone) return;
-	const size_t tb = (size_t)dst * 64 + (b & 63);
-	const float* leaf = M.leaf + tb * 64;
-	const uint32_t old = M.meta[tb];
-	float bmax = -3.402823466e+38f;
-	uint32_t bfl = 0, meta = 0;
-	for (int o = 0; o < 8; ++o) {
-		float omax = -3.402823466e+38f;
-		uint32_t ofl = 0;
-		for (int j = 0; j < 8; ++j) {
-			const float v = *reinterpret_cast<const volatile float*>(&leaf[8 * o + j]);
-			omax = fmaxf(omax, v);
-			ofl |= leaf_flags(M, v);
+	if ((__ldg(&M.ctr->overflow) & ~4u) || !__ldg(&M.ctr->alias_marks)) return;
+	const size_t n = (size_t)__ldg(&M.ctr->n_touched) * 64;
+	for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+		const uint32_t brick = M.touched[e >> 6];
+		const size_t b = (size_t)brick * 64 + (e & 63);
+		uint32_t tx, ty, tz;
+		if (!alias_source(M, brick, tx, ty, tz)) continue;
+		unsigned long long m = (hits ? M.alias_hit : M.alias_miss)[b];
+		if (!m) continue;
+		const uint32_t dst = brick_find(M, pack_key(tx, ty, tz));
+		if (dst == kNone) continue;
+		float* leaf = M.leaf + ((size_t)dst * 64 + (b & 63)) * 64;
+		while (m) {
+			const uint32_t bit = __ffsll((long long)m) - 1;
+			m &= m - 1;
+			// mask bit order is linear (x + 4y + 16z), leaves are in Morton order
+			atomic_apply(M, leaf + morton2(bit & 3u, (bit >> 2) & 3u, bit >> 4), upd);
 		}
-		M.sum1[tb * 8 + o] = omax;
-		bmax = fmaxf(bmax, omax);
-		bfl |= ofl;
-		meta |= ofl << (2 * o);
 	}
-	// every octet now holds real values; several sources refreshing one target write the same
-	M.agg2[tb] = {bmax, bfl};
-	M.meta[tb] = meta | 0xff0000u | (M.scan_id << 24);
-	(void)old;
+}
+
+// one thread per (touched alias brick, child block): recompute the wrapped block's aggregates
+__global__ void __launch_bounds__(256) k_alias_refresh(DeviceMap M)
+{
+	if ((__ldg(&M.ctr->overflow) & ~4u) || !__ldg(&M.ctr->alias_marks)) return;
+	const size_t n = (size_t)__ldg(&M.ctr->n_touched) * 64;
+	for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+		const uint32_t brick = M.touched[e >> 6];
+		const size_t b = (size_t)brick * 64 + (e & 63);
+		uint32_t tx, ty, tz;
+		if (!alias_source(M, brick, tx, ty, tz)) continue;
+		if (!(M.alias_hit[b] | M.alias_miss[b])) continue;
+		M.alias_hit[b] = 0ull;
+		M.alias_miss[b] = 0ull;
+		const uint32_t dst = brick_find(M, pack_key(tx, ty, tz));
+		if (dst == kNone) continue;
+		const size_t tb = (size_t)dst * 64 + (b & 63);
+		const float* leaf = M.leaf + tb * 64;
+		float bmax = -3.402823466e+38f;
+		uint32_t bfl = 0, meta = 0;
+		for (int o = 0; o < 8; ++o) {
+			float omax = -3.402823466e+38f;
+			uint32_t ofl = 0;
+			for (int j = 0; j < 8; ++j) {
+				const float v = *reinterpret_cast<const volatile float*>(&leaf[8 * o + j]);
+				omax = fmaxf(omax, v);
+				ofl |= leaf_flags(M, v);
+			}
+			M.sum1[tb * 8 + o] = omax;
+			bmax = fmaxf(bmax, omax);
+			bfl |= ofl;
+			meta |= ofl << (2 * o);
+		}
+		// every octet now holds real values; several sources refreshing one target write the same
+		M.agg2[tb] = {bmax, bfl};
+		M.meta[tb] = meta | 0xff0000u | (M.scan_id << 24);
+	}
 }
 
 // ---------------------------------------------------------------------------
 // K4: upper levels (depth >= 5)
 // ---------------------------------------------------------------------------
 // Seeds the depth-5 dirty list with the parents of the bricks touched this scan.
-__global__ void __launch_bounds__(256) k_upper_seed(DeviceMap M, uint32_t n_bricks, uint32_t* list,
-                                                    uint32_t list_cap)
+// Grid-stride over the touched list; the pass is identified by M.up_epoch (a pass repeated after
+// the upper-node pool was regrown gets a fresh epoch, so every node is listed again).
+__global__ void __launch_bounds__(256) k_upper_seed(DeviceMap M, uint32_t* list, uint32_t list_cap)
 {
-	uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b >= n_bricks || M.brick_stamp[b] != M.scan_id) return;
-	uint32_t x, y, z;
-	unpack_key(M.brick_key[b], x, y, z);
-	if ((x | y | z) & ~(M.g.key_mask >> 4)) return;  // alias collector brick
-	uint32_t s = upper_find_or_create(M, upper_key(5, x >> 1, y >> 1, z >> 1));
-	if (s == kNone) return;
-	if (atomicExch(&M.up_stamp[s], M.scan_id) != M.scan_id) {
-		uint32_t idx = atomicAdd(&M.ctr->list_count[5 % 3], 1u);
-		if (idx < list_cap) list[idx] = s;
+	if (__ldg(&M.ctr->overflow)) return;
+	const uint32_t n = __ldg(&M.ctr->n_touched);
+	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+		const uint32_t b = M.touched[e];
+		uint32_t x, y, z;
+		unpack_key(M.brick_key[b], x, y, z);
+		if ((x | y | z) & ~(M.g.key_mask >> 4)) continue;  // alias collector brick
+		uint32_t s = upper_find_or_create(M, upper_key(5, x >> 1, y >> 1, z >> 1));
+		if (s == kNone) continue;
+		if (atomicExch(&M.up_stamp[s], M.up_epoch) != M.up_epoch) {
+			uint32_t idx = atomicAdd(&M.ctr->list_count[5 % 3], 1u);
+			if (idx < list_cap) list[idx] = s;
+		}
 	}
 }
 
@@ -1474,7 +1050,7 @@ __device__ __forceinline__ void upper_level_pass(const DeviceMap& M, uint32_t de
 			atomicAdd(&M.ctr->upper_nodes, 1ull);
 			if (depth < M.g.depth_levels) {
 				uint32_t p = upper_find_or_create(M, upper_key(depth + 1, x >> 1, y >> 1, z >> 1));
-				if (p != kNone && atomicExch(&M.up_stamp[p], M.scan_id) != M.scan_id) {
+				if (p != kNone && atomicExch(&M.up_stamp[p], M.up_epoch) != M.up_epoch) {
 					uint32_t idx = atomicAdd(out_count, 1u);
 					if (idx < list_cap) out[idx] = p;
 				}

@@ -25,6 +25,7 @@
 #include "../../include/ufomap_b200.h"
 #include "ufo_kernels.cuh"
 #include "ufo_export.cuh"
+#include "ufo_walk.cuh"
 
 using namespace ufo_b200;
 
@@ -79,19 +80,34 @@ void dev_grow(T*& p, size_t old_n, size_t new_n, int fill_byte, cudaStream_t s, 
 double to_logit(double p) { return std::log(p / (1.0 - p)); }
 }  // namespace
 
+struct MapError {
+	int code;
+};
+
+// everything needed to enqueue a scan again after a pool growth
+struct PendingScan {
+	bool valid = false;
+	ScanArgs a{};
+	bool use_color = false, need_table = false, simple = false, has_vol = false;
+	VolumeArgs vol{};
+	float set_value = 0.0f;
+	uint32_t regrows = 0;
+};
+
 struct ufo_b200_map {
 	ufo_b200_params params{};
 	DeviceMap M{};
 	int device = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-	cudaEvent_t ev_marked = nullptr;
+	cudaEvent_t ev_copy0 = nullptr, ev_copied = nullptr;
 	// sensor model as the reference stores it (double log-odds)
 	double occ_thr_log = 0, free_thr_log = 0, hit_log = 0, miss_log = 0, cmin_log = 0, cmax_log = 0;
 	// host mirror of the counters (pinned)
 	Counters* h_ctr = nullptr;
-	// scan staging
-	void* d_points = nullptr;
-	size_t d_points_cap = 0;
+	// scan staging: two point buffers, so that the H2D copy of scan k+1 overlaps scan k
+	void* d_points[2] = {nullptr, nullptr};
+	size_t d_points_cap[2] = {0, 0};
+	uint32_t stage = 0;
 	double* d_ray_end = nullptr;
 	uint32_t* d_hit_tab = nullptr;
 	size_t ray_cap = 0;
@@ -99,24 +115,33 @@ struct ufo_b200_map {
 	uint32_t* d_tab_min = nullptr;
 	uint32_t tab_size = 0;
 	uint32_t* d_list[2] = {nullptr, nullptr};
-	QEntry* d_seg = nullptr;          // ray-walk records
+	// generic marking path: ray-walk records
+	QEntry* d_seg = nullptr;
 	unsigned long long seg_cap = 0;
 	uint32_t *d_seg_base = nullptr, *d_seg_count = nullptr;
 	uint32_t* d_order = nullptr;
+	// fused walk: segments, validity masks, per-ray constants
+	Item* d_items = nullptr;
+	uint32_t* d_vmask = nullptr;
+	RayConst* d_rc = nullptr;
+	size_t item_cap = 0;
 	// bookkeeping
-	uint32_t n_blocks = 0, n_bricks = 0, n_upper = 0;  // host view after the last sync
+	uint32_t n_blocks = 0, n_bricks = 0, n_upper = 0;  // host view after the last completed scan
 	size_t device_bytes = 0;
 	int profiling = 0;
+	int force_records = 0;  // UFO_B200_MARK=records: always use the record path (A/B runs)
 	uint64_t launches = 0;
 	cudaEvent_t ev[8]{};
-	bool ev_valid = false, ev7_valid = false;
-	cudaEvent_t ev_done = nullptr;
-	ufo_b200_scan_stats stats{};
+	bool ev_valid = false, ev7_valid = false, h2d_valid = false;
+	ufo_b200_scan_stats stats{};       // scan in flight / last scan
+	ufo_b200_scan_stats done_stats{};  // last scan whose counters are folded into the host view
 	bool stats_pending = false;
+	PendingScan pending;
+	bool poisoned = false;
 	double min_change[3], max_change[3];
 	std::string err;
 	int sm_count = 148;
-	int ray_blocks_per_sm = 4;
+	int ray_blocks_per_sm = 4, walk_blocks_per_sm = 4;
 
 	void set_error(const char* fmt, ...)
 	{
@@ -179,6 +204,7 @@ void alloc_pools(Map* m, uint32_t brick_cap, uint32_t up_cap)
 	dev_alloc(M.bh_tab, (size_t)M.bh_mask + 1, 0xff, s, tot);
 	dev_alloc(M.brick_key, brick_cap, 0, s, tot);
 	dev_alloc(M.brick_stamp, brick_cap, 0, s, tot);
+	dev_alloc(M.touched, brick_cap, 0, s, tot);
 	dev_alloc(M.brick_sum3, (size_t)brick_cap * 8, 0, s, tot);
 	dev_alloc(M.brick_sum4, brick_cap, 0, s, tot);
 	dev_alloc(M.leaf, nb * 64, 0, s, tot);
@@ -208,11 +234,11 @@ void alloc_pools(Map* m, uint32_t brick_cap, uint32_t up_cap)
 void free_pools(Map* m)
 {
 	DeviceMap& M = m->M;
-	void* ptrs[] = {M.bh_tab, M.brick_key, M.brick_stamp, M.brick_sum3, M.brick_sum4, M.brick_rgb3, M.brick_rgb4,
+	void* ptrs[] = {M.bh_tab, M.brick_key, M.brick_stamp, M.touched, M.brick_sum3, M.brick_sum4, M.brick_rgb3, M.brick_rgb4,
 	                M.leaf, M.leaf_rgb, M.miss_mask, M.hit_mask, M.agg2, M.meta, M.sum1, M.rgb2, M.sum1_rgb,
 	                M.alias_miss, M.alias_hit, M.uh_keys, M.uh_vals, M.up_key, M.up_agg, M.up_rgb, M.up_stamp, M.ctr, m->d_list[0],
-	                m->d_list[1], m->d_points, m->d_ray_end, m->d_hit_tab, m->d_tab_keys, m->d_tab_min,
-	                m->d_seg, m->d_seg_base, m->d_seg_count, m->d_order};
+	                m->d_list[1], m->d_points[0], m->d_points[1], m->d_ray_end, m->d_hit_tab, m->d_tab_keys, m->d_tab_min,
+	                m->d_seg, m->d_seg_base, m->d_seg_count, m->d_order, m->d_items, m->d_vmask, m->d_rc};
 	for (void* p : ptrs)
 		if (p) cudaFree(p);
 }
@@ -234,8 +260,7 @@ void push_counters(Map* m)
 
 // grow whichever pool overflowed; `want_*` are the allocation counters the failed
 // run reached (an over-estimate of the need)
-void grow_pools(Map* m, uint32_t overflow, uint32_t want_blocks, uint32_t want_bricks,
-                uint32_t want_upper)
+void grow_pools(Map* m, uint32_t overflow, uint32_t want_bricks, uint32_t want_upper)
 {
 	DeviceMap& M = m->M;
 	cudaStream_t s = m->stream;
@@ -243,7 +268,9 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_blocks, uint32_t want_b
 	CK(cudaStreamSynchronize(s));
 	if (overflow & 2u) {
 		uint32_t oc = M.brick_cap;
-		uint32_t nc = (uint32_t)std::max<uint64_t>(2ull * oc, (uint64_t)want_bricks + want_bricks / 4);
+		// marking stops creating bricks once the pool is exhausted, so `want` is barely above the old
+		// capacity: small pools grow by 4x, large ones by 2x
+		uint32_t nc = (uint32_t)std::max<uint64_t>((oc < (1u << 18) ? 4ull : 2ull) * oc, (uint64_t)want_bricks + want_bricks / 4);
 		if ((uint64_t)nc * 64 > 0xfffffff0ull) throw std::bad_alloc();
 		const size_t ob = (size_t)oc * 64, nb = (size_t)nc * 64;
 		dev_grow(M.leaf, ob * 64, nb * 64, 0, s, tot);
@@ -259,6 +286,7 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_blocks, uint32_t want_b
 		dev_grow(M.alias_hit, ob, nb, 0, s, tot);
 		dev_grow(M.brick_key, oc, nc, 0, s, tot);
 		dev_grow(M.brick_stamp, oc, nc, 0, s, tot);
+		dev_grow(M.touched, oc, nc, 0, s, tot);
 		dev_grow(M.brick_sum3, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
 		dev_grow(M.brick_sum4, oc, nc, 0, s, tot);
 		dev_grow(M.brick_rgb3, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
@@ -273,10 +301,11 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_blocks, uint32_t want_b
 		dev_alloc(M.bh_tab, new_tab, 0xff, s, tot);
 		uint32_t live = std::min(m->h_ctr->n_bricks, oc);
 		if (live) k_rebuild_brick_hash<<<(live + 255) / 256, 256, 0, s>>>(M, live);
+		if (M.up_cap < nc / 2) overflow |= 4u;  // keep the upper-node pool in proportion
 	}
 	if (overflow & 4u) {
 		uint32_t oc = M.up_cap;
-		uint32_t nc = (uint32_t)std::max<uint64_t>(2ull * oc, (uint64_t)want_upper + want_upper / 4);
+		uint32_t nc = (uint32_t)std::max<uint64_t>(std::max<uint64_t>(2ull * oc, M.brick_cap / 2), (uint64_t)want_upper + want_upper / 4);
 		dev_grow(M.up_key, oc, nc, 0, s, tot);
 		dev_grow(M.up_agg, oc, nc, 0, s, tot);
 		dev_grow(M.up_stamp, oc, nc, 0, s, tot);
@@ -309,31 +338,50 @@ size_t layout_stride(int layout)
 	}
 }
 
-void ensure_scan_buffers(Map* m, size_t n, bool need_table)
+// called with the stream idle
+void ensure_scan_buffers(Map* m, size_t n, bool need_table, bool records, bool fused)
 {
 	size_t& tot = m->device_bytes;
 	if (n > m->ray_cap) {
-		CK(cudaStreamSynchronize(m->stream));
 		if (m->d_ray_end) {
 			cudaFree(m->d_ray_end);
 			cudaFree(m->d_hit_tab);
+			tot -= m->ray_cap * (3 * sizeof(double) + sizeof(uint32_t));
+		}
+		if (m->d_seg_base) {
 			cudaFree(m->d_seg_base);
 			cudaFree(m->d_seg_count);
 			cudaFree(m->d_order);
-			tot -= m->ray_cap * (3 * sizeof(double) + sizeof(uint32_t)) + (m->ray_cap / 32 + 1) * 12;
+			m->d_seg_base = m->d_seg_count = m->d_order = nullptr;
+			tot -= (m->ray_cap / 32 + 1) * 12;
 		}
 		size_t cap = std::max<size_t>(n, 1024);
 		dev_alloc(m->d_ray_end, cap * 3, 0, m->stream, tot);
 		dev_alloc(m->d_hit_tab, cap, 0xff, m->stream, tot);
-		dev_alloc(m->d_seg_base, cap / 32 + 1, 0, m->stream, tot);
-		dev_alloc(m->d_seg_count, cap / 32 + 1, 0, m->stream, tot);
-		dev_alloc(m->d_order, cap / 32 + 1, 0, m->stream, tot);
 		m->ray_cap = cap;
+	}
+	if (records && !m->d_seg_base) {
+		dev_alloc(m->d_seg_base, m->ray_cap / 32 + 1, 0, m->stream, tot);
+		dev_alloc(m->d_seg_count, m->ray_cap / 32 + 1, 0, m->stream, tot);
+		dev_alloc(m->d_order, m->ray_cap / 32 + 1, 0, m->stream, tot);
+	}
+	if (fused && m->item_cap < m->ray_cap) {
+		if (m->d_items) {
+			cudaFree(m->d_items);
+			cudaFree(m->d_vmask);
+			cudaFree(m->d_rc);
+			tot -= m->item_cap * (kShells * sizeof(Item) + sizeof(RayConst)) + (m->item_cap / 32 + 1) * kShells * 4;
+		}
+		m->item_cap = m->ray_cap;
+		m->d_items = nullptr;
+		CK(cudaMalloc(reinterpret_cast<void**>(&m->d_items), m->item_cap * kShells * sizeof(Item)));  // written before read
+		tot += m->item_cap * kShells * sizeof(Item);
+		dev_alloc(m->d_vmask, (m->item_cap / 32 + 1) * kShells, 0, m->stream, tot);
+		dev_alloc(m->d_rc, m->item_cap, 0, m->stream, tot);
 	}
 	if (need_table) {
 		uint32_t want = std::max(1u << 12, next_pow2(4ull * n));
 		if (want > m->tab_size) {
-			CK(cudaStreamSynchronize(m->stream));
 			if (m->d_tab_keys) {
 				cudaFree(m->d_tab_keys);
 				cudaFree(m->d_tab_min);
@@ -379,30 +427,20 @@ void finish_stats(Map* m)
 	}
 	if (m->ev_valid) {
 		cudaEventElapsedTime(&st.ms_total, m->ev[0], m->ev[6]);
+		if (m->h2d_valid) cudaEventElapsedTime(&st.ms_h2d, m->ev_copy0, m->ev_copied);
 		if (m->profiling) {
-			cudaEventElapsedTime(&st.ms_h2d, m->ev[0], m->ev[1]);
-			cudaEventElapsedTime(&st.ms_points, m->ev[1], m->ev[2]);
+			cudaEventElapsedTime(&st.ms_points, m->ev[0], m->ev[2]);
 			if (m->ev7_valid) {
 				cudaEventElapsedTime(&st.ms_rays, m->ev[2], m->ev[7]);
 				cudaEventElapsedTime(&st.ms_scatter, m->ev[7], m->ev[3]);
 			} else {
 				cudaEventElapsedTime(&st.ms_rays, m->ev[2], m->ev[3]);
 			}
-			cudaEventElapsedTime(&st.ms_update, m->ev[4], m->ev[5]);
+			cudaEventElapsedTime(&st.ms_update, m->ev[3], m->ev[5]);
 			cudaEventElapsedTime(&st.ms_propagate, m->ev[5], m->ev[6]);
 		}
 	}
 	m->stats_pending = false;
-}
-
-int sync_map(Map* m)
-{
-	CK(cudaStreamSynchronize(m->stream));
-	if (m->stats_pending) {
-		// end-of-scan counters were copied to h_ctr by the scan itself
-		finish_stats(m);
-	}
-	return UFO_B200_OK;
 }
 
 void ensure_seg(Map* m, unsigned long long want)
@@ -419,48 +457,27 @@ void ensure_seg(Map* m, unsigned long long want)
 	m->device_bytes += want * sizeof(QEntry);
 }
 
-// k_update over the bricks [first, last)
-void launch_update(Map* m, float miss, uint32_t first, uint32_t last, bool set_mode = false)
+// K3 over the scan's touched list: persistent CTAs, the list length is read on the device
+void launch_update(Map* m, float miss, bool set_mode = false)
 {
-	const uint32_t groups = (last - first) * 64u;  // one eight-lane group per (brick, child)
-#if defined(UFO_UPD_FLAT) || defined(UFO_UPD_FLAT_COLOR)
-	const uint32_t grid = (groups + kUpdThreads / 8 - 1) / (kUpdThreads / 8);
-#endif
-	if (set_mode) {
-		// setValueVolume: the flat kernel in SET mode (not a hot path)
-		const uint32_t sgrid = (groups + kUpdThreads / 8 - 1) / (kUpdThreads / 8);
-		if (m->M.color) k_update<true, true><<<sgrid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
-		else k_update<false, true><<<sgrid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
-		++m->launches;
-		return;
+	const uint32_t grid = (uint32_t)m->sm_count * (m->M.color ? UFO_UC_MINBLOCKS_COLOR : UFO_UC_GRID_PER_SM);
+	if (m->M.color) {
+		if (set_mode) k_update_compact<true, true><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
+		else k_update_compact<true, false><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
+	} else {
+		if (set_mode) k_update_compact<false, true><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
+		else k_update_compact<false, false><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
 	}
-#ifdef UFO_UPD_FLAT
-	if (m->M.color) k_update<true><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
-	else k_update<false><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
-#else
-	{
-		// persistent CTAs (all resident), each looping over chunks of kUcBlocks blocks
-		const uint32_t n_chunks = (groups + kUcBlocks - 1) / kUcBlocks;
-		if (m->M.color) {
-#ifdef UFO_UPD_FLAT_COLOR
-			k_update<true><<<grid, kUpdThreads, 0, m->stream>>>(m->M, miss, first, last);
-#else
-			const uint32_t ugrid = std::min<uint32_t>(n_chunks, (uint32_t)m->sm_count * UFO_UC_MINBLOCKS_COLOR);
-			k_update_compact<true><<<ugrid, kUcThreads, 0, m->stream>>>(m->M, miss, first, last, n_chunks);
-#endif
-		} else {
-			const uint32_t ugrid = std::min<uint32_t>(n_chunks, (uint32_t)m->sm_count * UFO_UC_GRID_PER_SM);
-			k_update_compact<false><<<ugrid, kUcThreads, 0, m->stream>>>(m->M, miss, first, last, n_chunks);
-		}
-	}
-#endif
 	++m->launches;
 }
 
-void launch_rays(Map* m, const ScanArgs& a, int simple)
+// generic marking path: walk -> (block, mask) records -> k_scatter.  Handles every insert depth,
+// out-of-tree keys and the fixed-step variant.
+void launch_rays_records(Map* m, const ScanArgs& a, int simple)
 {
 	if (simple) {
 		k_rays_simple<<<(a.n + 127) / 128, 128, 0, m->stream>>>(m->M, a);
+		++m->launches;
 		return;
 	}
 	// one resident wave; batches are ordered by work and dealt round-robin over the CTAs
@@ -479,6 +496,7 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 		else if (a.depth == 1) k_rays<1, false><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
 		else k_rays<2, false><<<grid, kRayThreads, 0, m->stream>>>(m->M, a, counter);
 	}
+	++m->launches;
 	if (m->profiling) {
 		CK(cudaEventRecord(m->ev[7], m->stream));
 		m->ev7_valid = true;
@@ -498,6 +516,285 @@ void launch_rays(Map* m, const ScanArgs& a, int simple)
 		else k_scatter<false, false><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
 	}
 	++m->launches;
+}
+
+template <int DEPTH>
+void launch_fused_depth(Map* m, const ScanArgs& a)
+{
+	cudaStream_t s = m->stream;
+	const uint32_t n_batches = (a.n + 31) / 32;
+	const uint32_t sgrid = (n_batches * 32 + 127) / 128;
+	if (a.count_visits) k_split<DEPTH, true><<<sgrid, 128, 0, s>>>(m->M, a);
+	else k_split<DEPTH, false><<<sgrid, 128, 0, s>>>(m->M, a);
+	const uint32_t grid = (uint32_t)m->sm_count * m->walk_blocks_per_sm;
+	const bool shard = m->M.shard_world > 1;
+	if (a.count_visits) {
+		if (shard) k_walk_mark<DEPTH, true, true><<<grid, kWalkThreads, 0, s>>>(m->M, a);
+		else k_walk_mark<DEPTH, false, true><<<grid, kWalkThreads, 0, s>>>(m->M, a);
+	} else {
+		if (shard) k_walk_mark<DEPTH, true, false><<<grid, kWalkThreads, 0, s>>>(m->M, a);
+		else k_walk_mark<DEPTH, false, false><<<grid, kWalkThreads, 0, s>>>(m->M, a);
+	}
+	m->launches += 2;
+}
+
+// fused path (ufo_walk.cuh): insert depth <= 2, no out-of-tree keys seen by this map
+void launch_rays_fused(Map* m, const ScanArgs& a)
+{
+	if (a.depth == 0) launch_fused_depth<0>(m, a);
+	else if (a.depth == 1) launch_fused_depth<1>(m, a);
+	else launch_fused_depth<2>(m, a);
+}
+
+bool use_fused(const Map* m, const PendingScan& p)
+{
+	return !p.has_vol && !p.simple && p.a.depth <= 2 && !m->M.alias_miss && !m->force_records;
+}
+
+// K4: upper levels, depth 5 .. L, from the touched list
+void launch_upper(Map* m)
+{
+	DeviceMap& M = m->M;
+	cudaStream_t s = m->stream;
+	if (M.g.depth_levels < 5) return;
+	// list_count[] is zero at this point; level d reads list d&1 ? 0 : 1
+	k_upper_seed<<<m->sm_count * 2, 256, 0, s>>>(M, m->d_list[0], M.up_cap);
+	++m->launches;
+	const uint32_t L = M.g.depth_levels;
+	for (uint32_t d = 5; d <= std::min(6u, L); ++d) {
+		k_upper_level<<<m->sm_count, 256, 0, s>>>(M, d, m->d_list[(d & 1) ? 0 : 1], m->d_list[(d & 1) ? 1 : 0], M.up_cap);
+		++m->launches;
+	}
+	if (L >= 7) {
+		k_upper_tail<<<1, 1024, 0, s>>>(M, 7, m->d_list[0], m->d_list[1], M.up_cap);
+		++m->launches;
+	}
+	CK(cudaGetLastError());
+}
+
+__global__ void k_reset_upper_pass(Counters* c, uint32_t n_upper)
+{
+	c->overflow = 0;
+	c->list_count[0] = c->list_count[1] = c->list_count[2] = 0;
+	c->upper_nodes = 0;
+	c->n_upper = n_upper;
+}
+
+// Enqueues every kernel of one scan and the read-back of its counters; never waits.
+void enqueue_scan(Map* m, PendingScan& p)
+{
+	DeviceMap& M = m->M;
+	cudaStream_t s = m->stream;
+	ScanArgs& a = p.a;
+	M.scan_id++;
+	if (M.scan_id == 0) M.scan_id = 1;
+	M.up_epoch++;
+	if (M.up_epoch == 0) M.up_epoch = 1;
+	const bool fused = use_fused(m, p);
+	// (re-)bind the scan buffers: they may have been regrown since the scan was first enqueued
+	a.ray_end = m->d_ray_end;
+	a.tab_keys = m->d_tab_keys;
+	a.tab_min = m->d_tab_min;
+	a.tab_mask = m->tab_size ? m->tab_size - 1 : 0;
+	a.hit_tab = p.use_color ? m->d_hit_tab : nullptr;
+	a.seg = nullptr;
+	a.seg_base = a.seg_count = a.order = nullptr;
+	a.items = nullptr;
+	if (fused) {
+		a.items = m->d_items;
+		a.item_stride = m->item_cap;
+		a.vmask = m->d_vmask;
+		a.rc = m->d_rc;
+	} else if (!p.simple && !p.has_vol) {
+		a.seg = m->d_seg;
+		a.seg_cap = m->seg_cap;
+		a.seg_base = m->d_seg_base;
+		a.seg_count = m->d_seg_count;
+		a.order = m->d_order;
+	}
+	m->ev7_valid = false;
+	push_counters(m);
+	if (p.need_table) {
+		CK(cudaMemsetAsync(m->d_tab_keys, 0xff, (size_t)m->tab_size * sizeof(unsigned long long), s));
+		CK(cudaMemsetAsync(m->d_tab_min, 0xff, (size_t)m->tab_size * sizeof(uint32_t), s));
+	}
+	if (p.has_vol) {
+		// setValueVolume: the marks come from the box instead of a scan
+		k_volume_mark<<<p.vol.nx * p.vol.ny * p.vol.nz, 64, 0, s>>>(M, p.vol);
+		++m->launches;
+		if (m->profiling) CK(cudaEventRecord(m->ev[2], s));
+	} else if (a.n) {
+		uint32_t grid = (uint32_t)((a.n + 255) / 256);
+		k_points<<<grid, 256, 0, s>>>(M, a);
+		++m->launches;
+		if (p.use_color) {
+			k_hits<<<grid, 256, 0, s>>>(M, a);
+			++m->launches;
+		}
+		if (m->profiling) CK(cudaEventRecord(m->ev[2], s));
+		if (fused) launch_rays_fused(m, a);
+		else launch_rays_records(m, a, p.simple);
+	} else if (m->profiling) {
+		CK(cudaEventRecord(m->ev[2], s));
+	}
+	if (m->profiling) CK(cudaEventRecord(m->ev[3], s));
+	CK(cudaGetLastError());
+	// K3 and K4 run off the device-side touched list; if a pool overflowed while marking they
+	// back off by themselves and the scan is repeated by finalize_scan() after the growth.
+	const bool aliases = M.alias_miss != nullptr;
+	const uint32_t agrid = (uint32_t)m->sm_count * 4;
+	if (aliases) {
+		k_alias_apply<<<agrid, 256, 0, s>>>(M, M.hit, 1);
+		++m->launches;
+	}
+	launch_update(m, p.has_vol ? p.set_value : a.miss, p.has_vol);
+	if (aliases) {
+		k_alias_apply<<<agrid, 256, 0, s>>>(M, a.miss, 0);
+		k_alias_refresh<<<agrid, 256, 0, s>>>(M);
+		if (M.color) k_brick_agg<true><<<agrid, 256, 0, s>>>(M);
+		else k_brick_agg<false><<<agrid, 256, 0, s>>>(M);
+		m->launches += 3;
+	}
+	if (m->profiling) CK(cudaEventRecord(m->ev[5], s));
+	launch_upper(m);
+	CK(cudaEventRecord(m->ev[6], s));
+	m->ev_valid = true;
+	CK(cudaMemcpyAsync(m->h_ctr, M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+	m->stats_pending = true;
+	p.valid = true;
+}
+
+// Waits for the scan in flight, repeats it if a device pool overflowed, and folds its counters
+// into the host view.  Throws MapError if the scan cannot be completed.
+void finalize_scan(Map* m)
+{
+	CK(cudaStreamSynchronize(m->stream));
+	PendingScan& p = m->pending;
+	if (!p.valid) {
+		finish_stats(m);
+		return;
+	}
+	DeviceMap& M = m->M;
+	while (true) {
+		const uint32_t ov = m->h_ctr->overflow;
+		if (!ov) break;
+		++p.regrows;
+		if (p.regrows > 16 || (ov & 16u)) {
+			if (ov & 16u) m->set_error("internal error: a ray walk exceeded its record bound");
+			else m->set_error("device pools keep overflowing");
+			p.valid = false;
+			m->stats_pending = false;
+			m->poisoned = true;  // marks of the failed scan are still in the masks
+			throw MapError{(ov & 16u) ? UFO_B200_E_CUDA : UFO_B200_E_NOMEM};
+		}
+		try {
+			if (ov == 4u) {
+				// only the upper-node pool overflowed: the leaves are updated, repeat the propagation
+				const uint32_t nu = std::min(m->h_ctr->n_upper, M.up_cap);
+				grow_pools(m, 4u, 0, m->h_ctr->n_upper);
+				M.up_epoch++;
+				k_reset_upper_pass<<<1, 1, 0, m->stream>>>(M.ctr, nu);
+				launch_upper(m);
+				CK(cudaEventRecord(m->ev[6], m->stream));
+				CK(cudaMemcpyAsync(m->h_ctr, M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+			} else {
+				// an allocation failed while marking: nothing was consumed (K3/K4 backed off).  Grow,
+				// keep the bricks that were created, and run the whole scan again under a new scan id
+				// (marking is idempotent: OR into masks, find-or-create of bricks).
+				m->n_bricks = std::min(m->h_ctr->n_bricks, M.brick_cap);
+				if (ov & 32u) {
+					// first out-of-tree key ever seen by this map: allocate the alias mask arrays;
+					// from now on this map uses the generic record path
+					if (!M.alias_miss) {
+						dev_alloc(M.alias_miss, (size_t)M.brick_cap * 64, 0, m->stream, m->device_bytes);
+						dev_alloc(M.alias_hit, (size_t)M.brick_cap * 64, 0, m->stream, m->device_bytes);
+					}
+				}
+				const bool fused = use_fused(m, p);
+				if (!fused && !p.simple && !p.has_vol) {
+					ensure_scan_buffers(m, p.a.n, false, true, false);
+					unsigned long long want = std::max<unsigned long long>(m->h_ctr->seg_total + m->h_ctr->seg_total / 4 + 1024,
+					                                                        std::max<unsigned long long>(p.a.n, 1024) * 48ull);
+					ensure_seg(m, want);
+				}
+				if (ov & 6u) grow_pools(m, ov & 6u, m->h_ctr->n_bricks, m->h_ctr->n_upper);
+				enqueue_scan(m, p);
+			}
+		} catch (std::bad_alloc&) {
+			m->set_error("block pool cannot grow beyond 2^32 slots");
+			p.valid = false;
+			m->stats_pending = false;
+			m->poisoned = true;
+			throw MapError{UFO_B200_E_NOMEM};
+		}
+		CK(cudaStreamSynchronize(m->stream));
+	}
+	m->stats.regrows = p.regrows;
+	m->stats.launches = m->launches;
+	m->stats.result_bytes = sizeof(Counters) * (1 + p.regrows);
+	p.valid = false;
+	finish_stats(m);
+	m->done_stats = m->stats;
+}
+
+// every brick of the map becomes the "touched list" (whole-map passes: threshold changes)
+__global__ void k_touch_all(DeviceMap M, uint32_t n_bricks)
+{
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_bricks; b += gridDim.x * blockDim.x) {
+		M.touched[b] = b;
+		M.brick_stamp[b] = M.scan_id;
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) M.ctr->n_touched = n_bricks;
+}
+
+// contains_free / contains_unknown of depth 1 and 2 from the leaves, under the current thresholds
+__global__ void __launch_bounds__(256) k_reflag(DeviceMap M, uint32_t n_bricks)
+{
+	const size_t n = (size_t)n_bricks * 64;
+	for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += (size_t)gridDim.x * blockDim.x) {
+		const uint32_t mt = M.meta[b];
+		if (!(mt & 0xff0000u)) continue;
+		const float* leaf = M.leaf + b * 64;
+		uint32_t bfl = 0, fl16 = 0;
+		for (uint32_t o = 0; o < 8; ++o) {
+			uint32_t ofl = M.default_flags;
+			if ((mt >> (16 + o)) & 1u) {
+				ofl = 0;
+				for (int j = 0; j < 8; ++j) ofl |= leaf_flags(M, leaf[8 * o + j]);
+				fl16 |= ofl << (2 * o);
+			}
+			bfl |= ofl;
+		}
+		M.meta[b] = (mt & 0xffff0000u) | fl16;
+		M.agg2[b].flags = bfl;
+	}
+}
+
+// The reference re-reads the whole tree when the occupied / free thresholds change
+// (setOccupiedFreeThres, occupancy_map_base.h:748-761): the contains_free / contains_unknown
+// flags of every inner node are functions of the thresholds.  Same effect here.
+void rebuild_flags(Map* m)
+{
+	finalize_scan(m);
+	if (!m->n_bricks) return;
+	DeviceMap& M = m->M;
+	cudaStream_t s = m->stream;
+	M.scan_id++;
+	if (M.scan_id == 0) M.scan_id = 1;
+	M.up_epoch++;
+	push_counters(m);
+	k_touch_all<<<m->sm_count, 256, 0, s>>>(M, m->n_bricks);
+	k_reflag<<<m->sm_count * 8, 256, 0, s>>>(M, m->n_bricks);
+	if (M.color) k_brick_agg<true><<<m->sm_count * 4, 256, 0, s>>>(M);
+	else k_brick_agg<false><<<m->sm_count * 4, 256, 0, s>>>(M);
+	launch_upper(m);
+	CK(cudaStreamSynchronize(s));
+}
+
+int sync_map(Map* m)
+{
+	finalize_scan(m);
+	return UFO_B200_OK;
 }
 
 int do_insert(Map* m, const double origin[3], const void* points, bool on_device, size_t n,
@@ -534,31 +831,57 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		m->set_error("insert depth %u > 4 (free-space nodes larger than a brick) is not supported", depth);
 		return UFO_B200_E_UNSUPPORTED;
 	}
+	if (m->poisoned) {
+		m->set_error("an earlier scan failed half-way; ufo_b200_clear() the map before inserting again");
+		return UFO_B200_E_INVALID;
+	}
 	CK(cudaSetDevice(m->device));
+
+	// The points go to the device first, on the copy stream, into the staging buffer the scan in
+	// flight is not using: the H2D copy of scan k+1 overlaps the kernels of scan k (the reference
+	// overlaps its own front end with the previous scan's helper thread the same way, OMB:315).
+	const size_t bytes = n * stride;
+	const bool copied = !on_device && bytes;
+	const uint32_t stg = m->stage ^ 1u;
+	if (copied) {
+		if (bytes > m->d_points_cap[stg]) {
+			if (m->d_points[stg]) {
+				cudaFree(m->d_points[stg]);
+				m->device_bytes -= m->d_points_cap[stg];
+			}
+			m->d_points[stg] = nullptr;
+			m->d_points_cap[stg] = std::max<size_t>(bytes + bytes / 8, 1 << 16);
+			CK(cudaMalloc(&m->d_points[stg], m->d_points_cap[stg]));
+			m->device_bytes += m->d_points_cap[stg];
+		}
+		CK(cudaEventRecord(m->ev_copy0, m->copy_stream));
+		CK(cudaMemcpyAsync(m->d_points[stg], points, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+		CK(cudaEventRecord(m->ev_copied, m->copy_stream));
+	}
 	// one integration in flight at most (insertPointCloudWait, occupancy_map_base.h:315)
-	sync_map(m);
+	finalize_scan(m);
 
 	DeviceMap& M = m->M;
 	cudaStream_t s = m->stream;
 	const bool has_rgb = layout == UFO_B200_XYZRGB_F64 || layout == UFO_B200_XYZRGB_F32 || pc2_rgb;
-	const bool use_color = M.color && has_rgb;
-	const bool need_table = discrete || use_color;
-	ensure_scan_buffers(m, n, need_table);
+	PendingScan& p = m->pending;
+	p = PendingScan{};
+	p.use_color = M.color && has_rgb;
+	p.need_table = discrete || p.use_color;
+	p.simple = simple != 0;
+	p.has_vol = vol != nullptr;
+	if (vol) p.vol = *vol;
+	p.set_value = set_value;
 
-	ScanArgs a{};
+	ScanArgs& a = p.a;
 	a.origin = {origin[0], origin[1], origin[2]};
 	a.max_range = max_range;
 	a.n = (uint32_t)n;
 	a.depth = depth;
 	a.layout = layout;
 	a.discrete = discrete;
-	a.use_color = use_color;
+	a.use_color = p.use_color;
 	a.miss = (float)(m->miss_log / (double)((2.0 * depth) + 1));
-	a.ray_end = m->d_ray_end;
-	a.tab_keys = m->d_tab_keys;
-	a.tab_min = m->d_tab_min;
-	a.tab_mask = m->tab_size ? m->tab_size - 1 : 0;
-	a.hit_tab = use_color ? m->d_hit_tab : nullptr;
 	a.count_visits = m->profiling >= 2;
 	if (pc2) {
 		a.pc2_step = pc2->point_step;
@@ -574,179 +897,26 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		a.frame = Frame{frame_pose[3], frame_pose[4], frame_pose[5], frame_pose[6],
 		                frame_pose[0], frame_pose[1], frame_pose[2]};
 	}
-	if (!simple) {
+	const bool fused = use_fused(m, p);
+	const bool records = !fused && !p.simple && !p.has_vol;
+	ensure_scan_buffers(m, n, p.need_table, records, fused);
+	if (records) {
 		// first guess for the record buffer: 48 records per ray; grown on demand
 		ensure_seg(m, std::max<unsigned long long>(m->seg_cap, std::max<unsigned long long>(n, 1024) * 48ull));
-		a.seg = m->d_seg;
-		a.seg_cap = m->seg_cap;
-		a.seg_base = m->d_seg_base;
-		a.seg_count = m->d_seg_count;
-		a.order = m->d_order;
 	}
+	// an on-device cloud is read in place: it has to stay valid until the scan is done
+	a.points = on_device ? points : m->d_points[stg];
+	if (copied) m->stage = stg;
 
 	m->stats = ufo_b200_scan_stats{};
-	m->ev7_valid = false;
 	m->stats.points = n;
 	m->launches = 0;
-	M.scan_id++;
-	if (M.scan_id == 0) M.scan_id = 1;
-
+	m->h2d_valid = copied;
 	CK(cudaEventRecord(m->ev[0], s));
-	if (on_device) {
-		a.points = points;
-	} else {
-		size_t bytes = n * stride;
-		if (bytes > m->d_points_cap) {
-			if (m->d_points) {
-				cudaFree(m->d_points);
-				m->device_bytes -= m->d_points_cap;
-			}
-			m->d_points_cap = std::max<size_t>(bytes, 1 << 16);
-			CK(cudaMalloc(&m->d_points, m->d_points_cap));
-			m->device_bytes += m->d_points_cap;
-		}
-		if (bytes) CK(cudaMemcpyAsync(m->d_points, points, bytes, cudaMemcpyHostToDevice, s));
-		a.points = m->d_points;
-	}
-	if (m->profiling) CK(cudaEventRecord(m->ev[1], s));
-
-	push_counters(m);
-	const uint32_t bricks_before = m->n_bricks;
-	uint32_t regrows = 0;
-	bool speculated = false;
-	while (true) {
-		if (need_table) {
-			CK(cudaMemsetAsync(m->d_tab_keys, 0xff, (size_t)m->tab_size * sizeof(unsigned long long), s));
-			CK(cudaMemsetAsync(m->d_tab_min, 0xff, (size_t)m->tab_size * sizeof(uint32_t), s));
-		}
-		if (vol) {
-			// setValueVolume: the marks come from the box instead of a scan
-			k_volume_mark<<<vol->nx * vol->ny * vol->nz, 64, 0, s>>>(M, *vol);
-			++m->launches;
-			if (m->profiling) CK(cudaEventRecord(m->ev[2], s));
-		} else if (n) {
-			uint32_t grid = (uint32_t)((n + 255) / 256);
-			k_points<<<grid, 256, 0, s>>>(M, a);
-			++m->launches;
-			if (use_color) {
-				k_hits<<<grid, 256, 0, s>>>(M, a);
-				++m->launches;
-			}
-			if (m->profiling && regrows == 0) CK(cudaEventRecord(m->ev[2], s));
-			launch_rays(m, a, simple);
-			++m->launches;
-		} else if (m->profiling) {
-			CK(cudaEventRecord(m->ev[2], s));
-		}
-		if (m->profiling) CK(cudaEventRecord(m->ev[3], s));
-		CK(cudaGetLastError());
-		// The counters of the marking kernels are read back on a second stream while the update
-		// of the bricks that existed before this scan already runs (it backs off by itself if a
-		// pool overflowed); bricks created by this scan follow once their number is known.
-		CK(cudaEventRecord(m->ev_marked, s));
-		const bool aliases_possible = M.alias_miss != nullptr;
-		const bool speculate = !aliases_possible && bricks_before > 0 && !vol;
-		if (speculate) {
-			if (m->profiling) CK(cudaEventRecord(m->ev[4], s));
-			launch_update(m, a.miss, 0, bricks_before);
-		}
-		CK(cudaStreamWaitEvent(m->copy_stream, m->ev_marked, 0));
-		CK(cudaMemcpyAsync(m->h_ctr, M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->copy_stream));
-		CK(cudaStreamSynchronize(m->copy_stream));
-		speculated = speculate;
-		uint32_t ov = m->h_ctr->overflow;
-		if (!ov) break;
-		// an allocation failed: grow, restore consistent counters, run K1/K2 again
-		// (marking is idempotent: OR into masks, find-or-create of blocks)
-		++regrows;
-		if (regrows > 8) {
-			m->set_error("device pools keep overflowing");
-			return UFO_B200_E_NOMEM;
-		}
-		if (ov & 16u) {
-			m->set_error("internal error: a ray walk exceeded its record bound");
-			return UFO_B200_E_CUDA;
-		}
-		uint32_t wb = 0, wk = m->h_ctr->n_bricks, wu = m->h_ctr->n_upper;
-		m->n_bricks = std::min(wk, M.brick_cap);
-		if (ov & 32u) {
-			// first out-of-tree key ever seen by this map: allocate the alias mask arrays
-			CK(cudaStreamSynchronize(s));
-			if (!M.alias_miss) {
-				dev_alloc(M.alias_miss, (size_t)M.brick_cap * 64, 0, s, m->device_bytes);
-				dev_alloc(M.alias_hit, (size_t)M.brick_cap * 64, 0, s, m->device_bytes);
-			}
-		}
-		if (ov & 8u) {
-			unsigned long long want = m->h_ctr->seg_total + m->h_ctr->seg_total / 4 + 1024;
-			ensure_seg(m, want);
-			a.seg = m->d_seg;
-			a.seg_cap = m->seg_cap;
-
-		}
-		try {
-			grow_pools(m, ov, wb, wk, wu);
-		} catch (std::bad_alloc&) {
-			m->set_error("block pool cannot grow beyond 2^32 slots");
-			return UFO_B200_E_NOMEM;
-		}
-		push_counters(m);  // resets the per-scan counters; n_rays/bbox are recomputed by the re-run
-	}
-	m->n_bricks = m->h_ctr->n_bricks;
-	m->stats.regrows = regrows;
-
-	const bool aliases = m->h_ctr->alias_marks != 0 && M.alias_miss;
-	const uint32_t alias_grid = (uint32_t)(((size_t)m->n_bricks * 64 + 255) / 256);
-	if (m->profiling && !speculated) CK(cudaEventRecord(m->ev[4], s));
-	if (aliases) {
-		k_alias_apply<<<alias_grid, 256, 0, s>>>(M, m->n_bricks, M.hit, 1);
-		++m->launches;
-	}
-	// K3 (the part not launched speculatively above)
-	if (m->n_bricks) {
-		const uint32_t first = speculated ? bricks_before : 0u;
-		if (first < m->n_bricks) launch_update(m, vol ? set_value : a.miss, first, m->n_bricks, vol != nullptr);
-		const uint32_t agrid = (m->n_bricks + 7) / 8;
-		if (aliases) {
-			k_alias_apply<<<alias_grid, 256, 0, s>>>(M, m->n_bricks, a.miss, 0);
-			k_alias_refresh<<<alias_grid, 256, 0, s>>>(M, m->n_bricks);
-			m->launches += 2;
-		}
-		if (M.color) k_brick_agg<true><<<agrid, 256, 0, s>>>(M, m->n_bricks);
-		else k_brick_agg<false><<<agrid, 256, 0, s>>>(M, m->n_bricks);
-		++m->launches;
-	}
-	if (m->profiling) CK(cudaEventRecord(m->ev[5], s));
-	// K4: upper levels, depth 5 .. L.  Only bricks created by this scan can create upper
-	// nodes (at most one per level each), so the pool is grown up front to the exact
-	// worst case and the kernels never overflow.
-	if (M.g.depth_levels >= 5 && m->n_bricks) {
-		uint64_t new_bricks = m->n_bricks - bricks_before;
-		uint64_t need = (uint64_t)m->n_upper + new_bricks * (M.g.depth_levels - 4) + 1;
-		if (need > M.up_cap) {
-			m->h_ctr->n_upper = m->n_upper;
-			grow_pools(m, 4u, 0, 0, (uint32_t)std::min<uint64_t>(need, 0x7fffffffull));
-		}
-		// list_count[] is zero at this point (push_counters); level d reads list d&1 ? 0 : 1
-		k_upper_seed<<<(m->n_bricks + 255) / 256, 256, 0, s>>>(M, m->n_bricks, m->d_list[0], M.up_cap);
-		++m->launches;
-		const uint32_t L = M.g.depth_levels;
-		for (uint32_t d = 5; d <= std::min(6u, L); ++d) {
-			k_upper_level<<<m->sm_count, 256, 0, s>>>(M, d, m->d_list[(d & 1) ? 0 : 1], m->d_list[(d & 1) ? 1 : 0], M.up_cap);
-			++m->launches;
-		}
-		if (L >= 7) {
-			k_upper_tail<<<1, 1024, 0, s>>>(M, 7, m->d_list[0], m->d_list[1], M.up_cap);
-			++m->launches;
-		}
-		CK(cudaGetLastError());
-	}
-	CK(cudaEventRecord(m->ev[6], s));
-	m->ev_valid = true;
-	m->stats.launches = m->launches;
-	m->stats.result_bytes = sizeof(Counters) * (1 + regrows + 1);  // mid-scan check(s) + end-of-scan copy
-	CK(cudaMemcpyAsync(m->h_ctr, M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-	m->stats_pending = true;
+	if (copied) CK(cudaStreamWaitEvent(s, m->ev_copied, 0));
+	enqueue_scan(m, p);
+	// the caller's buffer is free again when this returns (the reference takes the cloud by value)
+	if (copied) CK(cudaEventSynchronize(m->ev_copied));
 	if (!async) return sync_map(m);
 	return UFO_B200_OK;
 }
@@ -763,6 +933,8 @@ int guarded(Map* m, F&& f)
 	} catch (CudaError& e) {
 		if (m) m->set_error("CUDA error %s (%d) at ufo_map.cu:%d: %s", cudaGetErrorName(e.e), (int)e.e, e.line, e.what);
 		return UFO_B200_E_CUDA;
+	} catch (MapError& e) {
+		return e.code;
 	} catch (std::bad_alloc&) {
 		if (m) m->set_error("out of memory");
 		return UFO_B200_E_NOMEM;
@@ -826,10 +998,17 @@ int ufo_b200_create(const ufo_b200_params* p, ufo_b200_map** out)
 		m->sm_count = prop.multiProcessorCount;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->ray_blocks_per_sm, k_rays<0, false>, kRayThreads, 0));
 		if (m->ray_blocks_per_sm < 1) m->ray_blocks_per_sm = 1;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->walk_blocks_per_sm, k_walk_mark<0, false, false>, kWalkThreads, 0));
+		if (m->walk_blocks_per_sm < 1) m->walk_blocks_per_sm = 1;
+		{
+			const char* e = getenv("UFO_B200_MARK");
+			m->force_records = e && !strcmp(e, "records");
+		}
 		m->params = *p;
 		CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
 		CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-		CK(cudaEventCreateWithFlags(&m->ev_marked, cudaEventDisableTiming));
+		CK(cudaEventCreate(&m->ev_copy0));
+		CK(cudaEventCreate(&m->ev_copied));
 		m->stream = m->own_stream;
 		for (auto& e : m->ev) CK(cudaEventCreate(&e));
 		CK(cudaHostAlloc(reinterpret_cast<void**>(&m->h_ctr), sizeof(Counters), cudaHostAllocDefault));
@@ -883,7 +1062,8 @@ void ufo_b200_destroy(ufo_b200_map* m)
 	if (m->h_ctr) cudaFreeHost(m->h_ctr);
 	if (m->own_stream) cudaStreamDestroy(m->own_stream);
 	if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
-	if (m->ev_marked) cudaEventDestroy(m->ev_marked);
+	if (m->ev_copy0) cudaEventDestroy(m->ev_copy0);
+	if (m->ev_copied) cudaEventDestroy(m->ev_copied);
 	delete m;
 }
 
@@ -1593,6 +1773,20 @@ int ufo_b200_set_sensor_model(ufo_b200_map* m, const double p[6])
 		m->cmin_log = to_logit(p[4]);
 		m->cmax_log = to_logit(p[5]);
 		refresh_model(m);
+		rebuild_flags(m);
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_set_sensor_model_field(ufo_b200_map* m, int index, double probability)
+{
+	if (!m || index < 0 || index > 5) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		sync_map(m);
+		double* field[6] = {&m->occ_thr_log, &m->free_thr_log, &m->hit_log, &m->miss_log, &m->cmin_log, &m->cmax_log};
+		*field[index] = to_logit(probability);
+		refresh_model(m);
+		if (index <= 1) rebuild_flags(m);
 		return (int)UFO_B200_OK;
 	});
 }
@@ -1640,6 +1834,13 @@ int ufo_b200_last_scan_stats(ufo_b200_map* m, ufo_b200_scan_stats* out)
 	});
 }
 
+int ufo_b200_completed_scan_stats(ufo_b200_map* m, ufo_b200_scan_stats* out)
+{
+	if (!m || !out) return UFO_B200_E_INVALID;
+	*out = m->done_stats;
+	return UFO_B200_OK;
+}
+
 int ufo_b200_set_profiling(ufo_b200_map* m, int enable)
 {
 	if (!m) return UFO_B200_E_INVALID;
@@ -1667,7 +1868,11 @@ int ufo_b200_clear(ufo_b200_map* m)
 	if (!m) return UFO_B200_E_INVALID;
 	return guarded(m, [&]() {
 		CK(cudaSetDevice(m->device));
-		sync_map(m);
+		try {
+			sync_map(m);
+		} catch (MapError&) {
+			// a scan that failed half-way: its marks are wiped below
+		}
 		DeviceMap& M = m->M;
 		cudaStream_t s = m->stream;
 		CK(cudaMemsetAsync(M.bh_tab, 0xff, ((size_t)M.bh_mask + 1) * sizeof(ulonglong2), s));
@@ -1690,6 +1895,8 @@ int ufo_b200_clear(ufo_b200_map* m)
 		m->n_bricks = 0;
 		m->n_upper = 0;
 		M.scan_id = 0;
+		M.up_epoch = 0;
+		m->poisoned = false;
 		reset_bbox(m);
 		CK(cudaStreamSynchronize(s));
 		return (int)UFO_B200_OK;
