@@ -12,9 +12,8 @@ import bench  # noqa: E402
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
-bench.RINGS, bench.AZIMUTHS = 4, 64  # tiny scans: only origins / shapes matter here
-origins, clouds = bench.make_scans(2, rank)
-assert clouds[0].shape == (256, 3) and clouds[0].dtype == np.float32
+origins, clouds, layout, xyzs, rgbs = bench.make_scans(bench.CONFIGS[2], 2, rank)
+assert clouds[0].shape == (131072, 3) and clouds[0].dtype == np.float32 and layout == 1
 # every rank integrates its own sensor: origins differ between ranks
 gathered = [None] * world
 dist.all_gather_object(gathered, origins[0].tolist())
