@@ -181,6 +181,17 @@ def make_scans(cfg, count, rank):
     return origins, packed, layout, xyzs, rgbs
 
 
+def route_slice(n_pts, rank, world, columns=2048):
+    """Rays of `rank` in the routed mode: a contiguous azimuth sector of every ring (ring-major
+    scan of `columns` azimuths per ring): neighbouring rays share bricks, so a rank's marks stay
+    mostly in bricks only it touches and little has to cross GPUs."""
+    if n_pts % columns:
+        return np.arange(rank, n_pts, world)
+    az = np.arange(n_pts) % columns
+    lo, hi = rank * columns // world, (rank + 1) * columns // world
+    return np.nonzero((az >= lo) & (az < hi))[0]
+
+
 def max_over_ranks(value, world, device=None):
     """MAX-reduce a per-rank scalar (the timed region of the slowest rank is the job's time)."""
     if world <= 1:
@@ -274,10 +285,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained e2e loop (0: skip)")
     ap.add_argument("--ref-budget", type=float, default=1200.0, help="--impl reference: wall-clock budget in seconds")
-    ap.add_argument("--mode", default="sensors", choices=["sensors", "shard"],
-                    help="N>1: 'sensors' = one sensor stream + map per GPU (weak scaling, default); "
-                         "'shard' = ONE scan stream, broadcast over NCCL, map sharded by brick ownership "
-                         "(strong scaling, SURVEY.md 8(e) variant 1)")
+    ap.add_argument("--mode", default="route", choices=["route", "merge", "sensors", "shard"],
+                    help="N>1: 'route' (default) = ONE scan stream, rays split over the GPUs, space-owned state, "
+                         "foreign marks written to the owners over NVLink peer memory (strong scaling, SURVEY.md "
+                         "8(e) variant 2); 'merge' = one sensor per GPU, owners apply the sensors in sensor order "
+                         "(BASELINE config #5, weak scaling); 'sensors' = independent replicas (one sensor stream + "
+                         "map per GPU, no merge); 'shard' = one stream broadcast, every GPU walks every ray and "
+                         "keeps its own bricks (variant 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     cfg = CONFIGS[args.config]
@@ -301,12 +315,24 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     total = args.steps + args.warmup
-    shard = args.mode == "shard" and world > 1
-    origins, packed, layout, xyzs, rgbs = make_scans(cfg, total, 0 if shard else rank)
+    mode = args.mode if world > 1 else "single"
+    if mode in ("route", "merge") and (cfg["color"] or cfg["discrete"]):
+        mode = "sensors"  # routed passes: mono maps, plain insertion
+    shard = mode == "shard"
+    routed = mode in ("route", "merge")
+    one_stream = mode in ("route", "shard")
+    origins, packed, layout, xyzs, rgbs = make_scans(cfg, total, 0 if one_stream else rank)
     n_pts = packed[0].shape[0]
     p_in = packed[0].nbytes // n_pts
+    if mode == "route":
+        # this rank's rays: an azimuth sector of every ring (the scan is ring-major, 2048 columns)
+        idx = route_slice(n_pts, rank, world)
+        packed = [np.ascontiguousarray(c[idx]) for c in packed]
+    n_mine = packed[0].shape[0]
     stream = torch.cuda.current_stream(dev)
     ins_kw = dict(max_range=cfg["max_range"], discrete=cfg["discrete"])
+    token = torch.zeros(1, device=dev) if routed else None
+    opened = []
 
     def barrier():
         if world > 1:
@@ -318,7 +344,35 @@ def main():
         m.set_stream(stream.cuda_stream)
         if shard:
             m.set_shard(rank, world)
+        if routed:
+            # inboxes: one cudaIpc handle per rank through the control plane, mapped by every peer
+            ptr = m.route_setup(rank, world, cap_bricks=max(1 << 16, 400000 // world), cap_hits=1 << 18)
+            handles = [None] * world
+            dist.all_gather_object(handles, capi.ipc_export(ptr))
+            peers = [ptr if r == rank else capi.ipc_open(handles[r]) for r in range(world)]
+            opened.extend(p for r, p in enumerate(peers) if r != rank)
+            m.route_connect(peers)
+            dist.barrier()
         return m
+
+    def close_map(m):
+        m.wait()
+        if routed:
+            dist.barrier()  # nobody writes into a peer inbox any more
+            while opened:
+                capi.ipc_close(opened.pop())
+            dist.barrier()
+        m.close()
+
+    def routed_step(mm, k, ptr, on_device):
+        mm.route_mark(origins[k], ptr, n_mine, layout, max_range=cfg["max_range"], on_device=on_device,
+                      self_too=(mode == "merge"))
+        dist.all_reduce(token)  # the barrier between forwarding and applying, ordered on the map's stream
+        if mode == "merge":
+            for s_ in range(world):
+                mm.route_apply(s_, 1, s_ == world - 1)
+        else:
+            mm.route_apply(0, world, True)
 
     def timed_loop(m, feed, first, count, sync_each=False):
         """`count` steps starting at scan index `first`; returns (ms, per-scan stats, launches, clocks)."""
@@ -357,13 +411,16 @@ def main():
 
     def feed_device(mm, k):
         src = d_clouds[k]
+        if routed:
+            routed_step(mm, k, src.data_ptr(), True)
+            return
         if shard:
             # the one collective of the sharded mode: rank 0's scan goes to every GPU
             if rank == 0:
                 bcast.copy_(src)
             dist.broadcast(bcast, src=0)
             src = bcast
-        mm.insert_packed(origins[k], src.data_ptr(), n_pts, layout, on_device=True, async_=True, **ins_kw)
+        mm.insert_packed(origins[k], src.data_ptr(), n_mine, layout, on_device=True, async_=True, **ins_kw)
 
     for k in range(args.warmup):
         feed_device(m, k)
@@ -373,7 +430,7 @@ def main():
     m.set_profiling(2)
     feed_device(m, total - 1)
     counted = m.stats()
-    m.close()
+    close_map(m)
     del d_clouds
     torch.cuda.empty_cache()
 
@@ -383,20 +440,23 @@ def main():
     stage = torch.empty_like(torch.from_numpy(packed[0]), device=dev) if shard else None
 
     def feed_host(mm, k):
+        if routed:
+            routed_step(mm, k, h_clouds[k].data_ptr(), False)
+            return
         if shard:
             if rank == 0:
                 stage.copy_(h_clouds[k], non_blocking=True)  # H2D once, on rank 0
             dist.broadcast(stage, src=0)
             mm.insert_packed(origins[k], stage.data_ptr(), n_pts, layout, on_device=True, async_=True, **ins_kw)
             return
-        mm.insert_packed(origins[k], h_clouds[k].data_ptr(), n_pts, layout, on_device=False, async_=True, **ins_kw)
+        mm.insert_packed(origins[k], h_clouds[k].data_ptr(), n_mine, layout, on_device=False, async_=True, **ins_kw)
 
     for k in range(args.warmup):
         feed_host(m, k)
     ms_e2e, e2e_scans, _, clocks_e2e = timed_loop(m, feed_host, args.warmup, args.steps)
     d2h = int(e2e_scans[-1]["result_bytes"])
     # fully serialised variant on a fresh map (same scans)
-    m.close()
+    close_map(m)
     m = fresh_map()
     for k in range(args.warmup):
         feed_host(m, k)
@@ -407,14 +467,14 @@ def main():
         est = max(ms_e2e / args.steps, 1e-3)
         count = int(args.sustain * 1e3 / est) + 1
         ms_sus, _, _, clocks_sus = timed_loop(m, feed_host, 0, count)
-        streams_ = 1 if shard else world
+        streams_ = 1 if one_stream else world
         sustained = {"seconds": ms_sus * 1e-3, "steps": count, "value": streams_ * count * n_pts / (ms_sus * 1e-3),
                      "unit": "points/s", "ms_per_step": ms_sus / count, "clocks": clocks_sus,
                      "note": "scans cycle through the same %d poses (the map stops growing; work per scan unchanged)" % total}
-    m.close()
+    close_map(m)
 
     steps = args.steps
-    streams = 1 if shard else world  # sharded mode integrates ONE stream with all GPUs
+    streams = 1 if one_stream else world  # route / shard integrate ONE stream with all GPUs
     value = streams * steps * n_pts / (ms_dev * 1e-3)
     e2e = streams * steps * n_pts / (ms_e2e * 1e-3)
     e2e_sync = streams * steps * n_pts / (ms_sync * 1e-3)
@@ -441,17 +501,24 @@ def main():
         line = {
             "metric": "points_integrated_per_s", "value": value, "unit": "points/s",
             "scans_per_s": value / n_pts, "n_gpus": world, "steps": steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "strong" if shard else "weak",
+            "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "strong" if one_stream else "weak",
             "vs_baseline": None, "dtype": "f64 geometry + f32 log-odds", "data": "synthetic",
             "config": {"workload": cfg["workload"], "points_per_scan": n_pts,
                        "input": "float32 xyz" + (" + rgb" if color else ""),
-                       "parallelism": ("1 map per GPU" if world == 1 else
-                                       ("one scan stream broadcast over NCCL, map sharded by brick ownership"
-                                        if shard else "one sensor stream + map per GPU, no merge (replicas)")),
+                       "parallelism": {
+                           "single": "1 map on 1 GPU",
+                           "route": "ONE scan stream; rays split over the GPUs by azimuth sector, state owned by space "
+                                    "(hash of the 16^3 brick), foreign brick masks / hit voxels written into the "
+                                    "owner's inbox over NVLink peer memory, one 4-byte NCCL all-reduce as barrier",
+                           "merge": "one sensor per GPU (BASELINE config #5 shape); owners apply the sensors' marks in "
+                                    "sensor order; marks forwarded over NVLink peer memory",
+                           "shard": "one scan stream broadcast over NCCL, every GPU walks every ray, map sharded by brick ownership",
+                           "sensors": "one sensor stream + map per GPU, no merge (independent replicas)"}[mode],
+                       "mode": mode,
                        "l2": "per-scan working set (%.1f GB leaf data touched, map %.1f GB) exceeds the 126 MB L2; no flush"
                              % (last["touched_blocks"] * (512 if color else 256) / 1e9, dev_bytes / 1e9)},
             "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e / steps,
-                    "h2d_bytes_per_step": int(n_pts * p_in), "d2h_bytes_per_step": d2h,
+                    "h2d_bytes_per_step": int(n_mine * p_in), "d2h_bytes_per_step": d2h,
                     "mode": "async=1 (server default): H2D of scan k+1 overlaps the kernels of scan k",
                     "sync": {"value": e2e_sync, "ms_per_step": ms_sync / steps,
                              "mode": "wait + read the scan's own counters after every insert"}},

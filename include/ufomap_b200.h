@@ -204,6 +204,15 @@ int ufo_b200_write_file(ufo_b200_map* m, const char* filename, const double* box
 int ufo_b200_write_data(ufo_b200_map* m, const double* box6, uint32_t min_depth, void* buf, size_t cap,
                         size_t* size);
 
+/* Octree::write / writeData with compress = true (octree.h:812-917, :1428-1456): the node stream
+ * as one LZ4 block (LZ4_compress_fast with acceleration_level when compression_level <= 0, else
+ * LZ4_compress_HC), behind the text header with "compressed 1" unless data_only.  liblz4.so.1 is
+ * loaded at run time, like the reference links it; UFO_B200_E_UNSUPPORTED if it is absent.
+ * *uncompressed_size = what the header's uncompressed_data_size says (writeData's return value). */
+int ufo_b200_write_compressed(ufo_b200_map* m, const double* box6, uint32_t min_depth, int data_only,
+                              int acceleration_level, int compression_level, void* buf, size_t cap, size_t* size,
+                              size_t* uncompressed_size);
+
 /* Sensor model  occupancy_map_base.h:734-773.  out6/in: occupied_thres,
  * free_thres, prob_hit, prob_miss, clamping_thres_min, clamping_thres_max as
  * probabilities (setters) or as stored double log-odds (ufo_b200_sensor_model_logit). */
@@ -220,6 +229,16 @@ int ufo_b200_sensor_model_logit(const ufo_b200_map* m, double logit6[6]);
 /* min/max change detection  occupancy_map_base.h:792-822 (always enabled). */
 int ufo_b200_change_bbox(ufo_b200_map* m, double min_change[3], double max_change[3]);
 int ufo_b200_reset_change_bbox(ufo_b200_map* m);
+
+/* Change detection  occupancy_map_base.h:779-790 (enableChangeDetection / resetChangeDetection /
+ * changesBegin..changesEnd / numChangedDetected): the set of nodes whose occupancy value changed
+ * since the last reset (updateOccupancy returned true, :1070, :1094, :1106).  Recorded per voxel on
+ * the device; ufo_b200_changed_codes returns the set at `depth` -- the insert depth the caller
+ * used, 0 for the server's default -- as Code values (with the centre bits a Code built from a
+ * depth-d Key carries), unordered like the reference's CodeSet.  codes == NULL: count only. */
+int ufo_b200_enable_change_detection(ufo_b200_map* m, int enable);
+int ufo_b200_reset_change_detection(ufo_b200_map* m);
+int ufo_b200_changed_codes(ufo_b200_map* m, uint32_t depth, uint64_t* codes, size_t cap, size_t* n);
 
 /* Counters and timings of the most recent insert (waits for it to finish). */
 typedef struct {
@@ -268,6 +287,46 @@ int ufo_b200_set_profiling(ufo_b200_map* m, int enable);
  * ranks' value fields is the single-GPU map; no state is exchanged.  Aggregates of depth >= 5 are
  * per rank (partial) in this mode.  Must be called on an empty map.  world <= 1 turns it off. */
 int ufo_b200_set_shard(ufo_b200_map* m, uint32_t rank, uint32_t world);
+
+/* Routed multi-GPU mode (variant 2; BASELINE configs #4 "octant shard" and #5
+ * "one GPU per sensor with boundary merge").  The reference integrates on one thread
+ * (occupancy_map_base.h:270-327); this is the multi-GPU form of the same insertPointCloud:
+ * state is owned by space (rank = hash of the 16^3-voxel brick key, as in ufo_b200_set_shard),
+ * marking is parallel over rays.  Every rank walks ITS rays -- a slice of one scan, or its own
+ * sensor's scan -- and the per-brick free-space masks / hit voxels of bricks another rank owns
+ * are written straight into that rank's inbox over NVLink peer memory; the only collective is a
+ * barrier between the two calls below (the caller's: e.g. a 4-byte NCCL all-reduce on the map's
+ * stream).  Mono maps, insert depth 0, plain (non-discrete) insertion.
+ *
+ *   ufo_b200_route_setup    allocates this rank's inbox (cap_bricks brick records and cap_hits hit
+ *                           voxels per source rank and parity) and returns its device pointer
+ *   ufo_b200_ipc_export/_open   cudaIpc handle of that pointer / mapping of a peer's handle, for
+ *                           one-process-per-GPU launches (handles travel through the caller's
+ *                           control plane, e.g. torch.distributed.all_gather_object)
+ *   ufo_b200_route_connect  peer_inboxes[r] = device pointer of rank r's inbox as seen from this
+ *                           process (its own for r == rank)
+ *   ufo_b200_route_mark     enqueue: H2D, K1, fused walk, forwarding of foreign marks.  self_too != 0:
+ *                           the rank's own marks go through its inbox as well, which lets the
+ *                           owner apply several sensors one after the other (clamping makes the
+ *                           order matter)
+ *   -- barrier across the ranks, ordered after route_mark on the map's stream --
+ *   ufo_b200_route_apply    enqueue: marks received from sources [first_source, first_source +
+ *                           n_sources) -> K3; last != 0 additionally runs the inner-node
+ *                           propagation and ends the pass.  One scan split over the ranks:
+ *                           route_apply(0, world, 1).  One sensor per rank, merged in sensor order:
+ *                           route_apply(s, 1, s == world - 1) for s = 0..world-1.
+ * The union of the ranks' value fields equals the single-GPU map (tests/test_gpu_route.py).  Pools
+ * do not grow during a routed pass: size the map with initial_bricks. */
+int ufo_b200_route_inbox_bytes(uint32_t world, uint32_t cap_bricks, uint32_t cap_hits, size_t* bytes);
+int ufo_b200_route_setup(ufo_b200_map* m, uint32_t rank, uint32_t world, uint32_t cap_bricks, uint32_t cap_hits,
+                         void** inbox);
+int ufo_b200_route_connect(ufo_b200_map* m, void* const* peer_inboxes);
+int ufo_b200_route_mark(ufo_b200_map* m, const double origin[3], const void* points, size_t n, int layout,
+                        double max_range, int on_device, int self_too);
+int ufo_b200_route_apply(ufo_b200_map* m, uint32_t first_source, uint32_t n_sources, int last);
+int ufo_b200_ipc_export(void* dev_ptr, void* handle64);
+int ufo_b200_ipc_open(const void* handle64, void** dev_ptr);
+int ufo_b200_ipc_close(void* dev_ptr);
 
 /* Forget everything (Octree::clear, octree.h:541-560): keeps device pools. */
 int ufo_b200_clear(ufo_b200_map* m);

@@ -586,6 +586,27 @@ class MapFacade
 	void setClampingThresMax(double p) { ufo_b200_set_sensor_model_field(map_, 5, p); }
 
 	//
+	// Change detection (occupancy_map_base.h:779-790): the nodes whose value changed since the last
+	// reset, recorded per voxel on the device and read out at the depth of the last insert (0 for
+	// the server's default), unordered like the reference's CodeSet
+	//
+	using ChangeSet = std::vector<Code>;
+	void enableChangeDetection(bool enable) noexcept
+	{
+		ufo_b200_enable_change_detection(map_, enable);
+		change_enabled_ = enable;
+	}
+	bool isChangeDetectionEnabled() const noexcept { return change_enabled_; }
+	void resetChangeDetection() noexcept
+	{
+		ufo_b200_reset_change_detection(map_);
+		changes_.clear();
+	}
+	std::size_t numChangedDetected() const { return changes().size(); }
+	ChangeSet::const_iterator changesBegin() const { return changes().begin(); }
+	ChangeSet::const_iterator changesEnd() const { return changes_.end(); }
+
+	//
 	// Min/max change detection (occupancy_map_base.h:792-822); always recorded on the device
 	//
 	void enableMinMaxChangeDetection(bool enable) noexcept
@@ -658,6 +679,7 @@ class MapFacade
 	            ufo::math::Pose6 const* frame = nullptr)
 	{
 		using P = std::decay_t<decltype(cloud[0])>;
+		change_depth_ = depth;
 		double pose[7];
 		if (frame) frame->pack(pose);
 		constexpr bool has_color = std::is_base_of_v<Point3Color, P>;
@@ -716,7 +738,22 @@ class MapFacade
 		return s.good() ? (int)n : -1;
 	}
 
+	ChangeSet const& changes() const
+	{
+		std::size_t n = 0;
+		ufo_b200_changed_codes(map_, change_depth_, nullptr, 0, &n);
+		std::vector<std::uint64_t> raw(n ? n : 1);
+		ufo_b200_changed_codes(map_, change_depth_, raw.data(), n, &n);
+		changes_.clear();
+		changes_.reserve(n);
+		for (std::size_t i = 0; i < n; ++i) changes_.emplace_back(raw[i], change_depth_);
+		return changes_;
+	}
+
 	ufo_b200_map* map_ = nullptr;
+	mutable ChangeSet changes_;
+	bool change_enabled_ = false;
+	DepthType change_depth_ = 0;
 	ufo_b200_params params_{};
 	mutable double model_[6] = {0, 0, 0, 0, 0, 0};
 	bool minmax_enabled_ = false;

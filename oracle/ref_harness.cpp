@@ -23,12 +23,38 @@
 #include <string>
 #include <vector>
 
-// ---- LZ4 stubs (compressed file I/O is never used by the oracle) -------------
+// ---- LZ4 (the image has liblz4.so.1 without development files): the four entry points the
+// reference calls (octree.h:1436-1445, :1473) forward to the system library, loaded on first use
+#include <dlfcn.h>
+namespace
+{
+void* lz4_sym(const char* name)
+{
+	static void* lib = dlopen("liblz4.so.1", RTLD_NOW | RTLD_LOCAL);
+	return lib ? dlsym(lib, name) : nullptr;
+}
+}  // namespace
 extern "C" {
-int LZ4_compressBound(int) { return 0; }
-int LZ4_compress_fast(const char*, char*, int, int, int) { return -1; }
-int LZ4_decompress_safe(const char*, char*, int, int) { return -1; }
-int LZ4_compress_HC(const char*, char*, int, int, int) { return -1; }
+int LZ4_compressBound(int n)
+{
+	auto f = reinterpret_cast<int (*)(int)>(lz4_sym("LZ4_compressBound"));
+	return f ? f(n) : 0;
+}
+int LZ4_compress_fast(const char* a, char* b, int c, int d, int e)
+{
+	auto f = reinterpret_cast<int (*)(const char*, char*, int, int, int)>(lz4_sym("LZ4_compress_fast"));
+	return f ? f(a, b, c, d, e) : -1;
+}
+int LZ4_decompress_safe(const char* a, char* b, int c, int d)
+{
+	auto f = reinterpret_cast<int (*)(const char*, char*, int, int)>(lz4_sym("LZ4_decompress_safe"));
+	return f ? f(a, b, c, d) : -1;
+}
+int LZ4_compress_HC(const char* a, char* b, int c, int d, int e)
+{
+	auto f = reinterpret_cast<int (*)(const char*, char*, int, int, int)>(lz4_sym("LZ4_compress_HC"));
+	return f ? f(a, b, c, d, e) : -1;
+}
 }
 
 namespace
@@ -370,6 +396,34 @@ void ufo_ref_node_batch(void* h, const uint64_t* codes, const uint32_t* depths, 
 	});
 }
 
+// Change detection (occupancy_map_base.h:779-790): the reference's own changes_ set.
+void ufo_ref_enable_changes(void* h, int enable)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	withMap(m, [&](auto& map) { map.enableChangeDetection(enable != 0); });
+}
+
+void ufo_ref_reset_changes(void* h)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	withMap(m, [&](auto& map) { map.resetChangeDetection(); });
+}
+
+size_t ufo_ref_changes(void* h, uint64_t* codes, uint32_t* depths, size_t cap)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	return withMap(m, [&](auto& map) {
+		size_t n = 0;
+		for (auto it = map.changesBegin(); it != map.changesEnd(); ++it, ++n) {
+			if (codes && n < cap) {
+				codes[n] = (*it).getCode();
+				depths[n] = (*it).getDepth();
+			}
+		}
+		return n;
+	});
+}
+
 // Returns 1 if a node exists at exactly (code, depth); out describes the deepest
 // existing node on the path either way.
 int ufo_ref_node(void* h, uint64_t code, unsigned depth, float* occ, uint8_t* rgb,
@@ -509,6 +563,18 @@ size_t ufo_ref_write(void* h, uint8_t* buf, size_t cap)
 	RefMap* m = static_cast<RefMap*>(h);
 	std::stringstream ss(std::ios_base::in | std::ios_base::out | std::ios_base::binary);
 	withMap(m, [&](auto& map) { return map.write(ss, false); });
+	const std::string str = ss.str();
+	if (buf && str.size() <= cap) std::memcpy(buf, str.data(), str.size());
+	return str.size();
+}
+
+// Octree::write(ostream, compress = true, min_depth, acceleration, level): LZ4-compressed file image
+size_t ufo_ref_write_compressed(void* h, unsigned min_depth, int acceleration, int level, uint8_t* buf, size_t cap)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	std::stringstream ss(std::ios_base::in | std::ios_base::out | std::ios_base::binary);
+	bool ok = withMap(m, [&](auto& map) { return map.write(ss, true, min_depth, acceleration, level); });
+	if (!ok) return 0;
 	const std::string str = ss.str();
 	if (buf && str.size() <= cap) std::memcpy(buf, str.data(), str.size());
 	return str.size();

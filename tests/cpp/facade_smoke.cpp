@@ -1,6 +1,7 @@
-// Reads like a program written against the reference: only the include line differs
-// (#include <ufo/map/ufomap.h> there).  Built and run by tests/test_facade.py.
-#include <ufomap_b200/ufomap.hpp>
+// Reads like a program written against the reference, include lines included (include/ufo/ holds
+// forwarding headers under the reference's own paths).  Built and run by tests/test_facade.py.
+#include <ufo/map/occupancy_map.h>
+#include <ufo/map/occupancy_map_color.h>
 
 #include <cstdio>
 #include <cstring>

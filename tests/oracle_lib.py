@@ -89,6 +89,10 @@ def _load(path, prefix):
         api["clear"] = sig("clear", None, [vp, dbl, u32])
         api["field"] = sig("field", sz, [vp, vp, vp, vp, sz])
         api["node_batch"] = sig("node_batch", None, [vp, vp, vp, sz, vp, vp, vp, vp])
+        api["write_compressed"] = sig("write_compressed", sz, [vp, u32, i32, i32, vp, sz])
+        api["enable_changes"] = sig("enable_changes", None, [vp, i32])
+        api["reset_changes"] = sig("reset_changes", None, [vp])
+        api["changes"] = sig("changes", sz, [vp, vp, vp, sz])
     if prefix == "ufo_oracle_":
         api["last_counters"] = sig("last_counters", None, [vp, vp])
         api["canonicalize"] = sig("canonicalize", None, [vp])
@@ -299,6 +303,30 @@ class RefMap(_CpuMap):
                                     rgb.ctypes.data if self.color else None, n)
             assert got == n
         return codes, occ, rgb
+
+    def write_compressed(self, min_depth=0, acceleration=1, level=0):
+        """Octree::write(ostream, compress=True, ...): LZ4-compressed file image (b"" on failure)."""
+        n = self.api["write_compressed"](self.h, int(min_depth), int(acceleration), int(level), None, 0)
+        buf = np.empty(max(n, 1), np.uint8)
+        if n:
+            assert self.api["write_compressed"](self.h, int(min_depth), int(acceleration), int(level), buf.ctypes.data, n) == n
+        return buf[:n].tobytes()
+
+    def enable_change_detection(self, enable=True):
+        self.api["enable_changes"](self.h, int(enable))
+
+    def reset_change_detection(self):
+        self.api["reset_changes"](self.h)
+
+    def changed_codes(self):
+        """(sorted codes, depths) of the reference's changes_ set."""
+        n = self.api["changes"](self.h, None, None, 0)
+        codes = np.empty(n, np.uint64)
+        depths = np.empty(n, np.uint32)
+        if n:
+            self.api["changes"](self.h, codes.ctypes.data, depths.ctypes.data, n)
+        order = np.argsort(codes, kind="stable")
+        return codes[order], depths[order]
 
     def field_count(self):
         """Number of non-default depth-0 voxels (collapsed nodes counted as 8^depth)."""

@@ -144,3 +144,31 @@ def test_region_file_and_reset(tmp_path):
     a, b = gpu.value_field(), ref.value_field()
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
     gpu.close()
+
+
+@pytest.mark.parametrize("name", ["velodyne", "rgbd_color_discrete"])
+def test_compressed_image_matches_the_reference(name):
+    """write(compress=True): one LZ4 block behind the header (octree.h:1428-1456).  The same liblz4
+    on both sides -> byte-identical to the reference's own compressed file, for the fast and the
+    HC compressor; the data-only form decompresses to the uncompressed node stream."""
+    if not have_ref():
+        pytest.skip("needs the compiled reference")
+    import ctypes
+    kw, inserts, color = _scenario(name)
+    gpu, ref = Map(color=color, initial_blocks=1 << 12, **kw), RefMap(color=color, **kw)
+    for ins in inserts:
+        gpu.insert(**ins)
+        ref.insert(**ins)
+    for accel, level in ((1, 0), (4, 0), (1, 6)):
+        image, usize = gpu.write_compressed(acceleration=accel, level=level)
+        want = ref.write_compressed(acceleration=accel, level=level)
+        assert len(want) > 0 and image == want, (accel, level, len(image), len(want))
+        assert b"compressed 1\n" in image[:300] and (b"uncompressed_data_size %d\n" % usize) in image[:300]
+    raw = gpu.write_data()
+    packed, usize = gpu.write_compressed(data_only=True)
+    assert usize == len(raw) and len(packed) < len(raw)
+    lz4 = ctypes.CDLL("liblz4.so.1")
+    out = ctypes.create_string_buffer(usize)
+    n = lz4.LZ4_decompress_safe(packed, out, len(packed), usize)
+    assert n == usize and out.raw == raw
+    gpu.close()

