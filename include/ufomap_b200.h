@@ -204,6 +204,25 @@ int ufo_b200_write_file(ufo_b200_map* m, const char* filename, const double* box
 int ufo_b200_write_data(ufo_b200_map* m, const double* box6, uint32_t min_depth, void* buf, size_t cap,
                         size_t* size);
 
+/* castRay  occupancy_map_base.h:449-486, batched.  The reference's own version does not compile
+ * (SURVEY.md G5); this is its intent (DESIGN.md section 8 states it; the CPU checker restates it): max_range < 0 -> the map's
+ * diagonal; the ray origin + t * direction, clipped into the map, is walked forward at `depth`;
+ * the first occupied node is the hit (hit[i] = 1, codes[i] = its Code), an unknown node ends the
+ * ray unless ignore_unknown.  Node state follows the intended getNode semantics of ufo_b200_query. */
+int ufo_b200_cast_rays(ufo_b200_map* m, const double* origins, const double* directions, size_t n,
+                       int ignore_unknown, double max_range, uint32_t depth, uint64_t* codes, uint8_t* hit);
+
+/* Leaf iteration with state and bounding-volume filters (beginLeaves(occupied, free, unknown,
+ * contains = false, min_depth) and its bounding-volume form, occupancy_map_base.h:130-216; validity
+ * rule iterator/occupancy_map.h:168-207), as a batch: every node of depth `depth` in the known
+ * space whose own state passes the filter (occupied: value > occupied threshold; free: value <
+ * free threshold; unknown: in between; an inner node carries the maximum of its subtree) and whose
+ * cube intersects the AABB box6 (centre, half size; NULL: everywhere).  codes carry the depth's
+ * centre bits; unordered.  A leaf the reference keeps collapsed above `depth` appears as its
+ * depth-`depth` cells.  codes == NULL: count only. */
+int ufo_b200_export_nodes(ufo_b200_map* m, uint32_t depth, int occupied, int free_space, int unknown, const double* box6,
+                          uint64_t* codes, float* logodds, uint8_t* rgb, size_t cap, size_t* n);
+
 /* Octree::write / writeData with compress = true (octree.h:812-917, :1428-1456): the node stream
  * as one LZ4 block (LZ4_compress_fast with acceleration_level when compression_level <= 0, else
  * LZ4_compress_HC), behind the text header with "compressed 1" unless data_only.  liblz4.so.1 is

@@ -424,6 +424,33 @@ size_t ufo_ref_changes(void* h, uint64_t* codes, uint32_t* depths, size_t cap)
 	});
 }
 
+// beginLeaves(occupied, free, unknown, contains = false, min_depth) with an optional AABB
+// (occupancy_map_base.h:130-216): the reference's own leaf iteration, for the filtered read-out.
+size_t ufo_ref_leaves(void* h, int occupied, int free_space, int unknown, const double* box6, unsigned min_depth,
+                      uint64_t* codes, uint32_t* depths, float* occ, size_t cap)
+{
+	RefMap* m = static_cast<RefMap*>(h);
+	return withMap(m, [&](auto& map) {
+		size_t n = 0;
+		auto emit = [&](auto it, auto end) {
+			for (; it != end; ++it, ++n) {
+				if (codes && n < cap) {
+					codes[n] = it.getCode().getCode();
+					depths[n] = it.getDepth();
+					occ[n] = (float)it->occupancy;
+				}
+			}
+		};
+		if (box6) {
+			ufo::geometry::AABB box(Point3(box6[0], box6[1], box6[2]), Point3(box6[3], box6[4], box6[5]));
+			emit(map.beginLeaves(box, occupied != 0, free_space != 0, unknown != 0, false, min_depth), map.endLeaves());
+		} else {
+			emit(map.beginLeaves(occupied != 0, free_space != 0, unknown != 0, false, min_depth), map.endLeaves());
+		}
+		return n;
+	});
+}
+
 // Returns 1 if a node exists at exactly (code, depth); out describes the deepest
 // existing node on the path either way.
 int ufo_ref_node(void* h, uint64_t code, unsigned depth, float* occ, uint8_t* rgb,

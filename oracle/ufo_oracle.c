@@ -982,6 +982,51 @@ size_t ufo_oracle_compute_ray(void* h, const double* origin, const double* end_i
 	return n;
 }
 
+/* castRay, OMB:449-486 -- the reference version does not compile (it tests
+ * isOccupied(std::optional) and derives the default range from getMin().distance(getMin())), so
+ * this is its INTENT, written down once and shared by the checker and the product:
+ *   max_range < 0 -> the map's diagonal; direction normalised; end = origin + direction * max_range;
+ *   both clipped into the map (moveLineIntoBBX; outside: no hit); forward walk at `depth` from the
+ *   origin's node: an occupied node is returned, an unknown node stops the ray unless
+ *   ignore_unknown; the walk ends like computeRay (current == ending or min t_max > max_range) and
+ *   the node it stopped in is tested once more.  Node state = the intended getNode semantics (value
+ *   of the deepest existing node on the path; inner nodes carry the maximum of their subtree).
+ * Returns 1 and the Code (with the depth's centre bits) on a hit. */
+int ufo_oracle_cast_ray(void* h, const double* origin_in, const double* dir_in, int ignore_unknown,
+                        double max_range, unsigned depth, uint64_t* code)
+{
+	omap* m = (omap*)h;
+	double o[3] = {origin_in[0], origin_in[1], origin_in[2]};
+	double d[3] = {dir_in[0], dir_in[1], dir_in[2]};
+	if (0 > max_range) {
+		double hs = node_half(m, m->levels), diag[3] = {hs + hs, hs + hs, hs + hs};
+		max_range = v3_norm(diag);
+	}
+	double nrm = v3_norm(d);
+	for (int i = 0; i < 3; ++i) d[i] /= nrm;
+	double e[3];
+	for (int i = 0; i < 3; ++i) e[i] = o[i] + (d[i] * max_range);
+	if (!move_line_inside(m, o, e)) return 0;
+	dda s;
+	dda_init(m, o, e, d, depth, &s);
+	for (;;) {
+		float occ;
+		uint8_t rgb[3], fl;
+		unsigned fd;
+		uint64_t c = key_to_code(s.cur);
+		ufo_oracle_node(h, c, depth, &occ, rgb, &fl, &fd);
+		int occupied = m->occ_thr < (double)occ;
+		int last = s.same || key_eq(s.cur, s.end) || !(min3(s.t_max) <= max_range);
+		if (occupied) {
+			*code = c;
+			return 1;
+		}
+		if (last) return 0;
+		if (!ignore_unknown && is_unknown(m, occ)) return 0;
+		dda_step(&s);
+	}
+}
+
 size_t ufo_oracle_free_set(void* h, const double* origin, const double* ends, size_t n,
                            unsigned depth, int simple, unsigned early_stopping, uint64_t* codes,
                            size_t cap)

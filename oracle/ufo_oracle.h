@@ -34,6 +34,9 @@ int ufo_oracle_node(void* h, uint64_t code, unsigned depth, float* occ, uint8_t*
 
 size_t ufo_oracle_compute_ray(void* h, const double* origin, const double* end, double max_range,
                               unsigned depth, uint64_t* codes, size_t cap);
+/* castRay as intended (the reference's does not compile, see ufo_oracle.c); 1 = hit */
+int ufo_oracle_cast_ray(void* h, const double* origin, const double* direction, int ignore_unknown,
+                        double max_range, unsigned depth, uint64_t* code);
 size_t ufo_oracle_free_set(void* h, const double* origin, const double* ends, size_t n,
                            unsigned depth, int simple, unsigned early_stopping, uint64_t* codes,
                            size_t cap);

@@ -89,12 +89,14 @@ def _load(path, prefix):
         api["clear"] = sig("clear", None, [vp, dbl, u32])
         api["field"] = sig("field", sz, [vp, vp, vp, vp, sz])
         api["node_batch"] = sig("node_batch", None, [vp, vp, vp, sz, vp, vp, vp, vp])
+        api["leaves"] = sig("leaves", sz, [vp, i32, i32, i32, vp, u32, vp, vp, vp, sz])
         api["write_compressed"] = sig("write_compressed", sz, [vp, u32, i32, i32, vp, sz])
         api["enable_changes"] = sig("enable_changes", None, [vp, i32])
         api["reset_changes"] = sig("reset_changes", None, [vp])
         api["changes"] = sig("changes", sz, [vp, vp, vp, sz])
     if prefix == "ufo_oracle_":
         api["last_counters"] = sig("last_counters", None, [vp, vp])
+        api["cast_ray"] = sig("cast_ray", i32, [vp, vp, vp, i32, dbl, u32, vp])
         api["canonicalize"] = sig("canonicalize", None, [vp])
     _libs[key] = api
     return api
@@ -304,6 +306,19 @@ class RefMap(_CpuMap):
             assert got == n
         return codes, occ, rgb
 
+    def leaves(self, occupied=True, free=True, unknown=False, box=None, min_depth=0):
+        """The reference's beginLeaves(...) iteration: (codes, depths, occ) in iteration order."""
+        b = None if box is None else np.ascontiguousarray(np.concatenate([box[0], box[1]]), np.float64)
+        bp = None if b is None else b.ctypes.data
+        n = self.api["leaves"](self.h, int(occupied), int(free), int(unknown), bp, int(min_depth), None, None, None, 0)
+        codes = np.empty(n, np.uint64)
+        depths = np.empty(n, np.uint32)
+        occ = np.empty(n, np.float32)
+        if n:
+            self.api["leaves"](self.h, int(occupied), int(free), int(unknown), bp, int(min_depth), codes.ctypes.data,
+                               depths.ctypes.data, occ.ctypes.data, n)
+        return codes, depths, occ
+
     def write_compressed(self, min_depth=0, acceleration=1, level=0):
         """Octree::write(ostream, compress=True, ...): LZ4-compressed file image (b"" on failure)."""
         n = self.api["write_compressed"](self.h, int(min_depth), int(acceleration), int(level), None, 0)
@@ -358,6 +373,19 @@ class RefMap(_CpuMap):
 class OracleMap(_CpuMap):
     _path = ORACLE_SO
     _prefix = "ufo_oracle_"
+
+    def cast_rays(self, origins, directions, ignore_unknown=False, max_range=-1.0, depth=0):
+        """castRay (intended semantics) for every (origin, direction): (hit bool[n], code u64[n])."""
+        o, d = _f64(origins).reshape(-1, 3), _f64(directions).reshape(-1, 3)
+        hit = np.zeros(len(o), bool)
+        codes = np.zeros(len(o), np.uint64)
+        c = C.c_uint64()
+        for i in range(len(o)):
+            if self.api["cast_ray"](self.h, o[i].ctypes.data, d[i].ctypes.data, int(ignore_unknown),
+                                    float(max_range), int(depth), C.byref(c)):
+                hit[i] = True
+                codes[i] = c.value
+        return hit, codes
 
     def canonicalize(self):
         """Collapse every collapsible node: the canonical minimal tree of the value field."""

@@ -405,3 +405,68 @@ def test_change_detection_matches_the_reference_set():
     before = gpu.changed_codes(1)
     gpu.insert(o, p, max_range=12.0)
     assert np.array_equal(gpu.changed_codes(1), before)
+
+
+def test_cast_rays_against_the_specified_intent():
+    """castRay (occupancy_map_base.h:449-486; the reference's version does not compile, its intent
+    is restated in oracle/ufo_oracle.c): batched on the device == the checker, ray by ray."""
+    gpu, cpu = Map(0.1), OracleMap(0.1)
+    for k in range(3):
+        o, p = scans.velodyne64(k=k, rings=32, azimuths=256)
+        gpu.insert(o, p, max_range=25.0)
+        cpu.insert(o, p, max_range=25.0)
+    rng = np.random.default_rng(11)
+    o, p = scans.velodyne64(k=1, rings=32, azimuths=256)
+    idx = rng.integers(0, len(p), 400)
+    # origins inside observed free space (part of the way along measured rays), random directions,
+    # plus rays that start outside the map and rays along the measured directions
+    origins = o + (p[idx] - o) * rng.uniform(0.1, 0.8, (len(idx), 1))
+    dirs = rng.normal(size=(len(idx), 3))
+    dirs[:100] = p[idx[:100]] - o
+    origins[-10:] = origins[-10:] + 5000.0
+    for depth in (0, 1, 3, 5):
+        for ign in (False, True):
+            for rng_max in (-1.0, 6.0):
+                hg, cg = gpu.cast_rays(origins, dirs, ignore_unknown=ign, max_range=rng_max, depth=depth)
+                hc, cc = cpu.cast_rays(origins, dirs, ignore_unknown=ign, max_range=rng_max, depth=depth)
+                assert np.array_equal(hg, hc), (depth, ign, rng_max, int((hg != hc).sum()))
+                assert np.array_equal(cg[hg], cc[hc])
+        if depth == 0:
+            assert hg.sum() > 50  # ignore_unknown, 6 m: plenty of rays end in an occupied voxel
+
+
+def test_filtered_leaf_iteration_matches_the_reference():
+    """beginLeaves(occupied, free, unknown, contains=false, min_depth) [+ AABB]
+    (occupancy_map_base.h:130-216) against ufo_b200_export_nodes: same set of depth-d cells with
+    the same values (a leaf the reference keeps collapsed above d is expanded into its cells)."""
+    if not have_ref():
+        pytest.skip("needs the compiled reference")
+    gpu, ref = Map(0.1), RefMap(0.1)
+    for k in range(3):
+        o, p = scans.velodyne64(k=k, rings=16, azimuths=256)
+        gpu.insert(o, p, max_range=15.0)
+        ref.insert(o, p, max_range=15.0)
+    box = (np.array([-3.05, -2.05, -1.55]), np.array([6.05, 4.05, 2.05]))
+
+    def expand(codes, depths, occ, d):
+        out_c, out_v = [], []
+        for D in np.unique(depths):
+            sel = depths == D
+            base = (codes[sel] >> np.uint64(3 * D)) << np.uint64(3 * D)
+            reps = 1 << (3 * (int(D) - d))
+            offs = (np.arange(reps, dtype=np.uint64) << np.uint64(3 * d))
+            out_c.append((base[:, None] + offs[None, :]).reshape(-1))
+            out_v.append(np.repeat(occ[sel], reps))
+        c, v = np.concatenate(out_c), np.concatenate(out_v)
+        order = np.argsort(c, kind="stable")
+        return c[order], v[order]
+
+    for d in (0, 1, 2, 3, 4, 6):
+        for kw in (dict(), dict(free=False), dict(occupied=False), dict(box=box), dict(box=box, occupied=False)):
+            rc, rd, rv = ref.leaves(min_depth=d, **kw)
+            assert (rd >= d).all()
+            want_c, want_v = expand(rc, rd, rv, d)
+            gc, gv, _ = gpu.export_nodes(depth=d, **kw)
+            gc = (gc >> np.uint64(3 * d)) << np.uint64(3 * d)
+            assert np.array_equal(gc, want_c), (d, kw.keys(), len(gc), len(want_c))
+            assert np.array_equal(gv.view(np.uint32), want_v.view(np.uint32)), (d, kw.keys())

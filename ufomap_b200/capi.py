@@ -62,7 +62,7 @@ SYMBOLS = [
     "ufo_b200_completed_scan_stats", "ufo_b200_set_sensor_model_field",
     "ufo_b200_route_inbox_bytes", "ufo_b200_route_setup", "ufo_b200_route_connect", "ufo_b200_route_mark",
     "ufo_b200_route_apply", "ufo_b200_ipc_export", "ufo_b200_ipc_open", "ufo_b200_ipc_close",
-    "ufo_b200_write_compressed", "ufo_b200_enable_change_detection", "ufo_b200_reset_change_detection", "ufo_b200_changed_codes",
+    "ufo_b200_write_compressed", "ufo_b200_cast_rays", "ufo_b200_export_nodes", "ufo_b200_enable_change_detection", "ufo_b200_reset_change_detection", "ufo_b200_changed_codes",
 ]
 
 class Cloud2(C.Structure):
@@ -128,6 +128,8 @@ def load():
     lib.ufo_b200_set_sensor_model_field.argtypes = [vp, i32, dbl]
     lib.ufo_b200_set_profiling.argtypes = [vp, i32]
     lib.ufo_b200_write_compressed.argtypes = [vp, vp, u32, i32, i32, i32, vp, sz, C.POINTER(sz), C.POINTER(sz)]
+    lib.ufo_b200_export_nodes.argtypes = [vp, u32, i32, i32, i32, vp, vp, vp, vp, sz, C.POINTER(sz)]
+    lib.ufo_b200_cast_rays.argtypes = [vp, vp, vp, sz, i32, dbl, u32, vp, vp]
     lib.ufo_b200_enable_change_detection.argtypes = [vp, i32]
     lib.ufo_b200_reset_change_detection.argtypes = [vp]
     lib.ufo_b200_changed_codes.argtypes = [vp, u32, vp, sz, C.POINTER(sz)]
@@ -419,6 +421,36 @@ class Map:
                                             occ.ctypes.data, flags.ctypes.data,
                                             rgb.ctypes.data if self.color else None))
         return occ, flags, rgb
+
+    def export_nodes(self, depth=0, occupied=True, free=True, unknown=False, box=None):
+        """Filtered leaf iteration as a batch: (codes sorted, occ, rgb) of the depth-`depth` nodes
+        whose state passes the filter and whose cube intersects box = (min xyz, max xyz)."""
+        b = self._box6(box)
+        bp = None if b is None else b.ctypes.data
+        n = C.c_size_t()
+        self._check(self.lib.ufo_b200_export_nodes(self.h, int(depth), int(occupied), int(free), int(unknown), bp,
+                                                   None, None, None, 0, C.byref(n)))
+        cnt = n.value
+        codes = np.empty(cnt, np.uint64)
+        occ = np.empty(cnt, np.float32)
+        rgb = np.zeros((cnt, 3), np.uint8)
+        if cnt:
+            self._check(self.lib.ufo_b200_export_nodes(self.h, int(depth), int(occupied), int(free), int(unknown), bp,
+                                                       codes.ctypes.data, occ.ctypes.data,
+                                                       rgb.ctypes.data if self.color else None, cnt, C.byref(n)))
+        order = np.argsort(codes, kind="stable")
+        return codes[order], occ[order], rgb[order]
+
+    def cast_rays(self, origins, directions, ignore_unknown=False, max_range=-1.0, depth=0):
+        """Batched castRay: (hit bool[n], code u64[n])."""
+        o = np.ascontiguousarray(origins, dtype=np.float64).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
+        assert o.shape == d.shape
+        codes = np.zeros(len(o), np.uint64)
+        hit = np.zeros(len(o), np.uint8)
+        self._check(self.lib.ufo_b200_cast_rays(self.h, o.ctypes.data, d.ctypes.data, len(o), int(ignore_unknown),
+                                                float(max_range), int(depth), codes.ctypes.data, hit.ctypes.data))
+        return hit.astype(bool), codes
 
     # -- geometry -----------------------------------------------------------
     def compute_ray(self, origin, end, max_range=-1.0, depth=0):

@@ -293,6 +293,112 @@ __global__ void __launch_bounds__(64) k_brick_stream(DeviceMap M, uint32_t n_bri
 }
 
 // ---------------------------------------------------------------------------
+// Filtered node read-out: the leaf iteration of the reference with state and
+// bounding-volume filters (beginLeaves(occupied, free, unknown, contains = false, min_depth),
+// occupancy_map_base.h:130-216; validity rule iterator/occupancy_map.h:168-207), on the value
+// field: every node of depth `depth` inside the known space (existing bricks / upper nodes) whose
+// own state -- occupied: value > occupied threshold, free: value < free threshold, unknown: in
+// between, the value of an inner node being the maximum of its subtree -- passes the filter and
+// whose cube intersects the box.  The reference returns a collapsed leaf above `depth` as one
+// node; here it appears as its depth-`depth` cells (same space, same state).
+// One thread per (brick, block) for depth 0..4; k_export_upper for depth >= 5.
+struct NodeFilter {
+	uint32_t depth;
+	int occupied, free_, unknown;
+	ExportBox box;
+};
+
+__device__ __forceinline__ bool node_passes(const DeviceMap& M, const NodeFilter& f, float v)
+{
+	const bool occ = M.occ_thr < (double)v, fre = M.free_thr > (double)v;
+	return (f.occupied && occ) || (f.free_ && fre) || (f.unknown && !occ && !fre);
+}
+
+__device__ __forceinline__ void node_emit(const DeviceMap& M, const NodeFilter& f, uint32_t x, uint32_t y, uint32_t z,
+                                          float v, uint32_t rgb, unsigned long long* codes, float* occ, uint32_t* rgbs,
+                                          unsigned long long cap, unsigned long long* count)
+{
+	if (!node_passes(M, f, v)) return;
+	const uint32_t d = f.depth;
+	const uint32_t centre = d ? (1u << (d - 1)) : 0u, snap = ~((1u << d) - 1u);
+	const Key3 k = {(x & snap) | centre, (y & snap) | centre, (z & snap) | centre};
+	if (f.box.on) {
+		const Vec3 c = key_to_coord(M.g, k, d);
+		const double cc[3] = {c.x, c.y, c.z};
+		if (!box_hits(f.box, cc, M.g.half_size[d])) return;
+	}
+	const unsigned long long at = atomicAdd(count, 1ull);
+	if (codes && at < cap) {
+		codes[at] = key_to_code(k);
+		occ[at] = v;
+		if (rgbs) rgbs[at] = rgb;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_export_nodes(DeviceMap M, uint32_t n_bricks, NodeFilter f, unsigned long long* codes,
+                                                      float* occ, uint32_t* rgbs, unsigned long long cap,
+                                                      unsigned long long* count)
+{
+	const size_t blk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (blk >= (size_t)n_bricks * 64) return;
+	const uint32_t brick = (uint32_t)(blk >> 6), ch = (uint32_t)(blk & 63);
+	uint32_t bx, by, bz;
+	unpack_key(M.brick_key[brick], bx, by, bz);
+	if ((bx | by | bz) & ~(M.g.key_mask >> 4)) return;  // alias collector brick
+	const uint32_t cx = (ch & 1u) | ((ch >> 2) & 2u), cy = ((ch >> 1) & 1u) | ((ch >> 3) & 2u),
+	               cz = ((ch >> 2) & 1u) | ((ch >> 4) & 2u);
+	const uint32_t x0 = (bx << 4) | (cx << 2), y0 = (by << 4) | (cy << 2), z0 = (bz << 4) | (cz << 2);
+	const uint32_t d = f.depth;
+	if (d == 4) {
+		if (ch == 0) node_emit(M, f, x0, y0, z0, M.brick_sum4[brick].occ, M.color ? M.brick_rgb4[brick] : 0u, codes, occ, rgbs, cap, count);
+		return;
+	}
+	if (d == 3) {
+		if ((ch & 7u) == 0) {
+			const uint32_t j = ch >> 3;
+			node_emit(M, f, x0, y0, z0, M.brick_sum3[(size_t)brick * 8 + j].occ, M.color ? M.brick_rgb3[(size_t)brick * 8 + j] : 0u, codes,
+			          occ, rgbs, cap, count);
+		}
+		return;
+	}
+	const uint32_t meta = M.meta[blk];
+	const bool init = (meta >> 16) != 0;
+	if (d == 2) {
+		node_emit(M, f, x0, y0, z0, init ? M.agg2[blk].occ : 0.0f, (init && M.color) ? M.rgb2[blk] : 0u, codes, occ, rgbs, cap, count);
+		return;
+	}
+	for (uint32_t o = 0; o < 8; ++o) {
+		const bool oi = init && ((meta >> (16 + o)) & 1u);
+		const uint32_t ox = x0 | ((o & 1u) << 1), oy = y0 | (o & 2u), oz = z0 | ((o & 4u) >> 1);
+		if (d == 1) {
+			node_emit(M, f, ox, oy, oz, oi ? M.sum1[blk * 8 + o] : 0.0f, (oi && M.color) ? M.sum1_rgb[blk * 8 + o] : 0u, codes, occ, rgbs,
+			          cap, count);
+			continue;
+		}
+		for (uint32_t j = 0; j < 8; ++j) {
+			const float v = oi ? M.leaf[blk * 64 + 8 * o + j] : 0.0f;
+			const uint32_t c = (oi && M.color) ? M.leaf_rgb[blk * 64 + 8 * o + j] : 0u;
+			node_emit(M, f, ox | (j & 1u), oy | ((j >> 1) & 1u), oz | (j >> 2), v, c, codes, occ, rgbs, cap, count);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) k_export_upper(DeviceMap M, uint32_t n_upper, NodeFilter f, unsigned long long* codes,
+                                                      float* occ, uint32_t* rgbs, unsigned long long cap,
+                                                      unsigned long long* count)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_upper) return;
+	uint32_t x, y, z;
+	const unsigned long long key = M.up_key[i];
+	unpack_key(key, x, y, z);
+	const uint32_t d = x >> 16;  // depth tag (upper_key)
+	if (d != f.depth) return;
+	x &= 0xffffu;
+	node_emit(M, f, x << d, y << d, z << d, M.up_agg[i].occ, M.color ? M.up_rgb[i] : 0u, codes, occ, rgbs, cap, count);
+}
+
+// ---------------------------------------------------------------------------
 // setValueVolume(AABB, value, min_depth)   occupancy_map_base.h:492-518, :986-1031
 // ---------------------------------------------------------------------------
 // The reference descends from the root and, at every level down to min_depth, keeps the children

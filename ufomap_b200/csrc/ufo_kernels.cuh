@@ -46,7 +46,10 @@ struct __align__(16) RayConst {
 	double dx, dy, dz;  // t_delta
 	double dist;        // length of the (clipped) ray: the walk continues while min t_max <= dist
 };
-constexpr uint32_t kShells = 16;  // segments per ray at most
+#ifndef UFO_SHELLS
+#define UFO_SHELLS 16
+#endif
+constexpr uint32_t kShells = UFO_SHELLS;  // segments per ray at most
 
 struct ScanArgs {
 	Vec3 origin;       // sensor origin
@@ -1245,20 +1248,16 @@ __global__ void __launch_bounds__(256) k_changed(DeviceMap M, uint32_t n_bricks,
 	}
 }
 
-// node queries with the intended getNode semantics
-__global__ void __launch_bounds__(256) k_query(DeviceMap M, const unsigned long long* codes,
-                                               const uint32_t* depths, uint32_t n, float* occ,
-                                               uint8_t* flags, uint32_t* rgb)
+// value of node (key, depth) with the intended getNode semantics: the aggregate the map keeps
+// for it, the default (0.0, unknown) where nothing was ever written
+__device__ __forceinline__ void node_value(const DeviceMap& M, Key3 k, uint32_t d, float& o, uint32_t& f, uint32_t& c)
 {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	Key3 k = code_to_key(codes[i]);
 	k.x &= M.g.key_mask;
 	k.y &= M.g.key_mask;
 	k.z &= M.g.key_mask;
-	uint32_t d = depths[i];
-	float o = 0.0f;
-	uint32_t f = M.default_flags, c = 0;
+	o = 0.0f;
+	f = M.default_flags;
+	c = 0;
 	if (d >= 5) {
 		if (d <= M.g.depth_levels) {
 			uint32_t s = upper_find(M, upper_key(d, k.x >> d, k.y >> d, k.z >> d));
@@ -1268,46 +1267,97 @@ __global__ void __launch_bounds__(256) k_query(DeviceMap M, const unsigned long 
 				if (M.color) c = M.up_rgb[s];
 			}
 		}
+		return;
+	}
+	uint32_t brick = brick_find(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
+	if (brick == kNone) return;
+	if (d == 4) {
+		o = M.brick_sum4[brick].occ;
+		f = M.brick_sum4[brick].flags;
+		if (M.color) c = M.brick_rgb4[brick];
+	} else if (d == 3) {
+		uint32_t j = ((k.x >> 3) & 1u) | (((k.y >> 3) & 1u) << 1) | (((k.z >> 3) & 1u) << 2);
+		o = M.brick_sum3[(size_t)brick * 8 + j].occ;
+		f = M.brick_sum3[(size_t)brick * 8 + j].flags;
+		if (M.color) c = M.brick_rgb3[(size_t)brick * 8 + j];
 	} else {
-		uint32_t brick = brick_find(M, pack_key(k.x >> 4, k.y >> 4, k.z >> 4));
-		if (brick != kNone) {
-			if (d == 4) {
-				o = M.brick_sum4[brick].occ;
-				f = M.brick_sum4[brick].flags;
-				if (M.color) c = M.brick_rgb4[brick];
-			} else if (d == 3) {
-				uint32_t j = ((k.x >> 3) & 1u) | (((k.y >> 3) & 1u) << 1) | (((k.z >> 3) & 1u) << 2);
-				o = M.brick_sum3[(size_t)brick * 8 + j].occ;
-				f = M.brick_sum3[(size_t)brick * 8 + j].flags;
-				if (M.color) c = M.brick_rgb3[(size_t)brick * 8 + j];
-			} else {
-				const size_t slot = (size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2);
-				const uint32_t meta = M.meta[slot];
-				if (meta >> 16) {
-					if (d == 2) {
-						o = M.agg2[slot].occ;
-						f = M.agg2[slot].flags;
-						if (M.color) c = M.rgb2[slot];
-					} else if (d == 1) {
-						uint32_t j = ((k.x >> 1) & 1u) | (((k.y >> 1) & 1u) << 1) | (((k.z >> 1) & 1u) << 2);
-						if ((meta >> (16 + j)) & 1u) {
-							o = M.sum1[slot * 8 + j];
-							f = (meta >> (2 * j)) & 3u;
-							if (M.color) c = M.sum1_rgb[slot * 8 + j];
-						}
-					} else {
-						uint32_t v = morton2(k.x, k.y, k.z);
-						o = M.leaf[slot * 64 + v];
-						f = leaf_flags(M, o);
-						if (M.color) c = M.leaf_rgb[slot * 64 + v];
-					}
-				}
+		const size_t slot = (size_t)brick * 64 + morton2(k.x >> 2, k.y >> 2, k.z >> 2);
+		const uint32_t meta = M.meta[slot];
+		if (!(meta >> 16)) return;
+		if (d == 2) {
+			o = M.agg2[slot].occ;
+			f = M.agg2[slot].flags;
+			if (M.color) c = M.rgb2[slot];
+		} else if (d == 1) {
+			uint32_t j = ((k.x >> 1) & 1u) | (((k.y >> 1) & 1u) << 1) | (((k.z >> 1) & 1u) << 2);
+			if ((meta >> (16 + j)) & 1u) {
+				o = M.sum1[slot * 8 + j];
+				f = (meta >> (2 * j)) & 3u;
+				if (M.color) c = M.sum1_rgb[slot * 8 + j];
 			}
+		} else {
+			uint32_t v = morton2(k.x, k.y, k.z);
+			o = M.leaf[slot * 64 + v];
+			f = leaf_flags(M, o);
+			if (M.color) c = M.leaf_rgb[slot * 64 + v];
 		}
 	}
+}
+
+// node queries with the intended getNode semantics
+__global__ void __launch_bounds__(256) k_query(DeviceMap M, const unsigned long long* codes,
+                                               const uint32_t* depths, uint32_t n, float* occ,
+                                               uint8_t* flags, uint32_t* rgb)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float o;
+	uint32_t f, c;
+	node_value(M, code_to_key(codes[i]), depths[i], o, f, c);
 	occ[i] = o;
 	flags[i] = (uint8_t)f;
 	if (rgb) rgb[i] = c;
+}
+
+// castRay (occupancy_map_base.h:449-486, intended semantics -- DESIGN.md section 8 states them):
+// one thread per ray, forward walk at `depth` from the origin's node; an occupied node is the
+// hit, an unknown one stops the ray unless ignore_unknown.  rays: [n][6] = origin, direction.
+__global__ void __launch_bounds__(128) k_cast_rays(DeviceMap M, const double* rays, uint32_t n, int ignore_unknown,
+                                                   double max_range, uint32_t depth, unsigned long long* codes,
+                                                   uint8_t* hit)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double* r = rays + 6 * (size_t)i;
+	Vec3 o = {r[0], r[1], r[2]}, d = {r[3], r[4], r[5]};
+	if (0 > max_range) {
+		const double hs = node_half(M.g, M.g.depth_levels), e = dop::add(hs, hs);
+		max_range = vnorm({e, e, e});
+	}
+	d = vdiv(d, vnorm(d));
+	Vec3 e = vadd(o, vscale(d, max_range));
+	unsigned long long code = 0;
+	uint8_t h = 0;
+	if (move_line_inside(M.g, o, e)) {
+		Walk w;
+		walk_init(M.g, o, e, d, depth, w);
+		while (true) {
+			float occ;
+			uint32_t f, c;
+			node_value(M, w.cur, depth, occ, f, c);
+			const bool last = w.same || w.cur == w.end || !(walk_tmin(w) <= max_range);
+			if (M.occ_thr < (double)occ) {
+				code = key_to_code({w.cur.x & 0x1fffffu, w.cur.y & 0x1fffffu, w.cur.z & 0x1fffffu});
+				h = 1;
+				break;
+			}
+			if (last) break;
+			if (!ignore_unknown && M.free_thr <= (double)occ && M.occ_thr >= (double)occ) break;
+			walk_step(w);
+		}
+	}
+	codes[i] = code;
+	hit[i] = h;
 }
 
 }  // namespace ufo_b200

@@ -2502,7 +2502,125 @@ int ufo_b200_write_compressed(ufo_b200_map* m, const double* box6, uint32_t min_
 	});
 }
 
+int ufo_b200_cast_rays(ufo_b200_map* m, const double* origins, const double* directions, size_t n,
+                       int ignore_unknown, double max_range, uint32_t depth, uint64_t* codes, uint8_t* hit)
+{
+	if (!m || (n && (!origins || !directions || !codes || !hit)) || n > 0x7fffffffull) return UFO_B200_E_INVALID;
+	if (!n) return UFO_B200_OK;
+	return guarded(m, [&]() {
+		if (depth > m->M.g.depth_levels) return (int)UFO_B200_E_INVALID;
+		CK(cudaSetDevice(m->device));
+		sync_map(m);
+		cudaStream_t s = m->stream;
+		std::vector<double> rays(6 * n);
+		for (size_t i = 0; i < n; ++i) {
+			for (int k = 0; k < 3; ++k) {
+				rays[6 * i + k] = origins[3 * i + k];
+				rays[6 * i + 3 + k] = directions[3 * i + k];
+			}
+		}
+		double* d_rays = nullptr;
+		unsigned long long* d_codes = nullptr;
+		uint8_t* d_hit = nullptr;
+		auto cleanup = [&]() {
+			if (d_rays) cudaFree(d_rays);
+			if (d_codes) cudaFree(d_codes);
+			if (d_hit) cudaFree(d_hit);
+		};
+		try {
+			CK(cudaMalloc(&d_rays, rays.size() * 8));
+			CK(cudaMalloc(&d_codes, n * 8));
+			CK(cudaMalloc(&d_hit, n));
+			CK(cudaMemcpyAsync(d_rays, rays.data(), rays.size() * 8, cudaMemcpyHostToDevice, s));
+			k_cast_rays<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(m->M, d_rays, (uint32_t)n, ignore_unknown, max_range, depth, d_codes, d_hit);
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync(codes, d_codes, n * 8, cudaMemcpyDeviceToHost, s));
+			CK(cudaMemcpyAsync(hit, d_hit, n, cudaMemcpyDeviceToHost, s));
+			CK(cudaStreamSynchronize(s));
+		} catch (...) {
+			cleanup();
+			throw;
+		}
+		cleanup();
+		return (int)UFO_B200_OK;
+	});
+}
+
+int ufo_b200_export_nodes(ufo_b200_map* m, uint32_t depth, int occupied, int free_space, int unknown, const double* box6,
+                          uint64_t* codes, float* logodds, uint8_t* rgb, size_t cap, size_t* n)
+{
+	if (!m || !n) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		CK(cudaSetDevice(m->device));
+		sync_map(m);
+		*n = 0;
+		if (depth > m->M.g.depth_levels) return (int)UFO_B200_E_INVALID;
+		NodeFilter f{};
+		f.depth = depth;
+		f.occupied = occupied;
+		f.free_ = free_space;
+		f.unknown = unknown;
+		if (box6) {
+			f.box.on = 1;
+			for (int k = 0; k < 3; ++k) {
+				f.box.lo[k] = box6[k] - box6[3 + k];
+				f.box.hi[k] = box6[k] + box6[3 + k];
+			}
+		}
+		cudaStream_t s = m->stream;
+		unsigned long long *d_count = nullptr, *d_codes = nullptr;
+		float* d_occ = nullptr;
+		uint32_t* d_rgb = nullptr;
+		auto cleanup = [&]() {
+			for (void* p : {(void*)d_count, (void*)d_codes, (void*)d_occ, (void*)d_rgb})
+				if (p) cudaFree(p);
+		};
+		try {
+			CK(cudaMalloc(&d_count, 8));
+			const bool fill = codes != nullptr && cap > 0;
+			if (fill) {
+				CK(cudaMalloc(&d_codes, cap * 8));
+				CK(cudaMalloc(&d_occ, cap * 4));
+				if (rgb) CK(cudaMalloc(&d_rgb, cap * 4));
+			}
+			CK(cudaMemsetAsync(d_count, 0, 8, s));
+			if (depth <= 4) {
+				const size_t threads = (size_t)m->n_bricks * 64;
+				if (threads) k_export_nodes<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>(m->M, m->n_bricks, f, d_codes, d_occ, d_rgb, fill ? cap : 0, d_count);
+			} else if (m->n_upper) {
+				k_export_upper<<<(m->n_upper + 255) / 256, 256, 0, s>>>(m->M, m->n_upper, f, d_codes, d_occ, d_rgb, fill ? cap : 0, d_count);
+			}
+			CK(cudaGetLastError());
+			unsigned long long cnt = 0;
+			CK(cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, s));
+			CK(cudaStreamSynchronize(s));
+			*n = (size_t)cnt;
+			if (fill) {
+				const size_t k = std::min<size_t>(cnt, cap);
+				CK(cudaMemcpy(codes, d_codes, k * 8, cudaMemcpyDeviceToHost));
+				if (logodds) CK(cudaMemcpy(logodds, d_occ, k * 4, cudaMemcpyDeviceToHost));
+				if (rgb) {
+					std::vector<uint32_t> h(k);
+					CK(cudaMemcpy(h.data(), d_rgb, k * 4, cudaMemcpyDeviceToHost));
+					for (size_t i = 0; i < k; ++i) {
+						rgb[3 * i] = h[i] & 0xff;
+						rgb[3 * i + 1] = (h[i] >> 8) & 0xff;
+						rgb[3 * i + 2] = (h[i] >> 16) & 0xff;
+					}
+				}
+			}
+		} catch (...) {
+			cleanup();
+			throw;
+		}
+		cleanup();
+		return (int)UFO_B200_OK;
+	});
+}
+
 }  // extern "C"
+
+
 
 
 

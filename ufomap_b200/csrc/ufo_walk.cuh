@@ -99,7 +99,13 @@ __global__ void __launch_bounds__(256) k_gather(DeviceMap M)
 				const uint32_t slot = brick_find_or_create(M, key);
 				if (slot == kNone) continue;  // pool exhausted: flagged, the scan is repeated
 				M.brick_stamp[slot] = M.scan_id;
-				const uint32_t i = atomicAdd(&M.ctr->n_touched, 1u);
+				// one list-cursor atomic per group of lanes, not per brick (same-address atomics serialise)
+				const uint32_t peers = __activemask();
+				const uint32_t leader = __ffs(peers) - 1;
+				uint32_t base = 0;
+				if (lane == leader) base = atomicAdd(&M.ctr->n_touched, (uint32_t)__popc(peers));
+				base = __shfl_sync(peers, base, leader);
+				const uint32_t i = base + __popc(peers & ((1u << lane) - 1u));
 				M.touched[i] = slot;
 				M.touched_mi[i] = vb;
 			}
@@ -465,10 +471,13 @@ __device__ __forceinline__ uint32_t resolve_brick(const DeviceMap& M, unsigned l
 #define UFO_WALK_MINBLOCKS 7
 #endif
 constexpr int kWalkThreads = 128;
-constexpr uint32_t kUnitsPerGrab = 4;
+#ifndef UFO_UNITS_PER_GRAB
+#define UFO_UNITS_PER_GRAB 1
+#endif
+constexpr uint32_t kUnitsPerGrab = UFO_UNITS_PER_GRAB;
 
-// Work unit = (shell, batch of 32 consecutive rays); units are numbered outermost shell first and
-// handed out through an atomic cursor, kUnitsPerGrab at a time.
+// Work unit = (shell, batch of 32 consecutive rays); units are numbered shell by shell and handed
+// out through an atomic cursor, kUnitsPerGrab at a time.
 // DENSE: marks go to the scan volume (computed address + dirty bit, nothing is loaded in the
 // loop); otherwise to the bricks' miss masks through the brick hash, one probe per brick change.
 template <int DEPTH, bool SHARD, bool COUNT, bool DENSE>
@@ -497,7 +506,13 @@ __global__ void __launch_bounds__(kWalkThreads, UFO_WALK_MINBLOCKS) k_walk_mark(
 		const uint32_t u1 = min(u0 + kUnitsPerGrab, units);
 		for (uint32_t u = u0; u < u1; ++u) {
 			const uint32_t rs = u / n_batches, batch = u - rs * n_batches;
+#ifdef UFO_SHELL_OUTER_FIRST
 			const uint32_t shell = kShells - 1 - rs;
+#else
+			// innermost shell first: the sparse outer shells (few, partial segments) come last, which
+			// keeps the end-of-kernel tail short
+			const uint32_t shell = rs;
+#endif
 			const uint32_t vm = __ldg(&a.vmask[(size_t)shell * n_batches + batch]);
 			if (!vm) continue;
 			const uint32_t i = batch * 32 + lane;
