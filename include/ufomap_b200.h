@@ -232,6 +232,18 @@ int ufo_b200_write_compressed(ufo_b200_map* m, const double* box6, uint32_t min_
                               int acceleration_level, int compression_level, void* buf, size_t cap, size_t* size,
                               size_t* uncompressed_size);
 
+/* Octree::readData (octree.h:733-770 -> readNodes, occupancy_map_base.h:1379-1456): merges a node
+ * stream -- the body of a UFOMap file, or a UFOMap message the way the ROS layer applies it
+ * (msgToUfo, ufomap_msgs/conversions.h:122-134) -- into the map: every leaf of the stream sets all
+ * voxels below it to its payload, nodes whose cube misses the AABB box6 (centre, half size; NULL:
+ * none) are skipped exactly like the writer skipped them.  The stream must have been written for
+ * this map's resolution / depth_levels (the reference clears and resizes otherwise: call
+ * ufo_b200_clear_resize first).  compressed != 0: `data` is one LZ4 block of uncompressed_size
+ * bytes.  A collapsed non-default node above the brick level is expanded into bricks (at most 2^20
+ * per call, else UFO_B200_E_UNSUPPORTED). */
+int ufo_b200_read_data(ufo_b200_map* m, const double* box6, const void* data, size_t size, int compressed,
+                       size_t uncompressed_size);
+
 /* Sensor model  occupancy_map_base.h:734-773.  out6/in: occupied_thres,
  * free_thres, prob_hit, prob_miss, clamping_thres_min, clamping_thres_max as
  * probabilities (setters) or as stored double log-odds (ufo_b200_sensor_model_logit). */

@@ -27,6 +27,10 @@
 #include <cmath>
 #include <cstdint>
 #include <stdexcept>
+#include <fstream>
+#include <istream>
+#include <iterator>
+#include <optional>
 #include <ostream>
 #include <string>
 #include <type_traits>
@@ -376,28 +380,35 @@ class MapFacade
 	virtual std::string getTreeType() const noexcept { return COLOR ? "occupancy_map_color" : "occupancy_map"; }
 
 	//
-	// File / wire format (octree.h:776-864), uncompressed: whole map or the part inside an AABB,
-	// truncated at min_depth (0..4).  compress = true is not supported and returns false.
+	// File / wire format (octree.h:776-864): whole map or the part inside an AABB, truncated at
+	// min_depth (0..4); compress = true packs the node stream as one LZ4 block like the reference
+	// (needs liblz4.so.1 at run time, else false).
 	//
 	bool write(std::string const& filename, bool compress = false, DepthType min_depth = 0,
-	           int /*compression_acceleration_level*/ = 1, int /*compression_level*/ = 0) const
+	           int compression_acceleration_level = 1, int compression_level = 0) const
 	{
-		if (compress) return false;
+		if (compress) {
+			std::ofstream f(filename.c_str(), std::ios_base::out | std::ios_base::binary);
+			return f.is_open() && writeCompressed(f, nullptr, false, min_depth, compression_acceleration_level, compression_level) >= 0;
+		}
 		return UFO_B200_OK == ufo_b200_write_file(map_, filename.c_str(), nullptr, min_depth, 0);
 	}
 	bool write(std::string const& filename, ufo::geometry::AABB const& bounding_volume, bool compress = false,
-	           DepthType min_depth = 0, int /*compression_acceleration_level*/ = 1,
-	           int /*compression_level*/ = 0) const
+	           DepthType min_depth = 0, int compression_acceleration_level = 1,
+	           int compression_level = 0) const
 	{
-		if (compress) return false;
 		double box[6];
 		packBox(bounding_volume, box);
+		if (compress) {
+			std::ofstream f(filename.c_str(), std::ios_base::out | std::ios_base::binary);
+			return f.is_open() && writeCompressed(f, box, false, min_depth, compression_acceleration_level, compression_level) >= 0;
+		}
 		return UFO_B200_OK == ufo_b200_write_file(map_, filename.c_str(), box, min_depth, 0);
 	}
 	bool write(std::ostream& s, bool compress = false, DepthType min_depth = 0,
-	           int /*compression_acceleration_level*/ = 1, int /*compression_level*/ = 0) const
+	           int compression_acceleration_level = 1, int compression_level = 0) const
 	{
-		if (compress) return false;
+		if (compress) return writeCompressed(s, nullptr, false, min_depth, compression_acceleration_level, compression_level) >= 0;
 		std::size_t n = 0;
 		if (UFO_B200_OK != ufo_b200_write(map_, nullptr, min_depth, 0, nullptr, 0, &n)) return false;
 		std::vector<char> image(n);
@@ -421,17 +432,46 @@ class MapFacade
 	// part inside an AABB, truncated at min_depth (0..4).  Returns the number of bytes written, -1
 	// on error (as the reference does).
 	int writeData(std::ostream& s, bool compress = false, DepthType min_depth = 0,
-	              int /*compression_acceleration_level*/ = 1, int /*compression_level*/ = 0) const
+	              int compression_acceleration_level = 1, int compression_level = 0) const
 	{
+		if (compress) return writeCompressed(s, nullptr, true, min_depth, compression_acceleration_level, compression_level);
 		return writeDataImpl(s, nullptr, compress, min_depth);
 	}
 	int writeData(std::ostream& s, ufo::geometry::AABB const& bounding_volume, bool compress = false,
-	              DepthType min_depth = 0, int /*compression_acceleration_level*/ = 1,
-	              int /*compression_level*/ = 0) const
+	              DepthType min_depth = 0, int compression_acceleration_level = 1,
+	              int compression_level = 0) const
 	{
 		double box[6];
 		packBox(bounding_volume, box);
+		if (compress) return writeCompressed(s, box, true, min_depth, compression_acceleration_level, compression_level);
 		return writeDataImpl(s, box, compress, min_depth);
+	}
+
+	// Octree::readData (octree.h:733-770): merges a node stream (the data of a UFOMap message,
+	// ufomap_msgs/conversions.h:122-134) into the map.  Like the reference, a stream written for
+	// another resolution / depth clears and resizes the map first.
+	bool readData(std::istream& s, double resolution, DepthType depth_levels, int uncompressed_data_size = 1,
+	              bool compressed = false)
+	{
+		return readDataImpl(s, nullptr, resolution, depth_levels, uncompressed_data_size, compressed);
+	}
+	bool readData(std::istream& s, ufo::geometry::AABB const& bounding_volume, double resolution,
+	              DepthType depth_levels, int uncompressed_data_size = 1, bool compressed = false)
+	{
+		double box[6];
+		packBox(bounding_volume, box);
+		return readDataImpl(s, box, resolution, depth_levels, uncompressed_data_size, compressed);
+	}
+
+	// castRay (occupancy_map_base.h:449-486), intended semantics
+	std::optional<Code> castRay(Point3 origin, Point3 direction, bool ignore_unknown = false, double max_range = -1,
+	                            DepthType depth = 0) const
+	{
+		std::uint64_t code = 0;
+		std::uint8_t hit = 0;
+		if (UFO_B200_OK != ufo_b200_cast_rays(map_, origin.data(), direction.data(), 1, ignore_unknown, max_range, depth, &code, &hit) || !hit)
+			return std::nullopt;
+		return Code(code, depth);
 	}
 
 	//
@@ -726,6 +766,25 @@ class MapFacade
 		box[3] = b.half_size.x();
 		box[4] = b.half_size.y();
 		box[5] = b.half_size.z();
+	}
+	// compressed stream (data_only) or file image; returns the UNCOMPRESSED data size like the
+	// reference's writeData, -1 on error
+	int writeCompressed(std::ostream& s, double const* box, bool data_only, DepthType min_depth, int accel, int level) const
+	{
+		std::size_t n = 0, u = 0;
+		if (UFO_B200_OK != ufo_b200_write_compressed(map_, box, min_depth, data_only, accel, level, nullptr, 0, &n, &u)) return -1;
+		std::vector<char> data(n ? n : 1);
+		if (UFO_B200_OK != ufo_b200_write_compressed(map_, box, min_depth, data_only, accel, level, data.data(), n, &n, &u)) return -1;
+		s.write(data.data(), (std::streamsize)n);
+		return s.good() ? (int)u : -1;
+	}
+	bool readDataImpl(std::istream& s, double const* box, double resolution, DepthType depth_levels, int uncompressed_data_size,
+	                  bool compressed)
+	{
+		if (getResolution() != resolution || getTreeDepthLevels() != depth_levels) clear(resolution, depth_levels);
+		std::vector<char> data((std::istreambuf_iterator<char>(s)), std::istreambuf_iterator<char>());
+		return UFO_B200_OK == ufo_b200_read_data(map_, box, data.data(), data.size(), compressed,
+		                                         compressed ? (std::size_t)uncompressed_data_size : 0);
 	}
 	int writeDataImpl(std::ostream& s, double const* box, bool compress, DepthType min_depth) const
 	{

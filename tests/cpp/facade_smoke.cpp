@@ -71,7 +71,11 @@ int main(int argc, char** argv)
 	std::ostringstream os;
 	if (!fused.write(os) || os.str().compare(0, 13, "# UFOMap file") != 0) return 12;
 	if (os.str().find("id occupancy_map\nresolution 0.05\ndepth_levels 16\ncompressed 0\n") == std::string::npos) return 13;
-	if (fused.write(os, /*compress*/ true)) return 14;
+	// compress = true: one LZ4 block behind a header that says "compressed 1" (octree.h:1428-1456)
+	std::ostringstream zs;
+	if (!fused.write(zs, /*compress*/ true) || zs.str().find("compressed 1\n") == std::string::npos ||
+	    zs.str().size() >= os.str().size())
+		return 14;
 	// Octree::writeData with the change box, as ufoToMsg calls it (ufomap_msgs/conversions.h:176-178)
 	std::ostringstream part, whole;
 	ufo::geometry::AABB aabb(world[10] - Point3(0.3, 0.3, 0.3), world[10] + Point3(0.3, 0.3, 0.3));
@@ -81,6 +85,18 @@ int main(int argc, char** argv)
 	Point3 r(0.2, 0.2, 0.1);
 	fused.setValueVolume(ufo::geometry::AABB(world[20] - r, world[20] + r), fused.getClampingThresMin(), 0);
 	if (fused.lastStatus() != UFO_B200_OK || !fused.isFree(world[20])) return 16;
+	// readData: the node stream of one map merged into an empty one gives the same occupancy
+	{
+		std::stringstream data(std::ios_base::in | std::ios_base::out | std::ios_base::binary);
+		int n_data = fused.writeData(data, false, 0);
+		OccupancyMap copy(0.05);
+		if (n_data <= 0 || !copy.readData(data, 0.05, 16, n_data, false)) return 24;
+		for (std::size_t i = 0; i < world.size(); ++i)
+			if (copy.getOccupancy(world[i]) != fused.getOccupancy(world[i])) return 25;
+		// castRay from the sensor along a measured ray hits the ray's occupied end voxel
+		auto hit = copy.castRay(tilt.translation() + (world[30] - tilt.translation()) * 0.05, world[30] - tilt.translation(), true, 20.0);
+		if (!hit || !copy.isOccupied(*hit)) return 26;
+	}
 	// a setter changes ONE stored log-odds; the others stay bit for bit (occupancy_map_base.h:748-773)
 	{
 		OccupancyMap a(0.05), b(0.05);

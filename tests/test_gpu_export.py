@@ -172,3 +172,42 @@ def test_compressed_image_matches_the_reference(name):
     n = lz4.LZ4_decompress_safe(packed, out, len(packed), usize)
     assert n == usize and out.raw == raw
     gpu.close()
+
+
+@pytest.mark.parametrize("name", ["velodyne", "rgbd_color_discrete"])
+def test_read_data_merges_like_the_reference(name):
+    """Octree::readData: a node stream written by one map is merged into another map that already
+    holds different content -- whole stream, a stream truncated at min_depth 2 (its leaves overwrite
+    whole blocks), and a stream / read restricted to a box -- and the result is the reference's,
+    value for value; inner aggregates follow."""
+    from helpers import assert_value_fields_equal, check_inner_against_field
+    kw, inserts, color = _scenario(name)
+    src = Map(color=color, initial_blocks=1 << 12, **kw)
+    for ins in inserts:
+        src.insert(**ins)
+    lo = np.array(inserts[0]["origin"]) - 1.5
+    box = (lo, lo + np.array([4.0, 3.0, 2.5]))
+    for stream_kw in (dict(), dict(min_depth=2), dict(box=box), dict(box=box, min_depth=1)):
+        data = src.write_data(**stream_kw)
+        gpu = Map(color=color, initial_blocks=1 << 12, **kw)
+        cpus = _cpu_maps(color, **kw)
+        # other content first: the second half of the scenario seen from a shifted pose
+        other = dict(inserts[-1])
+        other["origin"] = np.array(other["origin"]) + np.array([0.37, -0.21, 0.05])
+        gpu.insert(**other)
+        for c in cpus:
+            c.insert(**other)
+        gpu.read_data(data, box=stream_kw.get("box"))
+        for c in cpus:
+            assert c.read_data(data, box=stream_kw.get("box"))
+        field = gpu.value_field()
+        for c in cpus:
+            assert_value_fields_equal(field, c.value_field(), color_tol=0, what="%s %s" % (type(c).__name__, stream_kw.keys()))
+        check_inner_against_field(gpu, cpus[0].value_field(), cpus[0].sensor_model(), levels=(1, 2, 3, 4, 5, 7))
+        # and the merged map keeps integrating scans like the reference's
+        gpu.insert(**inserts[0])
+        for c in cpus:
+            c.insert(**inserts[0])
+        assert_value_fields_equal(gpu.value_field(), cpus[0].value_field(), color_tol=1 if color else 0, what="scan after merge")
+        gpu.close()
+    src.close()

@@ -62,7 +62,7 @@ SYMBOLS = [
     "ufo_b200_completed_scan_stats", "ufo_b200_set_sensor_model_field",
     "ufo_b200_route_inbox_bytes", "ufo_b200_route_setup", "ufo_b200_route_connect", "ufo_b200_route_mark",
     "ufo_b200_route_apply", "ufo_b200_ipc_export", "ufo_b200_ipc_open", "ufo_b200_ipc_close",
-    "ufo_b200_write_compressed", "ufo_b200_cast_rays", "ufo_b200_export_nodes", "ufo_b200_enable_change_detection", "ufo_b200_reset_change_detection", "ufo_b200_changed_codes",
+    "ufo_b200_write_compressed", "ufo_b200_cast_rays", "ufo_b200_export_nodes", "ufo_b200_read_data", "ufo_b200_enable_change_detection", "ufo_b200_reset_change_detection", "ufo_b200_changed_codes",
 ]
 
 class Cloud2(C.Structure):
@@ -128,6 +128,7 @@ def load():
     lib.ufo_b200_set_sensor_model_field.argtypes = [vp, i32, dbl]
     lib.ufo_b200_set_profiling.argtypes = [vp, i32]
     lib.ufo_b200_write_compressed.argtypes = [vp, vp, u32, i32, i32, i32, vp, sz, C.POINTER(sz), C.POINTER(sz)]
+    lib.ufo_b200_read_data.argtypes = [vp, vp, vp, sz, i32, sz]
     lib.ufo_b200_export_nodes.argtypes = [vp, u32, i32, i32, i32, vp, vp, vp, vp, sz, C.POINTER(sz)]
     lib.ufo_b200_cast_rays.argtypes = [vp, vp, vp, sz, i32, dbl, u32, vp, vp]
     lib.ufo_b200_enable_change_detection.argtypes = [vp, i32]
@@ -355,6 +356,14 @@ class Map:
         self._check(self.lib.ufo_b200_write_compressed(self.h, bp, int(min_depth), int(data_only), int(acceleration),
                                                        int(level), buf.ctypes.data, n.value, C.byref(n), C.byref(u)))
         return buf[:n.value].tobytes(), int(u.value)
+
+    def read_data(self, data, box=None, compressed=False, uncompressed_size=0):
+        """Octree::readData: merge a node stream (bytes) into the map; box = (min xyz, max xyz)."""
+        b = self._box6(box)
+        buf = np.frombuffer(data, np.uint8)
+        self._check(self.lib.ufo_b200_read_data(self.h, None if b is None else b.ctypes.data,
+                                                buf.ctypes.data if len(buf) else None, len(buf), int(compressed),
+                                                int(uncompressed_size)))
 
     def write_file(self, filename, expanded=False, box=None, min_depth=0):
         b = self._box6(box)

@@ -1000,9 +1000,26 @@ __global__ void __launch_bounds__(256) k_alias_refresh(DeviceMap M)
 // ---------------------------------------------------------------------------
 // K4: upper levels (depth >= 5)
 // ---------------------------------------------------------------------------
-// Seeds the depth-5 dirty list with the parents of the bricks touched this scan.
-// Grid-stride over the touched list; the pass is identified by M.up_epoch (a pass repeated after
-// the upper-node pool was regrown gets a fresh epoch, so every node is listed again).
+// Push-up propagation.  A node that changed reports its aggregate into its parent's child slot
+// and puts the parent on the next level's dirty list; a dirty node is recomputed from its eight
+// child slots (one 64-byte read by eight lanes), never from hash lookups.  Parent slots are
+// resolved through the hash once and cached (brick_parent / up_parent).
+__device__ __forceinline__ void report_to_parent(const DeviceMap& M, uint32_t p, uint32_t ci, Agg a, uint32_t rgb,
+                                                 uint32_t* out, uint32_t* out_count, uint32_t list_cap)
+{
+	*reinterpret_cast<volatile unsigned long long*>(&M.up_child[(size_t)p * 8 + ci]) =
+	    (unsigned long long)__float_as_uint(a.occ) | ((unsigned long long)a.flags << 32);
+	if (M.color) st_volatile_u32(&M.up_child_rgb[(size_t)p * 8 + ci], rgb);
+	if (!((ld_volatile_u32(&M.up_valid[p]) >> ci) & 1u)) atomicOr(&M.up_valid[p], 1u << ci);
+	if (atomicExch(&M.up_stamp[p], M.up_epoch) != M.up_epoch) {
+		const uint32_t idx = atomicAdd(out_count, 1u);
+		if (idx < list_cap) out[idx] = p;
+	}
+}
+
+// Seeds the depth-5 dirty list from the bricks touched this scan.  Grid-stride over the touched
+// list; the pass is identified by M.up_epoch (a pass repeated after the upper-node pool was
+// regrown gets a fresh epoch, so every node is listed again).
 __global__ void __launch_bounds__(256) k_upper_seed(DeviceMap M, uint32_t* list, uint32_t list_cap)
 {
 	if (__ldg(&M.ctr->overflow)) return;
@@ -1012,17 +1029,19 @@ __global__ void __launch_bounds__(256) k_upper_seed(DeviceMap M, uint32_t* list,
 		uint32_t x, y, z;
 		unpack_key(M.brick_key[b], x, y, z);
 		if ((x | y | z) & ~(M.g.key_mask >> 4)) continue;  // alias collector brick
-		uint32_t s = upper_find_or_create(M, upper_key(5, x >> 1, y >> 1, z >> 1));
-		if (s == kNone) continue;
-		if (atomicExch(&M.up_stamp[s], M.up_epoch) != M.up_epoch) {
-			uint32_t idx = atomicAdd(&M.ctr->list_count[5 % 3], 1u);
-			if (idx < list_cap) list[idx] = s;
+		uint32_t p = M.brick_parent[b];
+		if (p == kNone) {
+			p = upper_find_or_create(M, upper_key(5, x >> 1, y >> 1, z >> 1));
+			if (p == kNone) continue;
+			M.brick_parent[b] = p;
 		}
+		report_to_parent(M, p, (x & 1u) | ((y & 1u) << 1) | ((z & 1u) << 2), M.brick_sum4[b], M.color ? M.brick_rgb4[b] : 0u, list,
+		                 &M.ctr->list_count[5 % 3], list_cap);
 	}
 }
 
-// Recomputes the nodes of `in` (all at depth d) from their 8 children and pushes their
-// parents to `out`.  Eight lanes per node, one child each.  Counters rotate three ways:
+// Recomputes the nodes of `in` (all at depth d) from their child slots and reports them to their
+// parents (-> `out`).  Eight lanes per node, one child each.  Counters rotate three ways:
 // level d reads list_count[d % 3], appends to [(d + 1) % 3] and clears [(d + 2) % 3]
 // (the next level's output), so no separate reset launches are needed.
 __device__ __forceinline__ void upper_level_pass(const DeviceMap& M, uint32_t depth, const uint32_t* in,
@@ -1037,30 +1056,12 @@ __device__ __forceinline__ void upper_level_pass(const DeviceMap& M, uint32_t de
 		uint32_t s = valid ? ld_volatile_u32(&in[i]) : 0;
 		float occ = 0.0f;
 		uint32_t fl = M.default_flags, rgb = 0;
-		uint32_t x = 0, y = 0, z = 0;
-		if (valid) {
-			uint64_t key = ld_volatile_u64(&M.up_key[s]);
-			unpack_key(key, x, y, z);
-			x &= 0xffffu;  // strip the depth tag
-			uint32_t cx = 2 * x + (lane8 & 1), cy = 2 * y + ((lane8 >> 1) & 1), cz = 2 * z + (lane8 >> 2);
-			if (depth == 5) {
-				uint32_t c = brick_find(M, pack_key(cx, cy, cz));
-				if (c != kNone) {
-					Agg a = M.brick_sum4[c];
-					occ = a.occ;
-					fl = a.flags;
-					if (M.color) rgb = M.brick_rgb4[c];
-				}
-			} else {
-				uint32_t c = upper_find(M, upper_key(depth - 1, cx, cy, cz));
-				if (c != kNone) {
-					// volatile: in k_upper_tail the child was written by this same CTA a level earlier
-					unsigned long long raw = ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&M.up_agg[c]));
-					occ = __uint_as_float((uint32_t)raw);
-					fl = (uint32_t)(raw >> 32);
-					if (M.color) rgb = ld_volatile_u32(&M.up_rgb[c]);
-				}
-			}
+		if (valid && ((ld_volatile_u32(&M.up_valid[s]) >> lane8) & 1u)) {
+			// volatile: in k_upper_tail the slot was written by this same CTA a level earlier
+			const unsigned long long raw = ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&M.up_child[(size_t)s * 8 + lane8]));
+			occ = __uint_as_float((uint32_t)raw);
+			fl = (uint32_t)(raw >> 32);
+			if (M.color) rgb = ld_volatile_u32(&M.up_child_rgb[(size_t)s * 8 + lane8]);
 		}
 		uint32_t crgb[8];
 		if (M.color) {
@@ -1073,15 +1074,20 @@ __device__ __forceinline__ void upper_level_pass(const DeviceMap& M, uint32_t de
 			fl |= __shfl_xor_sync(0xffffffffu, fl, o);
 		}
 		if (valid && lane8 == 0) {
+			const uint32_t my_rgb = M.color ? rms_rgb(crgb, 8) : 0u;
 			M.up_agg[s] = {occ, fl};
-			if (M.color) M.up_rgb[s] = rms_rgb(crgb, 8);
+			if (M.color) M.up_rgb[s] = my_rgb;
 			atomicAdd(&M.ctr->upper_nodes, 1ull);
 			if (depth < M.g.depth_levels) {
-				uint32_t p = upper_find_or_create(M, upper_key(depth + 1, x >> 1, y >> 1, z >> 1));
-				if (p != kNone && atomicExch(&M.up_stamp[p], M.up_epoch) != M.up_epoch) {
-					uint32_t idx = atomicAdd(out_count, 1u);
-					if (idx < list_cap) out[idx] = p;
+				uint32_t x, y, z;
+				unpack_key(ld_volatile_u64(&M.up_key[s]), x, y, z);
+				x &= 0xffffu;  // strip the depth tag
+				uint32_t p = ld_volatile_u32(&M.up_parent[s]);
+				if (p == kNone) {
+					p = upper_find_or_create(M, upper_key(depth + 1, x >> 1, y >> 1, z >> 1));
+					if (p != kNone) st_volatile_u32(&M.up_parent[s], p);
 				}
+				if (p != kNone) report_to_parent(M, p, (x & 1u) | ((y & 1u) << 1) | ((z & 1u) << 2), {occ, fl}, my_rgb, out, out_count, list_cap);
 			}
 		}
 	}

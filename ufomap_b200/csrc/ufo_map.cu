@@ -28,6 +28,7 @@
 #include "ufo_export.cuh"
 #include "ufo_walk.cuh"
 #include "ufo_route.cuh"
+#include "ufo_import.cuh"
 
 using namespace ufo_b200;
 
@@ -223,6 +224,7 @@ void alloc_pools(Map* m, uint32_t brick_cap, uint32_t up_cap)
 	dev_alloc(M.touched, brick_cap, 0, s, tot);
 	dev_alloc(M.touched_alt, brick_cap, 0, s, tot);
 	dev_alloc(M.touched_mi, brick_cap, 0, s, tot);
+	dev_alloc(M.vol_list, brick_cap, 0, s, tot);
 	dev_alloc(M.touched_alt_mi, brick_cap, 0, s, tot);
 	dev_alloc(M.brick_sum3, (size_t)brick_cap * 8, 0, s, tot);
 	dev_alloc(M.brick_sum4, brick_cap, 0, s, tot);
@@ -237,6 +239,10 @@ void alloc_pools(Map* m, uint32_t brick_cap, uint32_t up_cap)
 	dev_alloc(M.up_key, up_cap, 0, s, tot);
 	dev_alloc(M.up_agg, up_cap, 0, s, tot);
 	dev_alloc(M.up_stamp, up_cap, 0, s, tot);
+	dev_alloc(M.up_child, (size_t)up_cap * 8, 0, s, tot);
+	dev_alloc(M.up_valid, up_cap, 0, s, tot);
+	dev_alloc(M.up_parent, up_cap, 0xff, s, tot);
+	dev_alloc(M.brick_parent, brick_cap, 0xff, s, tot);
 	dev_alloc(m->d_list[0], up_cap, 0, s, tot);
 	dev_alloc(m->d_list[1], up_cap, 0, s, tot);
 	if (M.color) {
@@ -246,6 +252,7 @@ void alloc_pools(Map* m, uint32_t brick_cap, uint32_t up_cap)
 		dev_alloc(M.sum1_rgb, nb * 8, 0, s, tot);
 		dev_alloc(M.rgb2, nb, 0, s, tot);
 		dev_alloc(M.up_rgb, up_cap, 0, s, tot);
+		dev_alloc(M.up_child_rgb, (size_t)up_cap * 8, 0, s, tot);
 	}
 	dev_alloc(M.ctr, 1, 0, s, tot);
 }
@@ -253,9 +260,9 @@ void alloc_pools(Map* m, uint32_t brick_cap, uint32_t up_cap)
 void free_pools(Map* m)
 {
 	DeviceMap& M = m->M;
-	void* ptrs[] = {M.bh_tab, M.brick_key, M.brick_stamp, M.touched, M.touched_alt, M.touched_mi, M.touched_alt_mi, M.chg_mask, M.vol, M.vol_dirty, M.route, m->route_inbox, M.brick_sum3, M.brick_sum4, M.brick_rgb3, M.brick_rgb4,
+	void* ptrs[] = {M.bh_tab, M.brick_key, M.brick_stamp, M.touched, M.touched_alt, M.touched_mi, M.touched_alt_mi, M.chg_mask, M.vol, M.vol_dirty, M.vol_list, M.route, m->route_inbox, M.brick_sum3, M.brick_sum4, M.brick_rgb3, M.brick_rgb4,
 	                M.leaf, M.leaf_rgb, M.miss_mask, M.hit_mask, M.agg2, M.meta, M.sum1, M.rgb2, M.sum1_rgb,
-	                M.alias_miss, M.alias_hit, M.uh_keys, M.uh_vals, M.up_key, M.up_agg, M.up_rgb, M.up_stamp, M.ctr, m->d_list[0],
+	                M.alias_miss, M.alias_hit, M.uh_keys, M.uh_vals, M.up_key, M.up_agg, M.up_rgb, M.up_stamp, M.up_child, M.up_child_rgb, M.up_valid, M.up_parent, M.brick_parent, M.ctr, m->d_list[0],
 	                m->d_list[1], m->d_points[0], m->d_points[1], m->d_ray_end, m->d_hit_tab, m->d_tab_keys, m->d_tab_min,
 	                m->d_seg, m->d_seg_base, m->d_seg_count, m->d_order, m->d_items, m->d_vmask, m->d_rc};
 	for (void* p : ptrs)
@@ -306,9 +313,11 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_bricks, uint32_t want_u
 		dev_grow(M.alias_hit, ob, nb, 0, s, tot);
 		dev_grow(M.brick_key, oc, nc, 0, s, tot);
 		dev_grow(M.brick_stamp, oc, nc, 0, s, tot);
+		dev_grow(M.brick_parent, oc, nc, 0xff, s, tot);
 		dev_grow(M.touched, oc, nc, 0, s, tot);
 		dev_grow(M.touched_alt, oc, nc, 0, s, tot);
 		dev_grow(M.touched_mi, oc, nc, 0, s, tot);
+		dev_grow(M.vol_list, oc, nc, 0, s, tot);
 		dev_grow(M.touched_alt_mi, oc, nc, 0, s, tot);
 		dev_grow(M.brick_sum3, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
 		dev_grow(M.brick_sum4, oc, nc, 0, s, tot);
@@ -333,6 +342,10 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_bricks, uint32_t want_u
 		dev_grow(M.up_agg, oc, nc, 0, s, tot);
 		dev_grow(M.up_stamp, oc, nc, 0, s, tot);
 		dev_grow(M.up_rgb, oc, nc, 0, s, tot);
+		dev_grow(M.up_child, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
+		dev_grow(M.up_child_rgb, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
+		dev_grow(M.up_valid, oc, nc, 0, s, tot);
+		dev_grow(M.up_parent, oc, nc, 0xff, s, tot);
 		dev_grow(m->d_list[0], oc, nc, 0, s, tot);
 		dev_grow(m->d_list[1], oc, nc, 0, s, tot);
 		M.up_cap = nc;
@@ -715,6 +728,10 @@ void enqueue_scan(Map* m, PendingScan& p)
 	}
 	m->ev7_valid = false;
 	push_counters(m);
+	if (M.dense) {
+		const size_t vb = (size_t)M.vol_db * M.vol_db * M.vol_db;
+		CK(cudaMemsetAsync(M.vol_dirty, 0, (vb / 64 + 1) * 8, s));  // the "seen" filter of the dirty list
+	}
 	if (p.need_table) {
 		CK(cudaMemsetAsync(m->d_tab_keys, 0xff, (size_t)m->tab_size * sizeof(unsigned long long), s));
 		CK(cudaMemsetAsync(m->d_tab_min, 0xff, (size_t)m->tab_size * sizeof(uint32_t), s));
@@ -1166,6 +1183,10 @@ int do_route_mark(Map* m, const double origin[3], const void* points, bool on_de
 	M.scan_id += 1;
 	if (M.scan_id == 0) M.scan_id = 1;
 	push_counters(m);
+	if (M.dense) {
+		const size_t vb = (size_t)M.vol_db * M.vol_db * M.vol_db;
+		CK(cudaMemsetAsync(M.vol_dirty, 0, (vb / 64 + 1) * 8, s));
+	}
 	if (n) {
 		k_points<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(M, a);
 		++m->launches;
@@ -2240,6 +2261,9 @@ int ufo_b200_clear(ufo_b200_map* m)
 		CK(cudaMemsetAsync(M.uh_vals, 0xff, ((size_t)M.uh_mask + 1) * 4, s));
 		CK(cudaMemsetAsync(M.brick_stamp, 0, (size_t)m->n_bricks * 4, s));
 		CK(cudaMemsetAsync(M.up_stamp, 0, (size_t)m->n_upper * 4, s));
+		CK(cudaMemsetAsync(M.up_valid, 0, (size_t)m->n_upper * 4, s));
+		CK(cudaMemsetAsync(M.up_parent, 0xff, (size_t)m->n_upper * 4, s));
+		CK(cudaMemsetAsync(M.brick_parent, 0xff, (size_t)m->n_bricks * 4, s));
 		const size_t nb = (size_t)m->n_bricks * 64;
 		CK(cudaMemsetAsync(M.leaf, 0, nb * 64 * 4, s));
 		CK(cudaMemsetAsync(M.miss_mask, 0, nb * 8, s));
@@ -2619,6 +2643,233 @@ int ufo_b200_export_nodes(ufo_b200_map* m, uint32_t depth, int occupied, int fre
 }
 
 }  // extern "C"
+
+namespace
+{
+struct StreamReader {
+	const uint8_t* p;
+	size_t n, at = 0;
+	bool ok = true;
+	bool get(void* out, size_t len)
+	{
+		if (at + len > n) {
+			ok = false;
+			std::memset(out, 0, len);
+			at = n + 1;
+			return false;
+		}
+		std::memcpy(out, p + at, len);
+		at += len;
+		return true;
+	}
+};
+
+struct ImportPlan {
+	std::vector<ImportRec> small, bricks, wipe;  // depth <= 2, depth 4, depth >= 5
+	const Geometry* g = nullptr;
+	ExportBox box{};
+	uint32_t P = 4;
+	uint64_t budget = 1ull << 20;  // bricks a stream may create through collapsed nodes above the brick level
+	bool too_big = false;
+};
+
+void import_leaf(ImportPlan& plan, uint64_t code, uint32_t depth, float occ, uint32_t rgb)
+{
+	const ImportRec r{code, depth, occ, rgb, 0u};
+	if (depth <= 2) {
+		plan.small.push_back(r);
+	} else if (depth == 3) {
+		for (uint64_t i = 0; i < 8; ++i) plan.small.push_back(ImportRec{code + (i << 6), 2u, occ, rgb, 0u});
+	} else if (depth == 4) {
+		plan.bricks.push_back(r);
+	} else {
+		// existing bricks below the node take the payload; if it is not the default, the bricks that
+		// do not exist yet have to be created as well (the value field has no collapsed nodes)
+		plan.wipe.push_back(r);
+		if (occ != 0.0f || rgb != 0u) {
+			const uint64_t nb = depth >= 11 ? ~0ull : 1ull << (3 * (depth - 4));
+			if (nb > plan.budget) {
+				plan.too_big = true;
+				return;
+			}
+			plan.budget -= nb;
+			for (uint64_t i = 0; i < nb; ++i) plan.bricks.push_back(ImportRec{code + (i << 12), 4u, occ, rgb, 0u});
+		}
+	}
+}
+
+void read_payload(StreamReader& in, uint32_t P, float& occ, uint32_t& rgb)
+{
+	uint8_t b[7] = {0, 0, 0, 0, 0, 0, 0};
+	in.get(b, P);
+	std::memcpy(&occ, b, 4);
+	rgb = P == 7 ? ((uint32_t)b[4] | ((uint32_t)b[5] << 8) | ((uint32_t)b[6] << 16)) : 0u;
+}
+
+// readNodesRecurs (occupancy_map_base.h:1403-1456): `code` = first voxel of the node of depth `depth`
+void import_rec(ImportPlan& plan, StreamReader& in, uint64_t code, uint32_t depth, const double c[3])
+{
+	const uint32_t cd = depth - 1;
+	const double chs = plan.g->half_size[cd];
+	uint8_t children = 0;
+	if (!in.get(&children, 1)) return;
+	for (uint32_t i = 0; i < 8 && in.ok; ++i) {
+		double cc[3];
+		child_center(c, chs, i, cc);
+		if (!box_hits(plan.box, cc, chs)) continue;
+		const uint64_t ccode = code + ((uint64_t)i << (3 * cd));
+		if ((children >> i) & 1u) {
+			if (1 == cd) {
+				for (uint32_t j = 0; j < 8; ++j) {
+					double gc[3];
+					child_center(cc, plan.g->half_size[0], j, gc);
+					if (!box_hits(plan.box, gc, plan.g->half_size[0])) continue;
+					float occ;
+					uint32_t rgb;
+					read_payload(in, plan.P, occ, rgb);
+					import_leaf(plan, ccode + j, 0, occ, rgb);
+				}
+			} else {
+				import_rec(plan, in, ccode, cd, cc);
+			}
+		} else {
+			float occ;
+			uint32_t rgb;
+			read_payload(in, plan.P, occ, rgb);
+			import_leaf(plan, ccode, cd, occ, rgb);
+		}
+	}
+}
+
+int import_stream(Map* m, const uint8_t* data, size_t size, const double* box6)
+{
+	DeviceMap& M = m->M;
+	if (M.g.depth_levels < 5) {
+		m->set_error("readData needs depth_levels >= 5");
+		return UFO_B200_E_UNSUPPORTED;
+	}
+	if (M.route_world > 1 || M.shard_world > 1) {
+		m->set_error("readData on a sharded / routed map is not supported");
+		return UFO_B200_E_UNSUPPORTED;
+	}
+	CK(cudaSetDevice(m->device));
+	finalize_scan(m);
+	ImportPlan plan;
+	plan.g = &M.g;
+	plan.P = M.color ? 7 : 4;
+	if (box6) {
+		plan.box.on = 1;
+		for (int k = 0; k < 3; ++k) {
+			plan.box.lo[k] = box6[k] - box6[3 + k];
+			plan.box.hi[k] = box6[k] + box6[3 + k];
+		}
+	}
+	const double c0[3] = {0.0, 0.0, 0.0};
+	if (!box_hits(plan.box, c0, M.g.half_size[M.g.depth_levels])) return UFO_B200_OK;  // no node intersects
+	StreamReader in{data, size};
+	uint8_t children = 0;
+	in.get(&children, 1);
+	if (0 == children) {
+		float occ;
+		uint32_t rgb;
+		read_payload(in, plan.P, occ, rgb);
+		import_leaf(plan, 0, M.g.depth_levels, occ, rgb);
+	} else {
+		import_rec(plan, in, 0, M.g.depth_levels, c0);
+	}
+	if (!in.ok) {
+		m->set_error("readData: the node stream is truncated");
+		return UFO_B200_E_INVALID;
+	}
+	if (plan.too_big) {
+		m->set_error("readData: a collapsed node above the brick level would expand into more than 2^20 bricks");
+		return UFO_B200_E_UNSUPPORTED;
+	}
+	// the codes of a tree of L levels use 3L bits; the pools must hold the bricks the stream creates
+	cudaStream_t s = m->stream;
+	const size_t n_small = plan.small.size(), n_bricks = plan.bricks.size(), n_wipe = plan.wipe.size();
+	ImportRec *d_small = nullptr, *d_bricks = nullptr, *d_wipe = nullptr;
+	auto cleanup = [&]() {
+		for (void* p : {(void*)d_small, (void*)d_bricks, (void*)d_wipe})
+			if (p) cudaFree(p);
+	};
+	try {
+		if (n_small) {
+			CK(cudaMalloc(&d_small, n_small * sizeof(ImportRec)));
+			CK(cudaMemcpyAsync(d_small, plan.small.data(), n_small * sizeof(ImportRec), cudaMemcpyHostToDevice, s));
+		}
+		if (n_bricks) {
+			CK(cudaMalloc(&d_bricks, n_bricks * sizeof(ImportRec)));
+			CK(cudaMemcpyAsync(d_bricks, plan.bricks.data(), n_bricks * sizeof(ImportRec), cudaMemcpyHostToDevice, s));
+		}
+		if (n_wipe) {
+			CK(cudaMalloc(&d_wipe, n_wipe * sizeof(ImportRec)));
+			CK(cudaMemcpyAsync(d_wipe, plan.wipe.data(), n_wipe * sizeof(ImportRec), cudaMemcpyHostToDevice, s));
+		}
+		for (int attempt = 0;; ++attempt) {
+			M.scan_id++;
+			if (M.scan_id == 0) M.scan_id = 1;
+			M.up_epoch++;
+			M.dense = 0;
+			M.mask_base = M.miss_mask;
+			push_counters(m);
+			if (n_wipe && m->n_bricks)
+				k_import_wipe<<<(uint32_t)(((size_t)m->n_bricks * 64 + 255) / 256), 256, 0, s>>>(M, m->n_bricks, d_wipe, (uint32_t)n_wipe);
+			if (n_bricks) k_import_bricks<<<(uint32_t)std::min<size_t>(n_bricks, (size_t)m->sm_count * 16), 64, 0, s>>>(M, d_bricks, (uint32_t)n_bricks);
+			if (n_small) k_import_small<<<m->sm_count * 8, 256, 0, s>>>(M, d_small, (uint32_t)n_small);
+			k_import_refresh<<<m->sm_count * 8, 256, 0, s>>>(M);
+			if (M.color) k_brick_agg<true><<<m->sm_count * 4, 256, 0, s>>>(M);
+			else k_brick_agg<false><<<m->sm_count * 4, 256, 0, s>>>(M);
+			launch_upper(m);
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync(m->h_ctr, M.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+			CK(cudaStreamSynchronize(s));
+			const uint32_t ov = m->h_ctr->overflow;
+			if (!ov) break;
+			if (attempt > 16) {
+				m->set_error("readData: device pools keep overflowing");
+				cleanup();
+				return UFO_B200_E_NOMEM;
+			}
+			// writing leaves is idempotent: grow and run the whole import again
+			m->n_bricks = std::min(m->h_ctr->n_bricks, M.brick_cap);
+			grow_pools(m, ov & 6u, m->h_ctr->n_bricks, m->h_ctr->n_upper);
+		}
+		m->n_bricks = std::min(m->h_ctr->n_bricks, M.brick_cap);
+		m->n_upper = std::min(m->h_ctr->n_upper, M.up_cap);
+	} catch (...) {
+		cleanup();
+		throw;
+	}
+	cleanup();
+	return UFO_B200_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ufo_b200_read_data(ufo_b200_map* m, const double* box6, const void* data, size_t size, int compressed,
+                       size_t uncompressed_size)
+{
+	if (!m || (!data && size)) return UFO_B200_E_INVALID;
+	return guarded(m, [&]() {
+		if (!compressed) return import_stream(m, static_cast<const uint8_t*>(data), size, box6);
+		if (!lz4().ok) {
+			m->set_error("liblz4.so.1 not found: compressed input is unavailable");
+			return (int)UFO_B200_E_UNSUPPORTED;
+		}
+		std::vector<uint8_t> raw(std::max<size_t>(uncompressed_size, 1));
+		const int n = lz4().decompress(static_cast<const char*>(data), reinterpret_cast<char*>(raw.data()), (int)size, (int)uncompressed_size);
+		if (n < 0) {
+			m->set_error("readData: LZ4 decompression failed");
+			return (int)UFO_B200_E_INVALID;
+		}
+		return import_stream(m, raw.data(), (size_t)n, box6);
+	});
+}
+
+}  // extern "C"
+
 
 
 

@@ -57,59 +57,38 @@ __device__ __forceinline__ void mark_dense(const DeviceMap& M, uint32_t x, uint3
 	vol_touch(M, vb);
 }
 
-// Dense mode, after the walk: every dirty volume brick becomes an entry of the scan's touched
-// list -- (brick slot in the map, found or created through the brick hash; volume brick holding
-// its masks).  One thread per word of the dirty bitmap.  SHARD: bricks of another GPU are dropped
+// Dense mode, after the walk: every volume brick on the scan's dirty list becomes an entry of the
+// touched list -- (brick slot in the map, found or created through the brick hash; volume brick
+// holding its masks).  One thread per dirty brick.  SHARD: bricks of another GPU are dropped
 // (their masks zeroed) instead.
 template <bool SHARD>
 __global__ void __launch_bounds__(256) k_gather(DeviceMap M)
 {
 	if (ld_volatile_u32(&M.ctr->overflow) & ~4u) return;
-	constexpr uint32_t FULL = 0xffffffffu;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t db = M.vol_db;
-	const uint32_t n_words = (db * db * db + 63u) / 64u;
-	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-	// a warp scans 32 words at a time (one coalesced load) and then works through the non-empty
-	// ones with all its lanes: lane l takes bits l and l + 32 of the word
-	for (uint32_t w0 = warp * 32u; w0 < n_words; w0 += n_warps * 32u) {
-		const uint32_t wi = w0 + lane;
-		unsigned long long mine = 0ull;
-		if (wi < n_words) {
-			mine = M.vol_dirty[wi];
-			if (mine) M.vol_dirty[wi] = 0ull;
+	const uint32_t n = min(ld_volatile_u32(&M.ctr->n_dirty), M.brick_cap);
+	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+		const uint32_t vb = M.vol_list[e];
+		const uint32_t rx = vb % db, ry = (vb / db) % db, rz = vb / (db * db);
+		const unsigned long long key = pack_key(M.vol_g0x + rx, M.vol_g0y + ry, M.vol_g0z + rz);
+		if (SHARD && brick_owner(key, M.shard_world) != M.shard_rank) {
+			unsigned long long* v = M.vol + (size_t)vb * 64;
+			for (int c = 0; c < 64; ++c) v[c] = 0ull;
+			continue;
 		}
-		uint32_t todo = __ballot_sync(FULL, mine != 0ull);
-		while (todo) {
-			const uint32_t src = __ffs(todo) - 1;
-			todo &= todo - 1;
-			const unsigned long long w = __shfl_sync(FULL, mine, src);
-#pragma unroll
-			for (uint32_t h = 0; h < 2; ++h) {
-				const uint32_t bit = lane + 32u * h;
-				if (!((w >> bit) & 1ull)) continue;
-				const uint32_t vb = (w0 + src) * 64u + bit;
-				const uint32_t rx = vb % db, ry = (vb / db) % db, rz = vb / (db * db);
-				const unsigned long long key = pack_key(M.vol_g0x + rx, M.vol_g0y + ry, M.vol_g0z + rz);
-				if (SHARD && brick_owner(key, M.shard_world) != M.shard_rank) {
-					unsigned long long* v = M.vol + (size_t)vb * 64;
-					for (int c = 0; c < 64; ++c) v[c] = 0ull;
-					continue;
-				}
-				const uint32_t slot = brick_find_or_create(M, key);
-				if (slot == kNone) continue;  // pool exhausted: flagged, the scan is repeated
-				M.brick_stamp[slot] = M.scan_id;
-				// one list-cursor atomic per group of lanes, not per brick (same-address atomics serialise)
-				const uint32_t peers = __activemask();
-				const uint32_t leader = __ffs(peers) - 1;
-				uint32_t base = 0;
-				if (lane == leader) base = atomicAdd(&M.ctr->n_touched, (uint32_t)__popc(peers));
-				base = __shfl_sync(peers, base, leader);
-				const uint32_t i = base + __popc(peers & ((1u << lane) - 1u));
-				M.touched[i] = slot;
-				M.touched_mi[i] = vb;
-			}
-		}
+		const uint32_t slot = brick_find_or_create(M, key);
+		if (slot == kNone) continue;  // pool exhausted: flagged, the scan is repeated
+		M.brick_stamp[slot] = M.scan_id;
+		// one list-cursor atomic per group of lanes, not per brick (same-address atomics serialise)
+		const uint32_t peers = __activemask();
+		const uint32_t leader = __ffs(peers) - 1;
+		uint32_t base = 0;
+		if (lane == leader) base = atomicAdd(&M.ctr->n_touched, (uint32_t)__popc(peers));
+		base = __shfl_sync(peers, base, leader);
+		const uint32_t i = base + __popc(peers & ((1u << lane) - 1u));
+		M.touched[i] = slot;
+		M.touched_mi[i] = vb;
 	}
 }
 
