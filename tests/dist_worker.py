@@ -18,6 +18,13 @@ assert clouds[0].shape == (131072, 3) and clouds[0].dtype == np.float32 and layo
 gathered = [None] * world
 dist.all_gather_object(gathered, origins[0].tolist())
 assert len({tuple(g) for g in gathered}) == world, gathered
+# routed mode: the ranks' azimuth sectors partition the rays of one scan
+mine = bench.route_slice(131072, rank, world)
+parts = [None] * world
+dist.all_gather_object(parts, mine.tolist())
+allidx = np.sort(np.concatenate([np.asarray(p_) for p_ in parts]))
+assert np.array_equal(allidx, np.arange(131072)), "sectors must cover every ray exactly once"
+assert len(mine) == 131072 // world and (np.diff(mine) > 0).all()
 # the job's time is the slowest rank's
 ms = bench.max_over_ranks(10.0 + rank, world)
 assert ms == 10.0 + world - 1, ms

@@ -133,9 +133,24 @@ def test_insert_depth_3_and_4():
                dict(origin=o, xyz=p, max_range=4.0, depth=3, simple=True)])
     gpu = Map(0.05)
     with pytest.raises(UfoError) as e:
-        gpu.insert(o, p, depth=5)
+        gpu.insert(o, p, depth=7)
     assert e.value.status == E_UNSUPPORTED
     gpu.close()
+
+
+def test_insert_depth_5_and_6():
+    """Free-space nodes above the brick level (32^3 and 64^3 voxels): collected into the scan's node
+    set, expanded into bricks, applied to every voxel below them; mixed with finer scans."""
+    o, p, c = scans.rgbd(width=80, height=60)
+    o2, p2, c2 = scans.rgbd(k=3, width=80, height=60)
+    _run_case(dict(resolution=0.01),
+              [dict(origin=o, xyz=p, rgb=c, max_range=3.0, discrete=True, depth=5),
+               dict(origin=o2, xyz=p2, rgb=c2, max_range=3.0, discrete=True, depth=0),
+               dict(origin=o2, xyz=p2, rgb=c2, max_range=3.0, discrete=True, depth=6)], color=True,
+              levels=(1, 2, 3, 4, 5, 6, 7, 9))
+    _run_case(dict(resolution=0.02),
+              [dict(origin=o, xyz=p, max_range=3.0, depth=6), dict(origin=o2, xyz=p2, max_range=4.0, depth=5),
+               dict(origin=o, xyz=p, max_range=4.0, depth=5, simple=True)], levels=(1, 2, 4, 5, 6, 7))
 
 
 def test_simple_ray_casting():

@@ -47,6 +47,9 @@ def _cases():
         ins.append(dict(origin=o, xyz=p, rgb=g, max_range=5.0, discrete=True, depth=4))
     # 2 * 10^9 voxels when expanded: compared by voxel count + 2 M sampled voxels, not as a field
     c["c3d4"] = dict(map_kw=dict(resolution=0.002), color=True, inserts=ins, sampled=True)
+    # the reference's only fast regime at 2 mm: insert depth 6 (64^3-voxel free nodes)
+    c["c3d6"] = dict(map_kw=dict(resolution=0.002), color=True, sampled=True,
+                     inserts=[dict(i, depth=6) for i in ins])
     ins = []
     for s in range(2):
         so = scans.sensor_ring(s, 8)
@@ -118,11 +121,14 @@ def test_config3_reduced_2mm_color(cpu_results):
     _compare("c3r", cpu_results, color_tol=1)
 
 
-def test_config3_full_size_depth4_color(cpu_results):
-    """Full-size #3 at insert depth 4: number of non-default voxels, and occupancy (bit-exact) +
+@pytest.mark.parametrize("name", ["c3d4", "c3d6"])
+def test_config3_full_size_coarse_insert_color(cpu_results, name):
+    """Full-size #3 at insert depth 4 / 6: number of non-default voxels, and occupancy (bit-exact) +
     colour (+-1) of 2 M voxels sampled along the rays (free space) and at the end points (hits)."""
     cases, futures = cpu_results
-    case = cases["c3d4"]
+    if not have_ref():
+        pytest.skip("needs the compiled reference (batched node lookup)")
+    case = cases[name]
     gpu = Map(color=True, initial_bricks=1 << 19, **case["map_kw"])
     rng = np.random.default_rng(3)
     pts = []
@@ -139,14 +145,15 @@ def test_config3_full_size_depth4_color(cpu_results):
     codes = spread(keys[:, 0]) | (spread(keys[:, 1]) << np.uint64(1)) | (spread(keys[:, 2]) << np.uint64(2))
     assert int(codes[0]) == gpu.to_code(pts[0], 0)
     occ, flags, rgb = gpu.query(codes, 0)
-    ref = futures["c3d4"].result()
+    ref = futures[name].result()
     rocc, rrgb, _, _ = ref["map"].node_batch(codes, 0)
     assert np.array_equal(occ.view(np.uint32), rocc.view(np.uint32))
     assert np.abs(rgb.astype(np.int32) - rrgb.astype(np.int32)).max() <= 1
     assert (occ > 0).sum() > 100000 and (occ < 0).sum() > 100000
+    st = gpu.stats()
+    print("%s: gpu %.3f ms/scan vs %.3f s/scan on the CPU" % (name, st["ms_total"], ref["secs"] / len(case["inserts"])))
     n_gpu = gpu.value_field_count()
-    if hasattr(ref["map"], "field_count"):
-        assert n_gpu == ref["map"].field_count()
+    assert n_gpu == ref["map"].field_count()
     mn, mx = gpu.change_bbox()
     assert np.array_equal(mn, ref["bbox"][0]) and np.array_equal(mx, ref["bbox"][1])
     ref["map"].close()

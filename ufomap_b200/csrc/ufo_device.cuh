@@ -276,14 +276,17 @@ __device__ __forceinline__ uint32_t vol_brick(const DeviceMap& M, uint32_t bx, u
 }
 // first mark of a volume brick in this scan (the dirty bitmap is the "seen" filter): the brick goes
 // on the scan's dirty list, which k_gather turns into the touched list
-__device__ __forceinline__ void vol_touch(const DeviceMap& M, uint32_t vb)
+__device__ __forceinline__ void vol_list_push(const DeviceMap& M, uint32_t vb)
 {
-	const unsigned long long bit = 1ull << (vb & 63u);
-	if (ld_volatile_u64(&M.vol_dirty[vb >> 6]) & bit) return;
-	if (atomicOr(&M.vol_dirty[vb >> 6], bit) & bit) return;
 	const uint32_t i = atomicAdd(&M.ctr->n_dirty, 1u);
 	if (i < M.brick_cap) M.vol_list[i] = vb;
 	else atomicOr(&M.ctr->overflow, 2u);  // more bricks than the pool can hold: grow and repeat
+}
+__device__ __forceinline__ void vol_touch(const DeviceMap& M, uint32_t vb)
+{
+	const unsigned long long bit = 1ull << (vb & 63u);
+	if (atomicOr(&M.vol_dirty[vb >> 6], bit) & bit) return;
+	vol_list_push(M, vb);
 }
 
 // continues a probe sequence at table index i (entry e already loaded or not)

@@ -87,6 +87,10 @@ struct ScanArgs {
 	size_t item_stride;
 	uint32_t* vmask;
 	RayConst* rc;                // [n]
+	// insert depth 5/6: free-space nodes larger than a brick are collected here (deduplicated through
+	// the scan-local table) and expanded into bricks by k_expand_nodes
+	unsigned long long* nodes;   // [nodes_cap] packed (key >> depth)
+	uint32_t nodes_cap;
 };
 
 // returns false for a point the ingestion drops (PointCloud2 records with a NaN coordinate)
@@ -221,11 +225,52 @@ __device__ __noinline__ void mark_node_miss(const DeviceMap M, uint32_t x, uint3
 	for (uint32_t c = 0; c < count; ++c) atomicOr(&M.miss_mask[(size_t)brick * 64 + first + c], ~0ull);
 }
 
-__device__ __noinline__ void scatter_slow(const DeviceMap M, uint32_t x, uint32_t y, uint32_t z,
+// Free-space node above the brick level (insert depth 5, 6): updateAllChildren
+// (occupancy_map_base.h:1085-1120) reaches every voxel below it, i.e. every block of every brick
+// below it.  Thousands of rays cross the same node, so the node goes into the scan's set first
+// (the reference's CodeMap does the same) and k_expand_nodes marks its bricks once.
+__device__ __noinline__ void collect_node(const DeviceMap M, const ScanArgs& a, uint32_t x, uint32_t y, uint32_t z,
+                                          uint32_t depth)
+{
+	if ((x | y | z) & ~M.g.key_mask) {
+		atomicOr(&M.ctr->overflow, 128u);  // out-of-tree node at this depth: not supported
+		return;
+	}
+	const unsigned long long node = pack_key(x >> depth, y >> depth, z >> depth);
+	bool first;
+	table_insert(a, node | (3ull << 62), &first);
+	if (!first) return;
+	const uint32_t i = atomicAdd(&M.ctr->n_dirty, 1u);  // (the dense volume is not used on this path)
+	if (i < a.nodes_cap) a.nodes[i] = node;
+	else atomicOr(&M.ctr->overflow, 8u);
+}
+
+__device__ __noinline__ void scatter_slow(const DeviceMap M, const ScanArgs& a, uint32_t x, uint32_t y, uint32_t z,
                                           unsigned long long bits, uint32_t depth)
 {
-	if (depth >= 3) mark_node_miss(M, x, y, z, depth);
+	if (depth >= 5) collect_node(M, a, x, y, z, depth);
+	else if (depth >= 3) mark_node_miss(M, x, y, z, depth);
 	else mark_alias(M, x >> 2, y >> 2, z >> 2, bits, false);
+}
+
+// one thread per (collected node, brick below it): find-or-create the brick, full miss masks
+__global__ void __launch_bounds__(256) k_expand_nodes(DeviceMap M, ScanArgs a)
+{
+	if (ld_volatile_u32(&M.ctr->overflow) & ~4u) return;
+	const uint32_t per = 1u << (3 * (a.depth - 4));  // bricks per node
+	const uint32_t side = 1u << (a.depth - 4);
+	const size_t n = (size_t)min(ld_volatile_u32(&M.ctr->n_dirty), a.nodes_cap) * per;
+	for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+		uint32_t nx, ny, nz;
+		unpack_key(a.nodes[e / per], nx, ny, nz);
+		const uint32_t j = (uint32_t)(e % per);
+		const uint32_t bx = nx * side + (j % side), by = ny * side + ((j / side) % side), bz = nz * side + j / (side * side);
+		const uint32_t brick = brick_find_or_create(M, pack_key(bx, by, bz));
+		if (brick == kNone) continue;
+		touch_brick(M, brick);
+		ulonglong2* mm = reinterpret_cast<ulonglong2*>(M.miss_mask + (size_t)brick * 64);
+		for (int c = 0; c < 32; ++c) mm[c] = make_ulonglong2(~0ull, ~0ull);
+	}
 }
 
 // A brick received a mark: it joins the scan's touched list -- directly, or in dense mode through
@@ -757,7 +802,7 @@ __device__ __forceinline__ void scatter_record(const DeviceMap& M, const ScanArg
 		// rare: free-space nodes larger than a block, or a key outside the tree.  The lean
 		// variant has no slow path: it asks the host for the alias arrays (bit 5), and the
 		// re-run -- like every later scan of this map -- uses the generic variant.
-		if (GENERIC) scatter_slow(M, x, y, z, v.x, a.depth);
+		if (GENERIC) scatter_slow(M, a, x, y, z, v.x, a.depth);
 		else atomicOr(&M.ctr->overflow, 32u);
 		return;
 	}
@@ -890,7 +935,8 @@ __global__ void __launch_bounds__(128) k_rays_simple(DeviceMap M, ScanArgs a)
 	for (int s = 0; s <= num_steps; ++s) {
 		Key3 k = point_to_key(M.g, cur, a.depth);
 		if (a.depth >= 3) {
-			mark_node_miss(M, k.x & 0x1fffffu, k.y & 0x1fffffu, k.z & 0x1fffffu, a.depth);
+			if (a.depth >= 5) collect_node(M, a, k.x & 0x1fffffu, k.y & 0x1fffffu, k.z & 0x1fffffu, a.depth);
+			else mark_node_miss(M, k.x & 0x1fffffu, k.y & 0x1fffffu, k.z & 0x1fffffu, a.depth);
 			++visits;
 			cur = vadd(cur, step);
 			continue;

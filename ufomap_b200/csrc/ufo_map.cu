@@ -125,6 +125,7 @@ struct ufo_b200_map {
 	unsigned long long seg_cap = 0;
 	uint32_t *d_seg_base = nullptr, *d_seg_count = nullptr;
 	uint32_t* d_order = nullptr;
+	unsigned long long* d_nodes = nullptr;  // insert depth 5/6: free-space nodes of the scan
 	// fused walk: segments, validity masks, per-ray constants
 	Item* d_items = nullptr;
 	uint32_t* d_vmask = nullptr;
@@ -264,7 +265,7 @@ void free_pools(Map* m)
 	                M.leaf, M.leaf_rgb, M.miss_mask, M.hit_mask, M.agg2, M.meta, M.sum1, M.rgb2, M.sum1_rgb,
 	                M.alias_miss, M.alias_hit, M.uh_keys, M.uh_vals, M.up_key, M.up_agg, M.up_rgb, M.up_stamp, M.up_child, M.up_child_rgb, M.up_valid, M.up_parent, M.brick_parent, M.ctr, m->d_list[0],
 	                m->d_list[1], m->d_points[0], m->d_points[1], m->d_ray_end, m->d_hit_tab, m->d_tab_keys, m->d_tab_min,
-	                m->d_seg, m->d_seg_base, m->d_seg_count, m->d_order, m->d_items, m->d_vmask, m->d_rc};
+	                m->d_seg, m->d_seg_base, m->d_seg_count, m->d_order, m->d_nodes, m->d_items, m->d_vmask, m->d_rc};
 	for (void* p : ptrs)
 		if (p) cudaFree(p);
 }
@@ -527,6 +528,10 @@ void launch_rays_records(Map* m, const ScanArgs& a, int simple)
 	if (simple) {
 		k_rays_simple<<<(a.n + 127) / 128, 128, 0, m->stream>>>(m->M, a);
 		++m->launches;
+		if (a.depth >= 5) {
+			k_expand_nodes<<<m->sm_count * 8, 256, 0, m->stream>>>(m->M, a);
+			++m->launches;
+		}
 		return;
 	}
 	// one resident wave; batches are ordered by work and dealt round-robin over the CTAs
@@ -565,6 +570,10 @@ void launch_rays_records(Map* m, const ScanArgs& a, int simple)
 		else k_scatter<false, false><<<sgrid, kChunk, 0, m->stream>>>(m->M, a);
 	}
 	++m->launches;
+	if (a.depth >= 5) {
+		k_expand_nodes<<<m->sm_count * 8, 256, 0, m->stream>>>(m->M, a);
+		++m->launches;
+	}
 }
 
 template <int DEPTH, bool DENSE>
@@ -726,6 +735,11 @@ void enqueue_scan(Map* m, PendingScan& p)
 		a.seg_count = m->d_seg_count;
 		a.order = m->d_order;
 	}
+	if (a.depth >= 5) {
+		if (!m->d_nodes) dev_alloc(m->d_nodes, (size_t)1 << 20, 0, s, m->device_bytes);
+		a.nodes = m->d_nodes;
+		a.nodes_cap = 1u << 20;
+	}
 	m->ev7_valid = false;
 	push_counters(m);
 	if (M.dense) {
@@ -810,14 +824,15 @@ void finalize_scan(Map* m)
 		const uint32_t ov = m->h_ctr->overflow;
 		if (!ov) break;
 		++p.regrows;
-		if (p.regrows > 16 || (ov & 16u) || p.routed) {
-			if (ov & 16u) m->set_error("internal error: a ray walk exceeded its record bound");
+		if (p.regrows > 16 || (ov & (16u | 128u)) || p.routed) {
+			if (ov & 128u) m->set_error("insert depth >= 5 with rays that leave the map (out-of-tree nodes) is not supported");
+			else if (ov & 16u) m->set_error("internal error: a ray walk exceeded its record bound");
 			else if (p.routed) m->set_error("routed mode: a device pool overflowed (flags %u); create the map with a larger initial_bricks", ov);
 			else m->set_error("device pools keep overflowing");
 			p.valid = false;
 			m->stats_pending = false;
 			m->poisoned = true;  // marks of the failed scan are still in the masks
-			throw MapError{(ov & 16u) ? UFO_B200_E_CUDA : UFO_B200_E_NOMEM};
+			throw MapError{(ov & 128u) ? UFO_B200_E_UNSUPPORTED : ((ov & 16u) ? UFO_B200_E_CUDA : UFO_B200_E_NOMEM)};
 		}
 		try {
 			if (ov == 4u) {
@@ -975,8 +990,8 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 		m->set_error("early_stopping is order-dependent in the reference (occupancy_map_base.h:1289-1298) and is not supported");
 		return UFO_B200_E_UNSUPPORTED;
 	}
-	if (depth > 4) {
-		m->set_error("insert depth %u > 4 (free-space nodes larger than a brick) is not supported", depth);
+	if (depth > 6) {
+		m->set_error("insert depth %u > 6 is not supported (a free-space node of depth 7 covers 512 bricks of the dense value field)", depth);
 		return UFO_B200_E_UNSUPPORTED;
 	}
 	if (m->poisoned) {
@@ -1015,7 +1030,7 @@ int do_insert(Map* m, const double origin[3], const void* points, bool on_device
 	PendingScan& p = m->pending;
 	p = PendingScan{};
 	p.use_color = M.color && has_rgb;
-	p.need_table = discrete || p.use_color;
+	p.need_table = discrete || p.use_color || depth >= 5;  // depth 5/6: the scan's set of free-space nodes
 	p.simple = simple != 0;
 	p.has_vol = vol != nullptr;
 	if (vol) p.vol = *vol;

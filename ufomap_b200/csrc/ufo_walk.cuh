@@ -392,12 +392,23 @@ __device__ __forceinline__ bool walk_iteration_ring(double& tx, double& ty, doub
 }
 
 // Drains up to 32 records of the warp's ring, starting at `head`: lane l takes record head + l.
-// One reduction per record into the scan volume; the brick's dirty bit is set by one lane per
-// distinct brick among the 32 records.
+// One reduction per record into the scan volume.  One lane per distinct brick among the 32 records
+// sets the brick's bit in the dirty bitmap with a RETURNING atomic whose result -- was this the
+// brick's first mark of the scan? -- is only looked at by the NEXT drain (pend_*), so the walk never
+// waits for it; first marks go on the scan's dirty list.
+__device__ __forceinline__ void drain_pending(const DeviceMap& M, uint32_t& pend_vb, unsigned long long pend_old)
+{
+	if (pend_vb != kNone) {
+		if (!((pend_old >> (pend_vb & 63u)) & 1ull)) vol_list_push(M, pend_vb);
+		pend_vb = kNone;
+	}
+}
+
 __device__ __forceinline__ void drain_marks(const DeviceMap& M, const ulonglong2* ring, uint32_t head, uint32_t n,
-                                            uint32_t lane)
+                                            uint32_t lane, uint32_t& pend_vb, unsigned long long& pend_old)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
+	drain_pending(M, pend_vb, pend_old);
 	uint32_t vb = kNone;
 	if (lane < n) {
 		const ulonglong2 e = ring[(head + lane) & (kRing - 1)];
@@ -413,8 +424,13 @@ __device__ __forceinline__ void drain_marks(const DeviceMap& M, const ulonglong2
 			atomicOr(&M.vol[(size_t)vb * 64 + morton2(x >> 2, y >> 2, z >> 2)], e.x);
 		}
 	}
+#ifndef UFO_TIMING_NO_DIRTY  // (timing experiments only: without this the touched list stays empty)
 	const uint32_t grp = __match_any_sync(FULL, vb);
-	if (vb != kNone && lane == (uint32_t)(__ffs(grp) - 1)) vol_touch(M, vb);
+	if (vb != kNone && lane == (uint32_t)(__ffs(grp) - 1)) {
+		pend_old = atomicOr(&M.vol_dirty[vb >> 6], 1ull << (vb & 63u));
+		pend_vb = vb;
+	}
+#endif
 }
 
 // brick slot of `bkey` for marking: one probe of the two-entry bucket (L1-cached: neighbouring
@@ -476,6 +492,8 @@ __global__ void __launch_bounds__(kWalkThreads, UFO_WALK_MINBLOCKS) k_walk_mark(
 	const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	uint32_t q_head = 0, q_tail = 0;  // warp-uniform running counters
+	uint32_t pend_vb = kNone;         // dirty-bit atomic of the previous drain, result not yet looked at
+	unsigned long long pend_old = 0ull;
 #endif
 	while (true) {
 		uint32_t u0 = 0;
@@ -541,7 +559,7 @@ __global__ void __launch_bounds__(kWalkThreads, UFO_WALK_MINBLOCKS) k_walk_mark(
 					                          voxel_bits<DEPTH>(Key3{kx, ky, kz}), active, q_tail, ring_base, lt_mask);
 					if (q_tail - q_head >= 32u) {
 						__syncwarp();
-						drain_marks(M, ring, q_head, 32u, lane);
+						drain_marks(M, ring, q_head, 32u, lane, pend_vb, pend_old);
 						__syncwarp();
 						q_head += 32u;
 					}
@@ -583,9 +601,12 @@ __global__ void __launch_bounds__(kWalkThreads, UFO_WALK_MINBLOCKS) k_walk_mark(
 		}
 	}
 #ifndef UFO_WALK_BRANCH
-	if (DENSE && q_tail != q_head) {
-		__syncwarp();
-		drain_marks(M, ring, q_head, q_tail - q_head, lane);
+	if (DENSE) {
+		if (q_tail != q_head) {
+			__syncwarp();
+			drain_marks(M, ring, q_head, q_tail - q_head, lane, pend_vb, pend_old);
+		}
+		drain_pending(M, pend_vb, pend_old);
 	}
 #endif
 	if (COUNT && visits) atomicAdd(&M.ctr->visits, (unsigned long long)visits);
