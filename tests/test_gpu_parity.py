@@ -499,3 +499,32 @@ def test_filtered_leaf_iteration_matches_the_reference():
             gc = (gc >> np.uint64(3 * d)) << np.uint64(3 * d)
             assert np.array_equal(gc, want_c), (d, kw.keys(), len(gc), len(want_c))
             assert np.array_equal(gv.view(np.uint32), want_v.view(np.uint32)), (d, kw.keys())
+
+
+def test_scan_cost_does_not_depend_on_the_map_size():
+    """K3 / K4 iterate over the scan's touched-brick list, not over the map: the same scan costs the
+    same device time in a map that holds ten times as many bricks elsewhere."""
+    o, p = scans.velodyne64(k=0, rings=32, azimuths=1024)
+
+    def cost(prefill):
+        m = Map(0.05, initial_bricks=1 << 17)
+        m.set_profiling(1)
+        for j in range(prefill):
+            # the same scan shape far away: bricks the timed scan never touches
+            shift = np.array([200.0 * (j + 1), 150.0 * (j % 3), 0.0])
+            m.insert(o + shift, p + shift, max_range=30.0)
+        bricks_before = m.stats()["bricks_in_map"] if prefill else 0
+        times = []
+        for _ in range(4):
+            m.insert(o, p, max_range=30.0)
+            st = m.stats()
+            times.append((st["ms_update"], st["ms_propagate"], st["ms_total"]))
+        m.close()
+        return np.min(np.array(times[1:]), axis=0), bricks_before, st["bricks_in_map"]
+
+    small, _, n_small = cost(0)
+    big, n_before, n_big = cost(10)
+    assert n_big > 8 * n_small and n_before > 8 * n_small
+    # update + propagation within 25 % (+ 20 us of timer noise) of the small map's
+    assert big[0] <= 1.25 * small[0] + 0.02, (small, big)
+    assert big[1] <= 1.25 * small[1] + 0.02, (small, big)

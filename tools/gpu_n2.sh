@@ -1,13 +1,16 @@
 #!/bin/bash
+# 2-GPU bench lines (run with: gpurun --gpus 2 -- tools/gpu_n2.sh): routed (strong), merge (config #5), replicas
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_n2.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 3 --mode shard 2>&1 | tail -1 > gpurun_out/bench_shard_n2.json
-python - <<'PY'
+for mode in route merge sensors; do
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) \
+    bench.py --gpus 2 --steps 10 --warmup 3 --sustain 0 --mode $mode > gpurun_out/r02_bench_n2_$mode.json 2> gpurun_out/r02_bench_n2_$mode.err
+  echo "== $mode rc=$?"; tail -c 400 gpurun_out/r02_bench_n2_$mode.err
+  python - <<PY
 import json
-for f in ("bench_n2", "bench_shard_n2"):
-    try:
-        d = json.load(open("gpurun_out/%s.json" % f))
-        print(f, "value %.1f M e2e %.1f M ms/step %.3f scaling %s launches %s" % (d["value"] / 1e6, d["e2e"]["value"] / 1e6, d["ms_per_step"], d["scaling"], d["gpu_launches"]))
-    except Exception as e:
-        print(f, "FAILED", e, open("gpurun_out/%s.json" % f).read()[-600:])
+try:
+    d = json.load(open("gpurun_out/r02_bench_n2_$mode.json"))
+    print("$mode", "value %.1f M" % (d["value"] / 1e6), "e2e %.1f M" % (d["e2e"]["value"] / 1e6), "ms/step %.3f" % d["ms_per_step"], d["kernels_ms"])
+except Exception as e:
+    print("$mode: no line", e)
 PY
+done

@@ -46,7 +46,7 @@ struct Counters {
 	uint32_t item_cursor;  // next work unit of the fused walk (k_walk_mark)
 	uint32_t max_span;     // longest ray of the scan in dominant-axis steps (sets the shell thickness)
 	uint32_t n_touched_alt;  // routed mode: length of DeviceMap::touched_alt
-	uint32_t n_dirty;        // dense mode: length of DeviceMap::vol_list
+	uint32_t n_dirty;        // dense mode: length of DeviceMap::vol_list (also: node list of insert depth 5/6)
 	uint32_t list_count[3];  // dirty-list lengths of the upper-level pass (rotating by depth % 3)
 	uint32_t n_rays;
 	uint32_t ray_batch;  // next batch of 32 rays for the persistent ray-walk warps
@@ -117,7 +117,7 @@ struct DeviceMap {
 	// the ray walk marks with a computed address and no lookup.  vol_dirty: one bit per volume brick.
 	unsigned long long* vol;
 	unsigned long long* vol_dirty;
-	uint32_t* vol_list;                  // [brick_cap] volume bricks that received their first mark this scan
+	uint32_t* vol_list;                  // [words of vol_dirty] non-empty words of the dirty bitmap (k_gather_scan)
 	uint32_t vol_db;                     // bricks per axis
 	uint32_t vol_g0x, vol_g0y, vol_g0z;  // brick coordinates (key >> 4) of the volume's origin
 	uint32_t dense;                      // this scan marks into the volume
@@ -274,19 +274,12 @@ __device__ __forceinline__ uint32_t vol_brick(const DeviceMap& M, uint32_t bx, u
 	if (rx >= M.vol_db || ry >= M.vol_db || rz >= M.vol_db) return kNone;
 	return (rz * M.vol_db + ry) * M.vol_db + rx;
 }
-// first mark of a volume brick in this scan (the dirty bitmap is the "seen" filter): the brick goes
-// on the scan's dirty list, which k_gather turns into the touched list
-__device__ __forceinline__ void vol_list_push(const DeviceMap& M, uint32_t vb)
-{
-	const uint32_t i = atomicAdd(&M.ctr->n_dirty, 1u);
-	if (i < M.brick_cap) M.vol_list[i] = vb;
-	else atomicOr(&M.ctr->overflow, 2u);  // more bricks than the pool can hold: grow and repeat
-}
+// a volume brick received a mark: one fire-and-forget reduction on the dirty bitmap (a returning
+// atomic here costs the walk 0.2 ms per scan, profiles/README.md); k_gather_scan / k_gather turn
+// the bitmap into the touched list
 __device__ __forceinline__ void vol_touch(const DeviceMap& M, uint32_t vb)
 {
-	const unsigned long long bit = 1ull << (vb & 63u);
-	if (atomicOr(&M.vol_dirty[vb >> 6], bit) & bit) return;
-	vol_list_push(M, vb);
+	atomicOr(&M.vol_dirty[vb >> 6], 1ull << (vb & 63u));
 }
 
 // continues a probe sequence at table index i (entry e already loaded or not)

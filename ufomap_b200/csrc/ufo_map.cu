@@ -225,7 +225,6 @@ void alloc_pools(Map* m, uint32_t brick_cap, uint32_t up_cap)
 	dev_alloc(M.touched, brick_cap, 0, s, tot);
 	dev_alloc(M.touched_alt, brick_cap, 0, s, tot);
 	dev_alloc(M.touched_mi, brick_cap, 0, s, tot);
-	dev_alloc(M.vol_list, brick_cap, 0, s, tot);
 	dev_alloc(M.touched_alt_mi, brick_cap, 0, s, tot);
 	dev_alloc(M.brick_sum3, (size_t)brick_cap * 8, 0, s, tot);
 	dev_alloc(M.brick_sum4, brick_cap, 0, s, tot);
@@ -318,7 +317,6 @@ void grow_pools(Map* m, uint32_t overflow, uint32_t want_bricks, uint32_t want_u
 		dev_grow(M.touched, oc, nc, 0, s, tot);
 		dev_grow(M.touched_alt, oc, nc, 0, s, tot);
 		dev_grow(M.touched_mi, oc, nc, 0, s, tot);
-		dev_grow(M.vol_list, oc, nc, 0, s, tot);
 		dev_grow(M.touched_alt_mi, oc, nc, 0, s, tot);
 		dev_grow(M.brick_sum3, (size_t)oc * 8, (size_t)nc * 8, 0, s, tot);
 		dev_grow(M.brick_sum4, oc, nc, 0, s, tot);
@@ -599,9 +597,10 @@ void launch_fused_depth(Map* m, const ScanArgs& a)
 			CK(cudaEventRecord(m->ev[7], s));
 			m->ev7_valid = true;
 		}
-		if (m->M.shard_world > 1) k_gather<true><<<m->sm_count * 4, 256, 0, s>>>(m->M);
-		else k_gather<false><<<m->sm_count * 4, 256, 0, s>>>(m->M);
-		++m->launches;
+		k_gather_scan<<<m->sm_count * 2, 256, 0, s>>>(m->M);
+		if (m->M.shard_world > 1) k_gather<true><<<m->sm_count * 8, 256, 0, s>>>(m->M);
+		else k_gather<false><<<m->sm_count * 8, 256, 0, s>>>(m->M);
+		m->launches += 2;
 	}
 }
 
@@ -642,13 +641,16 @@ void setup_volume(Map* m, PendingScan& p, uint32_t db)
 		if (M.vol) {
 			cudaFree(M.vol);
 			cudaFree(M.vol_dirty);
+			cudaFree(M.vol_list);
 			m->device_bytes -= (size_t)m->vol_db_cap * m->vol_db_cap * m->vol_db_cap * (512 + 1) ;
 		}
 		M.vol = nullptr;
 		M.vol_dirty = nullptr;
+		M.vol_list = nullptr;
 		const size_t nb = (size_t)db * db * db;
 		dev_alloc(M.vol, nb * 64, 0, m->stream, m->device_bytes);
 		dev_alloc(M.vol_dirty, nb / 64 + 1, 0, m->stream, m->device_bytes);
+		dev_alloc(M.vol_list, nb / 64 + 1, 0, m->stream, m->device_bytes);
 		m->vol_db_cap = db;
 	}
 	const Geometry& g = M.g;
@@ -742,10 +744,6 @@ void enqueue_scan(Map* m, PendingScan& p)
 	}
 	m->ev7_valid = false;
 	push_counters(m);
-	if (M.dense) {
-		const size_t vb = (size_t)M.vol_db * M.vol_db * M.vol_db;
-		CK(cudaMemsetAsync(M.vol_dirty, 0, (vb / 64 + 1) * 8, s));  // the "seen" filter of the dirty list
-	}
 	if (p.need_table) {
 		CK(cudaMemsetAsync(m->d_tab_keys, 0xff, (size_t)m->tab_size * sizeof(unsigned long long), s));
 		CK(cudaMemsetAsync(m->d_tab_min, 0xff, (size_t)m->tab_size * sizeof(uint32_t), s));
@@ -1198,10 +1196,6 @@ int do_route_mark(Map* m, const double origin[3], const void* points, bool on_de
 	M.scan_id += 1;
 	if (M.scan_id == 0) M.scan_id = 1;
 	push_counters(m);
-	if (M.dense) {
-		const size_t vb = (size_t)M.vol_db * M.vol_db * M.vol_db;
-		CK(cudaMemsetAsync(M.vol_dirty, 0, (vb / 64 + 1) * 8, s));
-	}
 	if (n) {
 		k_points<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(M, a);
 		++m->launches;

@@ -57,38 +57,68 @@ __device__ __forceinline__ void mark_dense(const DeviceMap& M, uint32_t x, uint3
 	vol_touch(M, vb);
 }
 
-// Dense mode, after the walk: every volume brick on the scan's dirty list becomes an entry of the
-// touched list -- (brick slot in the map, found or created through the brick hash; volume brick
-// holding its masks).  One thread per dirty brick.  SHARD: bricks of another GPU are dropped
-// (their masks zeroed) instead.
+// Dense mode, after the walk: the dirty bitmap becomes the scan's touched list in two steps.
+// k_gather_scan: all threads read the bitmap (coalesced) and append the non-empty words to a list;
+// k_gather: one warp per non-empty word, lane l takes bits l and l + 32: find-or-create the brick
+// through the brick hash and append (brick slot, volume brick holding its masks).  SHARD: bricks of
+// another GPU are dropped (their masks zeroed) instead.
+__global__ void __launch_bounds__(256) k_gather_scan(DeviceMap M)
+{
+	if (ld_volatile_u32(&M.ctr->overflow) & ~4u) return;
+	constexpr uint32_t FULL = 0xffffffffu;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t db = M.vol_db;
+	const uint32_t n_words = (db * db * db + 63u) / 64u;
+	const uint32_t n_round = (n_words + 31u) & ~31u;
+	for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_round; wi += gridDim.x * blockDim.x) {
+		const bool any = wi < n_words && M.vol_dirty[wi] != 0ull;
+		const uint32_t bal = __ballot_sync(FULL, any);
+		if (!bal) continue;
+		uint32_t base = 0;
+		if (lane == 0) base = atomicAdd(&M.ctr->n_dirty, (uint32_t)__popc(bal));
+		base = __shfl_sync(FULL, base, 0);
+		if (any) M.vol_list[base + __popc(bal & ((1u << lane) - 1u))] = wi;
+	}
+}
+
 template <bool SHARD>
 __global__ void __launch_bounds__(256) k_gather(DeviceMap M)
 {
 	if (ld_volatile_u32(&M.ctr->overflow) & ~4u) return;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t db = M.vol_db;
-	const uint32_t n = min(ld_volatile_u32(&M.ctr->n_dirty), M.brick_cap);
-	for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-		const uint32_t vb = M.vol_list[e];
-		const uint32_t rx = vb % db, ry = (vb / db) % db, rz = vb / (db * db);
-		const unsigned long long key = pack_key(M.vol_g0x + rx, M.vol_g0y + ry, M.vol_g0z + rz);
-		if (SHARD && brick_owner(key, M.shard_world) != M.shard_rank) {
-			unsigned long long* v = M.vol + (size_t)vb * 64;
-			for (int c = 0; c < 64; ++c) v[c] = 0ull;
-			continue;
+	const uint32_t n = ld_volatile_u32(&M.ctr->n_dirty);
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t e = warp; e < n; e += n_warps) {
+		const uint32_t wi = M.vol_list[e];
+		const unsigned long long w = M.vol_dirty[wi];
+		__syncwarp();
+		if (lane == 0) M.vol_dirty[wi] = 0ull;
+#pragma unroll
+		for (uint32_t h = 0; h < 2; ++h) {
+			const uint32_t bit = lane + 32u * h;
+			if (!((w >> bit) & 1ull)) continue;
+			const uint32_t vb = wi * 64u + bit;
+			const uint32_t rx = vb % db, ry = (vb / db) % db, rz = vb / (db * db);
+			const unsigned long long key = pack_key(M.vol_g0x + rx, M.vol_g0y + ry, M.vol_g0z + rz);
+			if (SHARD && brick_owner(key, M.shard_world) != M.shard_rank) {
+				unsigned long long* v = M.vol + (size_t)vb * 64;
+				for (int c = 0; c < 64; ++c) v[c] = 0ull;
+				continue;
+			}
+			const uint32_t slot = brick_find_or_create(M, key);
+			if (slot == kNone) continue;  // pool exhausted: flagged, the scan is repeated
+			M.brick_stamp[slot] = M.scan_id;
+			// one list-cursor atomic per group of lanes, not per brick (same-address atomics serialise)
+			const uint32_t peers = __activemask();
+			const uint32_t leader = __ffs(peers) - 1;
+			uint32_t base = 0;
+			if (lane == leader) base = atomicAdd(&M.ctr->n_touched, (uint32_t)__popc(peers));
+			base = __shfl_sync(peers, base, leader);
+			const uint32_t i = base + __popc(peers & ((1u << lane) - 1u));
+			M.touched[i] = slot;
+			M.touched_mi[i] = vb;
 		}
-		const uint32_t slot = brick_find_or_create(M, key);
-		if (slot == kNone) continue;  // pool exhausted: flagged, the scan is repeated
-		M.brick_stamp[slot] = M.scan_id;
-		// one list-cursor atomic per group of lanes, not per brick (same-address atomics serialise)
-		const uint32_t peers = __activemask();
-		const uint32_t leader = __ffs(peers) - 1;
-		uint32_t base = 0;
-		if (lane == leader) base = atomicAdd(&M.ctr->n_touched, (uint32_t)__popc(peers));
-		base = __shfl_sync(peers, base, leader);
-		const uint32_t i = base + __popc(peers & ((1u << lane) - 1u));
-		M.touched[i] = slot;
-		M.touched_mi[i] = vb;
 	}
 }
 
@@ -392,23 +422,12 @@ __device__ __forceinline__ bool walk_iteration_ring(double& tx, double& ty, doub
 }
 
 // Drains up to 32 records of the warp's ring, starting at `head`: lane l takes record head + l.
-// One reduction per record into the scan volume.  One lane per distinct brick among the 32 records
-// sets the brick's bit in the dirty bitmap with a RETURNING atomic whose result -- was this the
-// brick's first mark of the scan? -- is only looked at by the NEXT drain (pend_*), so the walk never
-// waits for it; first marks go on the scan's dirty list.
-__device__ __forceinline__ void drain_pending(const DeviceMap& M, uint32_t& pend_vb, unsigned long long pend_old)
-{
-	if (pend_vb != kNone) {
-		if (!((pend_old >> (pend_vb & 63u)) & 1ull)) vol_list_push(M, pend_vb);
-		pend_vb = kNone;
-	}
-}
-
+// One reduction per record into the scan volume; the brick's dirty bit is set by one lane per
+// distinct brick among the 32 records.
 __device__ __forceinline__ void drain_marks(const DeviceMap& M, const ulonglong2* ring, uint32_t head, uint32_t n,
-                                            uint32_t lane, uint32_t& pend_vb, unsigned long long& pend_old)
+                                            uint32_t lane)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
-	drain_pending(M, pend_vb, pend_old);
 	uint32_t vb = kNone;
 	if (lane < n) {
 		const ulonglong2 e = ring[(head + lane) & (kRing - 1)];
@@ -424,13 +443,8 @@ __device__ __forceinline__ void drain_marks(const DeviceMap& M, const ulonglong2
 			atomicOr(&M.vol[(size_t)vb * 64 + morton2(x >> 2, y >> 2, z >> 2)], e.x);
 		}
 	}
-#ifndef UFO_TIMING_NO_DIRTY  // (timing experiments only: without this the touched list stays empty)
 	const uint32_t grp = __match_any_sync(FULL, vb);
-	if (vb != kNone && lane == (uint32_t)(__ffs(grp) - 1)) {
-		pend_old = atomicOr(&M.vol_dirty[vb >> 6], 1ull << (vb & 63u));
-		pend_vb = vb;
-	}
-#endif
+	if (vb != kNone && lane == (uint32_t)(__ffs(grp) - 1)) vol_touch(M, vb);
 }
 
 // brick slot of `bkey` for marking: one probe of the two-entry bucket (L1-cached: neighbouring
@@ -492,8 +506,6 @@ __global__ void __launch_bounds__(kWalkThreads, UFO_WALK_MINBLOCKS) k_walk_mark(
 	const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	uint32_t q_head = 0, q_tail = 0;  // warp-uniform running counters
-	uint32_t pend_vb = kNone;         // dirty-bit atomic of the previous drain, result not yet looked at
-	unsigned long long pend_old = 0ull;
 #endif
 	while (true) {
 		uint32_t u0 = 0;
@@ -559,7 +571,7 @@ __global__ void __launch_bounds__(kWalkThreads, UFO_WALK_MINBLOCKS) k_walk_mark(
 					                          voxel_bits<DEPTH>(Key3{kx, ky, kz}), active, q_tail, ring_base, lt_mask);
 					if (q_tail - q_head >= 32u) {
 						__syncwarp();
-						drain_marks(M, ring, q_head, 32u, lane, pend_vb, pend_old);
+						drain_marks(M, ring, q_head, 32u, lane);
 						__syncwarp();
 						q_head += 32u;
 					}
@@ -601,12 +613,9 @@ __global__ void __launch_bounds__(kWalkThreads, UFO_WALK_MINBLOCKS) k_walk_mark(
 		}
 	}
 #ifndef UFO_WALK_BRANCH
-	if (DENSE) {
-		if (q_tail != q_head) {
-			__syncwarp();
-			drain_marks(M, ring, q_head, q_tail - q_head, lane, pend_vb, pend_old);
-		}
-		drain_pending(M, pend_vb, pend_old);
+	if (DENSE && q_tail != q_head) {
+		__syncwarp();
+		drain_marks(M, ring, q_head, q_tail - q_head, lane);
 	}
 #endif
 	if (COUNT && visits) atomicAdd(&M.ctr->visits, (unsigned long long)visits);
