@@ -8,7 +8,7 @@ for mode in route merge sensors; do
   python - <<PY
 import json
 try:
-    d = json.load(open("gpurun_out/r02_bench_n2_$mode.json"))
+    d = json.loads([l for l in open("gpurun_out/r02_bench_n2_$mode.json") if l.startswith("{")][-1])
     print("$mode", "value %.1f M" % (d["value"] / 1e6), "e2e %.1f M" % (d["e2e"]["value"] / 1e6), "ms/step %.3f" % d["ms_per_step"], d["kernels_ms"])
 except Exception as e:
     print("$mode: no line", e)

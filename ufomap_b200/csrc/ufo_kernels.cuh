@@ -1102,12 +1102,23 @@ __device__ __forceinline__ void upper_level_pass(const DeviceMap& M, uint32_t de
 		uint32_t s = valid ? ld_volatile_u32(&in[i]) : 0;
 		float occ = 0.0f;
 		uint32_t fl = M.default_flags, rgb = 0;
-		if (valid && ((ld_volatile_u32(&M.up_valid[s]) >> lane8) & 1u)) {
-			// volatile: in k_upper_tail the slot was written by this same CTA a level earlier
+		unsigned long long nkey = 0;
+		uint32_t npar = kNone;
+		if (valid) {
+			// everything this node needs is requested at once (one round trip per level, not four).
+			// volatile: in k_upper_tail the slots were written by this same CTA a level earlier
+			const uint32_t vmask = ld_volatile_u32(&M.up_valid[s]);
 			const unsigned long long raw = ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&M.up_child[(size_t)s * 8 + lane8]));
-			occ = __uint_as_float((uint32_t)raw);
-			fl = (uint32_t)(raw >> 32);
-			if (M.color) rgb = ld_volatile_u32(&M.up_child_rgb[(size_t)s * 8 + lane8]);
+			const uint32_t crgb1 = M.color ? ld_volatile_u32(&M.up_child_rgb[(size_t)s * 8 + lane8]) : 0u;
+			if (lane8 == 0) {
+				nkey = ld_volatile_u64(&M.up_key[s]);
+				npar = ld_volatile_u32(&M.up_parent[s]);
+			}
+			if ((vmask >> lane8) & 1u) {
+				occ = __uint_as_float((uint32_t)raw);
+				fl = (uint32_t)(raw >> 32);
+				rgb = crgb1;
+			}
 		}
 		uint32_t crgb[8];
 		if (M.color) {
@@ -1126,9 +1137,9 @@ __device__ __forceinline__ void upper_level_pass(const DeviceMap& M, uint32_t de
 			atomicAdd(&M.ctr->upper_nodes, 1ull);
 			if (depth < M.g.depth_levels) {
 				uint32_t x, y, z;
-				unpack_key(ld_volatile_u64(&M.up_key[s]), x, y, z);
+				unpack_key(nkey, x, y, z);
 				x &= 0xffffu;  // strip the depth tag
-				uint32_t p = ld_volatile_u32(&M.up_parent[s]);
+				uint32_t p = npar;
 				if (p == kNone) {
 					p = upper_find_or_create(M, upper_key(depth + 1, x >> 1, y >> 1, z >> 1));
 					if (p != kNone) st_volatile_u32(&M.up_parent[s], p);
