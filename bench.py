@@ -77,7 +77,7 @@ def atomic_ceiling():
 
 def algorithmic_bytes(st, color=False, p_in=12, part="scan"):
     """N*P_in + U*S_leaf + D1*8*S_leaf + sum_{l>=1} D_l*S_inner + sum_{l>=2} D_l*8*S_inner.
-    part="update" keeps the terms the leaf-update kernel (k_update_compact) is responsible for:
+    part="update" keeps the terms the leaf-update kernel (k_update_warp) is responsible for:
     everything except the point input and the levels above the brick (depth >= 5)."""
     s_leaf, s_inner = (8, 12) if color else (4, 8)
     n, u = st["points"], st["touched_voxels"]
@@ -525,7 +525,7 @@ def main():
             "sustained": sustained,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_update_compact: hit/miss log-odds update of the marked voxels and depth 1-4 "
+                         "kernel": "k_update_warp: hit/miss log-odds update of the marked voxels and depth 1-4 "
                                    "aggregates over the scan's touched bricks; CUDA events on the map's stream "
                                    "around every launch of the timed region",
                          "algorithmic_bytes_per_launch": alg_upd, "ms_per_launch": kern["ms_update"],
