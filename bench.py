@@ -77,7 +77,7 @@ def atomic_ceiling():
 
 def algorithmic_bytes(st, color=False, p_in=12, part="scan"):
     """N*P_in + U*S_leaf + D1*8*S_leaf + sum_{l>=1} D_l*S_inner + sum_{l>=2} D_l*8*S_inner.
-    part="update" keeps the terms the leaf-update kernel (k_update_warp) is responsible for:
+    part="update" keeps the terms the leaf-update kernel (k_update_brick) is responsible for:
     everything except the point input and the levels above the brick (depth >= 5)."""
     s_leaf, s_inner = (8, 12) if color else (4, 8)
     n, u = st["points"], st["touched_voxels"]
@@ -88,6 +88,24 @@ def algorithmic_bytes(st, color=False, p_in=12, part="scan"):
     inner_all = d1 + d2 + d3 + d4 + up
     inner_ge2 = d2 + d3 + d4 + up
     return n * p_in + u * s_leaf + d1 * 8 * s_leaf + inner_all * s_inner + inner_ge2 * 8 * s_inner
+
+
+def sector_ceiling():
+    """tools/sector_ceiling.cu: a kernel that does nothing but read-modify-write K3's sector set."""
+    path = os.path.join(ROOT, "profiles", "r02_sector_ceiling.jsonl")
+    out = {}
+    try:
+        for line in open(path):
+            d = json.loads(line)
+            if d["pattern"] in ("k3_leaf", "k3_all"):
+                out[d["pattern"] + "_ms"] = d["ms"]
+                out[d["pattern"] + "_sectors"] = d["sectors"]
+            elif d["pattern"] == "rmw" and d.get("bricks") == "scattered":
+                out["rmw_gbs_at_density_%s" % d["density"]] = d["GBps"]
+        out["source"] = "profiles/r02_sector_ceiling.jsonl"
+        return out
+    except Exception:
+        return None
 
 
 def measured_traffic():
@@ -490,6 +508,7 @@ def main():
     achieved = alg_upd / (kern["ms_update"] * 1e-3) / 1e9
     pipeline = alg / (t_scan_ms * 1e-3) / 1e9
     traffic, traffic_src = measured_traffic()
+    lines = float(np.mean([s.get("touched_lines", 0) for s in per_scan]))
     last = per_scan[-1]
     ceil = atomic_ceiling()
     t_walk = (kern["ms_rays"] + kern["ms_scatter"]) * 1e-3
@@ -525,18 +544,24 @@ def main():
             "sustained": sustained,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_update_warp: hit/miss log-odds update of the marked voxels and depth 1-4 "
+                         "kernel": "k_update_brick: hit/miss log-odds update of the marked voxels and depth 1-4 "
                                    "aggregates over the scan's touched bricks; CUDA events on the map's stream "
                                    "around every launch of the timed region",
                          "algorithmic_bytes_per_launch": alg_upd, "ms_per_launch": kern["ms_update"],
                          "traffic_source": traffic_src,
+                         # HBM moves whole 128 B lines (profiles/r02_sector_ceiling.jsonl: sparse 32 B sectors
+                         # cost what their lines cost): the leaf lines K3 touches, read + written, over its time
+                         "line_granular": {"leaf_lines_128B": lines, "leaf_line_bytes": lines * 256.0,
+                                           "leaf_line_gbs": lines * 256.0 / (kern["ms_update"] * 1e-3) / 1e9,
+                                           "frac_of_peak_leaf_lines_only": lines * 256.0 / (kern["ms_update"] * 1e-3) / 1e9 / peak,
+                                           "sector_ceiling": sector_ceiling()},
                          # SURVEY.md 8(d)'s whole-pipeline figure: all algorithmic bytes of a scan over the
                          # device time of the whole insert (K1..K4)
                          "pipeline": {"algorithmic_bytes_per_scan": alg, "device_ms_per_scan": t_scan_ms,
                                       "achieved": pipeline, "frac": pipeline / peak}},
             "raycast": raycast,
             "kernels_ms": kern,
-            "counters": {k: int(last[k]) for k in ("rays", "touched_voxels", "hit_voxels", "touched_octets",
+            "counters": {k: int(last[k]) for k in ("rays", "touched_voxels", "hit_voxels", "touched_octets", "touched_lines",
                                                     "touched_blocks", "touched_d3", "touched_bricks",
                                                     "upper_nodes", "blocks_in_map", "bricks_in_map", "regrows")},
             "gpu_launches": int(launches),

@@ -289,6 +289,7 @@ typedef struct {
 	uint64_t regrows;         /* pool growth events during this insert     */
 	uint64_t launches;        /* kernels launched by this insert           */
 	uint64_t result_bytes;    /* bytes of per-scan counters copied device -> host by this insert */
+	uint64_t touched_lines;   /* 128-byte lines of leaf data holding a touched octet (HBM moves whole lines) */
 	float ms_total;           /* CUDA-event time of the whole insert (device work) */
 	float ms_h2d;
 	float ms_points;          /* K1: discretise + hit marking              */

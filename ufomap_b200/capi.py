@@ -40,7 +40,7 @@ class ScanStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "points", "rays", "visits", "touched_voxels", "hit_voxels", "touched_octets",
         "touched_blocks", "touched_d3", "touched_bricks", "upper_nodes", "blocks_in_map", "bricks_in_map",
-        "device_bytes", "regrows", "launches", "result_bytes")] + [(n, C.c_float) for n in (
+        "device_bytes", "regrows", "launches", "result_bytes", "touched_lines")] + [(n, C.c_float) for n in (
             "ms_total", "ms_h2d", "ms_points", "ms_rays", "ms_scatter", "ms_update", "ms_propagate")]
 
     def as_dict(self):

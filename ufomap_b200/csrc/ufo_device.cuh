@@ -63,7 +63,7 @@ struct Counters {
 	unsigned long long upper_nodes;
 	unsigned long long bbox[6];  // order-preserving encoding of min xyz / max xyz of this scan
 	// k_update statistics spread over slots: [slot][0 voxels, 1 hit voxels, 2 octets, 3 blocks,
-	// 4 first-touched blocks, 5 bricks, 6 depth-3 nodes, 7 unused]
+	// 4 first-touched blocks, 5 bricks, 6 depth-3 nodes, 7 touched 128 B leaf lines]
 	unsigned long long stat[64][8];
 };
 

@@ -13,10 +13,11 @@
 //   k_scatter  K2b one thread per record: brick hash probe -> atomicOr into the block's miss
 //                  mask (set semantics of CodeMap::try_emplace, code.h:675-694)
 //   k_rays_simple  fixed-step variant (freeSpaceSimple, occupancy_map_base.h:1303-1339)
-//   k_update_compact / k_update<COLOR>
+//   k_update_brick (ufo_update.cuh)
 //              K3  hit-then-miss float log-odds update of the marked voxels
-//                  (updateOccupancy :1139-1145) and depth-1/2 aggregates per block;
-//   k_brick_agg    depth-3/4 aggregates per brick (updateNode :1179-1224)
+//                  (updateOccupancy :1139-1145) and depth 1-4 aggregates per brick
+//   k_brick_agg    depth-3/4 aggregates per brick (updateNode :1179-1224) when alias marks exist
+//   k_split / k_walk_mark / k_gather* (ufo_walk.cuh): the fused marking path
 //   k_alias_*      marks of keys outside the tree (octree.h:321), launched only when present
 //   k_upper_*  K4  aggregates of the dirty nodes of depth >= 5 (seed, levels 5-6, one-CTA tail)
 #pragma once

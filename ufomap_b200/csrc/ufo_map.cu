@@ -1,10 +1,12 @@
 // ufo_map.cu -- host side of libufomap_b200.so: device pools, scan orchestration
 // and the C ABI declared in include/ufomap_b200.h.
 //
-// One map = one CUDA device + one stream.  An insert enqueues
-//   H2D(points) -> K1 k_points [-> K1b k_hits] -> K2 k_rays -> K2b k_scatter -> speculative K3
-//   (k_update_compact / k_update<COLOR>) while the counters are read back on a second stream ->
-//   (grow pools and re-run K1/K2/K2b if an allocation overflowed) -> K3 remainder -> K4 k_upper_*
+// One map = one CUDA device + one stream (+ a copy stream for the points).  An insert enqueues
+//   H2D(points) -> K1 k_points [-> K1b k_hits] -> k_split -> k_walk_mark -> k_gather_scan ->
+//   k_gather -> K3 k_update_brick -> K4 k_upper_* -> D2H(counters)
+// and returns; the next call that looks at the map reads the counters, grows a pool and repeats
+// the scan if an allocation overflowed (finalize_scan).  Insert depth >= 3, maps that have seen
+// out-of-tree keys and the fixed-step walk use k_rays -> k_scatter instead of the fused walk,
 // which mirrors insertPointCloud + insertPointCloudHelper
 // (/root/reference/ufomap/include/ufo/map/occupancy_map_base.h:270-327, :1345-1373).
 // There is no CPU fallback anywhere in this file.
@@ -136,7 +138,7 @@ struct ufo_b200_map {
 	size_t device_bytes = 0;
 	int profiling = 0;
 	int force_records = 0;  // UFO_B200_MARK=records: always use the record path (A/B runs)
-	int k3_cta = 0;         // UFO_B200_K3=cta: CTA-cooperative K3 instead of the warp-autonomous one
+	int k3_blocks = 0;      // UFO_B200_K3_BLOCKS: resident K3 CTAs per SM (0: the kernel's launch bound)
 	int no_dense = 0;       // UFO_B200_MARK=probe, or a scan left the volume: fused walk through the brick hash
 	uint32_t vol_db_cap = 0;  // bricks per axis the allocated scan volume can hold
 	uint64_t launches = 0;
@@ -446,6 +448,7 @@ void finish_stats(Map* m)
 	st.touched_blocks = sum[3];
 	st.touched_d3 = sum[6];
 	st.touched_bricks = sum[5];
+	st.touched_lines = sum[7];
 	st.upper_nodes = c.upper_nodes;
 	m->n_blocks += (uint32_t)sum[4];
 	m->n_bricks = std::min(c.n_bricks, m->M.brick_cap);
@@ -492,29 +495,19 @@ void ensure_seg(Map* m, unsigned long long want)
 	m->device_bytes += want * sizeof(QEntry);
 }
 
-// K3 over the scan's touched list: persistent CTAs, the list length is read on the device.
-// UFO_B200_K3=cta selects the CTA-cooperative kernel (A/B runs); default is one warp per brick.
+// K3 over the scan's touched list: persistent warps, the list length is read on the device.
 void launch_update(Map* m, float miss, bool set_mode = false)
 {
-	if (m->k3_cta) {
-		const uint32_t grid = (uint32_t)m->sm_count * (m->M.color ? UFO_UC_MINBLOCKS_COLOR : UFO_UC_GRID_PER_SM);
-		if (m->M.color) {
-			if (set_mode) k_update_compact<true, true><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
-			else k_update_compact<true, false><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
-		} else {
-			if (set_mode) k_update_compact<false, true><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
-			else k_update_compact<false, false><<<grid, kUcThreads, 0, m->stream>>>(m->M, miss);
-		}
+	if (m->M.color) {
+		const uint32_t per_sm = UbShape<true>::kMinBlocks, T = UbShape<true>::kWarps * 32;
+		const uint32_t grid = (uint32_t)m->sm_count * (m->k3_blocks ? std::min<uint32_t>(per_sm, (uint32_t)m->k3_blocks) : per_sm);
+		if (set_mode) k_update_brick<true, true><<<grid, T, 0, m->stream>>>(m->M, miss);
+		else k_update_brick<true, false><<<grid, T, 0, m->stream>>>(m->M, miss);
 	} else {
-		const uint32_t grid = (uint32_t)m->sm_count * (m->M.color ? UFO_UW_MINBLOCKS_COLOR : UFO_UW_MINBLOCKS);
-		constexpr uint32_t T = UFO_UW_WARPS * 32;
-		if (m->M.color) {
-			if (set_mode) k_update_warp<true, true><<<grid, T, 0, m->stream>>>(m->M, miss);
-			else k_update_warp<true, false><<<grid, T, 0, m->stream>>>(m->M, miss);
-		} else {
-			if (set_mode) k_update_warp<false, true><<<grid, T, 0, m->stream>>>(m->M, miss);
-			else k_update_warp<false, false><<<grid, T, 0, m->stream>>>(m->M, miss);
-		}
+		const uint32_t per_sm = UbShape<false>::kMinBlocks, T = UbShape<false>::kWarps * 32;
+		const uint32_t grid = (uint32_t)m->sm_count * (m->k3_blocks ? std::min<uint32_t>(per_sm, (uint32_t)m->k3_blocks) : per_sm);
+		if (set_mode) k_update_brick<false, true><<<grid, T, 0, m->stream>>>(m->M, miss);
+		else k_update_brick<false, false><<<grid, T, 0, m->stream>>>(m->M, miss);
 	}
 	++m->launches;
 }
@@ -1344,8 +1337,11 @@ int ufo_b200_create(const ufo_b200_params* p, ufo_b200_map** out)
 			const char* e = getenv("UFO_B200_MARK");
 			m->force_records = e && !strcmp(e, "records");
 			m->no_dense = e && !strcmp(e, "probe");
-			const char* k3 = getenv("UFO_B200_K3");
-			m->k3_cta = k3 && !strcmp(k3, "cta");
+			// resident CTAs per SM of the two long kernels (tuning / co-residency experiments)
+			const char* kb = getenv("UFO_B200_K3_BLOCKS");
+			if (kb && atoi(kb) > 0) m->k3_blocks = atoi(kb);
+			const char* wb = getenv("UFO_B200_WALK_BLOCKS");
+			if (wb && atoi(wb) > 0) m->walk_blocks_per_sm = std::min(m->walk_blocks_per_sm, atoi(wb));
 		}
 		m->params = *p;
 		CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
