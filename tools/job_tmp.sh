@@ -1,0 +1,2 @@
+bash tools/gpu_variants.sh
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -2

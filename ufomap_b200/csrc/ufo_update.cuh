@@ -144,16 +144,20 @@ struct __align__(128) WarpSlab {
 //  * lane 0 stages the header slab of the warp's NEXT brick -- miss masks 512 B, hit masks 512 B,
 //    meta 256 B -- with three bulk copies (cp.async.bulk) on a per-warp mbarrier, two stages;
 //  * lane = block (twice: 64 blocks): masks from shared memory, touched-octet list of the WHOLE
-//    brick by warp prefix sums; the old depth-1 sectors / depth-2 aggregates the block lanes need
-//    at the end travel by cp.async into shared memory behind the leaf loop (no registers held);
+//    brick by warp prefix sums -- built one brick EARLY, right after the previous brick's leaf loop,
+//    so that the brick's leaf sectors can be pulled into the L2 (prefetch.global.L2, no registers)
+//    while the previous brick's aggregates are still being written;
+//  * the old depth-1 sectors / depth-2 aggregates the block lanes need at the end travel by
+//    cp.async into shared memory behind the leaf loop (no registers held across it);
 //  * lanes then own list entries = 32 B leaf sectors, UFO_UB_INFLIGHT requested per lane before the
 //    first is used: v = clamp(v + hit), then v = clamp(v + miss) (float, order fixed), written back
 //    in place; octet maxima / flags return through warp-private shared memory (__syncwarp only);
 //  * block lanes write the depth-1 sector, the depth-2 aggregate, the meta word, clear the masks;
 //    depth-3 / depth-4 aggregates by shuffles.
-// Measured (profiles/README.md): a list per half brick costs 0.88 ms instead of 0.73 (latency exposed
-// twice per brick), 2 sectors in flight 0.80, 6 CTAs of 80 registers 0.82, a cp.async leaf pipeline
-// across bricks 0.91-0.95 (fewer warps, more instructions).
+// Measured on the bench workload (profiles/README.md): 0.70 ms.  A list per half brick: 0.88 (latency
+// exposed twice per brick); 2 sectors in flight at 6 CTAs of 80 registers: 0.82; without the L2
+// prefetch: 0.75; 228 KB instead of 196 KB of shared memory per SM (28 KB of L1 left): 0.85; a
+// cp.async leaf pipeline through shared memory: 0.91-0.95 (fewer warps, more instructions).
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* g)
 {
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(g) : "memory");
@@ -166,29 +170,37 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* g)
 {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(g) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 #ifndef UFO_UB_MINBLOCKS
 #define UFO_UB_MINBLOCKS 5
 #endif
+#ifndef UFO_UB_PREFETCH
+#define UFO_UB_PREFETCH 1  // pull the next brick's leaf sectors into the L2 one brick early
+#endif
 #ifndef UFO_UB_INFLIGHT
 #define UFO_UB_INFLIGHT 3  // leaf sectors requested per lane before the first is used
 #endif
 #ifndef UFO_UB_MINBLOCKS_COLOR
-#define UFO_UB_MINBLOCKS_COLOR 8
+#define UFO_UB_MINBLOCKS_COLOR 7
 #endif
+// One warp's shared memory.  Kept small on purpose: with 5 CTAs per SM it has to fit the 196 KB
+// carve-out -- one step more (228 KB) leaves 28 KB of L1, too little for the leaf sectors the warps keep
+// in flight, and costs 15 % of the kernel (profiles/README.md).
 template <bool COLOR>
-struct __align__(128) BrickWork {  // one warp's shared memory
+struct __align__(128) BrickWork {
 	WarpSlab slab[2];
-	float4 s1lo[64], s1hi[64];  // old depth-1 sector of each block
+	// old depth-1 sector of a marked block; for an unmarked block the slot holds its old depth-2
+	// aggregate (first 8 bytes of s1lo) and colour (first 4 bytes of s1hi) instead
+	float4 s1lo[64], s1hi[64];
 	uint4 c1lo[COLOR ? 64 : 1], c1hi[COLOR ? 64 : 1];
-	Agg old2[64];  // old depth-2 aggregate of an unmarked block
-	uint32_t old2rgb[COLOR ? 64 : 2];
 	float omax[512];
 	uint32_t orgb[COLOR ? 512 : 2];
-	uint16_t list[512];  // touched octets of the brick: (block << 3) | octet
-	unsigned char ofl[512];
+	// touched octets of a brick: (block << 3) | octet; after use the slot carries the octet's flags.
+	// [it & 1]: the brick being processed, the other one: the warp's next brick (built one brick early)
+	uint16_t list[2][512];
 	unsigned long long bar[2];
 };
 template <bool COLOR>
@@ -236,23 +248,14 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 	__syncwarp();
 
 	unsigned int s_vox = 0, s_hit = 0, s_oct = 0, s_blk = 0, s_new = 0, s_lin = 0;
-	uint32_t it = 0;
-	for (uint32_t e = gw; e < n_touched; e += n_warps, ++it) {
-		const uint32_t st = it & 1u;
-		if (lane == 0 && e + n_warps < n_touched) issue(st ^ 1u, e + n_warps);  // stage st^1 was released by the __syncwarp below
-		mbar_wait(&S.bar[st], (it >> 1) & 1u);
-		const uint32_t brick = __shfl_sync(FULL, st == 0 ? st_brick0 : st_brick1, 0);
-		const uint32_t mi = __shfl_sync(FULL, st == 0 ? st_mi0 : st_mi1, 0);
-		const WarpSlab& slab = S.slab[st];
-		const size_t b0 = (size_t)brick * 64;
 
-		// lane = block lane of either half: touched octets, requests for what the block lanes need later
-		uint32_t t8[2], excl[2], total = 0;
+	// lane = block lane of either half: touched octets of the brick in `slab`, list by warp prefix sums
+	auto build_list = [&](const WarpSlab& slab, uint16_t* list, uint32_t (&t8)[2], uint32_t (&excl)[2], uint32_t& total) {
+		total = 0;
 #pragma unroll
 		for (uint32_t h = 0; h < 2; ++h) {
 			const uint32_t blk = h * 32 + lane;
 			const unsigned long long u = slab.mm[blk] | slab.hm[blk];
-			const uint32_t mt = slab.meta[blk];
 			uint32_t t = 0;
 			if (u) {
 #pragma unroll
@@ -260,17 +263,6 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 					const uint32_t base = ((o & 1u) << 1) | ((o & 2u) << 2) | ((o & 4u) << 3);
 					t |= (((u >> base) & 0x330033ull) ? 1u : 0u) << o;
 				}
-				if (t != 0xffu) {
-					cp_async16(&S.s1lo[blk], M.sum1 + (b0 + blk) * 8);
-					cp_async16(&S.s1hi[blk], M.sum1 + (b0 + blk) * 8 + 4);
-					if (COLOR) {
-						cp_async16(&S.c1lo[COLOR ? blk : 0], M.sum1_rgb + (b0 + blk) * 8);
-						cp_async16(&S.c1hi[COLOR ? blk : 0], M.sum1_rgb + (b0 + blk) * 8 + 4);
-					}
-				}
-			} else if (fold && (mt & 0xff0000u)) {
-				cp_async8(&S.old2[blk], &M.agg2[b0 + blk]);
-				if (COLOR) cp_async4(&S.old2rgb[COLOR ? blk : 0], &M.rgb2[b0 + blk]);
 			}
 			uint32_t incl = __popc(t);
 #pragma unroll
@@ -285,10 +277,46 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 				while (bits) {
 					const uint32_t o = __ffs(bits) - 1;
 					bits &= bits - 1;
-					S.list[at++] = (uint16_t)((blk << 3) | o);
+					list[at++] = (uint16_t)((blk << 3) | o);
 				}
 			}
 			total += __shfl_sync(FULL, incl, 31);
+		}
+	};
+
+	uint32_t t8[2], excl[2], total = 0;     // the brick being processed
+	uint32_t t8n[2], excln[2], totaln = 0;  // the warp's next brick (its list is built one brick early)
+	mbar_wait(&S.bar[0], 0u);
+	build_list(S.slab[0], S.list[0], t8, excl, total);
+	__syncwarp();
+	uint32_t it = 0;
+	for (uint32_t e = gw; e < n_touched; e += n_warps, ++it) {
+		const uint32_t st = it & 1u;
+		const bool has_next = e + n_warps < n_touched;
+		if (lane == 0 && has_next) issue(st ^ 1u, e + n_warps);  // stage st^1 was released by the __syncwarp at the end of the loop
+		const uint32_t brick = __shfl_sync(FULL, st == 0 ? st_brick0 : st_brick1, 0);
+		const uint32_t mi = __shfl_sync(FULL, st == 0 ? st_mi0 : st_mi1, 0);
+		const WarpSlab& slab = S.slab[st];
+		const uint16_t* list = S.list[st];
+		const size_t b0 = (size_t)brick * 64;
+
+		// what the block lanes need after the leaf loop: requested now, into shared memory
+#pragma unroll
+		for (uint32_t h = 0; h < 2; ++h) {
+			const uint32_t blk = h * 32 + lane;
+			if (t8[h]) {
+				if (t8[h] != 0xffu) {
+					cp_async16(&S.s1lo[blk], M.sum1 + (b0 + blk) * 8);
+					cp_async16(&S.s1hi[blk], M.sum1 + (b0 + blk) * 8 + 4);
+					if (COLOR) {
+						cp_async16(&S.c1lo[COLOR ? blk : 0], M.sum1_rgb + (b0 + blk) * 8);
+						cp_async16(&S.c1hi[COLOR ? blk : 0], M.sum1_rgb + (b0 + blk) * 8 + 4);
+					}
+				}
+			} else if (fold && (slab.meta[blk] & 0xff0000u)) {
+				cp_async8(&S.s1lo[blk], &M.agg2[b0 + blk]);
+				if (COLOR) cp_async4(&S.s1hi[blk], &M.rgb2[b0 + blk]);
+			}
 		}
 		cp_async_commit();
 		__syncwarp();
@@ -299,7 +327,7 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 #pragma unroll
 			for (int f = 0; f < UFO_UB_INFLIGHT; ++f) {
 				const uint32_t idx = i + 32 * f;
-				en[f] = idx < total ? (uint32_t)S.list[idx] : 0xffffffffu;
+				en[f] = idx < total ? (uint32_t)list[idx] : 0xffffffffu;
 				if (en[f] != 0xffffffffu) {
 					const float4* lp = reinterpret_cast<const float4*>(M.leaf + (b0 + (en[f] >> 3)) * 64 + 8 * (en[f] & 7u));
 					a0[f] = lp[0];
@@ -315,7 +343,7 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 				uint32_t ofl;
 				update_octet<SET>(M, miss, M.leaf + (b0 + t) * 64 + 8 * o, m8, h8, a0[f], a1[f], omax, ofl, b0 + t, o);
 				S.omax[idx] = omax;
-				S.ofl[idx] = (unsigned char)ofl;
+				S.list[st][idx] = (uint16_t)ofl;  // the entry has been consumed: the slot carries the flags back
 				if (COLOR) {
 					const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + (b0 + t) * 64 + 8 * o);
 					const uint4 x0 = cp[0], x1 = cp[1];
@@ -326,6 +354,24 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 				s_hit += __popc(h8);
 				s_oct += 1;
 			}
+		}
+		if (has_next) {
+			// the next brick of this warp: its slab was requested at the top of this iteration; build its
+			// list now and pull its leaf sectors into the L2 while this brick's aggregates are written
+			mbar_wait(&S.bar[st ^ 1u], ((it + 1u) >> 1) & 1u);
+			build_list(S.slab[st ^ 1u], S.list[st ^ 1u], t8n, excln, totaln);
+#if UFO_UB_PREFETCH
+			__syncwarp();
+			const uint32_t brick_n = __shfl_sync(FULL, st == 0 ? st_brick1 : st_brick0, 0);
+			const float* leaf_n = M.leaf + (size_t)brick_n * 64 * 64;
+			for (uint32_t i = lane; i < totaln; i += 32) {
+				const uint32_t en = S.list[st ^ 1u][i];
+				prefetch_l2(leaf_n + (en >> 3) * 64 + 8 * (en & 7u));
+			}
+#pragma unroll
+			for (uint32_t h = 0; h < 2; ++h)
+				if (t8n[h] && t8n[h] != 0xffu) prefetch_l2(M.sum1 + ((size_t)brick_n * 64 + h * 32 + lane) * 8);
+#endif
 		}
 		cp_async_wait_all();
 		__syncwarp();
@@ -364,7 +410,7 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 					uint32_t fl = M.default_flags, touched = 0, oc = 0;
 					if ((t8[h] >> o) & 1u) {
 						om = S.omax[at];
-						fl = S.ofl[at];
+						fl = S.list[st][at];
 						if (COLOR) oc = S.orgb[COLOR ? at : 0];
 						++at;
 						touched = 1;
@@ -399,10 +445,10 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 				my_occ = bmax;
 				my_fl = bfl | 0x100u;
 			} else if (fold && (mt & 0xff0000u)) {
-				const Agg o2 = S.old2[blk];
-				my_occ = o2.occ;
-				my_fl = o2.flags;
-				if (COLOR) my_rgb = S.old2rgb[COLOR ? blk : 0];
+				const float4 o2 = S.s1lo[blk];
+				my_occ = o2.x;
+				my_fl = __float_as_uint(o2.y);
+				if (COLOR) my_rgb = __float_as_uint(S.s1hi[blk].x);
 			}
 			agg_occ[h] = my_occ;
 			agg_fl[h] = my_fl;
@@ -465,6 +511,11 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 				atomicAdd(&slot[6], (unsigned long long)(__popc(ub0) + __popc(ub1)));
 			}
 		}
+		t8[0] = t8n[0];
+		t8[1] = t8n[1];
+		excl[0] = excln[0];
+		excl[1] = excln[1];
+		total = totaln;
 		__syncwarp();  // the slab stage, the list and the result arrays are reused
 	}
 	for (int o = 16; o > 0; o >>= 1) {
