@@ -35,6 +35,9 @@ def _run_case(map_kw, inserts, color=False, color_tol=1, with_ref=True, levels=(
     rmn, rmx = cpus[0].change_bbox()
     assert np.array_equal(mn, rmn) and np.array_equal(mx, rmx), (mn, rmn, mx, rmx)
     st = gpu.stats()
+    # every touched block holds 1 or 2 touched 128-byte leaf lines, every line 1..4 touched octets
+    assert st["touched_blocks"] <= st["touched_lines"] <= 2 * st["touched_blocks"]
+    assert st["touched_lines"] <= st["touched_octets"] <= 4 * st["touched_lines"]
     gpu.close()
     return st
 
