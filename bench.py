@@ -120,27 +120,87 @@ def measured_traffic():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING a timed region.  Sampled in-process through NVML (a thread,
+    one query every 20 ms): starting an `nvidia-smi` process next to a 30 ms timed region puts its
+    driver initialisation inside that region and can stall kernel launches for tens of ms (seen once
+    as a 42 ms hole in the pipelined loop).  Falls back to `nvidia-smi -lms` when pynvml is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    _nvml = None
+    _nvml_tried = False
+    REASON_BITS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                   (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index, period_ms=100):
+    @classmethod
+    def nvml(cls):
+        if not cls._nvml_tried:
+            cls._nvml_tried = True
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                cls._nvml = pynvml
+            except Exception:
+                cls._nvml = None
+        return cls._nvml
+
+    def __init__(self, gpu_index, period_ms=20):
         self.path = "/tmp/ufo_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
         self.proc = None
+        self.thread = None
         self.gpu = gpu_index
         self.period = period_ms
+        self.samples = []
+
+    def _loop(self, nv, handle):
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((float(sm), float(mx), int(rs)))
+            except Exception:
+                pass
+            self._stop.wait(self.period * 1e-3)
 
     def start(self):
+        nv = self.nvml()
+        if nv is not None:
+            try:
+                import threading
+                handle = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+                self._stop = threading.Event()
+                self.thread = threading.Thread(target=self._loop, args=(nv, handle), daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.thread = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", str(self.period)],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            if self.samples:
+                reasons = set()
+                for _, _, rs in self.samples:
+                    for bit, name in self.REASON_BITS:
+                        if rs & bit:
+                            reasons.add(name)
+                out.update(sm_mhz=float(np.median([x[0] for x in self.samples])),
+                           sm_max_mhz=float(max(x[1] for x in self.samples)), samples=len(self.samples),
+                           reasons=sorted(reasons), source="nvml")
+            return out
         if not self.proc:
             return out
         time.sleep(0.15)
@@ -168,7 +228,7 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm), source="nvidia-smi")
         out["reasons"] = sorted(reasons)
         return out
 
@@ -539,6 +599,8 @@ def main():
             "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": int(n_mine * p_in), "d2h_bytes_per_step": d2h,
                     "mode": "async=1 (server default): H2D of scan k+1 overlaps the kernels of scan k",
+                    "regrows": int(sum(s_["regrows"] for s_ in e2e_scans)),
+                    "max_scan_device_ms": float(max(s_["ms_total"] for s_ in e2e_scans)),
                     "sync": {"value": e2e_sync, "ms_per_step": ms_sync / steps,
                              "mode": "wait + read the scan's own counters after every insert"}},
             "sustained": sustained,

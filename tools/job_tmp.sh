@@ -1,3 +1,7 @@
-timeout 1100 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1.json 2> gpurun_out/bench_err.log; tail -c 600 gpurun_out/r02_bench_n1.json
-bash tools/profile_run.sh r02i > gpurun_out/prof.log 2>&1
+bash tools/gpu_variants.sh
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_a.json 2> gpurun_out/bench_err.log
+python - <<'P'
+import json
+d=json.loads([l for l in open('gpurun_out/bench_a.json') if l.startswith('{')][-1])
+print('value',d['value'],'e2e',d['e2e'])
+P
