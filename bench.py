@@ -121,7 +121,7 @@ def measured_traffic():
 
 class ClockSampler:
     """SM clock and throttle reasons DURING a timed region.  Sampled in-process through NVML (a thread,
-    one query every 20 ms): starting an `nvidia-smi` process next to a 30 ms timed region puts its
+    one query every 5 ms): starting an `nvidia-smi` process next to a 30 ms timed region puts its
     driver initialisation inside that region and can stall kernel launches for tens of ms (seen once
     as a 42 ms hole in the pipelined loop).  Falls back to `nvidia-smi -lms` when pynvml is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -144,7 +144,7 @@ class ClockSampler:
                 cls._nvml = None
         return cls._nvml
 
-    def __init__(self, gpu_index, period_ms=20):
+    def __init__(self, gpu_index, period_ms=5):
         self.path = "/tmp/ufo_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
         self.proc = None
         self.thread = None
