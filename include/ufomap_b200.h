@@ -133,7 +133,7 @@ int ufo_b200_pose_from_rpy(double x, double y, double z, double roll, double pit
                            double frame_pose[7]);
 
 int ufo_b200_wait(ufo_b200_map* m);           /* insertPointCloudWait */
-int ufo_b200_done(ufo_b200_map* m, int* done); /* insertPointCloudDone */
+int ufo_b200_done(ufo_b200_map* m, int* done); /* insertPointCloudDone; never blocks while device work is in flight (completes a scan that ran into a full pool once the device is idle) */
 
 /* Octree::computeRay  octree.h:449-496 -- forward walk, origin voxel included,
  * end voxel excluded.  Writes up to cap codes, *n receives the full count. */

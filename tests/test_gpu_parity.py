@@ -262,6 +262,24 @@ def test_async_matches_sync_and_determinism():
     assert_value_fields_equal(a.value_field(), b.value_field())
 
 
+def test_async_insert_returns_before_the_scan_is_done():
+    """insertPointCloud with async = true returns after enqueueing (occupancy_map_base.h:311-327):
+    right after the call of a full 131 072-point scan the integration is still running."""
+    m = Map(0.02, initial_bricks=1 << 19)
+    for k in range(2):
+        o, p = scans.velodyne64(k=k)
+        m.insert(o, p, max_range=30.0, dtype=np.float32)
+    o, p = scans.velodyne64(k=2)
+    p = np.ascontiguousarray(p, dtype=np.float32)
+    m.insert(o, p, max_range=30.0, dtype=np.float32, async_=True)
+    busy = not m.done()
+    m.wait()
+    assert m.done()
+    assert busy, "an async insert of a full scan (about 1.5 ms of device work) was already complete on return"
+    assert m.stats()["regrows"] == 0
+    m.close()
+
+
 def test_query_leaf_and_missing_nodes():
     gpu = Map(0.02)
     gpu.insert([0, 0, 0], [[1.0, 0, 0]], max_range=5.0)

@@ -308,6 +308,16 @@ __device__ __forceinline__ uint32_t brick_find_or_create_from(const DeviceMap& M
 			}
 		}
 		if (k == key) {
+			// The key is in the table but its slot may not be published yet (value == kPending).
+			// Forward progress of this wait: the thread that won the CAS publishes with straight-line
+			// code -- one atomicAdd, two stores, no wait of its own -- so it finishes as soon as it is
+			// scheduled.  (a) Winner in another warp: it is a resident thread (it executed the CAS), and
+			// resident warps keep being scheduled.  (b) Winner in THIS warp: it diverged from the waiting
+			// lanes at `k == kEmptyKey` above; sm_70+ schedules the diverged paths of a warp
+			// independently, and there is no convergence barrier (__syncwarp, *_sync shuffle or vote)
+			// between the CAS and the publishing store, so the winner's path runs while these lanes
+			// poll.  The volatile load keeps the loop an actual re-read.  Callers must not invoke this
+			// function from inside a region that some lanes leave through a warp-synchronous primitive.
 			uint32_t v;
 			while ((v = ld_volatile_u32(vp)) == kPending) {
 			}
@@ -362,6 +372,7 @@ __device__ __forceinline__ uint32_t upper_find_or_create(const DeviceMap& M, uin
 		}
 		if (k == key) {
 			uint32_t v;
+			// same wait as in brick_find_or_create_from (see the forward-progress argument there)
 			while ((v = ld_volatile_u32(&M.uh_vals[i])) == kPending) {
 			}
 			return v == kFailed ? kNone : v;

@@ -1531,6 +1531,15 @@ int ufo_b200_done(ufo_b200_map* m, int* done)
 	if (m->device == -2) return UFO_B200_E_CUDA;
 	cudaError_t e = cudaStreamQuery(m->stream);
 	if (e == cudaSuccess) {
+		// the stream is idle; if the scan ran into a full pool it is not integrated yet: grow and repeat
+		// it now, so that a caller polling this function always gets to "done"
+		if (m->pending.valid && m->h_ctr->overflow) {
+			const int rc = guarded(m, [&]() {
+				CK(cudaSetDevice(m->device));
+				return sync_map(m);
+			});
+			if (rc != UFO_B200_OK) return rc;
+		}
 		*done = 1;
 		return UFO_B200_OK;
 	}
