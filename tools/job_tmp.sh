@@ -1,7 +1,4 @@
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29617 bench.py --gpus 4 --steps 10 --warmup 3 --sustain 0 > gpurun_out/r02_bench_n4_route.json 2> gpurun_out/r02_bench_n4_route.err
-echo "rc=$?"; tail -c 300 gpurun_out/r02_bench_n4_route.err
-python - <<'P'
-import json
-d=json.loads([l for l in open('gpurun_out/r02_bench_n4_route.json') if l.startswith('{')][-1])
-print('route N=4 value %.1f M e2e %.1f M ms/step %.3f'%(d['value']/1e6,d['e2e']['value']/1e6,d['ms_per_step']), d['kernels_ms'], d['config']['mode'])
-P
+K="python tools/kbench.py --res 0.002 --range 5 --shape rgbd --discrete --scans 6 --bricks 1048576"
+$K 2>&1 | tail -1
+for v in variants/*.so; do UFOMAP_B200_LIB=$PWD/$v $K 2>&1 | tail -1; done
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "color or set_value or frame or pointcloud2" 2>&1 | tail -2

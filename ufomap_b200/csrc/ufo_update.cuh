@@ -180,6 +180,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #ifndef UFO_UB_PREFETCH
 #define UFO_UB_PREFETCH 1  // pull the next brick's leaf sectors into the L2 one brick early
 #endif
+#ifndef UFO_UB_INFLIGHT_COLOR
+#define UFO_UB_INFLIGHT_COLOR 1  // colour maps (each entry is two sectors: log-odds + colour): 1 / 2 / 3 in flight = 5.4 / 6.9 / 8.6 ms on config #3
+#endif
 #ifndef UFO_UB_INFLIGHT
 #define UFO_UB_INFLIGHT 3  // leaf sectors requested per lane before the first is used
 #endif
@@ -320,22 +323,31 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 		}
 		cp_async_commit();
 		__syncwarp();
-		// lanes own list entries = 32 B leaf sectors, UFO_UB_INFLIGHT of them in flight per lane
-		for (uint32_t i = lane; i < total; i += 32 * UFO_UB_INFLIGHT) {
-			float4 a0[UFO_UB_INFLIGHT], a1[UFO_UB_INFLIGHT];
-			uint32_t en[UFO_UB_INFLIGHT];
+		// lanes own list entries = 32 B leaf sectors (+ the colour sector of the same octet), NF of them
+		// requested per lane before the first is used
+		constexpr int NF = COLOR ? UFO_UB_INFLIGHT_COLOR : UFO_UB_INFLIGHT;
+		for (uint32_t i = lane; i < total; i += 32 * NF) {
+			float4 a0[NF], a1[NF];
+			uint4 x0[COLOR ? NF : 1], x1[COLOR ? NF : 1];
+			uint32_t en[NF];
 #pragma unroll
-			for (int f = 0; f < UFO_UB_INFLIGHT; ++f) {
+			for (int f = 0; f < NF; ++f) {
 				const uint32_t idx = i + 32 * f;
 				en[f] = idx < total ? (uint32_t)list[idx] : 0xffffffffu;
 				if (en[f] != 0xffffffffu) {
-					const float4* lp = reinterpret_cast<const float4*>(M.leaf + (b0 + (en[f] >> 3)) * 64 + 8 * (en[f] & 7u));
+					const size_t off = (b0 + (en[f] >> 3)) * 64 + 8 * (en[f] & 7u);
+					const float4* lp = reinterpret_cast<const float4*>(M.leaf + off);
 					a0[f] = lp[0];
 					a1[f] = lp[1];
+					if (COLOR) {
+						const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + off);
+						x0[COLOR ? f : 0] = cp[0];
+						x1[COLOR ? f : 0] = cp[1];
+					}
 				}
 			}
 #pragma unroll
-			for (int f = 0; f < UFO_UB_INFLIGHT; ++f) {
+			for (int f = 0; f < NF; ++f) {
 				if (en[f] == 0xffffffffu) continue;
 				const uint32_t idx = i + 32 * f, t = en[f] >> 3, o = en[f] & 7u;
 				const uint32_t m8 = octet_bits8(slab.mm[t], o), h8 = octet_bits8(slab.hm[t], o);
@@ -345,9 +357,8 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 				S.omax[idx] = omax;
 				S.list[st][idx] = (uint16_t)ofl;  // the entry has been consumed: the slot carries the flags back
 				if (COLOR) {
-					const uint4* cp = reinterpret_cast<const uint4*>(M.leaf_rgb + (b0 + t) * 64 + 8 * o);
-					const uint4 x0 = cp[0], x1 = cp[1];
-					const uint32_t cc[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+					const uint4 c0 = x0[COLOR ? f : 0], c1 = x1[COLOR ? f : 0];
+					const uint32_t cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 					S.orgb[COLOR ? idx : 0] = rms_rgb(cc, 8);
 				}
 				s_vox += __popc(m8 | h8);
@@ -367,6 +378,7 @@ __global__ void __launch_bounds__(UbShape<COLOR>::kWarps * 32, UbShape<COLOR>::k
 			for (uint32_t i = lane; i < totaln; i += 32) {
 				const uint32_t en = S.list[st ^ 1u][i];
 				prefetch_l2(leaf_n + (en >> 3) * 64 + 8 * (en & 7u));
+				if (COLOR) prefetch_l2(M.leaf_rgb + (size_t)brick_n * 64 * 64 + (en >> 3) * 64 + 8 * (en & 7u));
 			}
 #pragma unroll
 			for (uint32_t h = 0; h < 2; ++h)
