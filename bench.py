@@ -19,13 +19,19 @@ configurations the same way.
 * sustained: the e2e loop kept running for >= 2 s over the same scans (clock record included).
 * roofline: algorithmic bytes (SURVEY.md 8(d) formula on the live device counters) over CUDA-event
            time, against the measured HBM peak: for the dominant kernel and for the whole scan.
+           roofline.line_granular: HBM moves whole 128 B lines; the leaf lines the dominant kernel
+           touches (counted on the device) and the measured ceiling of that sparse access pattern
+           (tools/sector_ceiling.cu -> profiles/r02_sector_ceiling.jsonl).
+* cold_start: first scans into a map created with the default pool sizes (pool growth included).
 * raycast: voxel visits/s and mark atomics/s of the fused walk against the measured L2 atomic
            ceiling (tools/atomic_ceiling.cu -> profiles/r02_atomic_ceiling.jsonl).
 * cpu_baseline / --impl reference: the unmodified reference (oracle/_ref/libufo_ref.so) on a bounded
            sample of the same workload on the host cores.
 
-Multi-GPU (torchrun, one rank per GPU): --mode sensors = one sensor stream + map per GPU (weak
-scaling, replicas); --mode shard = ONE scan stream, map sharded by brick ownership.
+Multi-GPU (torchrun, one rank per GPU): --mode route (default) = ONE scan stream, rays split over
+the GPUs, state owned by space, marks forwarded over NVLink peer memory; --mode merge = one sensor
+per GPU merged in sensor order (BASELINE config #5); --mode sensors = one sensor stream + map per
+GPU (replicas); --mode shard = ONE scan stream broadcast, every GPU walks every ray.
 """
 import argparse
 import json
